@@ -1,0 +1,69 @@
+"""ctypes binding of libner_b200.so (the C-ABI in include/ner_b200.h).
+
+The library is the product path: if it is missing or cannot be loaded this module raises —
+there is no CPU or PyTorch fallback.  Tensors are passed as raw device pointers; torch is only
+the allocator / stream container.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libner_b200.so")
+
+_c = ctypes
+_vp, _i = _c.c_void_p, _c.c_int
+
+# name -> (restype, argtypes); must list every symbol include/ner_b200.h declares.
+SIGNATURES = {
+    "ner_strerror": (_c.c_char_p, [_i]),
+    "ner_abi_version": (_i, []),
+    "ner_crf_viterbi": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ner_crf_loglik_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ner_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+}
+
+_lib = None
+
+
+class NerB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if the extension is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NerB200Error(
+                f"{LIB_PATH} not found: build it with `python -m chinesener_b200.build` "
+                "(there is no CPU fallback for the sm_100a kernels)")
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise NerB200Error(lib().ner_strerror(status).decode())
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise NerB200Error("ner_b200 kernels take CUDA tensors (got a CPU tensor); there is no CPU path")
+        if t is not None and not t.is_contiguous():
+            raise NerB200Error("ner_b200 kernels take contiguous row-major tensors")

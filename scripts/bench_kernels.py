@@ -1,0 +1,69 @@
+"""Stand-alone kernel timings (CUDA events) used while tuning; not the driver's bench.py.
+
+usage: python scripts/bench_kernels.py [crf] [gemm]
+"""
+import json
+import sys
+
+import torch
+
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+from chinesener_b200 import ops  # noqa: E402
+
+
+def timeit(fn, warm=3, iters=10):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for s, e in evs:
+        s.record()
+        fn()
+        e.record()
+    torch.cuda.synchronize()
+    ts = sorted(s.elapsed_time(e) for s, e in evs)
+    return ts[len(ts) // 2], ts[0]
+
+
+def bench_crf(B=262144, L=128, K=10):
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.randn(B, L, K, device="cuda", generator=g)
+    tr = torch.randn(K, K, device="cuda", generator=g) * 0.5
+    lens = torch.full((B,), L, dtype=torch.int32, device="cuda")
+    tags = torch.randint(0, K, (B, L), device="cuda", dtype=torch.int32)
+    out = {}
+    med, best = timeit(lambda: ops.crf_viterbi(x, lens, tr))
+    byts = B * L * (4 * K) + 4 * B + 4 * K * K + B * L * 4 + 4 * B
+    out["viterbi"] = dict(ms=med, best_ms=best, GBps=byts / med / 1e6, bytes=byts)
+    for exact in (False, True):
+        med, best = timeit(lambda: ops.crf_loglik_fwd(x, tags, lens, tr, exact=exact))
+        byts = B * L * (4 * K + 4) + 8 * B + 4 * K * K
+        out["loglik_fwd_exact" if exact else "loglik_fwd"] = dict(ms=med, best_ms=best, GBps=byts / med / 1e6, bytes=byts)
+    # latency regime
+    xs, ls, ts = x[:64].contiguous(), lens[:64].contiguous(), tags[:64].contiguous()
+    out["viterbi_B64_us"] = timeit(lambda: ops.crf_viterbi(xs, ls, tr), iters=50)[0] * 1e3
+    out["loglik_B64_us"] = timeit(lambda: ops.crf_loglik_fwd(xs, ts, ls, tr), iters=50)[0] * 1e3
+    return out
+
+
+def bench_gemm():
+    out = {}
+    for (M, N, K) in [(8192, 2304, 768), (8192, 768, 768), (8192, 3072, 768), (8192, 768, 3072), (8192, 1024, 768)]:
+        a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+        w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+        bias = torch.randn(N, device="cuda")
+        for tn in (128, 256):
+            o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+            med, best = timeit(lambda: ops.gemm_bf16(a, w, bias, epilogue=ops.EPI_BF16, tile_n=tn, out=o), iters=20)
+            out[f"{M}x{N}x{K}_bn{tn}"] = dict(ms=med, TFLOPs=2.0 * M * N * K / med / 1e9)
+    return out
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["crf", "gemm"]
+    res = {}
+    if "crf" in which:
+        res["crf"] = bench_crf()
+    if "gemm" in which:
+        res["gemm"] = bench_gemm()
+    print(json.dumps(res, indent=1))
