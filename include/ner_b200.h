@@ -59,6 +59,19 @@ int ner_crf_loglik_fwd(const float* logits, const int32_t* tags, const int32_t* 
                        const float* trans, float* ll, float* logz_out, float* alpha_ws,
                        int B, int L, int K, int flags, ner_stream_t stream);
 
+/* Gradient of the log-likelihood (the reference gets it from tf.gradients,
+ * tools/train_utils.py:314): for g_b = (d_ll ? d_ll[b] : 1) * scale,
+ *   d_logits[b,t,j] = g_b * (1[y_t=j] - P(y_t=j|x))            (0 beyond seq_len)
+ *   d_trans[i,j]   += sum_b g_b * (count_b(i->j) - sum_t P(y_{t-1}=i,y_t=j|x))
+ * alpha_ws / logz come from ner_crf_loglik_fwd.  d_logits [B,L,K] is fully
+ * written; d_trans [K,K] is ACCUMULATED into (caller zeroes it).  For the
+ * reference loss mean(-ll) (model/bert_bilstm_crf.py:32) pass d_ll = NULL,
+ * scale = -1/B. */
+int ner_crf_loglik_bwd(const float* logits, const int32_t* tags, const int32_t* seq_len,
+                       const float* trans, const float* alpha_ws, const float* logz,
+                       const float* d_ll, float scale, float* d_logits, float* d_trans, int B,
+                       int L, int K, ner_stream_t stream);
+
 
 /* ------------------------------------------------------------------------ *
  * Dense layers on tcgen05 tensor cores — replaces tf.layers.dense /
