@@ -1,0 +1,305 @@
+// HBM-bound glue kernels of the encoder path (sm_100a): embedding-sum + LayerNorm, LayerNorm,
+// weight packing / casts, and the small-N (label_size) dense projection.
+//
+// Reference call sites: bert_base.bert.modeling (embedding_postprocessor, layer_norm) executed
+// from tools/layer.py:68-77; tf.layers.dense(units=label_size) at model/bert_bilstm_crf.py:26
+// and model/bert_crf.py:20; tools/transformer/modules.py:40-65 (layer_norm, eps = fp32 eps).
+#include "common.cuh"
+
+namespace {
+
+using namespace nerdev;
+
+constexpr int LN_MAXV = 8;  // float4 per lane -> H <= 1024
+
+// Row LayerNorm over registers: v holds this lane's float4s (nv4 valid), H = row length.
+// Matches tf.contrib.layers.layer_norm / tf.nn.moments: biased variance of (x - mean).
+__device__ __forceinline__ void ln_row(float4 (&v)[LN_MAXV], int nv4, int H, int lane, float eps,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k)
+    if (k < nv4 && (lane + 32 * k) * 4 < H) s += v[k].x + v[k].y + v[k].z + v[k].w;
+  s = warp_sum(s);
+  const float mean = s / (float)H;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k)
+    if (k < nv4 && (lane + 32 * k) * 4 < H) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+  q = warp_sum(q);
+  const float rstd = rsqrtf(q / (float)H + eps);
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k) {
+    const int e = (lane + 32 * k) * 4;
+    if (k < nv4 && e < H) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + e));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + e));
+      float4 o;
+      o.x = (v[k].x - mean) * rstd * g.x + b.x;
+      o.y = (v[k].y - mean) * rstd * g.y + b.y;
+      o.z = (v[k].z - mean) * rstd * g.z + b.z;
+      o.w = (v[k].w - mean) * rstd * g.w + b.w;
+      if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + e) = o;
+      if (out_bf16 != nullptr) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(out_bf16 + e) = pk;
+      }
+    }
+  }
+}
+
+// one warp per token
+__global__ void __launch_bounds__(256)
+bert_embed_ln_kernel(const float* __restrict__ word_emb, const float* __restrict__ type_emb,
+                     const float* __restrict__ pos_emb, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const int32_t* __restrict__ ids,
+                     const int32_t* __restrict__ seg, float* __restrict__ out_f32,
+                     __nv_bfloat16* __restrict__ out_bf16, int n_tok, int L, int H, int V, int n_type, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int nv4 = (H / 4 + 31) / 32;
+  for (int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tok < n_tok; tok += gridDim.x * (blockDim.x >> 5)) {
+    int id = ids[tok];
+    id = min(max(id, 0), V - 1);
+    int sg = (seg != nullptr) ? seg[tok] : 0;
+    sg = min(max(sg, 0), n_type - 1);
+    const int pos = tok % L;
+    const float* w = word_emb + (size_t)id * H;
+    const float* ty = type_emb + (size_t)sg * H;
+    const float* po = pos_emb + (size_t)pos * H;
+    float4 v[LN_MAXV];
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+      const int e = (lane + 32 * k) * 4;
+      if (k < nv4 && e < H) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(w + e));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(ty + e));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(po + e));
+        v[k] = make_float4(a.x + b.x + c.x, a.y + b.y + c.y, a.z + b.z + c.z, a.w + b.w + c.w);
+      }
+    }
+    ln_row(v, nv4, H, lane, eps, gamma, beta, out_f32 ? out_f32 + (size_t)tok * H : nullptr,
+           out_bf16 ? out_bf16 + (size_t)tok * H : nullptr);
+  }
+}
+
+// y (+ optional residual) -> LayerNorm -> fp32 and/or bf16
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ y, const float* __restrict__ residual, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
+                 int M, int H, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int nv4 = (H / 4 + 31) / 32;
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += gridDim.x * (blockDim.x >> 5)) {
+    const float* p = y + (size_t)row * H;
+    const float* r = residual ? residual + (size_t)row * H : nullptr;
+    float4 v[LN_MAXV];
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+      const int e = (lane + 32 * k) * 4;
+      if (k < nv4 && e < H) {
+        v[k] = *reinterpret_cast<const float4*>(p + e);
+        if (r != nullptr) {
+          const float4 b = *reinterpret_cast<const float4*>(r + e);
+          v[k].x += b.x;
+          v[k].y += b.y;
+          v[k].z += b.z;
+          v[k].w += b.w;
+        }
+      }
+    }
+    ln_row(v, nv4, H, lane, eps, gamma, beta, out_f32 ? out_f32 + (size_t)row * H : nullptr,
+           out_bf16 ? out_bf16 + (size_t)row * H : nullptr);
+  }
+}
+
+// TF dense kernel [K,N] fp32  ->  bf16 [N,K] (K contiguous) through a 32x33 smem tile
+__global__ void __launch_bounds__(256)
+pack_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int K, int N) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int k = k0 + i, n = n0 + tx;
+    tile[i][tx] = (k < K && n < N) ? src[(size_t)k * N + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int n = n0 + i, k = k0 + tx;
+    if (n < N && k < K) dst[(size_t)n * K + k] = __float2bfloat16_rn(tile[tx][i]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// out[M,N] = x[M,F] · W[F,N] + b[N], N <= 32 (label_size).  W staged in smem; one warp per row,
+// lanes split F, N partial sums reduced with shuffles.  x is fp32 or bf16.
+template <typename XT, int NMAX>
+__global__ void __launch_bounds__(256)
+dense_small_n_kernel(const XT* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                     float* __restrict__ out, int M, int F, int N) {
+  extern __shared__ float s_w[];  // [F][N]
+  for (int e = threadIdx.x; e < F * N; e += blockDim.x) s_w[e] = W[e];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += gridDim.x * (blockDim.x >> 5)) {
+    float acc[NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+    const XT* xr = x + (size_t)row * F;
+    for (int f = lane; f < F; f += 32) {
+      float xv;
+      if constexpr (sizeof(XT) == 2) xv = __bfloat162float(xr[f]);
+      else xv = xr[f];
+      const float* wr = s_w + f * N;
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n)
+        if (n < N) acc[n] = fmaf(xv, wr[n], acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) acc[n] = warp_sum(acc[n]);
+    if (lane < N) {
+      float v = 0.f;
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n)
+        if (n == lane) v = acc[n];
+      out[(size_t)row * N + lane] = v + (bias ? bias[lane] : 0.f);
+    }
+  }
+}
+
+
+// out[tok, 0:E] (row stride ld_out) = table[ids[tok], :]   (tf.nn.embedding_lookup)
+__global__ void __launch_bounds__(256)
+embedding_lookup_kernel(const float* __restrict__ table, const int32_t* __restrict__ ids, float* __restrict__ out,
+                        int n_tok, int E, int V, int ld_out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int tok = blockIdx.x * wpb + (threadIdx.x >> 5); tok < n_tok; tok += gridDim.x * wpb) {
+    const int id = min(max(ids[tok], 0), V - 1);
+    const float* row = table + (size_t)id * E;
+    float* o = out + (size_t)tok * ld_out;
+    for (int e = lane; e < E; e += 32) o[e] = __ldg(row + e);
+  }
+}
+
+// f32 [M,D] (row stride ld_src) -> bf16 [M,Dp], zero padded columns D..Dp-1
+__global__ void __launch_bounds__(256)
+cast_pad_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int M, int D, int Dp, int ld_src) {
+  const size_t total = (size_t)M * Dp;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / Dp;
+    const int c = (int)(i - r * Dp);
+    dst[i] = __float2bfloat16_rn(c < D ? src[r * ld_src + c] : 0.f);
+  }
+}
+
+int grid_for_rows(int rows, int rows_per_block) {
+  long g = ((long)rows + rows_per_block - 1) / rows_per_block;
+  if (g > 148L * 16) g = 148L * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+extern "C" int ner_bert_embed_ln(const float* word_emb, const float* type_emb, const float* pos_emb,
+                                 const float* gamma, const float* beta, const int32_t* ids, const int32_t* seg,
+                                 float* out_f32, void* out_bf16, int B, int L, int H, int vocab, int n_type,
+                                 int max_pos, float eps, ner_stream_t stream) {
+  if (B < 0 || L < 1 || H < 4 || vocab < 1 || n_type < 1) return NER_ERR_INVALID_ARG;
+  if (B == 0) return NER_OK;
+  if (!word_emb || !type_emb || !pos_emb || !gamma || !beta || !ids || (!out_f32 && !out_bf16)) return NER_ERR_INVALID_ARG;
+  if (H % 4 != 0 || H > 128 * LN_MAXV || L > max_pos) return NER_ERR_UNSUPPORTED;
+  const int n_tok = B * L;
+  bert_embed_ln_kernel<<<grid_for_rows(n_tok, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      word_emb, type_emb, pos_emb, gamma, beta, ids, seg, out_f32, static_cast<__nv_bfloat16*>(out_bf16), n_tok, L, H,
+      vocab, n_type, eps);
+  return ner_launch_status();
+}
+
+extern "C" int ner_layernorm(const float* y, const float* residual, const float* gamma, const float* beta,
+                             float* out_f32, void* out_bf16, int M, int H, float eps, ner_stream_t stream) {
+  if (M < 0 || H < 4) return NER_ERR_INVALID_ARG;
+  if (M == 0) return NER_OK;
+  if (!y || !gamma || !beta || (!out_f32 && !out_bf16)) return NER_ERR_INVALID_ARG;
+  if (H % 4 != 0 || H > 128 * LN_MAXV) return NER_ERR_UNSUPPORTED;
+  layernorm_kernel<<<grid_for_rows(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      y, residual, gamma, beta, out_f32, static_cast<__nv_bfloat16*>(out_bf16), M, H, eps);
+  return ner_launch_status();
+}
+
+extern "C" int ner_pack_weight_bf16(const float* w_kn, void* wt_nk_bf16, int K, int N, ner_stream_t stream) {
+  if (K < 1 || N < 1 || !w_kn || !wt_nk_bf16) return NER_ERR_INVALID_ARG;
+  dim3 grid((N + 31) / 32, (K + 31) / 32);
+  pack_weight_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w_kn, static_cast<__nv_bfloat16*>(wt_nk_bf16), K, N);
+  return ner_launch_status();
+}
+
+extern "C" int ner_cast_bf16(const float* src, void* dst_bf16, size_t n, ner_stream_t stream) {
+  if (!src || !dst_bf16) return n == 0 ? NER_OK : NER_ERR_INVALID_ARG;
+  if (n == 0) return NER_OK;
+  size_t g = (n + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  cast_bf16_kernel<<<(int)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, static_cast<__nv_bfloat16*>(dst_bf16), n);
+  return ner_launch_status();
+}
+
+extern "C" int ner_dense_small_n(const void* x, int x_is_bf16, const float* W, const float* bias, float* out, int M,
+                                 int F, int N, ner_stream_t stream) {
+  if (M < 0 || F < 1 || N < 1) return NER_ERR_INVALID_ARG;
+  if (M == 0) return NER_OK;
+  if (!x || !W || !out) return NER_ERR_INVALID_ARG;
+  if (N > 32 || (size_t)F * N * 4 > 200 * 1024) return NER_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)F * N * 4;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for_rows(M, 8 * 4);
+  cudaError_t e;
+#define LAUNCH(XT, NM)                                                                                   \
+  {                                                                                                      \
+    auto kern = dense_small_n_kernel<XT, NM>;                                                            \
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+    if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;                                             \
+    kern<<<grid, 256, smem, st>>>(static_cast<const XT*>(x), W, bias, out, M, F, N);                     \
+  }
+  if (x_is_bf16) {
+    if (N <= 16) LAUNCH(__nv_bfloat16, 16) else LAUNCH(__nv_bfloat16, 32)
+  } else {
+    if (N <= 16) LAUNCH(float, 16) else LAUNCH(float, 32)
+  }
+#undef LAUNCH
+  return ner_launch_status();
+}
+
+extern "C" int ner_embedding_lookup(const float* table, const int32_t* ids, float* out, int n_tok, int E, int V,
+                                    int ld_out, ner_stream_t stream) {
+  if (n_tok < 0 || E < 1 || V < 1 || ld_out < E) return NER_ERR_INVALID_ARG;
+  if (n_tok == 0) return NER_OK;
+  if (!table || !ids || !out) return NER_ERR_INVALID_ARG;
+  embedding_lookup_kernel<<<grid_for_rows(n_tok, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(table, ids, out, n_tok,
+                                                                                               E, V, ld_out);
+  return ner_launch_status();
+}
+
+extern "C" int ner_cast_pad_bf16(const float* src, void* dst_bf16, int M, int D, int Dp, int ld_src,
+                                 ner_stream_t stream) {
+  if (M < 0 || D < 1 || Dp < D || ld_src < D) return NER_ERR_INVALID_ARG;
+  if (M == 0) return NER_OK;
+  if (!src || !dst_bf16) return NER_ERR_INVALID_ARG;
+  size_t g = ((size_t)M * Dp + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  cast_pad_bf16_kernel<<<(int)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, static_cast<__nv_bfloat16*>(dst_bf16), M,
+                                                                              D, Dp, ld_src);
+  return ner_launch_status();
+}

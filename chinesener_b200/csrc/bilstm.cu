@@ -1,0 +1,220 @@
+// BiLSTM recurrence as a persistent thread-block-cluster kernel (sm_100a).
+//
+// Replaces tf.nn.bidirectional_dynamic_rnn over tf.nn.rnn_cell.LSTMCell as built by
+// reference tools/layer.py:10-41 (gate order i,j,f,o; forget_bias 1.0; zero initial state;
+// outputs zero and state carried for t >= seq_len; the backward direction runs over
+// reverse_sequence(x, seq_len) and is reversed back — SURVEY.md Appendix A.2).
+//
+// The input half of the LSTMCell matmul ([x_t] · kernel[:D]) + bias is hoisted out of the
+// recurrence into ONE tcgen05 GEMM for both directions (xproj [B*L, 8H], gemm_tc.cu).  This
+// kernel runs the sequential half: a cluster of C CTAs owns R batch rows of one direction for
+// all time steps.  Each CTA keeps its slice of the recurrent matrix kernel[D:, :] resident in
+// shared memory for the whole sequence (fp32, [H][4*H/C] laid out so one LDS.128 yields four
+// consecutive k for one gate column), computes the 4*H/C gate pre-activations of its H/C
+// hidden units, applies the cell, and broadcasts the new h slice to every CTA of the cluster
+// through distributed shared memory; one cluster barrier per time step.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int ACT>
+__device__ __forceinline__ float actf(float x) {
+  if (ACT == 1) return fmaxf(x, 0.f);
+  return tanhf(x);
+}
+
+template <int R, int ACT>
+__global__ void bilstm_rec_kernel(const float* __restrict__ xproj, const float* __restrict__ wh_fw,
+                                  const float* __restrict__ wh_bw, const int32_t* __restrict__ seq_len,
+                                  float* __restrict__ out, int B, int L, int H, int C, float forget_bias) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int HU = H / C;       // hidden units owned by this CTA
+  const int NC = 4 * HU;      // gate columns owned by this CTA
+  const int H4 = H / 4;
+  const int ngroups = (B + R - 1) / R;
+  const int cid = blockIdx.x / C;
+  const int dir = cid / ngroups;
+  const int b0 = (cid % ngroups) * R;
+  const int tid = threadIdx.x;
+
+  extern __shared__ __align__(16) float smem[];
+  float4* Ws4 = reinterpret_cast<float4*>(smem);                 // [H4][NC] float4 (4 consecutive k)
+  float* hbuf = smem + (size_t)H * NC;                           // [2][R][H]
+  float* zbuf = hbuf + 2 * R * H;                                // [R][NC]
+  int* s_len = reinterpret_cast<int*>(zbuf + R * NC);            // [R]
+
+  const float* wh = dir == 0 ? wh_fw : wh_bw;                    // [H][4H], columns (i,j,f,o) x H
+  for (int idx = tid; idx < H4 * NC; idx += blockDim.x) {
+    const int k4 = idx / NC, col = idx - k4 * NC;
+    const int g = col / HU, u = col - g * HU;
+    const size_t gc = (size_t)g * H + rank * HU + u;
+    float4 w;
+    w.x = wh[(size_t)(4 * k4 + 0) * 4 * H + gc];
+    w.y = wh[(size_t)(4 * k4 + 1) * 4 * H + gc];
+    w.z = wh[(size_t)(4 * k4 + 2) * 4 * H + gc];
+    w.w = wh[(size_t)(4 * k4 + 3) * 4 * H + gc];
+    Ws4[idx] = w;
+  }
+  for (int idx = tid; idx < 2 * R * H; idx += blockDim.x) hbuf[idx] = 0.f;
+  if (tid < R) s_len[tid] = (b0 + tid < B) ? min(max(seq_len[b0 + tid], 0), L) : 0;
+  __syncthreads();
+  int maxlen = 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) maxlen = max(maxlen, s_len[r]);
+  cluster.sync();  // every CTA's hbuf is zeroed before anyone writes remotely
+
+  // gate-column role
+  const bool col_ok = tid < NC;
+  const int g = col_ok ? tid / HU : 0, u = col_ok ? tid - g * HU : 0;
+  const size_t xcol = (size_t)dir * 4 * H + (size_t)g * H + rank * HU + u;
+  // cell role: thread (r,u2)
+  const bool cell_ok = tid < R * HU;
+  const int cr = cell_ok ? tid / HU : 0, cu = cell_ok ? tid - cr * HU : 0;
+  float c_state = 0.f, h_state = 0.f;
+
+  float xp[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    xp[r] = 0.f;
+    const int len = s_len[r];
+    if (col_ok && 0 < len) {
+      const int pos = dir == 0 ? 0 : len - 1;
+      xp[r] = xproj[((size_t)(b0 + r) * L + pos) * 8 * H + xcol];
+    }
+  }
+
+  for (int s = 0; s < maxlen; ++s) {
+    const float* hcur = hbuf + (s & 1) * R * H;
+    float* hnxt = hbuf + ((s + 1) & 1) * R * H;
+    if (col_ok) {
+      float acc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = xp[r];
+      // prefetch next step's input projection while the dot products run
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int len = s_len[r];
+        xp[r] = 0.f;
+        if (s + 1 < len) {
+          const int pos = dir == 0 ? s + 1 : len - 2 - s;
+          xp[r] = xproj[((size_t)(b0 + r) * L + pos) * 8 * H + xcol];
+        }
+      }
+      const float4* hc4 = reinterpret_cast<const float4*>(hcur);
+#pragma unroll 4
+      for (int k4 = 0; k4 < H4; ++k4) {
+        const float4 w = Ws4[k4 * NC + tid];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float4 hv = hc4[r * H4 + k4];
+          acc[r] = fmaf(w.x, hv.x, acc[r]);
+          acc[r] = fmaf(w.y, hv.y, acc[r]);
+          acc[r] = fmaf(w.z, hv.z, acc[r]);
+          acc[r] = fmaf(w.w, hv.w, acc[r]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) zbuf[r * NC + tid] = acc[r];
+    }
+    __syncthreads();
+    if (cell_ok) {
+      const int len = s_len[cr];
+      const int b = b0 + cr;
+      const int ug = rank * HU + cu;
+      if (s < len) {
+        const float zi = zbuf[cr * NC + 0 * HU + cu];
+        const float zj = zbuf[cr * NC + 1 * HU + cu];
+        const float zf = zbuf[cr * NC + 2 * HU + cu];
+        const float zo = zbuf[cr * NC + 3 * HU + cu];
+        c_state = sigmoidf_(zf + forget_bias) * c_state + sigmoidf_(zi) * actf<ACT>(zj);
+        h_state = sigmoidf_(zo) * actf<ACT>(c_state);
+        const int pos = dir == 0 ? s : len - 1 - s;
+        out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = h_state;
+      } else if (b < B) {
+        out[((size_t)b * L + s) * 2 * H + (size_t)dir * H + ug] = 0.f;
+      }
+      for (int dst = 0; dst < C; ++dst) {
+        float* remote = cluster.map_shared_rank(hnxt, dst);
+        remote[cr * H + ug] = h_state;
+      }
+    }
+    cluster.sync();
+  }
+
+  // positions past the longest row of this cluster: zeros
+  for (int idx = tid; idx < R * HU; idx += blockDim.x) {
+    const int r = idx / HU, uu = idx - r * HU;
+    const int b = b0 + r;
+    if (b < B)
+      for (int s = maxlen; s < L; ++s) out[((size_t)b * L + s) * 2 * H + (size_t)dir * H + rank * HU + uu] = 0.f;
+  }
+}
+
+int pick_cluster(int H) {
+  // smallest power-of-two cluster whose W_h slice (H * 4H/C floats) fits ~190 KB and divides H
+  for (int C = 1; C <= 8; C *= 2) {
+    if (H % C != 0) continue;
+    const size_t bytes = (size_t)H * 4 * (H / C) * 4;
+    if (bytes <= 190 * 1024 && 4 * (H / C) <= 1024) return C;
+  }
+  return 0;
+}
+
+template <int R, int ACT>
+int launch_rec(const float* xproj, const float* wh_fw, const float* wh_bw, const int32_t* seq_len, float* out, int B,
+               int L, int H, int C, float forget_bias, cudaStream_t st) {
+  const int HU = H / C, NC = 4 * HU;
+  const size_t smem = ((size_t)H * NC + 2 * R * H + (size_t)R * NC + 32) * 4;
+  auto kern = bilstm_rec_kernel<R, ACT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
+  const int ngroups = (B + R - 1) / R;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * ngroups * C));
+  cfg.blockDim = dim3((unsigned)((NC + 31) / 32 * 32));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias);
+  if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
+  return ner_launch_status();
+}
+
+}  // namespace
+
+extern "C" int ner_bilstm_recurrence(const float* xproj, const float* wh_fw, const float* wh_bw,
+                                     const int32_t* seq_len, float* out, int B, int L, int H, int activation,
+                                     float forget_bias, ner_stream_t stream) {
+  if (B < 0 || L < 1 || H < 1) return NER_ERR_INVALID_ARG;
+  if (B == 0) return NER_OK;
+  if (!xproj || !wh_fw || !wh_bw || !seq_len || !out) return NER_ERR_INVALID_ARG;
+  if (activation != 0 && activation != 1) return NER_ERR_INVALID_ARG;
+  if (H % 4 != 0) return NER_ERR_UNSUPPORTED;
+  const int C = pick_cluster(H);
+  if (C == 0) return NER_ERR_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // rows per cluster: fill the 148 SMs once when the batch is small, amortise W_h reads when large
+  int R = 1;
+  if ((long)2 * B * C > 148) R = 2;
+  if ((long)2 * ((B + 1) / 2) * C > 2 * 148) R = 4;
+#define GO(RR)                                                                                         \
+  return activation == 1 ? launch_rec<RR, 1>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, st) \
+                         : launch_rec<RR, 0>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, st)
+  if (R == 4) GO(4);
+  if (R == 2) GO(2);
+  GO(1);
+#undef GO
+}

@@ -1,0 +1,57 @@
+"""model_fn-equivalent glue: picks a plugin by name and runs PREDICT / EVAL steps.
+
+Mirrors reference tools/train_utils.py:145-187 (build_model_fn): the plugin is looked up by
+`importlib` under `model.<name>`, called as build_graph(features, labels, params, is_training)
+and its PREDICT output dict carries the keys 'pred_ids', 'label_ids', 'tokens'
+(tools/train_utils.py:181-185).  Host batches come in as (pinned) CPU tensors and are copied
+to the device inside `predict` — that copy is part of the end-to-end number bench.py reports.
+"""
+import importlib
+
+import torch
+
+from . import variables
+
+_DEVICE_KEYS = ('token_ids', 'mask', 'segment_ids', 'label_ids', 'seq_len', 'softlexicon_ids', 'softlexicon_weights',
+                'bichar_ids', 'softword_ids', 'ex_softword_ids', 'task_ids')
+
+
+def load_plugin(model_name):
+    mod = importlib.import_module(f'{__package__}.model.{model_name}')
+    return getattr(mod, 'build_graph'), getattr(mod, 'TRAIN_PARAMS')
+
+
+class Estimator:
+    """Minimal stand-in for tf.estimator.Estimator over one plugin + one variable store."""
+
+    def __init__(self, model_name, params, store=None, device='cuda'):
+        self.model_name = model_name
+        self.build_graph, train_params = load_plugin(model_name)
+        self.params = dict(train_params)
+        self.params.update(params)
+        self.device = torch.device(device)
+        self.store = store or variables.VariableStore(self.device)
+
+    def to_device(self, features):
+        out = {}
+        for k, v in features.items():
+            if k in _DEVICE_KEYS and torch.is_tensor(v):
+                out[k] = v.to(self.device, non_blocking=True)
+            else:
+                out[k] = v
+        return out
+
+    def forward_device(self, dev_features, is_training=False):
+        with variables.use_store(self.store):
+            return self.build_graph(dev_features, None, self.params, is_training)
+
+    def predict(self, features):
+        """PREDICT mode on one host batch -> dict(pred_ids int32 [B,L] on host, label_ids, tokens)."""
+        dev = self.to_device(features)
+        _, pred_ids = self.forward_device(dev, False)
+        return {'pred_ids': pred_ids.cpu(), 'label_ids': features.get('label_ids'), 'tokens': features.get('tokens')}
+
+    def evaluate(self, features):
+        dev = self.to_device(features)
+        loss, pred_ids = self.forward_device(dev, False)
+        return {'loss': float(loss), 'pred_ids': pred_ids.cpu()}

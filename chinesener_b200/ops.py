@@ -59,5 +59,149 @@ def gemm_bf16(a, wt, bias=None, residual=None, epilogue=EPI_BF16, tile_n=0, out=
         assert bias.dtype == torch.float32 and bias.numel() == N
     if residual is not None:
         assert residual.dtype == torch.float32 and residual.shape == (M, N)
-    check(lib().ner_gemm_bf16(ptr(a), ptr(wt), ptr(bias), ptr(residual), ptr(out), M, N, K, epilogue, tile_n, stream()))
+    hook = _lib._HOOK
+    if hook is not None:
+        with hook("gemm_bf16", 2.0 * M * N * K):
+            check(lib().ner_gemm_bf16(ptr(a), ptr(wt), ptr(bias), ptr(residual), ptr(out), M, N, K, epilogue, tile_n, stream()))
+    else:
+        check(lib().ner_gemm_bf16(ptr(a), ptr(wt), ptr(bias), ptr(residual), ptr(out), M, N, K, epilogue, tile_n, stream()))
     return out
+
+
+def pack_weight_bf16(w_kn):
+    """TF dense kernel [K,N] f32 -> bf16 [N,K] (B operand layout of gemm_bf16)."""
+    require_cuda(w_kn)
+    assert w_kn.dtype == torch.float32 and w_kn.dim() == 2
+    K, N = w_kn.shape
+    out = torch.empty((N, K), dtype=torch.bfloat16, device=w_kn.device)
+    check(lib().ner_pack_weight_bf16(ptr(w_kn), ptr(out), K, N, stream()))
+    return out
+
+
+def cast_bf16(x):
+    require_cuda(x)
+    assert x.dtype == torch.float32
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib().ner_cast_bf16(ptr(x), ptr(out), x.numel(), stream()))
+    return out
+
+
+def dense_small_n(x, w, bias=None):
+    """tf.layers.dense(units=label_size): x [M,F] (f32|bf16) @ w [F,N] f32 + bias -> f32 [M,N], N <= 32."""
+    require_cuda(x, w, bias)
+    assert w.dtype == torch.float32 and x.dtype in (torch.float32, torch.bfloat16)
+    M, F = x.shape
+    F2, N = w.shape
+    assert F == F2
+    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    check(lib().ner_dense_small_n(ptr(x), 1 if x.dtype == torch.bfloat16 else 0, ptr(w), ptr(bias), ptr(out), M, F, N,
+                                  stream()))
+    return out
+
+
+# --------------------------------------------------------------------------- BERT pieces
+def bert_embed_ln(word_emb, type_emb, pos_emb, gamma, beta, ids, seg, eps=1e-12, want_f32=True, want_bf16=True):
+    require_cuda(word_emb, type_emb, pos_emb, gamma, beta, ids, seg)
+    B, L = ids.shape
+    V, H = word_emb.shape
+    ids = _i32(ids)
+    seg = None if seg is None else _i32(seg)
+    of = torch.empty((B * L, H), dtype=torch.float32, device=ids.device) if want_f32 else None
+    ob = torch.empty((B * L, H), dtype=torch.bfloat16, device=ids.device) if want_bf16 else None
+    check(lib().ner_bert_embed_ln(ptr(word_emb), ptr(type_emb), ptr(pos_emb), ptr(gamma), ptr(beta), ptr(ids), ptr(seg),
+                                  ptr(of), ptr(ob), B, L, H, V, type_emb.shape[0], pos_emb.shape[0], eps, stream()))
+    return of, ob
+
+
+def layernorm(y, gamma, beta, residual=None, eps=1e-12, want_f32=True, want_bf16=True):
+    require_cuda(y, gamma, beta, residual)
+    assert y.dtype == torch.float32
+    M, H = y.shape
+    of = torch.empty((M, H), dtype=torch.float32, device=y.device) if want_f32 else None
+    ob = torch.empty((M, H), dtype=torch.bfloat16, device=y.device) if want_bf16 else None
+    check(lib().ner_layernorm(ptr(y), ptr(residual), ptr(gamma), ptr(beta), ptr(of), ptr(ob), M, H, eps, stream()))
+    return of, ob
+
+
+def bert_attention(qkv, mask, B, L, num_heads, head_dim=64, scale=None, mask_add=-10000.0):
+    require_cuda(qkv, mask)
+    assert qkv.dtype == torch.bfloat16 and qkv.shape == (B * L, 3 * num_heads * head_dim)
+    mask = _i32(mask)
+    ctx = torch.empty((B * L, num_heads * head_dim), dtype=torch.bfloat16, device=qkv.device)
+    if scale is None:
+        scale = 1.0 / (head_dim ** 0.5)
+    check(lib().ner_bert_attention(ptr(qkv), ptr(mask), ptr(ctx), B, L, num_heads, head_dim, scale, mask_add, stream()))
+    return ctx
+
+
+# --------------------------------------------------------------------------- BiLSTM
+def bilstm_recurrence(xproj, wh_fw, wh_bw, seq_len, B, L, H, activation="tanh", forget_bias=1.0):
+    require_cuda(xproj, wh_fw, wh_bw, seq_len)
+    assert xproj.dtype == torch.float32 and xproj.shape == (B * L, 8 * H)
+    assert wh_fw.shape == (H, 4 * H) and wh_bw.shape == (H, 4 * H)
+    act = {"tanh": 0, "relu": 1}[activation]
+    out = torch.empty((B, L, 2 * H), dtype=torch.float32, device=xproj.device)
+    check(lib().ner_bilstm_recurrence(ptr(xproj), ptr(wh_fw), ptr(wh_bw), ptr(_i32(seq_len)), ptr(out), B, L, H, act,
+                                      forget_bias, stream()))
+    return out
+
+
+# --------------------------------------------------------------------------- SoftLexicon
+def softlexicon_pool(table, ids, weights, G=4, S=10, out=None):
+    """ids/weights [..., G*S] -> [..., G*E]; `out` may be a wider [n_tok, >=G*E] buffer (concat target)."""
+    require_cuda(table, ids, weights, out)
+    assert table.dtype == torch.float32 and weights.dtype == torch.float32
+    V, E = table.shape
+    lead = ids.shape[:-1]
+    assert ids.shape[-1] == G * S and weights.shape == ids.shape
+    n_tok = ids.numel() // (G * S)
+    if out is None:
+        out = torch.empty((*lead, G * E), dtype=torch.float32, device=table.device)
+    ld = out.shape[-1]
+    check(lib().ner_softlexicon_pool_fwd(ptr(table), ptr(_i32(ids)), ptr(weights), ptr(out), n_tok, G, S, E, V, ld,
+                                         stream()))
+    return out
+
+
+def embedding_lookup(table, ids, out=None, col_offset=0):
+    """tf.nn.embedding_lookup into out[..., col_offset:col_offset+E] (out row-major [n_tok, ld])."""
+    require_cuda(table, ids, out)
+    assert table.dtype == torch.float32
+    V, E = table.shape
+    n_tok = ids.numel()
+    if out is None:
+        out = torch.empty((*ids.shape, E), dtype=torch.float32, device=table.device)
+    ld = out.shape[-1]
+    assert col_offset + E <= ld
+    check(lib().ner_embedding_lookup(ptr(table), ptr(_i32(ids)), out.data_ptr() + 4 * col_offset, n_tok, E, V, ld, stream()))
+    return out
+
+
+def cast_pad_bf16(x2d, Dp):
+    """f32 [M,D] -> bf16 [M,Dp] zero padded."""
+    require_cuda(x2d)
+    assert x2d.dtype == torch.float32 and x2d.dim() == 2
+    M, D = x2d.shape
+    out = torch.empty((M, Dp), dtype=torch.bfloat16, device=x2d.device)
+    check(lib().ner_cast_pad_bf16(ptr(x2d), ptr(out), M, D, Dp, D, stream()))
+    return out
+
+
+def softlexicon_pool_bwd(d_table, ids, weights, d_out, G=4, S=10):
+    require_cuda(d_table, ids, weights, d_out)
+    V, E = d_table.shape
+    n_tok = ids.numel() // (G * S)
+    check(lib().ner_softlexicon_pool_bwd(ptr(d_table), ptr(_i32(ids)), ptr(weights), ptr(d_out), n_tok, G, S, E, V,
+                                         stream()))
+    return d_table
+
+
+def crf_loglik_bwd(logits, tags, seq_len, trans, alpha, logz, d_ll=None, scale=1.0):
+    """-> d_logits [B,L,K], d_trans [K,K] for g_b = (d_ll|1) * scale."""
+    require_cuda(logits, tags, seq_len, trans, alpha, logz, d_ll)
+    B, L, K = logits.shape
+    d_logits = torch.empty_like(logits)
+    d_trans = torch.zeros_like(trans)
+    check(lib().ner_crf_loglik_bwd(ptr(logits), ptr(_i32(tags)), ptr(_i32(seq_len)), ptr(trans), ptr(alpha), ptr(logz),
+                                   ptr(d_ll), scale, ptr(d_logits), ptr(d_trans), B, L, K, stream()))
+    return d_logits, d_trans

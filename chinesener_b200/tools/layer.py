@@ -1,0 +1,97 @@
+"""Layer library with the reference's function surface (reference tools/layer.py), each a thin
+wrapper over the C-ABI kernels.  Same names, argument order and meaning; tensors are torch
+CUDA tensors, variables live in `chinesener_b200.variables` under the reference's TF names.
+"""
+import torch
+
+from .. import bert as _bert
+from .. import ops, variables
+
+
+class TrainingPathNotBuilt(NotImplementedError):
+    pass
+
+
+def _no_training(is_training, what):
+    if is_training:
+        raise TrainingPathNotBuilt(f"{what}: is_training=True needs the backward kernels (see DESIGN.md §scope)")
+
+
+def pretrain_bert_embedding(input_ids, input_mask, segment_ids, pretrain_dir, drop_out, is_training):
+    """reference tools/layer.py:63-81 — BertModel(...).get_sequence_output() (+ dropout when training).
+
+    Returns sequence_output [B,L,H] f32; its bf16 copy (what the next GEMM consumes) rides along
+    as attribute `.bf16`.
+    """
+    _no_training(is_training, "pretrain_bert_embedding")
+    cfg = _bert.load_bert_config(pretrain_dir)
+    B, L = input_ids.shape
+    x32, x16 = _bert.bert_forward(input_ids, input_mask, segment_ids, cfg)
+    emb = x32.view(B, L, -1)
+    emb.bf16 = x16.view(B, L, -1)
+    return emb
+
+
+def _lstm_pack(store, D, H, scope):
+    """bf16 [8H, Dp] input-projection pack (fw | bw), fused bias [8H], fp32 recurrent matrices."""
+    Dp = (D + 7) // 8 * 8
+
+    def build():
+        ks = [store.vars[f"{scope}/{d}/multi_rnn_cell/cell_0/lstm_cell/kernel"] for d in ("fw", "bw")]
+        bs = [store.vars[f"{scope}/{d}/multi_rnn_cell/cell_0/lstm_cell/bias"] for d in ("fw", "bw")]
+        wx = torch.cat([k[:D] for k in ks], dim=1)                      # [D, 8H]
+        if Dp != D:
+            wx = torch.nn.functional.pad(wx, (0, 0, 0, Dp - D))         # zero rows for the K padding
+        return dict(wx=ops.pack_weight_bf16(wx.contiguous()), bias=torch.cat(bs).contiguous(),
+                    wh_fw=ks[0][D:].contiguous(), wh_bw=ks[1][D:].contiguous(), Dp=Dp)
+    return store.cached(("lstm_pack", scope, D, H), build)
+
+
+def bilstm(embedding, cell_type, activation, hidden_units_list, keep_prob_list, cell_size, seq_len, dtype, is_training):
+    """reference tools/layer.py:27-41 — bidirectional_dynamic_rnn over LSTMCell; -> [B,L,2H] f32."""
+    _no_training(is_training, "bilstm")
+    if cell_type.lower() != 'lstm':
+        raise Exception('Only lstm is built on the sm_100a path (reference models all use cell_type=lstm)')
+    if cell_size != 1:
+        raise Exception('cell_size must be 1 (every reference model uses a single LSTM layer)')
+    B, L, D = embedding.shape
+    H = hidden_units_list[0]
+    store = variables.default_store()
+    scope = "bilstm_layer/bidirectional_rnn"
+    for d in ("fw", "bw"):
+        store.get_variable(f"{scope}/{d}/multi_rnn_cell/cell_0/lstm_cell/kernel", (D + H, 4 * H), variables.glorot_uniform)
+        store.get_variable(f"{scope}/{d}/multi_rnn_cell/cell_0/lstm_cell/bias", (4 * H,), variables.zeros)
+    pk = _lstm_pack(store, D, H, scope)
+    x16 = getattr(embedding, "bf16", None)
+    if x16 is not None and pk["Dp"] == D:
+        x16 = x16.reshape(B * L, D)
+    else:
+        x16 = ops.cast_pad_bf16(embedding.reshape(B * L, D), pk["Dp"])
+    xproj = ops.gemm_bf16(x16, pk["wx"], pk["bias"], epilogue=ops.EPI_F32)
+    return ops.bilstm_recurrence(xproj, pk["wh_fw"], pk["wh_bw"], seq_len, B, L, H, activation=activation, forget_bias=1.0)
+
+
+def dense(inputs, units, name='logits'):
+    """tf.layers.dense(inputs, units, activation=None, use_bias=True, name=name) for units <= 32."""
+    F = inputs.shape[-1]
+    lead = inputs.shape[:-1]
+    w = variables.get_variable(f"{name}/kernel", (F, units), variables.glorot_uniform)
+    b = variables.get_variable(f"{name}/bias", (units,), variables.zeros)
+    x = getattr(inputs, "bf16", None)
+    x = inputs if x is None else x
+    out = ops.dense_small_n(x.reshape(-1, F), w, b)
+    return out.view(*lead, units)
+
+
+def crf_layer(logits, label_ids, seq_len, label_size, is_training):
+    """reference tools/layer.py:112-131 -> (trans, log_likelihood [B])."""
+    trans = variables.get_variable("crf_layer/transitions", (label_size, label_size), variables.xavier)
+    if label_ids is None:
+        return trans, None
+    ll, _, _ = ops.crf_loglik_fwd(logits, label_ids, seq_len, trans)
+    return trans, ll
+
+
+def crf_decode(logits, trans, seq_len, idx2tag, is_training, mask=None):
+    """reference tools/layer.py:134-149 -> pred_ids [B,L] int32, zero beyond seq_len."""
+    return ops.crf_viterbi(logits, seq_len, trans)

@@ -93,6 +93,79 @@ int ner_gemm_bf16(const void* A, const void* Wt, const float* bias, const float*
                   void* out, int M, int N, int K, int epilogue, int tile_n,
                   ner_stream_t stream);
 
+/* TF dense kernel [K,N] f32 -> bf16 [N,K] (K contiguous), the B-operand layout of
+ * ner_gemm_bf16.  Done once per weight (or per optimizer step). */
+int ner_pack_weight_bf16(const float* w_kn, void* wt_nk_bf16, int K, int N, ner_stream_t stream);
+/* Elementwise f32 -> bf16 (round to nearest even). */
+int ner_cast_bf16(const float* src, void* dst_bf16, size_t n, ner_stream_t stream);
+
+/* tf.layers.dense(units=label_size) — model/bert_bilstm_crf.py:26, model/bert_crf.py:20.
+ * out[M,N] f32 = x[M,F] · W[F,N] + bias[N], N <= 32; x is f32 (x_is_bf16=0) or bf16;
+ * W is the TF kernel layout [F,N] f32. */
+int ner_dense_small_n(const void* x, int x_is_bf16, const float* W, const float* bias, float* out,
+                      int M, int F, int N, ner_stream_t stream);
+
+/* tf.nn.embedding_lookup (model/bilstm_crf.py:24): out[tok, 0:E] = table[ids[tok]], row
+ * stride ld_out >= E. */
+int ner_embedding_lookup(const float* table, const int32_t* ids, float* out, int n_tok, int E,
+                         int V, int ld_out, ner_stream_t stream);
+/* f32 [M,D] (row stride ld_src) -> bf16 [M,Dp] zero-padded to the GEMM's K % 8 == 0. */
+int ner_cast_pad_bf16(const float* src, void* dst_bf16, int M, int D, int Dp, int ld_src,
+                      ner_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * BERT encoder pieces — bert_base.bert.modeling.BertModel as driven from
+ * tools/layer.py:63-81 (pretrain_bert_embedding)
+ * ------------------------------------------------------------------------ */
+
+/* embedding_lookup + embedding_postprocessor: LN(word[ids] + type[seg] + pos[0:L]).
+ * Tables f32: word [vocab,H], type [n_type,H], pos [max_pos,H]; ids/seg [B,L] i32
+ * (seg may be NULL = all zero).  Writes f32 and/or bf16 [B*L,H] (either may be NULL). */
+int ner_bert_embed_ln(const float* word_emb, const float* type_emb, const float* pos_emb,
+                      const float* gamma, const float* beta, const int32_t* ids,
+                      const int32_t* seg, float* out_f32, void* out_bf16, int B, int L, int H,
+                      int vocab, int n_type, int max_pos, float eps, ner_stream_t stream);
+
+/* LayerNorm over the last axis of y (+ optional residual) [M,H] f32 -> f32 and/or bf16.
+ * modeling.layer_norm (eps 1e-12) and tools/transformer/modules.py:40-65 (eps = FLT_EPSILON). */
+int ner_layernorm(const float* y, const float* residual, const float* gamma, const float* beta,
+                  float* out_f32, void* out_bf16, int M, int H, float eps, ner_stream_t stream);
+
+/* attention_layer core: ctx = softmax(Q K^T * scale + (1-mask)*mask_add) V per head.
+ * qkv bf16 [B*L, 3*num_heads*head_dim] (Q | K | V blocks, heads contiguous inside each),
+ * mask [B,L] i32 (1 = keep), ctx bf16 [B*L, num_heads*head_dim].  head_dim must be 64.
+ * BERT: scale = 1/sqrt(64), mask_add = -10000. */
+int ner_bert_attention(const void* qkv_bf16, const int32_t* mask, void* ctx_bf16, int B, int L,
+                       int num_heads, int head_dim, float scale, float mask_add,
+                       ner_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * BiLSTM — tools/layer.py:27-41 bilstm() -> bidirectional_dynamic_rnn(LSTMCell)
+ * ------------------------------------------------------------------------ */
+
+/* Sequential half of both directions.  xproj [B*L, 8H] f32 = x · [kernel_fw[:D] | kernel_bw[:D]]
+ * + [bias_fw | bias_bw] (one ner_gemm_bf16 call, NER_EPI_F32); wh_fw / wh_bw = kernel[D:, :]
+ * [H,4H] f32 with TF's gate order (i, j, f, o).  out [B,L,2H] f32 = concat(fw, bw), zero for
+ * t >= seq_len.  activation: 0 tanh, 1 relu (params['rnn_activation']).  H % 4 == 0. */
+int ner_bilstm_recurrence(const float* xproj, const float* wh_fw, const float* wh_bw,
+                          const int32_t* seq_len, float* out, int B, int L, int H,
+                          int activation, float forget_bias, ner_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * SoftLexicon gather-and-pool — model/bilstm_crf_softlexicon.py:37-44
+ * ------------------------------------------------------------------------ */
+
+/* out[tok, g*E+e] = sum_s weights[tok, g*S+s] * table[ids[tok, g*S+s], e].
+ * table [V,E] f32, ids/weights [n_tok, G*S], out [n_tok, G*E] with row stride ld_out
+ * (>= G*E; lets the caller pool straight into a concat buffer).  G*S <= 64, E <= 128. */
+int ner_softlexicon_pool_fwd(const float* table, const int32_t* ids, const float* weights,
+                             float* out, int n_tok, int G, int S, int E, int V, int ld_out,
+                             ner_stream_t stream);
+/* d_table [V,E] += scatter of weights * d_out (caller zeroes / owns accumulation). */
+int ner_softlexicon_pool_bwd(float* d_table, const int32_t* ids, const float* weights,
+                             const float* d_out, int n_tok, int G, int S, int E, int V,
+                             ner_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

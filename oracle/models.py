@@ -1,0 +1,60 @@
+"""End-to-end CPU restatement of the reference's build_graph plugins (eval mode).
+
+  bert_bilstm_crf  <- model/bert_bilstm_crf.py:8-34
+  bert_crf         <- model/bert_crf.py:8-28
+  bilstm_crf       <- model/bilstm_crf.py:8-44
+  bilstm_crf_softlexicon <- model/bilstm_crf_softlexicon.py:14-64
+Each returns dict(logits, loss, pred_ids, ll).
+"""
+import numpy as np
+import torch
+
+from . import crf, nn
+
+
+def _crf_tail(logits, w, features):
+    lg = logits.detach().to(torch.float32).numpy()
+    trans = w["crf_layer/transitions"].to(torch.float32).numpy()
+    lens = features["seq_len"].numpy()
+    ll = crf.crf_log_likelihood(lg, features["label_ids"].numpy(), lens, trans, dtype=np.float64)
+    pred, _ = crf.crf_decode(lg, trans, lens, dtype=np.float32)
+    return dict(logits=logits, ll=ll, loss=float(np.mean(-ll)), pred_ids=pred)
+
+
+def bert_bilstm_crf(w, features, params, dtype=torch.float32, emulate_bf16=False, gelu_variant="tanh"):
+    seq = nn.bert_encoder(w, features["token_ids"], features["mask"], features["segment_ids"],
+                          num_layers=params.get("num_hidden_layers", 12), num_heads=params.get("num_attention_heads", 12),
+                          dtype=dtype, gelu_variant=gelu_variant, emulate_bf16=emulate_bf16)
+    lstm = nn.bilstm(seq, w, features["seq_len"], params["rnn_activation"], 1.0, dtype, emulate_bf16)
+    logits = nn.dense(lstm, w["logits/kernel"].to(dtype), w["logits/bias"].to(dtype))
+    return _crf_tail(logits, w, features)
+
+
+def bert_crf(w, features, params, dtype=torch.float32, emulate_bf16=False, gelu_variant="tanh"):
+    seq = nn.bert_encoder(w, features["token_ids"], features["mask"], features["segment_ids"],
+                          num_layers=params.get("num_hidden_layers", 12), num_heads=params.get("num_attention_heads", 12),
+                          dtype=dtype, gelu_variant=gelu_variant, emulate_bf16=emulate_bf16)
+    # CUDA path feeds the bf16 copy of sequence_output to the label projection
+    logits = nn.dense(nn._rb(seq, emulate_bf16), w["logits/kernel"].to(dtype), w["logits/bias"].to(dtype))
+    return _crf_tail(logits, w, features)
+
+
+def bilstm_crf(w, features, params, dtype=torch.float32, emulate_bf16=False):
+    emb = torch.as_tensor(params["embedding"]).to(dtype)[features["token_ids"].long()]
+    lstm = nn.bilstm(emb, w, features["seq_len"], params["rnn_activation"], 1.0, dtype, emulate_bf16)
+    logits = nn.dense(lstm, w["logits/kernel"].to(dtype), w["logits/bias"].to(dtype))
+    return _crf_tail(logits, w, features)
+
+
+def bilstm_crf_softlexicon(w, features, params, dtype=torch.float32, emulate_bf16=False):
+    B = features["token_ids"].shape[0]
+    L = params["max_seq_len"]
+    G, S = params["word_enhance_dim"], params["max_lexicon_len"]
+    emb = torch.as_tensor(params["embedding"]).to(dtype)[features["token_ids"].long()]
+    ids = features["softlexicon_ids"].view(B, L, G * S)
+    wts = features["softlexicon_weights"].view(B, L, G * S)
+    wh = nn.softlexicon_pool(w["word_enhance/softlexicon_embedding"].to(dtype), ids, wts, G, S)
+    x = torch.cat([wh, emb], dim=-1)
+    lstm = nn.bilstm(x, w, features["seq_len"], params["rnn_activation"], 1.0, dtype, emulate_bf16)
+    logits = nn.dense(lstm, w["logits/kernel"].to(dtype), w["logits/bias"].to(dtype))
+    return _crf_tail(logits, w, features)
