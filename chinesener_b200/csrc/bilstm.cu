@@ -29,8 +29,10 @@ __device__ __forceinline__ float actf(float x) {
   return tanhf(x);
 }
 
-template <int R, int ACT>
-__global__ void bilstm_rec_kernel(const float* __restrict__ xproj, const float* __restrict__ wh_fw,
+// H4REG > 0: this thread's gate column of W_h (H4REG float4 = H fp32 values) is register-resident
+// for the whole sequence (H <= 128); H4REG == 0: the slice is read from shared memory each step.
+template <int R, int ACT, int H4REG>
+__global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(const float* __restrict__ xproj, const float* __restrict__ wh_fw,
                                   const float* __restrict__ wh_bw, const int32_t* __restrict__ seq_len,
                                   float* __restrict__ out, int B, int L, int H, int C, float forget_bias) {
   cg::cluster_group cluster = cg::this_cluster();
@@ -45,22 +47,38 @@ __global__ void bilstm_rec_kernel(const float* __restrict__ xproj, const float* 
   const int tid = threadIdx.x;
 
   extern __shared__ __align__(16) float smem[];
-  float4* Ws4 = reinterpret_cast<float4*>(smem);                 // [H4][NC] float4 (4 consecutive k)
-  float* hbuf = smem + (size_t)H * NC;                           // [2][R][H]
+  constexpr bool WREG = H4REG > 0;
+  float4* Ws4 = reinterpret_cast<float4*>(smem);                 // [H4][NC] float4 (4 consecutive k), smem path only
+  float* hbuf = smem + (WREG ? 0 : (size_t)H * NC);              // [2][R][H]
   float* zbuf = hbuf + 2 * R * H;                                // [R][NC]
   int* s_len = reinterpret_cast<int*>(zbuf + R * NC);            // [R]
 
   const float* wh = dir == 0 ? wh_fw : wh_bw;                    // [H][4H], columns (i,j,f,o) x H
-  for (int idx = tid; idx < H4 * NC; idx += blockDim.x) {
-    const int k4 = idx / NC, col = idx - k4 * NC;
-    const int g = col / HU, u = col - g * HU;
-    const size_t gc = (size_t)g * H + rank * HU + u;
-    float4 w;
-    w.x = wh[(size_t)(4 * k4 + 0) * 4 * H + gc];
-    w.y = wh[(size_t)(4 * k4 + 1) * 4 * H + gc];
-    w.z = wh[(size_t)(4 * k4 + 2) * 4 * H + gc];
-    w.w = wh[(size_t)(4 * k4 + 3) * 4 * H + gc];
-    Ws4[idx] = w;
+  float4 wreg[WREG ? H4REG : 1];
+  if constexpr (WREG) {
+    if (tid < NC) {
+      const int g0 = tid / HU, u0 = tid - g0 * HU;
+      const size_t gc = (size_t)g0 * H + rank * HU + u0;
+#pragma unroll
+      for (int k4 = 0; k4 < H4REG; ++k4) {
+        wreg[k4].x = wh[(size_t)(4 * k4 + 0) * 4 * H + gc];
+        wreg[k4].y = wh[(size_t)(4 * k4 + 1) * 4 * H + gc];
+        wreg[k4].z = wh[(size_t)(4 * k4 + 2) * 4 * H + gc];
+        wreg[k4].w = wh[(size_t)(4 * k4 + 3) * 4 * H + gc];
+      }
+    }
+  } else {
+    for (int idx = tid; idx < H4 * NC; idx += blockDim.x) {
+      const int k4 = idx / NC, col = idx - k4 * NC;
+      const int g = col / HU, u = col - g * HU;
+      const size_t gc = (size_t)g * H + rank * HU + u;
+      float4 w;
+      w.x = wh[(size_t)(4 * k4 + 0) * 4 * H + gc];
+      w.y = wh[(size_t)(4 * k4 + 1) * 4 * H + gc];
+      w.z = wh[(size_t)(4 * k4 + 2) * 4 * H + gc];
+      w.w = wh[(size_t)(4 * k4 + 3) * 4 * H + gc];
+      Ws4[idx] = w;
+    }
   }
   for (int idx = tid; idx < 2 * R * H; idx += blockDim.x) hbuf[idx] = 0.f;
   if (tid < R) s_len[tid] = (b0 + tid < B) ? min(max(seq_len[b0 + tid], 0), L) : 0;
@@ -108,16 +126,31 @@ __global__ void bilstm_rec_kernel(const float* __restrict__ xproj, const float* 
         }
       }
       const float4* hc4 = reinterpret_cast<const float4*>(hcur);
-#pragma unroll 4
-      for (int k4 = 0; k4 < H4; ++k4) {
-        const float4 w = Ws4[k4 * NC + tid];
+      if constexpr (WREG) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float4 hv = hc4[r * H4 + k4];
-          acc[r] = fmaf(w.x, hv.x, acc[r]);
-          acc[r] = fmaf(w.y, hv.y, acc[r]);
-          acc[r] = fmaf(w.z, hv.z, acc[r]);
-          acc[r] = fmaf(w.w, hv.w, acc[r]);
+        for (int k4 = 0; k4 < H4REG; ++k4) {
+          const float4 w = wreg[k4];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float4 hv = hc4[r * H4 + k4];
+            acc[r] = fmaf(w.x, hv.x, acc[r]);
+            acc[r] = fmaf(w.y, hv.y, acc[r]);
+            acc[r] = fmaf(w.z, hv.z, acc[r]);
+            acc[r] = fmaf(w.w, hv.w, acc[r]);
+          }
+        }
+      } else {
+#pragma unroll 4
+        for (int k4 = 0; k4 < H4; ++k4) {
+          const float4 w = Ws4[k4 * NC + tid];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float4 hv = hc4[r * H4 + k4];
+            acc[r] = fmaf(w.x, hv.x, acc[r]);
+            acc[r] = fmaf(w.y, hv.y, acc[r]);
+            acc[r] = fmaf(w.z, hv.z, acc[r]);
+            acc[r] = fmaf(w.w, hv.w, acc[r]);
+          }
         }
       }
 #pragma unroll
@@ -162,17 +195,17 @@ int pick_cluster(int H) {
   for (int C = 1; C <= 8; C *= 2) {
     if (H % C != 0) continue;
     const size_t bytes = (size_t)H * 4 * (H / C) * 4;
-    if (bytes <= 190 * 1024 && 4 * (H / C) <= 1024) return C;
+    if (bytes <= 190 * 1024 && 4 * (H / C) <= 512) return C;
   }
   return 0;
 }
 
-template <int R, int ACT>
+template <int R, int ACT, int H4REG>
 int launch_rec(const float* xproj, const float* wh_fw, const float* wh_bw, const int32_t* seq_len, float* out, int B,
                int L, int H, int C, float forget_bias, cudaStream_t st) {
   const int HU = H / C, NC = 4 * HU;
-  const size_t smem = ((size_t)H * NC + 2 * R * H + (size_t)R * NC + 32) * 4;
-  auto kern = bilstm_rec_kernel<R, ACT>;
+  const size_t smem = ((H4REG > 0 ? 0 : (size_t)H * NC) + 2 * R * H + (size_t)R * NC + 32) * 4;
+  auto kern = bilstm_rec_kernel<R, ACT, H4REG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   const int ngroups = (B + R - 1) / R;
@@ -210,11 +243,16 @@ extern "C" int ner_bilstm_recurrence(const float* xproj, const float* wh_fw, con
   int R = 1;
   if ((long)2 * B * C > 148) R = 2;
   if ((long)2 * ((B + 1) / 2) * C > 2 * 148) R = 4;
-#define GO(RR)                                                                                         \
-  return activation == 1 ? launch_rec<RR, 1>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, st) \
-                         : launch_rec<RR, 0>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, st)
-  if (R == 4) GO(4);
-  if (R == 2) GO(2);
-  GO(1);
+#define GO(RR, HR)                                                                                          \
+  return activation == 1 ? launch_rec<RR, 1, HR>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, st) \
+                         : launch_rec<RR, 0, HR>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, st)
+  if (H == 128 && 4 * (H / C) <= 256) {  // register-resident W_h (the bert_bilstm_crf / bilstm_crf shape)
+    if (R == 4) GO(4, 32);
+    if (R == 2) GO(2, 32);
+    GO(1, 32);
+  }
+  if (R == 4) GO(4, 0);
+  if (R == 2) GO(2, 0);
+  GO(1, 0);
 #undef GO
 }

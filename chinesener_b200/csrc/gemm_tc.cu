@@ -6,15 +6,24 @@
 // reference tools/layer.py:68-77 (bert_base.bert.modeling) and model/bert_bilstm_crf.py:26,
 // and the input projection half of the LSTMCell matmul (tools/layer.py:16,35).
 //
-// Kernel shape (persistent, warp-specialised, 192 threads = 6 warps, 1 CTA/SM):
-//   warp 0   TMA producer : cp.async.bulk.tensor 2-D loads of a 128x64 A box and a BNx64 B box
-//                           per k-block into a STAGES-deep smem ring (SWIZZLE_128B), mbarrier tx
-//   warp 1   MMA issuer   : one thread issues tcgen05.mma.kind::f16 (128 x BN x 16) x 4 per
-//                           k-block; tcgen05.commit releases smem slots / publishes the accumulator
-//   warps 2-5 epilogue    : tcgen05.ld 32x32b (TMEM lane quarter = warp%4) -> bias / GELU /
-//                           residual -> 16-byte global stores
-// Two TMEM accumulator stages (2*BN columns) let the epilogue of tile i overlap the
-// main loop of tile i+1.
+// Kernel shape (persistent, warp-specialised, 320 threads = 10 warps, 1 CTA/SM):
+//   warp 0    TMA producer : cp.async.bulk.tensor 2-D loads of a 128x64 A box and a B box per
+//                            k-block into a STAGES-deep smem ring (SWIZZLE_128B), mbarrier tx
+//   warp 1    MMA issuer   : one thread issues tcgen05.mma.kind::f16 x4 per k-block;
+//                            tcgen05.commit releases smem slots / publishes the accumulator
+//   warps 2-9 epilogue     : tcgen05.ld 32x32b (TMEM lane quarter = warp%4, two warps per quarter
+//                            on alternating 32-column chunks) -> bias / GELU / residual ->
+//                            16-byte global stores
+// Two TMEM accumulator stages (2*BN columns) let the epilogue of tile i overlap the main loop
+// of tile i+1.
+//
+// Two variants:
+//   gemm_bf16_tc_kernel<BN>    cta_group::1, 128 x BN tile per CTA (BN = 64/128/256)
+//   gemm_bf16_tc2_kernel<BN>   cta_group::2: a CTA PAIR (cluster of 2, one per SM of a TPC)
+//                              computes a 256 x BN tile with M=256 MMAs issued by CTA 0; each CTA
+//                              stages its own 128 A rows and HALF of the B tile, so the L2->smem
+//                              bytes per FLOP drop by 1.5x vs the 128x256 single-CTA tile (the
+//                              single-CTA kernel is L2-feed-bound at ~9-10 TB/s).
 #include "tc_common.cuh"
 
 namespace {
@@ -22,17 +31,29 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128;
-constexpr int BK = 64;       // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+
+constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
 template <int BN>
 struct Cfg {
   static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int TMEM_COLS = tmem_cols_for(2 * BN);
   static constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + B_BYTES) + 256 /*barriers*/ + 1024 /*align slack*/;
+};
+
+template <int BN>
+struct Cfg2 {  // per CTA of the pair
+  static constexpr int STAGES = 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int TMEM_COLS = tmem_cols_for(2 * BN);
+  static constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + B_BYTES) + 256 + 1024;
 };
 
 struct EpiArgs {
@@ -43,10 +64,11 @@ struct EpiArgs {
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
-  // 0.5x(1+tanh(sqrt(2/pi)(x+0.044715x^3)))  (google-research/bert modeling.gelu)
-  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-  const float t = 1.f - 2.f / (__expf(2.f * u) + 1.f);
-  return 0.5f * x * (1.f + t);
+  // 0.5x(1+tanh(sqrt(2/pi)(x+0.044715x^3)))  (google-research/bert modeling.gelu).
+  // tanh.approx.f32 is one MUFU op (rel. error ~2^-11); the result is rounded to bf16 (2^-9).
+  const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+  const float hx = 0.5f * x;
+  return fmaf(hx, tanh_approx(u), hx);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865476f)); }
 
@@ -55,6 +77,75 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// One 32-column chunk of one accumulator row: TMEM registers -> fused epilogue -> global.
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const EpiArgs& ep, int row, int col0, int N) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  if (ep.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = __ldg(b4 + i);
+      v[4 * i + 0] += b.x;
+      v[4 * i + 1] += b.y;
+      v[4 * i + 2] += b.z;
+      v[4 * i + 3] += b.w;
+    }
+  }
+  const size_t off = (size_t)row * N + col0;
+  if (ep.mode == NER_EPI_F32 || ep.mode == NER_EPI_RES_F32) {
+    if (ep.mode == NER_EPI_RES_F32) {
+      const float4* r4 = reinterpret_cast<const float4*>(ep.residual + off);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = __ldg(r4 + i);
+        v[4 * i + 0] += b.x;
+        v[4 * i + 1] += b.y;
+        v[4 * i + 2] += b.z;
+        v[4 * i + 3] += b.w;
+      }
+    }
+    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+    if (ep.mode == NER_EPI_GELU_TANH_BF16) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+    } else if (ep.mode == NER_EPI_GELU_ERF_BF16) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    } else if (ep.mode == NER_EPI_RELU_BF16) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      o4[i] = make_uint4(pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                         pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+  }
+}
+
+// Epilogue of one 128 x BN accumulator (this warp's lane quarter, its half of the column chunks).
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int warp, int lane, const EpiArgs& ep, int row0,
+                                              int n0, int M, int N) {
+  const int q = warp & 3;              // TMEM lane quarter this warp may access
+  const int half = (warp - 2) >> 2;    // 0: even chunks, 1: odd chunks
+  const int row = row0 + q * 32 + lane;
+#pragma unroll 1
+  for (int c = half; c < BN / 32; c += 2) {
+    uint32_t r[32];
+    tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+    tmem_ld_wait();
+    const int col0 = n0 + c * 32;
+    if (row < M && col0 < N) epilogue_chunk(r, ep, row, col0, N);
+  }
+}
+
+// ===================================================================== cta_group::1
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -90,7 +181,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[s], NUM_EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -156,72 +247,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue warps (2..9) =====================
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      const int row = m_blk * BM + q * 32 + lane;
-      const bool row_ok = row < M;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
-        tmem_ld_wait();
-        const int col0 = n_blk * BN + c * 32;
-        if (row_ok && col0 < N) {
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if (ep.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b = __ldg(b4 + i);
-              v[4 * i + 0] += b.x;
-              v[4 * i + 1] += b.y;
-              v[4 * i + 2] += b.z;
-              v[4 * i + 3] += b.w;
-            }
-          }
-          const size_t off = (size_t)row * N + col0;
-          if (ep.mode == NER_EPI_F32 || ep.mode == NER_EPI_RES_F32) {
-            if (ep.mode == NER_EPI_RES_F32) {
-              const float4* r4 = reinterpret_cast<const float4*>(ep.residual + off);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 b = __ldg(r4 + i);
-                v[4 * i + 0] += b.x;
-                v[4 * i + 1] += b.y;
-                v[4 * i + 2] += b.z;
-                v[4 * i + 3] += b.w;
-              }
-            }
-            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else {
-            if (ep.mode == NER_EPI_GELU_TANH_BF16) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
-            } else if (ep.mode == NER_EPI_GELU_ERF_BF16) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-            } else if (ep.mode == NER_EPI_RELU_BF16) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-            }
-            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + off);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              o4[i] = make_uint4(pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                                 pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-          }
-        }
-      }
+      epilogue_tile<BN>(tmem_base + (uint32_t)(acc * BN), warp, lane, ep, m_blk * BM, n_blk * BN, M, N);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -237,6 +270,150 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ===================================================================== cta_group::2 (CTA pair)
+// Protocol (s = smem stage, a = accumulator stage):
+//   full[s]        lives in CTA 0, count 1: CTA 0's producer arrive.expect_tx's the bytes of BOTH CTAs;
+//                  both CTAs' TMA loads complete_tx on it (peer-bit-masked barrier address).
+//   empty[s]       one per CTA, count 1: the MMA thread's multicast commit arrives on both.
+//   tmem_full[a]   one per CTA, count 1: multicast commit after the last k-block.
+//   tmem_empty[a]  lives in CTA 0, count 2*NUM_EPI_WARPS: every epilogue warp of both CTAs arrives
+//                  (CTA 1 through its shared::cluster address).
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                     EpiArgs ep, int M, int N, int K) {
+  using C = Cfg2<BN>;
+  constexpr int STAGES = C::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * C::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (C::A_BYTES + C::B_BYTES));
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  const int num_m = (M + 2 * BM - 1) / (2 * BM);  // 256-row tiles
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 2 * NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();  // barrier inits visible cluster-wide before any remote arrive / TMA complete_tx
+  if (warp == 1) tmem_alloc_2sm<C::TMEM_COLS>(tmem_ptr);
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+        const int row_a = m_blk * 2 * BM + (int)rank * BM;
+        const int row_b = n_blk * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (C::A_BYTES + C::B_BYTES));
+          tma_load_2d_2sm(smem_a + stage * C::A_BYTES, &tma_a, &full_bar[stage], kb * BK, row_a);
+          tma_load_2d_2sm(smem_b + stage * C::B_BYTES, &tma_b, &full_bar[stage], kb * BK, row_b);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread of CTA 0) =====================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * C::A_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + stage * C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + k * UMMA_K * 2);
+            const uint64_t db = make_smem_desc_sw128(b_addr + k * UMMA_K * 2);
+            umma_f16_2sm(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage], 0b11);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit_2sm(&tmem_full[acc], 0b11);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..9), both CTAs =====================
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t empty_remote0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+    const uint32_t empty_remote1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      epilogue_tile<BN>(tmem_base + (uint32_t)(acc * BN), warp, lane, ep, m_blk * 2 * BM + (int)rank * BM, n_blk * BN, M,
+                        N);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc == 0 ? empty_remote0 : empty_remote1);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();  // both CTAs done with TMEM / remote barriers
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm<C::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -302,6 +479,24 @@ int launch_gemm(const void* A, const void* Wt, EpiArgs ep, int M, int N, int K, 
   return ner_launch_status();
 }
 
+template <int BN>
+int launch_gemm2(const void* A, const void* Wt, EpiArgs ep, int M, int N, int K, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  int rc = make_map_bf16_2d(&ma, A, (uint64_t)M, (uint64_t)K, BM);
+  if (rc != NER_OK) return rc;
+  rc = make_map_bf16_2d(&mb, Wt, (uint64_t)N, (uint64_t)K, BN / 2);
+  if (rc != NER_OK) return rc;
+  auto kern = gemm_bf16_tc2_kernel<BN>;
+  const size_t smem = Cfg2<BN>::SMEM;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
+  const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+  const int max_pairs = sm_count() / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  kern<<<2 * pairs, NUM_THREADS, smem, st>>>(ma, mb, ep, M, N, K);
+  return ner_launch_status();
+}
+
 }  // namespace
 
 extern "C" int ner_gemm_bf16(const void* A, const void* Wt, const float* bias, const float* residual, void* out,
@@ -319,8 +514,12 @@ extern "C" int ner_gemm_bf16(const void* A, const void* Wt, const float* bias, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int bn = tile_n;
   if (bn == 0) bn = (N % 256 == 0 && ((M + BM - 1) / BM) * (N / 256) >= sm_count()) ? 256 : 128;
-  if (bn == 256) return launch_gemm<256>(A, Wt, ep, M, N, K, st);
-  if (bn == 128) return launch_gemm<128>(A, Wt, ep, M, N, K, st);
-  if (bn == 64) return launch_gemm<64>(A, Wt, ep, M, N, K, st);
-  return NER_ERR_INVALID_ARG;
+  switch (bn) {
+    case 256: return launch_gemm<256>(A, Wt, ep, M, N, K, st);
+    case 128: return launch_gemm<128>(A, Wt, ep, M, N, K, st);
+    case 64: return launch_gemm<64>(A, Wt, ep, M, N, K, st);
+    case NER_TILE_2CTA_256: return launch_gemm2<256>(A, Wt, ep, M, N, K, st);
+    case NER_TILE_2CTA_128: return launch_gemm2<128>(A, Wt, ep, M, N, K, st);
+    default: return NER_ERR_INVALID_ARG;
+  }
 }

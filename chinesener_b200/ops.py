@@ -9,6 +9,7 @@ from . import _lib
 from ._lib import check, lib, ptr, require_cuda, stream
 
 EPI_F32, EPI_BF16, EPI_GELU_TANH_BF16, EPI_GELU_ERF_BF16, EPI_RELU_BF16, EPI_RES_F32 = range(6)
+TILE_2CTA_128, TILE_2CTA_256 = 1128, 1256   # CTA-pair (cta_group::2) tiles of ner_gemm_bf16
 
 
 def _i32(t):

@@ -85,10 +85,15 @@ int ner_crf_loglik_bwd(const float* logits, const int32_t* tags, const int32_t* 
 #define NER_EPI_RELU_BF16 4      /* out bf16 = relu(acc + bias)              */
 #define NER_EPI_RES_F32 5        /* out f32  = acc + bias + residual (f32)   */
 
+/* tile_n selectors of ner_gemm_bf16: 64/128/256 = one CTA per 128 x tile_n tile
+ * (cta_group::1); the 2CTA values = a CTA pair per 256 x N tile (cta_group::2). */
+#define NER_TILE_2CTA_128 1128
+#define NER_TILE_2CTA_256 1256
+
 /* out[M,N] = epilogue(A[M,K] · Wt[N,K]^T + bias[N]).  A and Wt are bf16,
  * K contiguous (Wt is the TF kernel [K,N] transposed once by
  * ner_pack_weight_bf16).  bias may be NULL.  K % 8 == 0, N % 32 == 0.
- * tile_n: 0 = auto, or 64/128/256. */
+ * tile_n: 0 = auto, or one of the selectors above. */
 int ner_gemm_bf16(const void* A, const void* Wt, const float* bias, const float* residual,
                   void* out, int M, int N, int K, int epilogue, int tile_n,
                   ner_stream_t stream);

@@ -52,10 +52,13 @@ def bench_gemm():
         a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
         w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
         bias = torch.randn(N, device="cuda")
-        for tn in (128, 256):
-            o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-            med, best = timeit(lambda: ops.gemm_bf16(a, w, bias, epilogue=ops.EPI_BF16, tile_n=tn, out=o), iters=20)
-            out[f"{M}x{N}x{K}_bn{tn}"] = dict(ms=med, TFLOPs=2.0 * M * N * K / med / 1e9)
+        res = torch.randn(M, N, device="cuda")
+        for tn in (128, 256, ops.TILE_2CTA_128, ops.TILE_2CTA_256):
+            for epi, nm in ((ops.EPI_BF16, "bf16"), (ops.EPI_GELU_TANH_BF16, "gelu"), (ops.EPI_RES_F32, "resf32")):
+                o = torch.empty(M, N, device="cuda", dtype=torch.float32 if epi == ops.EPI_RES_F32 else torch.bfloat16)
+                med, best = timeit(lambda: ops.gemm_bf16(a, w, bias, residual=res if epi == ops.EPI_RES_F32 else None,
+                                                         epilogue=epi, tile_n=tn, out=o), iters=20)
+                out[f"{M}x{N}x{K}_t{tn}_{nm}"] = dict(us=round(med * 1e3, 1), TFLOPs=round(2.0 * M * N * K / med / 1e9, 1))
     return out
 
 

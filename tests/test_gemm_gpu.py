@@ -25,7 +25,8 @@ def _ref(a, wt, bias, residual, epi):
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 256, 128), (256, 128, 768), (8192, 768, 768),
                                    (8192, 2304, 768), (1000, 768, 3072), (77, 96, 200), (4096, 3072, 768),
                                    (300, 1024, 768)])
-@pytest.mark.parametrize("tile_n", [128, 256])
+@pytest.mark.parametrize("tile_n", [128, 256, ops.TILE_2CTA_128, ops.TILE_2CTA_256])
+@pytest.mark.timeout(120)
 def test_gemm_matches_fp32_reference(M, N, K, tile_n):
     g = torch.Generator().manual_seed(M + N + K)
     a = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
@@ -36,16 +37,18 @@ def test_gemm_matches_fp32_reference(M, N, K, tile_n):
     torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("tile_n", [0, ops.TILE_2CTA_256])
 @pytest.mark.parametrize("epi", [ops.EPI_BF16, ops.EPI_GELU_TANH_BF16, ops.EPI_GELU_ERF_BF16, ops.EPI_RELU_BF16,
                                  ops.EPI_RES_F32])
-def test_gemm_epilogues(epi):
+@pytest.mark.timeout(120)
+def test_gemm_epilogues(epi, tile_n):
     M, N, K = 640, 768, 512
     g = torch.Generator().manual_seed(epi)
     a = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
     wt = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).cuda()
     bias = torch.randn(N, generator=g).cuda()
     res = torch.randn(M, N, generator=g).cuda() if epi == ops.EPI_RES_F32 else None
-    out = ops.gemm_bf16(a, wt, bias, residual=res, epilogue=epi)
+    out = ops.gemm_bf16(a, wt, bias, residual=res, epilogue=epi, tile_n=tile_n)
     ref = _ref(a, wt, bias, res, epi)
     if out.dtype == torch.bfloat16:
         torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=1e-2)
