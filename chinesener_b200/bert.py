@@ -73,8 +73,26 @@ def _packed(store, cfg, scope):
     return store.cached(("bert_pack", scope), build)
 
 
-def bert_forward(input_ids, input_mask, segment_ids, cfg, store=None, scope="bert", gelu="tanh"):
-    """-> (sequence_output f32 [B*L,H], bf16 copy [B*L,H])."""
+class PackInfo:
+    """Sequence-packing plan of one batch: token rows of all sequences back to back, no padding."""
+
+    def __init__(self, cu_seqlens, tok_src, total, B, L):
+        self.cu_seqlens, self.tok_src, self.total, self.B, self.L = cu_seqlens, tok_src, int(total), B, L
+
+
+def make_pack(input_mask, total_tokens=None):
+    """Plan from a prefix mask [B,L].  `total_tokens` (host int) avoids a device sync."""
+    B, L = input_mask.shape
+    if total_tokens is None:
+        total_tokens = getattr(input_mask, "total_tokens", None)
+    if total_tokens is None:
+        total_tokens = int(input_mask.sum().item())      # device sync; engine.Estimator passes the host count
+    cu, tok_src = ops.seq_pack_plan(input_mask)
+    return PackInfo(cu, tok_src, total_tokens, B, L)
+
+
+def bert_forward(input_ids, input_mask, segment_ids, cfg, store=None, scope="bert", gelu="tanh", pack=None):
+    """-> (sequence_output f32 [rows,H], bf16 copy [rows,H]); rows = B*L, or pack.total in packed mode."""
     store = store or variables.default_store()
     create_bert_variables(cfg, store, scope)
     B, L = input_ids.shape
@@ -83,11 +101,13 @@ def bert_forward(input_ids, input_mask, segment_ids, cfg, store=None, scope="ber
     layers = _packed(store, cfg, scope)
     x32, x16 = ops.bert_embed_ln(v[f"{scope}/embeddings/word_embeddings"], v[f"{scope}/embeddings/token_type_embeddings"],
                                  v[f"{scope}/embeddings/position_embeddings"], v[f"{scope}/embeddings/LayerNorm/gamma"],
-                                 v[f"{scope}/embeddings/LayerNorm/beta"], input_ids, segment_ids, eps=1e-12)
+                                 v[f"{scope}/embeddings/LayerNorm/beta"], input_ids, segment_ids, eps=1e-12,
+                                 tok_src=pack.tok_src if pack else None, n_packed=pack.total if pack else 0)
     epi_gelu = ops.EPI_GELU_ERF_BF16 if gelu == "erf" else ops.EPI_GELU_TANH_BF16
+    cu = pack.cu_seqlens if pack else None
     for w in layers:
         qkv = ops.gemm_bf16(x16, w["wqkv"], w["bqkv"], epilogue=ops.EPI_BF16)
-        ctx = ops.bert_attention(qkv, input_mask, B, L, NH, H // NH)
+        ctx = ops.bert_attention(qkv, input_mask, B, L, NH, H // NH, cu_seqlens=cu)
         y = ops.gemm_bf16(ctx, w["wo"], w["bo"], residual=x32, epilogue=ops.EPI_RES_F32)
         x32, x16 = ops.layernorm(y, w["g1"], w["b1"], eps=1e-12)
         inter = ops.gemm_bf16(x16, w["wi"], w["bi"], epilogue=epi_gelu)

@@ -36,17 +36,23 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 __global__ void __launch_bounds__(128)
 bert_attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ mask,
-                      __nv_bfloat16* __restrict__ ctx, int L, int NH, int Lp, float scale, float mask_add) {
+                      __nv_bfloat16* __restrict__ ctx, int Lpad, int NH, int Lp_max, float scale, float mask_add,
+                      const int32_t* __restrict__ cu_seqlens) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-  __nv_bfloat16* Vs = Ks + (size_t)Lp * PITCH;
-  float* s_madd = reinterpret_cast<float*>(Vs + (size_t)Lp * PITCH);
+  __nv_bfloat16* Vs = Ks + (size_t)Lp_max * PITCH;
+  float* s_madd = reinterpret_cast<float*>(Vs + (size_t)Lp_max * PITCH);
 
   const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HD = NH * D;
   const size_t rs = (size_t)3 * HD;  // qkv row stride (elements)
-  const __nv_bfloat16* base = qkv + (size_t)b * L * rs;
+  // padded mode: rows [b*L, (b+1)*L), keys masked by `mask`; packed mode: rows [cu[b], cu[b+1]), all valid
+  const size_t row_base = cu_seqlens ? (size_t)cu_seqlens[b] : (size_t)b * Lpad;
+  const int L = cu_seqlens ? (cu_seqlens[b + 1] - cu_seqlens[b]) : Lpad;
+  if (qt * QT >= L) return;  // (whole CTA) nothing to do for this query tile
+  const int Lp = cu_seqlens ? (L + KB - 1) / KB * KB : Lp_max;
+  const __nv_bfloat16* base = qkv + row_base * rs;
 
   for (int idx = tid; idx < Lp * 8; idx += 128) {
     const int row = idx >> 3, ch = idx & 7;
@@ -63,7 +69,7 @@ bert_attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __re
   }
   cp_async_commit();
   for (int k = tid; k < Lp; k += 128)
-    s_madd[k] = (k < L) ? (1.f - (float)mask[b * L + k]) * mask_add : -1e30f;
+    s_madd[k] = (k < L) ? (cu_seqlens ? 0.f : (1.f - (float)mask[(size_t)b * Lpad + k]) * mask_add) : -1e30f;
 
   // Q fragments straight from global (each element read once)
   const int q0 = qt * QT + warp * 16;
@@ -161,7 +167,7 @@ bert_attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __re
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float inv0 = 1.f / l0, inv1 = 1.f / l1;
-    __nv_bfloat16* ob = ctx + (size_t)b * L * HD + h * D;
+    __nv_bfloat16* ob = ctx + row_base * HD + h * D;
 #pragma unroll
     for (int dt = 0; dt < 8; ++dt) {
       if (r0 < L) *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * HD + dt * 8 + cq) = pack2(o[dt][0] * inv0, o[dt][1] * inv0);
@@ -173,10 +179,11 @@ bert_attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __re
 }  // namespace
 
 extern "C" int ner_bert_attention(const void* qkv_bf16, const int32_t* mask, void* ctx_bf16, int B, int L,
-                                  int num_heads, int head_dim, float scale, float mask_add, ner_stream_t stream) {
+                                  int num_heads, int head_dim, float scale, float mask_add,
+                                  const int32_t* cu_seqlens, ner_stream_t stream) {
   if (B < 0 || L < 1 || num_heads < 1) return NER_ERR_INVALID_ARG;
   if (B == 0) return NER_OK;
-  if (!qkv_bf16 || !mask || !ctx_bf16) return NER_ERR_INVALID_ARG;
+  if (!qkv_bf16 || (!mask && !cu_seqlens) || !ctx_bf16) return NER_ERR_INVALID_ARG;
   if (head_dim != D) return NER_ERR_UNSUPPORTED;
   const int Lp = (L + KB - 1) / KB * KB;
   const size_t smem = (size_t)2 * Lp * PITCH * 2 + (size_t)Lp * 4;
@@ -186,6 +193,6 @@ extern "C" int ner_bert_attention(const void* qkv_bf16, const int32_t* mask, voi
   dim3 grid((L + QT - 1) / QT, num_heads, B);
   bert_attention_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv_bf16), mask, static_cast<__nv_bfloat16*>(ctx_bf16), L, num_heads, Lp, scale,
-      mask_add);
+      mask_add, cu_seqlens);
   return ner_launch_status();
 }

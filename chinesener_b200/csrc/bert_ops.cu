@@ -61,15 +61,17 @@ bert_embed_ln_kernel(const float* __restrict__ word_emb, const float* __restrict
                      const float* __restrict__ pos_emb, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const int32_t* __restrict__ ids,
                      const int32_t* __restrict__ seg, float* __restrict__ out_f32,
-                     __nv_bfloat16* __restrict__ out_bf16, int n_tok, int L, int H, int V, int n_type, float eps) {
+                     __nv_bfloat16* __restrict__ out_bf16, int n_tok, int L, int H, int V, int n_type, float eps,
+                     const int32_t* __restrict__ tok_src) {
   const int lane = threadIdx.x & 31;
   const int nv4 = (H / 4 + 31) / 32;
   for (int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tok < n_tok; tok += gridDim.x * (blockDim.x >> 5)) {
-    int id = ids[tok];
+    const int src = tok_src ? tok_src[tok] : tok;  // packed row -> padded (b*L + pos) index
+    int id = ids[src];
     id = min(max(id, 0), V - 1);
-    int sg = (seg != nullptr) ? seg[tok] : 0;
+    int sg = (seg != nullptr) ? seg[src] : 0;
     sg = min(max(sg, 0), n_type - 1);
-    const int pos = tok % L;
+    const int pos = src % L;
     const float* w = word_emb + (size_t)id * H;
     const float* ty = type_emb + (size_t)sg * H;
     const float* po = pos_emb + (size_t)pos * H;
@@ -147,7 +149,7 @@ cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
 template <typename XT, int NMAX>
 __global__ void __launch_bounds__(256)
 dense_small_n_kernel(const XT* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
-                     float* __restrict__ out, int M, int F, int N) {
+                     float* __restrict__ out, int M, int F, int N, const int32_t* __restrict__ row_map) {
   extern __shared__ float s_w[];  // [F][N]
   for (int e = threadIdx.x; e < F * N; e += blockDim.x) s_w[e] = W[e];
   __syncthreads();
@@ -173,7 +175,8 @@ dense_small_n_kernel(const XT* __restrict__ x, const float* __restrict__ W, cons
 #pragma unroll
       for (int n = 0; n < NMAX; ++n)
         if (n == lane) v = acc[n];
-      out[(size_t)row * N + lane] = v + (bias ? bias[lane] : 0.f);
+      const size_t orow = row_map ? (size_t)row_map[row] : (size_t)row;
+      out[orow * N + lane] = v + (bias ? bias[lane] : 0.f);
     }
   }
 }
@@ -205,6 +208,32 @@ cast_pad_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ 
   }
 }
 
+// Sequence-packing plan from a prefix mask [B,L]: len_b = sum(mask[b,:]); cu[b] = exclusive prefix
+// sum; tok_src[cu[b] + t] = b*L + t.  One CTA (B <= 1024 rows handled by loops).
+__global__ void __launch_bounds__(1024)
+seq_pack_plan_kernel(const int32_t* __restrict__ mask, int32_t* __restrict__ cu, int32_t* __restrict__ tok_src, int B, int L) {
+  extern __shared__ int s_plan[];  // [B+1]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int b = warp; b < B; b += nw) {
+    int c = 0;
+    for (int t = lane; t < L; t += 32) c += (mask[(size_t)b * L + t] != 0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) s_plan[b + 1] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_plan[0] = 0;
+    for (int b = 0; b < B; ++b) s_plan[b + 1] += s_plan[b];
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b <= B; b += blockDim.x) cu[b] = s_plan[b];
+  for (int b = warp; b < B; b += nw) {
+    const int o = s_plan[b], n = s_plan[b + 1] - o;
+    for (int t = lane; t < n; t += 32) tok_src[o + t] = b * L + t;
+  }
+}
+
 int grid_for_rows(int rows, int rows_per_block) {
   long g = ((long)rows + rows_per_block - 1) / rows_per_block;
   if (g > 148L * 16) g = 148L * 16;
@@ -217,15 +246,17 @@ int grid_for_rows(int rows, int rows_per_block) {
 extern "C" int ner_bert_embed_ln(const float* word_emb, const float* type_emb, const float* pos_emb,
                                  const float* gamma, const float* beta, const int32_t* ids, const int32_t* seg,
                                  float* out_f32, void* out_bf16, int B, int L, int H, int vocab, int n_type,
-                                 int max_pos, float eps, ner_stream_t stream) {
+                                 int max_pos, float eps, const int32_t* tok_src, int n_packed, ner_stream_t stream) {
   if (B < 0 || L < 1 || H < 4 || vocab < 1 || n_type < 1) return NER_ERR_INVALID_ARG;
   if (B == 0) return NER_OK;
   if (!word_emb || !type_emb || !pos_emb || !gamma || !beta || !ids || (!out_f32 && !out_bf16)) return NER_ERR_INVALID_ARG;
   if (H % 4 != 0 || H > 128 * LN_MAXV || L > max_pos) return NER_ERR_UNSUPPORTED;
-  const int n_tok = B * L;
+  const int n_tok = tok_src ? n_packed : B * L;
+  if (n_tok < 0 || n_tok > B * L) return NER_ERR_INVALID_ARG;
+  if (n_tok == 0) return NER_OK;
   bert_embed_ln_kernel<<<grid_for_rows(n_tok, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       word_emb, type_emb, pos_emb, gamma, beta, ids, seg, out_f32, static_cast<__nv_bfloat16*>(out_bf16), n_tok, L, H,
-      vocab, n_type, eps);
+      vocab, n_type, eps, tok_src);
   return ner_launch_status();
 }
 
@@ -257,7 +288,7 @@ extern "C" int ner_cast_bf16(const float* src, void* dst_bf16, size_t n, ner_str
 }
 
 extern "C" int ner_dense_small_n(const void* x, int x_is_bf16, const float* W, const float* bias, float* out, int M,
-                                 int F, int N, ner_stream_t stream) {
+                                 int F, int N, const int32_t* row_map, ner_stream_t stream) {
   if (M < 0 || F < 1 || N < 1) return NER_ERR_INVALID_ARG;
   if (M == 0) return NER_OK;
   if (!x || !W || !out) return NER_ERR_INVALID_ARG;
@@ -271,7 +302,7 @@ extern "C" int ner_dense_small_n(const void* x, int x_is_bf16, const float* W, c
     auto kern = dense_small_n_kernel<XT, NM>;                                                            \
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
     if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;                                             \
-    kern<<<grid, 256, smem, st>>>(static_cast<const XT*>(x), W, bias, out, M, F, N);                     \
+    kern<<<grid, 256, smem, st>>>(static_cast<const XT*>(x), W, bias, out, M, F, N, row_map);                     \
   }
   if (x_is_bf16) {
     if (N <= 16) LAUNCH(__nv_bfloat16, 16) else LAUNCH(__nv_bfloat16, 32)
@@ -301,5 +332,20 @@ extern "C" int ner_cast_pad_bf16(const float* src, void* dst_bf16, int M, int D,
   if (g > 148 * 32) g = 148 * 32;
   cast_pad_bf16_kernel<<<(int)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, static_cast<__nv_bfloat16*>(dst_bf16), M,
                                                                               D, Dp, ld_src);
+  return ner_launch_status();
+}
+
+extern "C" int ner_seq_pack_plan(const int32_t* mask, int32_t* cu_seqlens, int32_t* tok_src, int B, int L,
+                                 ner_stream_t stream) {
+  if (B < 0 || L < 1) return NER_ERR_INVALID_ARG;
+  if (B == 0) return NER_OK;
+  if (!mask || !cu_seqlens || !tok_src) return NER_ERR_INVALID_ARG;
+  if ((size_t)(B + 1) * 4 > 200 * 1024) return NER_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)(B + 1) * 4;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(seq_pack_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
+  }
+  seq_pack_plan_kernel<<<1, 1024, smem, static_cast<cudaStream_t>(stream)>>>(mask, cu_seqlens, tok_src, B, L);
   return ner_launch_status();
 }

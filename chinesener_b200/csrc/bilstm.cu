@@ -34,7 +34,8 @@ __device__ __forceinline__ float actf(float x) {
 template <int R, int ACT, int H4REG>
 __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(const float* __restrict__ xproj, const float* __restrict__ wh_fw,
                                   const float* __restrict__ wh_bw, const int32_t* __restrict__ seq_len,
-                                  float* __restrict__ out, int B, int L, int H, int C, float forget_bias) {
+                                  float* __restrict__ out, int B, int L, int H, int C, float forget_bias,
+                                  const int32_t* __restrict__ cu_seqlens) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int HU = H / C;       // hidden units owned by this CTA
@@ -97,6 +98,11 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
   const int cr = cell_ok ? tid / HU : 0, cu = cell_ok ? tid - cr * HU : 0;
   float c_state = 0.f, h_state = 0.f;
 
+  // xproj row of (row r, position pos): padded layout b*L + pos, or packed layout cu_seqlens[b] + pos
+  size_t xrow0[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    xrow0[r] = (b0 + r < B) ? (cu_seqlens ? (size_t)cu_seqlens[b0 + r] : (size_t)(b0 + r) * L) : 0;
   float xp[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -104,7 +110,7 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
     const int len = s_len[r];
     if (col_ok && 0 < len) {
       const int pos = dir == 0 ? 0 : len - 1;
-      xp[r] = xproj[((size_t)(b0 + r) * L + pos) * 8 * H + xcol];
+      xp[r] = xproj[(xrow0[r] + pos) * 8 * H + xcol];
     }
   }
 
@@ -122,7 +128,7 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
         xp[r] = 0.f;
         if (s + 1 < len) {
           const int pos = dir == 0 ? s + 1 : len - 2 - s;
-          xp[r] = xproj[((size_t)(b0 + r) * L + pos) * 8 * H + xcol];
+          xp[r] = xproj[(xrow0[r] + pos) * 8 * H + xcol];
         }
       }
       const float4* hc4 = reinterpret_cast<const float4*>(hcur);
@@ -202,7 +208,7 @@ int pick_cluster(int H) {
 
 template <int R, int ACT, int H4REG>
 int launch_rec(const float* xproj, const float* wh_fw, const float* wh_bw, const int32_t* seq_len, float* out, int B,
-               int L, int H, int C, float forget_bias, cudaStream_t st) {
+               int L, int H, int C, float forget_bias, const int32_t* cu_seqlens, cudaStream_t st) {
   const int HU = H / C, NC = 4 * HU;
   const size_t smem = ((H4REG > 0 ? 0 : (size_t)H * NC) + 2 * R * H + (size_t)R * NC + 32) * 4;
   auto kern = bilstm_rec_kernel<R, ACT, H4REG>;
@@ -221,7 +227,7 @@ int launch_rec(const float* xproj, const float* wh_fw, const float* wh_bw, const
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kern, xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias);
+  e = cudaLaunchKernelEx(&cfg, kern, xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, cu_seqlens);
   if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   return ner_launch_status();
 }
@@ -230,7 +236,7 @@ int launch_rec(const float* xproj, const float* wh_fw, const float* wh_bw, const
 
 extern "C" int ner_bilstm_recurrence(const float* xproj, const float* wh_fw, const float* wh_bw,
                                      const int32_t* seq_len, float* out, int B, int L, int H, int activation,
-                                     float forget_bias, ner_stream_t stream) {
+                                     float forget_bias, const int32_t* cu_seqlens, ner_stream_t stream) {
   if (B < 0 || L < 1 || H < 1) return NER_ERR_INVALID_ARG;
   if (B == 0) return NER_OK;
   if (!xproj || !wh_fw || !wh_bw || !seq_len || !out) return NER_ERR_INVALID_ARG;
@@ -244,8 +250,8 @@ extern "C" int ner_bilstm_recurrence(const float* xproj, const float* wh_fw, con
   if ((long)2 * B * C > 148) R = 2;
   if ((long)2 * ((B + 1) / 2) * C > 2 * 148) R = 4;
 #define GO(RR, HR)                                                                                          \
-  return activation == 1 ? launch_rec<RR, 1, HR>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, st) \
-                         : launch_rec<RR, 0, HR>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, st)
+  return activation == 1 ? launch_rec<RR, 1, HR>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, cu_seqlens, st) \
+                         : launch_rec<RR, 0, HR>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, cu_seqlens, st)
   if (H == 128 && 4 * (H / C) <= 256) {  // register-resident W_h (the bert_bilstm_crf / bilstm_crf shape)
     if (R == 4) GO(4, 32);
     if (R == 2) GO(2, 32);

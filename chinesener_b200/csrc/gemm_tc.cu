@@ -141,6 +141,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int warp, int l
     tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
     tmem_ld_wait();
     const int col0 = n0 + c * 32;
+    if (ep.mode == NER_EPI_DIAG_DISCARD) continue;  // diagnostic: drain TMEM, store nothing
     if (row < M && col0 < N) epilogue_chunk(r, ep, row, col0, N);
   }
 }
@@ -504,7 +505,7 @@ extern "C" int ner_gemm_bf16(const void* A, const void* Wt, const float* bias, c
   if (M < 0 || N < 1 || K < 1) return NER_ERR_INVALID_ARG;
   if (M == 0) return NER_OK;
   if (!A || !Wt || !out) return NER_ERR_INVALID_ARG;
-  if (epilogue < NER_EPI_F32 || epilogue > NER_EPI_RES_F32) return NER_ERR_INVALID_ARG;
+  if ((epilogue < NER_EPI_F32 || epilogue > NER_EPI_RES_F32) && epilogue != NER_EPI_DIAG_DISCARD) return NER_ERR_INVALID_ARG;
   if (epilogue == NER_EPI_RES_F32 && !residual) return NER_ERR_INVALID_ARG;
   if ((K % 8) != 0 || (N % 32) != 0) return NER_ERR_UNSUPPORTED;  // 16-B TMA strides, 32-col epilogue chunks
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(Wt) & 15) ||

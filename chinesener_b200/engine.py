@@ -39,6 +39,10 @@ class Estimator:
                 out[k] = v.to(self.device, non_blocking=True)
             else:
                 out[k] = v
+        m = features.get('mask')
+        if torch.is_tensor(m) and not m.is_cuda and 'mask' in out:
+            # host-side token count rides along so sequence packing needs no device sync
+            out['mask'].total_tokens = int(m.sum())
         return out
 
     def forward_device(self, dev_features, is_training=False):

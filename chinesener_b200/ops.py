@@ -9,6 +9,7 @@ from . import _lib
 from ._lib import check, lib, ptr, require_cuda, stream
 
 EPI_F32, EPI_BF16, EPI_GELU_TANH_BF16, EPI_GELU_ERF_BF16, EPI_RELU_BF16, EPI_RES_F32 = range(6)
+EPI_DIAG_DISCARD = 99
 TILE_2CTA_128, TILE_2CTA_256 = 1128, 1256   # CTA-pair (cta_group::2) tiles of ner_gemm_bf16
 
 
@@ -87,30 +88,48 @@ def cast_bf16(x):
     return out
 
 
-def dense_small_n(x, w, bias=None):
-    """tf.layers.dense(units=label_size): x [M,F] (f32|bf16) @ w [F,N] f32 + bias -> f32 [M,N], N <= 32."""
-    require_cuda(x, w, bias)
+def dense_small_n(x, w, bias=None, row_map=None, out=None):
+    """tf.layers.dense(units=label_size): x [M,F] (f32|bf16) @ w [F,N] f32 + bias -> f32 [M,N], N <= 32.
+    row_map [M] i32 scatters input row r to out[row_map[r]] (packed -> padded); `out` then must be given."""
+    require_cuda(x, w, bias, row_map, out)
     assert w.dtype == torch.float32 and x.dtype in (torch.float32, torch.bfloat16)
     M, F = x.shape
     F2, N = w.shape
     assert F == F2
-    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    if out is None:
+        assert row_map is None
+        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
     check(lib().ner_dense_small_n(ptr(x), 1 if x.dtype == torch.bfloat16 else 0, ptr(w), ptr(bias), ptr(out), M, F, N,
-                                  stream()))
+                                  ptr(row_map), stream()))
     return out
 
 
+def seq_pack_plan(mask):
+    """prefix mask [B,L] -> (cu_seqlens [B+1] i32, tok_src [B*L] i32) on the device."""
+    require_cuda(mask)
+    B, L = mask.shape
+    mask = _i32(mask)
+    cu = torch.empty((B + 1,), dtype=torch.int32, device=mask.device)
+    tok_src = torch.empty((B * L,), dtype=torch.int32, device=mask.device)
+    check(lib().ner_seq_pack_plan(ptr(mask), ptr(cu), ptr(tok_src), B, L, stream()))
+    return cu, tok_src
+
+
 # --------------------------------------------------------------------------- BERT pieces
-def bert_embed_ln(word_emb, type_emb, pos_emb, gamma, beta, ids, seg, eps=1e-12, want_f32=True, want_bf16=True):
-    require_cuda(word_emb, type_emb, pos_emb, gamma, beta, ids, seg)
+def bert_embed_ln(word_emb, type_emb, pos_emb, gamma, beta, ids, seg, eps=1e-12, want_f32=True, want_bf16=True,
+                  tok_src=None, n_packed=0):
+    """Padded mode: B*L output rows.  Packed mode (tok_src, n_packed): n_packed rows."""
+    require_cuda(word_emb, type_emb, pos_emb, gamma, beta, ids, seg, tok_src)
     B, L = ids.shape
     V, H = word_emb.shape
     ids = _i32(ids)
     seg = None if seg is None else _i32(seg)
-    of = torch.empty((B * L, H), dtype=torch.float32, device=ids.device) if want_f32 else None
-    ob = torch.empty((B * L, H), dtype=torch.bfloat16, device=ids.device) if want_bf16 else None
+    rows = n_packed if tok_src is not None else B * L
+    of = torch.empty((rows, H), dtype=torch.float32, device=ids.device) if want_f32 else None
+    ob = torch.empty((rows, H), dtype=torch.bfloat16, device=ids.device) if want_bf16 else None
     check(lib().ner_bert_embed_ln(ptr(word_emb), ptr(type_emb), ptr(pos_emb), ptr(gamma), ptr(beta), ptr(ids), ptr(seg),
-                                  ptr(of), ptr(ob), B, L, H, V, type_emb.shape[0], pos_emb.shape[0], eps, stream()))
+                                  ptr(of), ptr(ob), B, L, H, V, type_emb.shape[0], pos_emb.shape[0], eps, ptr(tok_src),
+                                  n_packed, stream()))
     return of, ob
 
 
@@ -124,26 +143,30 @@ def layernorm(y, gamma, beta, residual=None, eps=1e-12, want_f32=True, want_bf16
     return of, ob
 
 
-def bert_attention(qkv, mask, B, L, num_heads, head_dim=64, scale=None, mask_add=-10000.0):
-    require_cuda(qkv, mask)
-    assert qkv.dtype == torch.bfloat16 and qkv.shape == (B * L, 3 * num_heads * head_dim)
-    mask = _i32(mask)
-    ctx = torch.empty((B * L, num_heads * head_dim), dtype=torch.bfloat16, device=qkv.device)
+def bert_attention(qkv, mask, B, L, num_heads, head_dim=64, scale=None, mask_add=-10000.0, cu_seqlens=None):
+    """Padded mode: qkv [B*L, 3HD] + mask.  Packed mode: qkv [T, 3HD] + cu_seqlens [B+1] (L = max length)."""
+    require_cuda(qkv, mask, cu_seqlens)
+    assert qkv.dtype == torch.bfloat16 and qkv.shape[1] == 3 * num_heads * head_dim
+    assert cu_seqlens is not None or qkv.shape[0] == B * L
+    mask = None if mask is None else _i32(mask)
+    ctx = torch.empty((qkv.shape[0], num_heads * head_dim), dtype=torch.bfloat16, device=qkv.device)
     if scale is None:
         scale = 1.0 / (head_dim ** 0.5)
-    check(lib().ner_bert_attention(ptr(qkv), ptr(mask), ptr(ctx), B, L, num_heads, head_dim, scale, mask_add, stream()))
+    check(lib().ner_bert_attention(ptr(qkv), ptr(mask), ptr(ctx), B, L, num_heads, head_dim, scale, mask_add,
+                                   ptr(cu_seqlens), stream()))
     return ctx
 
 
 # --------------------------------------------------------------------------- BiLSTM
-def bilstm_recurrence(xproj, wh_fw, wh_bw, seq_len, B, L, H, activation="tanh", forget_bias=1.0):
-    require_cuda(xproj, wh_fw, wh_bw, seq_len)
-    assert xproj.dtype == torch.float32 and xproj.shape == (B * L, 8 * H)
+def bilstm_recurrence(xproj, wh_fw, wh_bw, seq_len, B, L, H, activation="tanh", forget_bias=1.0, cu_seqlens=None):
+    require_cuda(xproj, wh_fw, wh_bw, seq_len, cu_seqlens)
+    assert xproj.dtype == torch.float32 and xproj.shape[1] == 8 * H
+    assert cu_seqlens is not None or xproj.shape[0] == B * L
     assert wh_fw.shape == (H, 4 * H) and wh_bw.shape == (H, 4 * H)
     act = {"tanh": 0, "relu": 1}[activation]
     out = torch.empty((B, L, 2 * H), dtype=torch.float32, device=xproj.device)
     check(lib().ner_bilstm_recurrence(ptr(xproj), ptr(wh_fw), ptr(wh_bw), ptr(_i32(seq_len)), ptr(out), B, L, H, act,
-                                      forget_bias, stream()))
+                                      forget_bias, ptr(cu_seqlens), stream()))
     return out
 
 

@@ -2,10 +2,16 @@
 wrapper over the C-ABI kernels.  Same names, argument order and meaning; tensors are torch
 CUDA tensors, variables live in `chinesener_b200.variables` under the reference's TF names.
 """
+import os
+
 import torch
 
 from .. import bert as _bert
 from .. import ops, variables
+
+# Remove padding rows from the token-major activations of the BERT plugins (exact for loss and
+# pred_ids: the CRF never reads t >= seq_len).  NER_B200_PACK=0 keeps the padded layout.
+PACK_SEQUENCES = os.environ.get("NER_B200_PACK", "1") != "0"
 
 
 class TrainingPathNotBuilt(NotImplementedError):
@@ -26,6 +32,12 @@ def pretrain_bert_embedding(input_ids, input_mask, segment_ids, pretrain_dir, dr
     _no_training(is_training, "pretrain_bert_embedding")
     cfg = _bert.load_bert_config(pretrain_dir)
     B, L = input_ids.shape
+    if PACK_SEQUENCES:
+        pack = _bert.make_pack(input_mask)
+        x32, x16 = _bert.bert_forward(input_ids, input_mask, segment_ids, cfg, pack=pack)
+        emb = x32                      # [total_tokens, H]: packed rows, see PackInfo
+        emb.bf16, emb.pack = x16, pack
+        return emb
     x32, x16 = _bert.bert_forward(input_ids, input_mask, segment_ids, cfg)
     emb = x32.view(B, L, -1)
     emb.bf16 = x16.view(B, L, -1)
@@ -54,7 +66,11 @@ def bilstm(embedding, cell_type, activation, hidden_units_list, keep_prob_list, 
         raise Exception('Only lstm is built on the sm_100a path (reference models all use cell_type=lstm)')
     if cell_size != 1:
         raise Exception('cell_size must be 1 (every reference model uses a single LSTM layer)')
-    B, L, D = embedding.shape
+    pack = getattr(embedding, "pack", None)
+    if pack is not None:
+        B, L, D = pack.B, pack.L, embedding.shape[-1]
+    else:
+        B, L, D = embedding.shape
     H = hidden_units_list[0]
     store = variables.default_store()
     scope = "bilstm_layer/bidirectional_rnn"
@@ -64,11 +80,12 @@ def bilstm(embedding, cell_type, activation, hidden_units_list, keep_prob_list, 
     pk = _lstm_pack(store, D, H, scope)
     x16 = getattr(embedding, "bf16", None)
     if x16 is not None and pk["Dp"] == D:
-        x16 = x16.reshape(B * L, D)
+        x16 = x16.reshape(-1, D)
     else:
-        x16 = ops.cast_pad_bf16(embedding.reshape(B * L, D), pk["Dp"])
+        x16 = ops.cast_pad_bf16(embedding.reshape(-1, D), pk["Dp"])
     xproj = ops.gemm_bf16(x16, pk["wx"], pk["bias"], epilogue=ops.EPI_F32)
-    return ops.bilstm_recurrence(xproj, pk["wh_fw"], pk["wh_bw"], seq_len, B, L, H, activation=activation, forget_bias=1.0)
+    return ops.bilstm_recurrence(xproj, pk["wh_fw"], pk["wh_bw"], seq_len, B, L, H, activation=activation, forget_bias=1.0,
+                                 cu_seqlens=pack.cu_seqlens if pack is not None else None)
 
 
 def dense(inputs, units, name='logits'):
@@ -79,6 +96,12 @@ def dense(inputs, units, name='logits'):
     b = variables.get_variable(f"{name}/bias", (units,), variables.zeros)
     x = getattr(inputs, "bf16", None)
     x = inputs if x is None else x
+    pack = getattr(inputs, "pack", None)
+    if pack is not None:
+        # packed rows -> padded [B, L, units]; padded positions stay 0 (never read by the CRF)
+        out = torch.zeros((pack.B * pack.L, units), dtype=torch.float32, device=x.device)
+        ops.dense_small_n(x.reshape(-1, F), w, b, row_map=pack.tok_src, out=out)
+        return out.view(pack.B, pack.L, units)
     out = ops.dense_small_n(x.reshape(-1, F), w, b)
     return out.view(*lead, units)
 

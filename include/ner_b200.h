@@ -84,6 +84,7 @@ int ner_crf_loglik_bwd(const float* logits, const int32_t* tags, const int32_t* 
 #define NER_EPI_GELU_ERF_BF16 3  /* out bf16 = gelu_erf(acc + bias)          */
 #define NER_EPI_RELU_BF16 4      /* out bf16 = relu(acc + bias)              */
 #define NER_EPI_RES_F32 5        /* out f32  = acc + bias + residual (f32)   */
+#define NER_EPI_DIAG_DISCARD 99  /* diagnostic only: accumulate, drain TMEM, store nothing */
 
 /* tile_n selectors of ner_gemm_bf16: 64/128/256 = one CTA per 128 x tile_n tile
  * (cta_group::1); the 2CTA values = a CTA pair per 256 x N tile (cta_group::2). */
@@ -106,9 +107,10 @@ int ner_cast_bf16(const float* src, void* dst_bf16, size_t n, ner_stream_t strea
 
 /* tf.layers.dense(units=label_size) — model/bert_bilstm_crf.py:26, model/bert_crf.py:20.
  * out[M,N] f32 = x[M,F] · W[F,N] + bias[N], N <= 32; x is f32 (x_is_bf16=0) or bf16;
- * W is the TF kernel layout [F,N] f32. */
+ * W is the TF kernel layout [F,N] f32.  row_map: NULL, or [M] i32 — input row r is written to
+ * output row row_map[r] (scatter of packed token rows back to the padded [B*L] layout). */
 int ner_dense_small_n(const void* x, int x_is_bf16, const float* W, const float* bias, float* out,
-                      int M, int F, int N, ner_stream_t stream);
+                      int M, int F, int N, const int32_t* row_map, ner_stream_t stream);
 
 /* tf.nn.embedding_lookup (model/bilstm_crf.py:24): out[tok, 0:E] = table[ids[tok]], row
  * stride ld_out >= E. */
@@ -118,6 +120,13 @@ int ner_embedding_lookup(const float* table, const int32_t* ids, float* out, int
 int ner_cast_pad_bf16(const float* src, void* dst_bf16, int M, int D, int Dp, int ld_src,
                       ner_stream_t stream);
 
+/* Sequence packing plan (removes padding rows from the token-major activations; padded
+ * positions never reach loss or pred_ids because the CRF ignores t >= seq_len).  mask [B,L] i32
+ * must be a prefix mask (1 for t < len_b), as data/base_preprocess.py:166-174 builds it.
+ * cu_seqlens [B+1]: exclusive prefix sum of the lengths; tok_src [B*L]: tok_src[cu[b]+t] = b*L+t. */
+int ner_seq_pack_plan(const int32_t* mask, int32_t* cu_seqlens, int32_t* tok_src, int B, int L,
+                      ner_stream_t stream);
+
 /* ------------------------------------------------------------------------ *
  * BERT encoder pieces — bert_base.bert.modeling.BertModel as driven from
  * tools/layer.py:63-81 (pretrain_bert_embedding)
@@ -125,11 +134,14 @@ int ner_cast_pad_bf16(const float* src, void* dst_bf16, int M, int D, int Dp, in
 
 /* embedding_lookup + embedding_postprocessor: LN(word[ids] + type[seg] + pos[0:L]).
  * Tables f32: word [vocab,H], type [n_type,H], pos [max_pos,H]; ids/seg [B,L] i32
- * (seg may be NULL = all zero).  Writes f32 and/or bf16 [B*L,H] (either may be NULL). */
+ * (seg may be NULL = all zero).  Writes f32 and/or bf16 [B*L,H] (either may be NULL).
+ * Packed mode: tok_src [n_packed] (from ner_seq_pack_plan) selects the padded index of every
+ * packed row; output has n_packed rows.  tok_src = NULL: padded mode, B*L rows. */
 int ner_bert_embed_ln(const float* word_emb, const float* type_emb, const float* pos_emb,
                       const float* gamma, const float* beta, const int32_t* ids,
                       const int32_t* seg, float* out_f32, void* out_bf16, int B, int L, int H,
-                      int vocab, int n_type, int max_pos, float eps, ner_stream_t stream);
+                      int vocab, int n_type, int max_pos, float eps, const int32_t* tok_src,
+                      int n_packed, ner_stream_t stream);
 
 /* LayerNorm over the last axis of y (+ optional residual) [M,H] f32 -> f32 and/or bf16.
  * modeling.layer_norm (eps 1e-12) and tools/transformer/modules.py:40-65 (eps = FLT_EPSILON). */
@@ -139,10 +151,11 @@ int ner_layernorm(const float* y, const float* residual, const float* gamma, con
 /* attention_layer core: ctx = softmax(Q K^T * scale + (1-mask)*mask_add) V per head.
  * qkv bf16 [B*L, 3*num_heads*head_dim] (Q | K | V blocks, heads contiguous inside each),
  * mask [B,L] i32 (1 = keep), ctx bf16 [B*L, num_heads*head_dim].  head_dim must be 64.
- * BERT: scale = 1/sqrt(64), mask_add = -10000. */
+ * BERT: scale = 1/sqrt(64), mask_add = -10000.  Packed mode: cu_seqlens [B+1] non-NULL — sequence b
+ * occupies rows [cu[b], cu[b+1]) of qkv/ctx, every key is valid, mask is ignored. */
 int ner_bert_attention(const void* qkv_bf16, const int32_t* mask, void* ctx_bf16, int B, int L,
                        int num_heads, int head_dim, float scale, float mask_add,
-                       ner_stream_t stream);
+                       const int32_t* cu_seqlens, ner_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
  * BiLSTM — tools/layer.py:27-41 bilstm() -> bidirectional_dynamic_rnn(LSTMCell)
@@ -151,10 +164,12 @@ int ner_bert_attention(const void* qkv_bf16, const int32_t* mask, void* ctx_bf16
 /* Sequential half of both directions.  xproj [B*L, 8H] f32 = x · [kernel_fw[:D] | kernel_bw[:D]]
  * + [bias_fw | bias_bw] (one ner_gemm_bf16 call, NER_EPI_F32); wh_fw / wh_bw = kernel[D:, :]
  * [H,4H] f32 with TF's gate order (i, j, f, o).  out [B,L,2H] f32 = concat(fw, bw), zero for
- * t >= seq_len.  activation: 0 tanh, 1 relu (params['rnn_activation']).  H % 4 == 0. */
+ * t >= seq_len.  activation: 0 tanh, 1 relu (params['rnn_activation']).  H % 4 == 0.
+ * cu_seqlens: NULL (xproj row of (b,t) = b*L+t) or [B+1] (packed xproj: row = cu[b]+t). */
 int ner_bilstm_recurrence(const float* xproj, const float* wh_fw, const float* wh_bw,
                           const int32_t* seq_len, float* out, int B, int L, int H,
-                          int activation, float forget_bias, ner_stream_t stream);
+                          int activation, float forget_bias, const int32_t* cu_seqlens,
+                          ner_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
  * SoftLexicon gather-and-pool — model/bilstm_crf_softlexicon.py:37-44

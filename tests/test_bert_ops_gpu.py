@@ -90,3 +90,19 @@ def test_attention(B, L, NH):
     s = q @ k.transpose(-1, -2) / math.sqrt(D) + (1.0 - mask.float())[:, None, None, :] * -10000.0
     ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, NH * D)
     torch.testing.assert_close(ctx.float(), ref, rtol=2e-2, atol=2e-2)
+
+
+def test_seq_pack_plan_and_packed_attention():
+    B, L, NH, D = 5, 70, 3, 64
+    g = torch.Generator().manual_seed(5)
+    lens = torch.tensor([70, 1, 33, 64, 17])
+    mask = (torch.arange(L)[None, :] < lens[:, None]).to(torch.int32).cuda()
+    cu, tok_src = ops.seq_pack_plan(mask)
+    assert cu.cpu().tolist() == [0, 70, 71, 104, 168, 185]
+    exp = torch.cat([b * L + torch.arange(int(n)) for b, n in enumerate(lens)])
+    assert torch.equal(tok_src[:185].cpu().long(), exp)
+    qkv = torch.randn(B * L, 3 * NH * D, generator=g).to(torch.bfloat16).cuda()
+    ref = ops.bert_attention(qkv, mask, B, L, NH, D)                    # padded
+    qkv_p = qkv[tok_src[:185].long()].contiguous()
+    out = ops.bert_attention(qkv_p, None, B, L, NH, D, cu_seqlens=cu)   # packed
+    torch.testing.assert_close(out.float(), ref[tok_src[:185].long()].float(), rtol=2e-2, atol=2e-2)

@@ -124,3 +124,30 @@ def test_softlexicon_model(tmp_path):
     ref = omodels.bilstm_crf_softlexicon(w, feats, est.params, dtype=torch.float64, emulate_bf16=True)
     assert abs(out['loss'] - ref['loss']) < 2e-3 * max(1.0, abs(ref['loss']))
     assert (out['pred_ids'].numpy() == ref['pred_ids']).mean() > 0.99
+
+
+@pytest.mark.parametrize("model_name", ["bert_bilstm_crf", "bert_crf"])
+def test_sequence_packing_matches_padded_layout(model_name, tmp_path, monkeypatch):
+    """Packed (no padding rows) vs padded execution of the same plugin: identical outputs up to
+    bf16 re-association in attention; pad positions never reach loss / pred_ids."""
+    import json
+    from chinesener_b200.tools import layer
+    (tmp_path / "bert_config.json").write_text(json.dumps(SMALL_BERT))
+    B, L = 9, 150
+    feats = synthetic.msra_batch(B, L, vocab=SMALL_BERT['vocab_size'], seed=11)
+    params = dict(synthetic.data_params(L), pretrain_dir=str(tmp_path))
+    est = engine.Estimator(model_name, params)
+    monkeypatch.setattr(layer, "PACK_SEQUENCES", False)
+    est.evaluate(feats)
+    _scale_up(est.store, ["logits/kernel"], 8.0)
+    padded = est.evaluate(feats)
+    monkeypatch.setattr(layer, "PACK_SEQUENCES", True)
+    packed = est.evaluate(feats)
+    assert abs(padded['loss'] - packed['loss']) < 2e-3 * max(1.0, abs(padded['loss']))
+    same = (padded['pred_ids'].numpy() == packed['pred_ids'].numpy()).mean()
+    assert same > 0.995, same
+    assert (packed['pred_ids'].numpy()[feats['mask'].numpy() == 0] == 0).all()
+    # without the host token-count hint (device-only features) the plan syncs but gives the same result
+    dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in feats.items()}
+    loss2, pred2 = est.forward_device(dev)
+    assert torch.equal(pred2.cpu(), packed['pred_ids'])
