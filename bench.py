@@ -290,10 +290,13 @@ def run_ours(args):
     roof = cpu = None
     if rank == 0:
         hbm_peak, tf_peak, how = measured_peaks()
+        from chinesener_b200 import bert as _bert
         timer = GemmTimer()
         _lib._HOOK = timer
+        _bert.PER_KERNEL = True          # same kernels, one C-ABI call each, so every GEMM launch gets its own events
         for i in range(min(args.steps, 5)):
             step_resident(i)
+        _bert.PER_KERNEL = False
         _lib._HOOK = None
         ms, fl, n = timer.summary()
         achieved = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0

@@ -37,6 +37,23 @@ SIGNATURES = {
     "ner_softlexicon_pool_bwd": (_i, [_vp] * 4 + [_i] * 5 + [_vp]),
 }
 
+
+
+class BertConfig(_c.Structure):
+    _fields_ = [("hidden_size", _i), ("num_heads", _i), ("intermediate_size", _i), ("num_layers", _i),
+                ("vocab_size", _i), ("type_vocab_size", _i), ("max_position", _i), ("ln_eps", _c.c_float),
+                ("gelu_erf", _i)]
+
+
+class BertLayerWeights(_c.Structure):
+    _fields_ = [(n, _vp) for n in ("wqkv", "bqkv", "wo", "bo", "ln1_gamma", "ln1_beta", "wi", "bi", "wd", "bd",
+                                   "ln2_gamma", "ln2_beta")]
+
+
+SIGNATURES["ner_bert_encoder_workspace_bytes"] = (_c.c_size_t, [_c.POINTER(BertConfig), _i])
+SIGNATURES["ner_bert_encoder_fwd"] = (_i, [_c.POINTER(BertConfig)] + [_vp] * 5 + [_c.POINTER(BertLayerWeights)] + [_vp] * 3
+                                      + [_i, _i, _vp, _vp, _i, _vp, _vp, _vp, _c.c_size_t, _vp])
+
 _lib = None
 
 

@@ -91,10 +91,67 @@ def make_pack(input_mask, total_tokens=None):
     return PackInfo(cu, tok_src, total_tokens, B, L)
 
 
-def bert_forward(input_ids, input_mask, segment_ids, cfg, store=None, scope="bert", gelu="tanh", pack=None):
-    """-> (sequence_output f32 [rows,H], bf16 copy [rows,H]); rows = B*L, or pack.total in packed mode."""
+def _c_tables(store, cfg, scope, gelu):
+    """ctypes config + per-layer pointer table for ner_bert_encoder_fwd (rebuilt with the packs)."""
+    layers = _packed(store, cfg, scope)
+
+    def build():
+        from . import _lib
+        c = _lib.BertConfig(cfg["hidden_size"], cfg["num_attention_heads"], cfg["intermediate_size"],
+                            cfg["num_hidden_layers"], cfg["vocab_size"], cfg["type_vocab_size"],
+                            cfg["max_position_embeddings"], 1e-12, 1 if gelu == "erf" else 0)
+        arr = (_lib.BertLayerWeights * len(layers))()
+        for i, w in enumerate(layers):
+            arr[i] = _lib.BertLayerWeights(w["wqkv"].data_ptr(), w["bqkv"].data_ptr(), w["wo"].data_ptr(), w["bo"].data_ptr(),
+                                           w["g1"].data_ptr(), w["b1"].data_ptr(), w["wi"].data_ptr(), w["bi"].data_ptr(),
+                                           w["wd"].data_ptr(), w["bd"].data_ptr(), w["g2"].data_ptr(), w["b2"].data_ptr())
+        return c, arr, layers  # keep `layers` alive with the table
+    return store.cached(("bert_ctable", scope, gelu), build)
+
+
+_ws_cache = {}
+PER_KERNEL = False   # True: drive the encoder one ops.* call per kernel (bench.py's per-kernel timing pass)
+
+
+def bert_forward(input_ids, input_mask, segment_ids, cfg, store=None, scope="bert", gelu="tanh", pack=None,
+                 per_kernel=None):
+    """-> (sequence_output f32 [rows,H], bf16 copy [rows,H]); rows = B*L, or pack.total in packed mode.
+
+    Default: ONE C-ABI call (ner_bert_encoder_fwd) enqueues the whole encoder.  per_kernel=True drives
+    the same kernels one ops.* call at a time (used by bench.py's per-kernel timing and the tests)."""
     store = store or variables.default_store()
     create_bert_variables(cfg, store, scope)
+    if per_kernel is None:
+        per_kernel = PER_KERNEL
+    if not per_kernel:
+        import ctypes
+        from . import _lib
+        B, L = input_ids.shape
+        H = cfg["hidden_size"]
+        v = store.vars
+        c, arr, _ = _c_tables(store, cfg, scope, gelu)
+        rows = pack.total if pack else B * L
+        dev = input_ids.device
+        of = torch.empty((rows, H), dtype=torch.float32, device=dev)
+        ob = torch.empty((rows, H), dtype=torch.bfloat16, device=dev)
+        need = _lib.lib().ner_bert_encoder_workspace_bytes(ctypes.byref(c), rows)
+        key = (dev.index, torch.cuda.current_stream().cuda_stream)
+        ws = _ws_cache.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+            _ws_cache[key] = ws
+        ids = ops._i32(input_ids)
+        seg = None if segment_ids is None else ops._i32(segment_ids)
+        mask = ops._i32(input_mask)
+        _lib.check(_lib.lib().ner_bert_encoder_fwd(
+            ctypes.byref(c), v[f"{scope}/embeddings/word_embeddings"].data_ptr(),
+            v[f"{scope}/embeddings/token_type_embeddings"].data_ptr(), v[f"{scope}/embeddings/position_embeddings"].data_ptr(),
+            v[f"{scope}/embeddings/LayerNorm/gamma"].data_ptr(), v[f"{scope}/embeddings/LayerNorm/beta"].data_ptr(), arr,
+            ids.data_ptr(), mask.data_ptr(), _lib.ptr(seg), B, L, _lib.ptr(pack.cu_seqlens if pack else None),
+            _lib.ptr(pack.tok_src if pack else None), pack.total if pack else 0, of.data_ptr(), ob.data_ptr(),
+            ws.data_ptr(), ws.numel(), _lib.stream()))
+        _lib.LAUNCHES += 7 * cfg["num_hidden_layers"]      # the call above enqueued 1 + 7/layer kernels
+        return of, ob
     B, L = input_ids.shape
     H, NH = cfg["hidden_size"], cfg["num_attention_heads"]
     v = store.vars

@@ -157,6 +157,38 @@ int ner_bert_attention(const void* qkv_bf16, const int32_t* mask, void* ctx_bf16
                        int num_heads, int head_dim, float scale, float mask_add,
                        const int32_t* cu_seqlens, ner_stream_t stream);
 
+/* Whole BertModel forward in one call (what tools/layer.py:68-77 gets from
+ * modeling.BertModel(...).get_sequence_output()).  `layers` is a HOST array of per-layer
+ * device pointers: dense kernels packed by ner_pack_weight_bf16 ([N,K] bf16; wqkv = the
+ * query|key|value kernels concatenated along N), biases / LayerNorm parameters f32.
+ * Padded mode: cu_seqlens = tok_src = NULL, outputs have B*L rows.  Packed mode: both from
+ * ner_seq_pack_plan, n_packed = total tokens, outputs have n_packed rows.
+ * out_f32 / out_bf16 [rows,H] receive sequence_output; workspace from the sizing call. */
+typedef struct {
+  int hidden_size, num_heads, intermediate_size, num_layers;
+  int vocab_size, type_vocab_size, max_position;
+  float ln_eps;   /* 1e-12 */
+  int gelu_erf;   /* 0: tanh approximation (google-research/bert modeling.gelu), 1: erf */
+} ner_bert_config;
+
+typedef struct {
+  const void* wqkv;  const float* bqkv;        /* [3H,H] bf16, [3H] */
+  const void* wo;    const float* bo;          /* attention/output/dense */
+  const float* ln1_gamma; const float* ln1_beta;
+  const void* wi;    const float* bi;          /* intermediate/dense [I,H] bf16 */
+  const void* wd;    const float* bd;          /* output/dense [H,I] bf16 */
+  const float* ln2_gamma; const float* ln2_beta;
+} ner_bert_layer_weights;
+
+size_t ner_bert_encoder_workspace_bytes(const ner_bert_config* cfg, int rows);
+int ner_bert_encoder_fwd(const ner_bert_config* cfg, const float* word_emb, const float* type_emb,
+                         const float* pos_emb, const float* emb_ln_gamma, const float* emb_ln_beta,
+                         const ner_bert_layer_weights* layers, const int32_t* ids,
+                         const int32_t* mask, const int32_t* seg, int B, int L,
+                         const int32_t* cu_seqlens, const int32_t* tok_src, int n_packed,
+                         float* out_f32, void* out_bf16, void* workspace, size_t workspace_bytes,
+                         ner_stream_t stream);
+
 /* ------------------------------------------------------------------------ *
  * BiLSTM — tools/layer.py:27-41 bilstm() -> bidirectional_dynamic_rnn(LSTMCell)
  * ------------------------------------------------------------------------ */

@@ -151,3 +151,18 @@ def test_sequence_packing_matches_padded_layout(model_name, tmp_path, monkeypatc
     dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in feats.items()}
     loss2, pred2 = est.forward_device(dev)
     assert torch.equal(pred2.cpu(), packed['pred_ids'])
+
+
+def test_composite_encoder_call_equals_per_kernel_path(tmp_path):
+    """ner_bert_encoder_fwd (one C-ABI call) enqueues exactly the kernels of the per-kernel path."""
+    import json
+    from chinesener_b200 import bert
+    cfg = dict(SMALL_BERT)
+    B, L = 5, 40
+    feats = synthetic.msra_batch(B, L, vocab=cfg['vocab_size'], seed=3)
+    store = variables.VariableStore("cuda")
+    ids, mask, seg = (feats[k].cuda() for k in ('token_ids', 'mask', 'segment_ids'))
+    for pack in (None, bert.make_pack(mask)):
+        a32, a16 = bert.bert_forward(ids, mask, seg, cfg, store=store, pack=pack, per_kernel=False)
+        b32, b16 = bert.bert_forward(ids, mask, seg, cfg, store=store, pack=pack, per_kernel=True)
+        assert torch.equal(a32, b32) and torch.equal(a16, b16)
