@@ -28,7 +28,7 @@ SIGNATURES = {
     "ner_dense_small_n": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "ner_seq_pack_plan": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "ner_bert_embed_ln": (_i, [_vp] * 9 + [_i] * 6 + [_c.c_float, _vp, _i, _vp]),
-    "ner_layernorm": (_i, [_vp] * 6 + [_i, _i, _c.c_float, _vp]),
+    "ner_layernorm": (_i, [_vp, _i] + [_vp] * 5 + [_i, _i, _c.c_float, _vp]),
     "ner_bert_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _c.c_float, _c.c_float, _vp, _vp]),
     "ner_bilstm_recurrence": (_i, [_vp] * 5 + [_i, _i, _i, _i, _c.c_float, _vp, _vp]),
     "ner_softlexicon_pool_fwd": (_i, [_vp] * 4 + [_i] * 6 + [_vp]),

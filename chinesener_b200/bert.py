@@ -1,9 +1,10 @@
 """BertModel forward on the sm_100a kernels (bert_base.bert.modeling.BertModel as driven by
 reference tools/layer.py:63-81; variable names per SURVEY.md §8 a9 / Appendix A.3).
 
-Per layer: fused-QKV tcgen05 GEMM -> attention kernel -> tcgen05 GEMM (+bias +residual, fp32)
--> LayerNorm (fp32 + bf16 copies) -> tcgen05 GEMM (+bias, GELU) -> tcgen05 GEMM (+bias
-+residual) -> LayerNorm.  The residual stream stays fp32; GEMM operands are bf16.
+Per layer: fused-QKV tcgen05 GEMM -> attention kernel -> tcgen05 GEMM (+bias, bf16 out) ->
+LayerNorm(+fp32 residual; writes fp32 + bf16 copies) -> tcgen05 GEMM (+bias, GELU) -> tcgen05
+GEMM (+bias, bf16 out) -> LayerNorm(+fp32 residual).  The residual stream stays fp32; GEMM
+operands and dense sub-layer outputs are bf16.
 """
 import json
 import os
@@ -165,9 +166,9 @@ def bert_forward(input_ids, input_mask, segment_ids, cfg, store=None, scope="ber
     for w in layers:
         qkv = ops.gemm_bf16(x16, w["wqkv"], w["bqkv"], epilogue=ops.EPI_BF16)
         ctx = ops.bert_attention(qkv, input_mask, B, L, NH, H // NH, cu_seqlens=cu)
-        y = ops.gemm_bf16(ctx, w["wo"], w["bo"], residual=x32, epilogue=ops.EPI_RES_F32)
-        x32, x16 = ops.layernorm(y, w["g1"], w["b1"], eps=1e-12)
+        y = ops.gemm_bf16(ctx, w["wo"], w["bo"], epilogue=ops.EPI_BF16)
+        x32, x16 = ops.layernorm(y, w["g1"], w["b1"], residual=x32, eps=1e-12)
         inter = ops.gemm_bf16(x16, w["wi"], w["bi"], epilogue=epi_gelu)
-        y = ops.gemm_bf16(inter, w["wd"], w["bd"], residual=x32, epilogue=ops.EPI_RES_F32)
-        x32, x16 = ops.layernorm(y, w["g2"], w["b2"], eps=1e-12)
+        y = ops.gemm_bf16(inter, w["wd"], w["bd"], epilogue=ops.EPI_BF16)
+        x32, x16 = ops.layernorm(y, w["g2"], w["b2"], residual=x32, eps=1e-12)
     return x32, x16

@@ -1,7 +1,9 @@
 // One C-ABI call for the whole BertModel forward (bert_base.bert.modeling.BertModel as driven
 // from reference tools/layer.py:63-81): embedding+LN, then per layer
-//   fused-QKV GEMM -> attention -> out-proj GEMM(+bias+residual) -> LayerNorm
-//   -> FFN1 GEMM(+bias+GELU) -> FFN2 GEMM(+bias+residual) -> LayerNorm.
+//   fused-QKV GEMM -> attention -> out-proj GEMM(+bias, bf16) -> LayerNorm(+f32 residual)
+//   -> FFN1 GEMM(+bias+GELU) -> FFN2 GEMM(+bias, bf16) -> LayerNorm(+f32 residual).
+// The residual stream itself stays fp32 (LayerNorm writes an f32 and a bf16 copy); only the
+// dense sub-layer outputs are rounded to bf16 before the add.
 // The host loop below only enqueues kernels (7 per layer) on the caller's stream; doing it here
 // instead of from Python removes ~85 ctypes round trips per step.
 #include "common.cuh"
@@ -15,7 +17,7 @@ extern "C" size_t ner_bert_encoder_workspace_bytes(const ner_bert_config* cfg, i
   const size_t R = (size_t)rows, H = (size_t)cfg->hidden_size, I = (size_t)cfg->intermediate_size;
   return align256(R * 3 * H * 2)    // qkv  bf16
          + align256(R * H * 2)      // ctx  bf16
-         + align256(R * H * 4)      // y    f32 (GEMM out + residual, LayerNorm input)
+         + align256(R * H * 4)      // y    bf16 dense output (LayerNorm adds the f32 residual); f32-sized
          + align256(R * H * 4)      // x1   f32 (post-attention LayerNorm)
          + align256(R * H * 2)      // x1   bf16
          + align256(R * I * 2);     // FFN intermediate bf16
@@ -59,15 +61,15 @@ extern "C" int ner_bert_encoder_fwd(const ner_bert_config* cfg, const float* wor
     if (rc != NER_OK) return rc;
     rc = ner_bert_attention(qkv, mask, ctx, B, L, NH, H / NH, scale, -10000.0f, cu_seqlens, stream);
     if (rc != NER_OK) return rc;
-    rc = ner_gemm_bf16(ctx, w.wo, w.bo, out_f32, y, rows, H, H, NER_EPI_RES_F32, 0, stream);
+    rc = ner_gemm_bf16(ctx, w.wo, w.bo, nullptr, y, rows, H, H, NER_EPI_BF16, 0, stream);
     if (rc != NER_OK) return rc;
-    rc = ner_layernorm(y, nullptr, w.ln1_gamma, w.ln1_beta, x1f, x1b, rows, H, cfg->ln_eps, stream);
+    rc = ner_layernorm(y, 1, out_f32, w.ln1_gamma, w.ln1_beta, x1f, x1b, rows, H, cfg->ln_eps, stream);
     if (rc != NER_OK) return rc;
     rc = ner_gemm_bf16(x1b, w.wi, w.bi, nullptr, inter, rows, I, H, gelu, 0, stream);
     if (rc != NER_OK) return rc;
-    rc = ner_gemm_bf16(inter, w.wd, w.bd, x1f, y, rows, H, I, NER_EPI_RES_F32, 0, stream);
+    rc = ner_gemm_bf16(inter, w.wd, w.bd, nullptr, y, rows, H, I, NER_EPI_BF16, 0, stream);
     if (rc != NER_OK) return rc;
-    rc = ner_layernorm(y, nullptr, w.ln2_gamma, w.ln2_beta, out_f32, out_bf16, rows, H, cfg->ln_eps, stream);
+    rc = ner_layernorm(y, 1, x1f, w.ln2_gamma, w.ln2_beta, out_f32, out_bf16, rows, H, cfg->ln_eps, stream);
     if (rc != NER_OK) return rc;
   }
   return NER_OK;

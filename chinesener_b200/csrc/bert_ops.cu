@@ -91,22 +91,29 @@ bert_embed_ln_kernel(const float* __restrict__ word_emb, const float* __restrict
   }
 }
 
-// y (+ optional residual) -> LayerNorm -> fp32 and/or bf16
+// y (+ optional residual) -> LayerNorm -> fp32 and/or bf16.  y is fp32 or (YBF16) bf16.
+template <bool YBF16>
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const float* __restrict__ y, const float* __restrict__ residual, const float* __restrict__ gamma,
+layernorm_kernel(const void* __restrict__ yv, const float* __restrict__ residual, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
                  int M, int H, float eps) {
   const int lane = threadIdx.x & 31;
   const int nv4 = (H / 4 + 31) / 32;
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += gridDim.x * (blockDim.x >> 5)) {
-    const float* p = y + (size_t)row * H;
     const float* r = residual ? residual + (size_t)row * H : nullptr;
     float4 v[LN_MAXV];
 #pragma unroll
     for (int k = 0; k < LN_MAXV; ++k) {
       const int e = (lane + 32 * k) * 4;
       if (k < nv4 && e < H) {
-        v[k] = *reinterpret_cast<const float4*>(p + e);
+        if constexpr (YBF16) {
+          const uint2 pk = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(yv) + (size_t)row * H + e);
+          const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&pk.x);
+          const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&pk.y);
+          v[k] = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+        } else {
+          v[k] = *reinterpret_cast<const float4*>(static_cast<const float*>(yv) + (size_t)row * H + e);
+        }
         if (r != nullptr) {
           const float4 b = *reinterpret_cast<const float4*>(r + e);
           v[k].x += b.x;
@@ -260,14 +267,19 @@ extern "C" int ner_bert_embed_ln(const float* word_emb, const float* type_emb, c
   return ner_launch_status();
 }
 
-extern "C" int ner_layernorm(const float* y, const float* residual, const float* gamma, const float* beta,
-                             float* out_f32, void* out_bf16, int M, int H, float eps, ner_stream_t stream) {
+extern "C" int ner_layernorm(const void* y, int y_is_bf16, const float* residual, const float* gamma,
+                             const float* beta, float* out_f32, void* out_bf16, int M, int H, float eps,
+                             ner_stream_t stream) {
   if (M < 0 || H < 4) return NER_ERR_INVALID_ARG;
   if (M == 0) return NER_OK;
   if (!y || !gamma || !beta || (!out_f32 && !out_bf16)) return NER_ERR_INVALID_ARG;
   if (H % 4 != 0 || H > 128 * LN_MAXV) return NER_ERR_UNSUPPORTED;
-  layernorm_kernel<<<grid_for_rows(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      y, residual, gamma, beta, out_f32, static_cast<__nv_bfloat16*>(out_bf16), M, H, eps);
+  if (y_is_bf16)
+    layernorm_kernel<true><<<grid_for_rows(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        y, residual, gamma, beta, out_f32, static_cast<__nv_bfloat16*>(out_bf16), M, H, eps);
+  else
+    layernorm_kernel<false><<<grid_for_rows(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        y, residual, gamma, beta, out_f32, static_cast<__nv_bfloat16*>(out_bf16), M, H, eps);
   return ner_launch_status();
 }
 

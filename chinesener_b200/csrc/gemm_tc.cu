@@ -44,7 +44,7 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int TMEM_COLS = tmem_cols_for(2 * BN);
-  static constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + B_BYTES) + 256 /*barriers*/ + 1024 /*align slack*/;
+  static constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + B_BYTES) + 256 /*barriers*/ + 2 * BN * 4 /*bias*/ + 1024 /*align slack*/;
 };
 
 template <int BN>
@@ -53,7 +53,7 @@ struct Cfg2 {  // per CTA of the pair
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;
   static constexpr int TMEM_COLS = tmem_cols_for(2 * BN);
-  static constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + B_BYTES) + 256 + 1024;
+  static constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + B_BYTES) + 256 + 2 * BN * 4 + 1024;
 };
 
 struct EpiArgs {
@@ -78,15 +78,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 
 // One 32-column chunk of one accumulator row: TMEM registers -> fused epilogue -> global.
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const EpiArgs& ep, int row, int col0, int N) {
+// `sbias` = this chunk's 32 bias values in shared memory (broadcast LDS.128), staged once per tile.
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const EpiArgs& ep, const float* sbias, int row,
+                                               int col0, int N) {
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-  if (ep.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+  {
+    const float4* b4 = reinterpret_cast<const float4*>(sbias);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float4 b = __ldg(b4 + i);
+      const float4 b = b4[i];
       v[4 * i + 0] += b.x;
       v[4 * i + 1] += b.y;
       v[4 * i + 2] += b.z;
@@ -128,21 +130,48 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ep
   }
 }
 
-// Epilogue of one 128 x BN accumulator (this warp's lane quarter, its half of the column chunks).
+__device__ __forceinline__ void epi_bar_sync() {  // named barrier 1 over the 8 epilogue warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
+}
+
+// Stage bias[n0 .. n0+BN) of the coming tile into smem (called by all epilogue threads BEFORE they
+// wait for the accumulator, so the global-load latency hides behind the main loop).
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int warp, int lane, const EpiArgs& ep, int row0,
-                                              int n0, int M, int N) {
+__device__ __forceinline__ void epilogue_stage_bias(float* sbias, const EpiArgs& ep, int n0, int N) {
+  const int t = (int)threadIdx.x - 64;  // 0 .. 255
+  for (int i = t; i < BN; i += 32 * NUM_EPI_WARPS) {
+    const int col = n0 + i;
+    sbias[i] = (ep.bias != nullptr && col < N) ? __ldg(ep.bias + col) : 0.f;
+  }
+  epi_bar_sync();
+}
+
+// Epilogue of one 128 x BN accumulator (this warp's lane quarter, its half of the column chunks).
+// TMEM loads are software-pipelined: the tcgen05.ld of chunk c+1 is in flight while chunk c is
+// converted and stored.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int warp, int lane, const EpiArgs& ep,
+                                              const float* sbias, int row0, int n0, int M, int N) {
+  constexpr int NCH = BN / 64;         // chunks per warp (two warps share a lane quarter)
   const int q = warp & 3;              // TMEM lane quarter this warp may access
   const int half = (warp - 2) >> 2;    // 0: even chunks, 1: odd chunks
   const int row = row0 + q * 32 + lane;
-#pragma unroll 1
-  for (int c = half; c < BN / 32; c += 2) {
-    uint32_t r[32];
-    tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+  const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16);
+  uint32_t ra[32], rb[32];
+  tmem_ld_32x32(tbase + (uint32_t)(half * 32), ra);
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = half + 2 * i;
     tmem_ld_wait();
+    if (i + 1 < NCH) {
+      if (i & 1) tmem_ld_32x32(tbase + (uint32_t)((c + 2) * 32), ra);
+      else tmem_ld_32x32(tbase + (uint32_t)((c + 2) * 32), rb);
+    }
     const int col0 = n0 + c * 32;
-    if (ep.mode == NER_EPI_DIAG_DISCARD) continue;  // diagnostic: drain TMEM, store nothing
-    if (row < M && col0 < N) epilogue_chunk(r, ep, row, col0, N);
+    if (ep.mode != NER_EPI_DIAG_DISCARD && row < M && col0 < N) {
+      if (i & 1) epilogue_chunk(rb, ep, sbias + c * 32, row, col0, N);
+      else epilogue_chunk(ra, ep, sbias + c * 32, row, col0, N);
+    }
   }
 }
 
@@ -164,6 +193,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // [2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -253,9 +283,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+      epilogue_stage_bias<BN>(sbias + acc * BN, ep, n_blk * BN, N);
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      epilogue_tile<BN>(tmem_base + (uint32_t)(acc * BN), warp, lane, ep, m_blk * BM, n_blk * BN, M, N);
+      epilogue_tile<BN>(tmem_base + (uint32_t)(acc * BN), warp, lane, ep, sbias + acc * BN, m_blk * BM, n_blk * BN, M, N);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -299,6 +330,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // [2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -396,10 +428,11 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     const uint32_t empty_remote1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+      epilogue_stage_bias<BN>(sbias + acc * BN, ep, n_blk * BN, N);
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      epilogue_tile<BN>(tmem_base + (uint32_t)(acc * BN), warp, lane, ep, m_blk * 2 * BM + (int)rank * BM, n_blk * BN, M,
-                        N);
+      epilogue_tile<BN>(tmem_base + (uint32_t)(acc * BN), warp, lane, ep, sbias + acc * BN,
+                        m_blk * 2 * BM + (int)rank * BM, n_blk * BN, M, N);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc == 0 ? empty_remote0 : empty_remote1);

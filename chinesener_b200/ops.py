@@ -135,11 +135,12 @@ def bert_embed_ln(word_emb, type_emb, pos_emb, gamma, beta, ids, seg, eps=1e-12,
 
 def layernorm(y, gamma, beta, residual=None, eps=1e-12, want_f32=True, want_bf16=True):
     require_cuda(y, gamma, beta, residual)
-    assert y.dtype == torch.float32
+    assert y.dtype in (torch.float32, torch.bfloat16)
     M, H = y.shape
     of = torch.empty((M, H), dtype=torch.float32, device=y.device) if want_f32 else None
     ob = torch.empty((M, H), dtype=torch.bfloat16, device=y.device) if want_bf16 else None
-    check(lib().ner_layernorm(ptr(y), ptr(residual), ptr(gamma), ptr(beta), ptr(of), ptr(ob), M, H, eps, stream()))
+    check(lib().ner_layernorm(ptr(y), 1 if y.dtype == torch.bfloat16 else 0, ptr(residual), ptr(gamma), ptr(beta), ptr(of),
+                              ptr(ob), M, H, eps, stream()))
     return of, ob
 
 

@@ -143,10 +143,12 @@ int ner_bert_embed_ln(const float* word_emb, const float* type_emb, const float*
                       int vocab, int n_type, int max_pos, float eps, const int32_t* tok_src,
                       int n_packed, ner_stream_t stream);
 
-/* LayerNorm over the last axis of y (+ optional residual) [M,H] f32 -> f32 and/or bf16.
+/* LayerNorm over the last axis of (y + optional f32 residual) [M,H] -> f32 and/or bf16.
+ * y is f32 (y_is_bf16 = 0) or bf16 (the dense layer's bf16 epilogue output).
  * modeling.layer_norm (eps 1e-12) and tools/transformer/modules.py:40-65 (eps = FLT_EPSILON). */
-int ner_layernorm(const float* y, const float* residual, const float* gamma, const float* beta,
-                  float* out_f32, void* out_bf16, int M, int H, float eps, ner_stream_t stream);
+int ner_layernorm(const void* y, int y_is_bf16, const float* residual, const float* gamma,
+                  const float* beta, float* out_f32, void* out_bf16, int M, int H, float eps,
+                  ner_stream_t stream);
 
 /* attention_layer core: ctx = softmax(Q K^T * scale + (1-mask)*mask_add) V per head.
  * qkv bf16 [B*L, 3*num_heads*head_dim] (Q | K | V blocks, heads contiguous inside each),

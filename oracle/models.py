@@ -58,3 +58,16 @@ def bilstm_crf_softlexicon(w, features, params, dtype=torch.float32, emulate_bf1
     lstm = nn.bilstm(x, w, features["seq_len"], params["rnn_activation"], 1.0, dtype, emulate_bf16)
     logits = nn.dense(lstm, w["logits/kernel"].to(dtype), w["logits/bias"].to(dtype))
     return _crf_tail(logits, w, features)
+
+
+def transformer_tener_crf_bichar(w, features, params, dtype=torch.float32):
+    """model/transformer_tener_crf_bichar.py:8-42 (eval mode)."""
+    from . import transformer as tfm
+    char = torch.as_tensor(params["embedding"]).to(dtype)[features["token_ids"].long()]
+    bichar = torch.as_tensor(params["bichar_embedding"]).to(dtype)[features["bichar_ids"].long()]
+    x = torch.cat([char, bichar], dim=-1)
+    if x.shape[-1] != params["d_model"]:
+        x = x @ w["embedding/dense/kernel"].to(dtype) + w["embedding/dense/bias"].to(dtype)
+    x = tfm.tener_encoder(x, features["seq_len"], w, params["encode_layers"], params["num_head"])
+    logits = nn.dense(x, w["logits/kernel"].to(dtype), w["logits/bias"].to(dtype))
+    return _crf_tail(logits, w, features)

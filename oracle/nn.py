@@ -71,10 +71,10 @@ def bert_encoder(w, input_ids, input_mask, segment_ids, num_layers=12, num_heads
         else:
             ctx = probs @ sh(v)
         ctx = rb(ctx.permute(0, 2, 1, 3).reshape(B, L, H))
-        a = dense(ctx, rb(g(f"{p}/attention/output/dense/kernel")), g(f"{p}/attention/output/dense/bias"))
+        a = rb(dense(ctx, rb(g(f"{p}/attention/output/dense/kernel")), g(f"{p}/attention/output/dense/bias")))
         x1 = layer_norm(a + x, g(f"{p}/attention/output/LayerNorm/gamma"), g(f"{p}/attention/output/LayerNorm/beta"), 1e-12)
         i = rb(gelu(dense(rb(x1), rb(g(f"{p}/intermediate/dense/kernel")), g(f"{p}/intermediate/dense/bias")), gelu_variant))
-        o = dense(i, rb(g(f"{p}/output/dense/kernel")), g(f"{p}/output/dense/bias"))
+        o = rb(dense(i, rb(g(f"{p}/output/dense/kernel")), g(f"{p}/output/dense/bias")))
         x = layer_norm(o + x1, g(f"{p}/output/LayerNorm/gamma"), g(f"{p}/output/LayerNorm/beta"), 1e-12)
         outs.append(x)
     return outs if return_all else x

@@ -45,6 +45,9 @@ def test_layernorm_with_residual(M, H, eps):
     torch.testing.assert_close(b16.float(), ref, rtol=1e-2, atol=1e-2)
     f32b, _ = ops.layernorm(y, gam, bet, eps=eps, want_bf16=False)
     torch.testing.assert_close(f32b, _ln(y, gam, bet, eps), rtol=1e-5, atol=1e-5)
+    y16 = y.to(torch.bfloat16)                                     # bf16 dense output + f32 residual
+    f32c, _ = ops.layernorm(y16, gam, bet, residual=r, eps=eps)
+    torch.testing.assert_close(f32c, _ln(y16.float() + r, gam, bet, eps), rtol=1e-5, atol=1e-5)
 
 
 def test_pack_cast_pad_lookup():
