@@ -34,6 +34,8 @@ SIGNATURES = {
     "ner_softlexicon_pool_fwd": (_i, [_vp] * 4 + [_i] * 6 + [_vp]),
     "ner_embedding_lookup": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ner_cast_pad_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "ner_split_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ner_attention_f32": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _c.c_float, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ner_softlexicon_pool_bwd": (_i, [_vp] * 4 + [_i] * 5 + [_vp]),
 }
 

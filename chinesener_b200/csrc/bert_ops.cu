@@ -241,6 +241,24 @@ seq_pack_plan_kernel(const int32_t* __restrict__ mask, int32_t* __restrict__ cu,
   }
 }
 
+// f32 [M,D] (row stride ld_src) -> (hi, lo) bf16 [M,Dp]: hi = bf16(x), lo = bf16(x - hi); zero padded.
+// hi + lo carries ~16 mantissa bits: three bf16 tensor-core products (hi*hi + hi*lo + lo*hi)
+// reproduce an fp32 product to ~2^-17 (the fp32-accurate dense mode).
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int M,
+                  int D, int Dp, int ld_src) {
+  const size_t total = (size_t)M * Dp;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / Dp;
+    const int c = (int)(i - r * Dp);
+    const float x = c < D ? src[r * ld_src + c] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+
 int grid_for_rows(int rows, int rows_per_block) {
   long g = ((long)rows + rows_per_block - 1) / rows_per_block;
   if (g > 148L * 16) g = 148L * 16;
@@ -359,5 +377,17 @@ extern "C" int ner_seq_pack_plan(const int32_t* mask, int32_t* cu_seqlens, int32
     if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   }
   seq_pack_plan_kernel<<<1, 1024, smem, static_cast<cudaStream_t>(stream)>>>(mask, cu_seqlens, tok_src, B, L);
+  return ner_launch_status();
+}
+
+extern "C" int ner_split_bf16(const float* src, void* hi_bf16, void* lo_bf16, int M, int D, int Dp, int ld_src,
+                              ner_stream_t stream) {
+  if (M < 0 || D < 1 || Dp < D || ld_src < D) return NER_ERR_INVALID_ARG;
+  if (M == 0) return NER_OK;
+  if (!src || !hi_bf16 || !lo_bf16) return NER_ERR_INVALID_ARG;
+  size_t g = ((size_t)M * Dp + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  split_bf16_kernel<<<(int)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(hi_bf16), static_cast<__nv_bfloat16*>(lo_bf16), M, D, Dp, ld_src);
   return ner_launch_status();
 }

@@ -96,8 +96,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ep
     }
   }
   const size_t off = (size_t)row * N + col0;
-  if (ep.mode == NER_EPI_F32 || ep.mode == NER_EPI_RES_F32) {
-    if (ep.mode == NER_EPI_RES_F32) {
+  if (ep.mode == NER_EPI_F32 || ep.mode == NER_EPI_RES_F32 || ep.mode == NER_EPI_RES_RELU_F32) {
+    if (ep.mode != NER_EPI_F32) {
       const float4* r4 = reinterpret_cast<const float4*>(ep.residual + off);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -107,6 +107,10 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ep
         v[4 * i + 2] += b.z;
         v[4 * i + 3] += b.w;
       }
+    }
+    if (ep.mode == NER_EPI_RES_RELU_F32) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
     }
     float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off);
 #pragma unroll
@@ -538,8 +542,8 @@ extern "C" int ner_gemm_bf16(const void* A, const void* Wt, const float* bias, c
   if (M < 0 || N < 1 || K < 1) return NER_ERR_INVALID_ARG;
   if (M == 0) return NER_OK;
   if (!A || !Wt || !out) return NER_ERR_INVALID_ARG;
-  if ((epilogue < NER_EPI_F32 || epilogue > NER_EPI_RES_F32) && epilogue != NER_EPI_DIAG_DISCARD) return NER_ERR_INVALID_ARG;
-  if (epilogue == NER_EPI_RES_F32 && !residual) return NER_ERR_INVALID_ARG;
+  if ((epilogue < NER_EPI_F32 || epilogue > NER_EPI_RES_RELU_F32) && epilogue != NER_EPI_DIAG_DISCARD) return NER_ERR_INVALID_ARG;
+  if ((epilogue == NER_EPI_RES_F32 || epilogue == NER_EPI_RES_RELU_F32) && !residual) return NER_ERR_INVALID_ARG;
   if ((K % 8) != 0 || (N % 32) != 0) return NER_ERR_UNSUPPORTED;  // 16-B TMA strides, 32-col epilogue chunks
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(Wt) & 15) ||
       (reinterpret_cast<uintptr_t>(out) & 15))

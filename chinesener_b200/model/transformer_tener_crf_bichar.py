@@ -1,0 +1,67 @@
+# -*-coding:utf-8 -*-
+"""Plugin mirror of reference model/transformer_tener_crf_bichar.py (build_graph :8-42, params :45-62)."""
+import torch
+
+from .. import ops
+from ..config import TRAIN_PARAMS as _BASE
+from ..tools.layer import crf_decode, crf_layer, dense, _no_training
+from ..tools.transformer.encoder import tener_encoder
+from ..tools.transformer.modules import embedding_project
+from .bilstm_crf import _const_table
+
+
+def build_graph(features, labels, params, is_training):
+    """
+    char + bichar embedding -> projection -> TENER encoder -> CRF
+    """
+    _no_training(is_training, "transformer_tener_crf_bichar")
+    input_ids = features['token_ids']
+    bichar_ids = features['bichar_ids']
+    label_ids = features['label_ids']
+    seq_len = features['seq_len']
+    B, L = input_ids.shape
+
+    char_table = _const_table(params, 'embedding')
+    bichar_table = _const_table(params, 'bichar_embedding')
+    Ec, Eb = char_table.shape[1], bichar_table.shape[1]
+    # concat([char_embedding, bichar_embedding], -1): both lookups write into one buffer
+    embedding = torch.empty((B * L, Ec + Eb), dtype=torch.float32, device=input_ids.device)
+    ops.embedding_lookup(char_table, input_ids, out=embedding)
+    ops.embedding_lookup(bichar_table, bichar_ids, out=embedding, col_offset=Ec)
+    embedding = embedding_project(embedding, params['d_model'])
+
+    transformer_output = tener_encoder(encoder_input=embedding.view(B, L, -1), seq_len=seq_len,
+                                       max_seq_len=params['max_seq_len'], encode_layers=params['encode_layers'],
+                                       num_head=params['num_head'], dropout_rate=params['dropout_rate'],
+                                       ffn_hidden=params['ffn_hidden'], is_training=is_training)
+
+    logits = dense(transformer_output, units=params['label_size'], name='logits')
+
+    trans, log_likelihood = crf_layer(logits, label_ids, seq_len, params['label_size'], is_training)
+    pred_ids = crf_decode(logits, trans, seq_len, params['idx2tag'], is_training)
+    crf_loss = (-log_likelihood).mean()
+
+    return crf_loss, pred_ids
+
+
+# below params from MSRA[smaller params: num_head=5/d_model=200 for people_daily]
+TRANSFORMER_PARAMS = {
+    'num_head': 8,  # giga embedding size is 50, must be divided by 5
+    'd_model': 160,  # giga char& bichar embedding dim are small, project to bigger dim
+    'ffn_hidden': 320,
+    'encode_layers': 2,
+    'batch_size': 16,
+    'wramup_ratio': 0.1,
+    'epochs': 100
+}
+
+TRAIN_PARAMS = dict(_BASE)
+TRAIN_PARAMS.update(TRANSFORMER_PARAMS)
+TRAIN_PARAMS.update({
+    'lr': 0.001,
+    'decay_rate': 0.95,  # lr * decay_rate ^ (global_step / train_steps_per_epoch)
+    'embedding_dropout': 0.3,
+    'fc_dropout': 0.4,
+    'dropout_rate': 0.2,  # used in transformer sublayer dropout
+    'early_stop_ratio': 2  # stop after no improvement after 1.5 epochs
+})

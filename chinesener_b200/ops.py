@@ -8,7 +8,7 @@ import torch
 from . import _lib
 from ._lib import check, lib, ptr, require_cuda, stream
 
-EPI_F32, EPI_BF16, EPI_GELU_TANH_BF16, EPI_GELU_ERF_BF16, EPI_RELU_BF16, EPI_RES_F32 = range(6)
+EPI_F32, EPI_BF16, EPI_GELU_TANH_BF16, EPI_GELU_ERF_BF16, EPI_RELU_BF16, EPI_RES_F32, EPI_RES_RELU_F32 = range(7)
 EPI_DIAG_DISCARD = 99
 TILE_2CTA_128, TILE_2CTA_256 = 1128, 1256   # CTA-pair (cta_group::2) tiles of ner_gemm_bf16
 
@@ -53,7 +53,7 @@ def gemm_bf16(a, wt, bias=None, residual=None, epilogue=EPI_BF16, tile_n=0, out=
     M, K = a.shape
     N, K2 = wt.shape
     assert K == K2
-    odt = torch.float32 if epilogue in (EPI_F32, EPI_RES_F32) else torch.bfloat16
+    odt = torch.float32 if epilogue in (EPI_F32, EPI_RES_F32, EPI_RES_RELU_F32) else torch.bfloat16
     if out is None:
         out = torch.empty((M, N), dtype=odt, device=a.device)
     assert out.dtype == odt and out.shape == (M, N)
@@ -230,3 +230,44 @@ def crf_loglik_bwd(logits, tags, seq_len, trans, alpha, logz, d_ll=None, scale=1
     check(lib().ner_crf_loglik_bwd(ptr(logits), ptr(_i32(tags)), ptr(_i32(seq_len)), ptr(trans), ptr(alpha), ptr(logz),
                                    ptr(d_ll), scale, ptr(d_logits), ptr(d_trans), B, L, K, stream()))
     return d_logits, d_trans
+
+
+# --------------------------------------------------------------------------- fp32-accurate dense (split bf16)
+def split_bf16(x2d, Dp=None):
+    """f32 [M,D] -> (hi, lo) bf16 [M,Dp] with hi + lo ~= x to 2^-17."""
+    require_cuda(x2d)
+    assert x2d.dtype == torch.float32 and x2d.dim() == 2 and x2d.stride(1) == 1
+    M, D = x2d.shape
+    Dp = Dp or (D + 7) // 8 * 8
+    hi = torch.empty((M, Dp), dtype=torch.bfloat16, device=x2d.device)
+    lo = torch.empty((M, Dp), dtype=torch.bfloat16, device=x2d.device)
+    check(lib().ner_split_bf16(ptr(x2d), ptr(hi), ptr(lo), M, D, Dp, x2d.stride(0), stream()))
+    return hi, lo
+
+
+def gemm_split_f32(a_hi, a_lo, w_hi, w_lo, bias=None, residual=None, relu=False, out=None):
+    """out f32 [M,N] = [relu](A·W^T + bias [+ residual]) at ~fp32 accuracy: A_hi·W_hi + A_hi·W_lo + A_lo·W_hi
+    as three tcgen05 launches chained through the f32 residual epilogue."""
+    M, N = a_hi.shape[0], w_hi.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a_hi.device)
+    gemm_bf16(a_hi, w_hi, bias, residual=residual, epilogue=EPI_RES_F32 if residual is not None else EPI_F32, out=out)
+    gemm_bf16(a_hi, w_lo, None, residual=out, epilogue=EPI_RES_F32, out=out)
+    gemm_bf16(a_lo, w_hi, None, residual=out, epilogue=EPI_RES_RELU_F32 if relu else EPI_RES_F32, out=out)
+    return out
+
+
+def attention_f32(q, k, v, seq_len, B, L, num_heads, head_dim, scale=1.0, bias_u=None, bias_v=None, rel_table=None,
+                  want_f32=True, want_split=False):
+    """fp32 attention (+ TENER relative term).  q/k/v: f32 2-D views [B*L, >= heads*head_dim] (row stride = stride(0))."""
+    require_cuda(seq_len, bias_u, bias_v, rel_table)
+    for t in (q, k, v):
+        assert t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.shape[0] == B * L
+    HD = num_heads * head_dim
+    of = torch.empty((B * L, HD), dtype=torch.float32, device=q.device) if want_f32 else None
+    hi = torch.empty((B * L, HD), dtype=torch.bfloat16, device=q.device) if want_split else None
+    lo = torch.empty((B * L, HD), dtype=torch.bfloat16, device=q.device) if want_split else None
+    check(lib().ner_attention_f32(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                                  ptr(bias_u), ptr(bias_v), ptr(rel_table), ptr(_i32(seq_len)), scale, ptr(of), ptr(hi), ptr(lo),
+                                  B, L, num_heads, head_dim, stream()))
+    return of, hi, lo

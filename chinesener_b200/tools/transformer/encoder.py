@@ -1,0 +1,14 @@
+# -*-coding:utf-8 -*-
+"""reference tools/transformer/encoder.py:21-33 — tener_encoder."""
+from .modules import ffn
+from .tener import relative_multi_head_attention
+
+
+def tener_encoder(encoder_input, seq_len, max_seq_len, encode_layers, num_head, dropout_rate, ffn_hidden, is_training):
+    B, L, d = encoder_input.shape
+    x = encoder_input.reshape(B * L, d)
+    for i in range(encode_layers):
+        scope = f"encoding/self_attention_layer_{i}"
+        x = relative_multi_head_attention(x, seq_len, B, L, num_head, dropout_rate, is_training, scope)
+        x = ffn(x, ffn_hidden, dropout_rate, is_training, scope)
+    return x.view(B, L, d)

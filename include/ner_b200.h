@@ -84,6 +84,7 @@ int ner_crf_loglik_bwd(const float* logits, const int32_t* tags, const int32_t* 
 #define NER_EPI_GELU_ERF_BF16 3  /* out bf16 = gelu_erf(acc + bias)          */
 #define NER_EPI_RELU_BF16 4      /* out bf16 = relu(acc + bias)              */
 #define NER_EPI_RES_F32 5        /* out f32  = acc + bias + residual (f32)   */
+#define NER_EPI_RES_RELU_F32 6   /* out f32  = relu(acc + bias + residual)   */
 #define NER_EPI_DIAG_DISCARD 99  /* diagnostic only: accumulate, drain TMEM, store nothing */
 
 /* tile_n selectors of ner_gemm_bf16: 64/128/256 = one CTA per 128 x tile_n tile
@@ -125,6 +126,25 @@ int ner_cast_pad_bf16(const float* src, void* dst_bf16, int M, int D, int Dp, in
  * must be a prefix mask (1 for t < len_b), as data/base_preprocess.py:166-174 builds it.
  * cu_seqlens [B+1]: exclusive prefix sum of the lengths; tok_src [B*L]: tok_src[cu[b]+t] = b*L+t. */
 int ner_seq_pack_plan(const int32_t* mask, int32_t* cu_seqlens, int32_t* tok_src, int B, int L,
+                      ner_stream_t stream);
+
+/* f32 [M,D] (row stride ld_src) -> hi = bf16(x), lo = bf16(x - hi), both [M,Dp] zero-padded.
+ * Operands of the fp32-accurate dense mode: out = A_hi·W_hi + A_hi·W_lo + A_lo·W_hi, three
+ * ner_gemm_bf16 launches chained through the f32 residual epilogue (error ~2^-17 relative). */
+int ner_split_bf16(const float* src, void* hi_bf16, void* lo_bf16, int M, int D, int Dp,
+                   int ld_src, ner_stream_t stream);
+
+/* fp32 self-attention for small heads with the optional TENER relative-position term
+ * (tools/transformer/tener.py:12-119): scores[q,k] = (Q_q+u_h)·K_k [+ (Q_q+v_h)·R_{k-q+L}],
+ * times `scale`; keys k >= seq_len[b] are masked; softmax; ·V.  Q/K/V are row-major
+ * [B*L, ld*] f32 with head h at columns [h*head_dim, (h+1)*head_dim).  u/v [heads, head_dim]
+ * or NULL; rel_table [2L, head_dim] (positions -L..L-1) or NULL.  Writes out_f32 and/or a
+ * (hi, lo) bf16 pair, all [B*L, heads*head_dim]; rows q >= seq_len[b] are zero.
+ * head_dim in {20, 32, 40, 64}, L <= 512. */
+int ner_attention_f32(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
+                      const float* bias_u, const float* bias_v, const float* rel_table,
+                      const int32_t* seq_len, float scale, float* out_f32, void* out_hi_bf16,
+                      void* out_lo_bf16, int B, int L, int num_heads, int head_dim,
                       ner_stream_t stream);
 
 /* ------------------------------------------------------------------------ *

@@ -1,0 +1,102 @@
+"""GPU: fp32-accurate dense (split-bf16 tcgen05), fp32 TENER attention and the TENER plugin vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from chinesener_b200 import engine, ops, synthetic
+from oracle import models as omodels, transformer as otf
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,K,N", [(8192, 160, 320), (1000, 100, 160), (300, 320, 160), (4096, 768, 768)])
+def test_split_bf16_gemm_reaches_fp32_accuracy(M, K, N):
+    g = torch.Generator().manual_seed(M + K)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(K, N, generator=g) * 0.2
+    b = torch.randn(N, generator=g)
+    r = torch.randn(M, N, generator=g)
+    Kp = (K + 7) // 8 * 8
+    wp = torch.nn.functional.pad(w, (0, 0, 0, Kp - K)).cuda().contiguous()
+    w_hi = ops.pack_weight_bf16(wp)
+    w_lo = ops.pack_weight_bf16((wp - w_hi.float().t()).contiguous())
+    a_hi, a_lo = ops.split_bf16(x.cuda(), Kp)
+    torch.testing.assert_close((a_hi.float() + a_lo.float())[:, :K].cpu(), x, rtol=2e-5, atol=1e-6)
+    out = ops.gemm_split_f32(a_hi, a_lo, w_hi, w_lo, b.cuda(), residual=r.cuda(), relu=True)
+    ref = torch.relu(x.double() @ w.double() + b.double() + r.double())
+    err = (out.cpu().double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err < 3e-5 * max(1.0, scale), (err, scale)
+
+
+@pytest.mark.parametrize("B,L,NH,DH,rel", [(4, 64, 8, 20, True), (3, 256, 8, 20, True), (2, 150, 4, 40, True),
+                                           (2, 128, 12, 64, False), (3, 33, 2, 32, False)])
+def test_attention_f32(B, L, NH, DH, rel):
+    g = torch.Generator().manual_seed(B * L + DH)
+    d = NH * DH
+    q, k, v = (torch.randn(B * L, d, generator=g) for _ in range(3))
+    u = torch.randn(NH, DH, generator=g) * 0.3
+    vb = torch.randn(NH, DH, generator=g) * 0.3
+    lens = torch.randint(1, L + 1, (B,), generator=g, dtype=torch.int32)
+    lens[0] = L
+    table = torch.from_numpy(np.asarray(otf.sinusoidal_positional_encoding(DH, np.arange(-L, L)), dtype=np.float32)) if rel else None
+    scale = 1.0 if rel else DH ** -0.5
+    out, hi, lo = ops.attention_f32(q.cuda(), k.cuda(), v.cuda(), lens.cuda(), B, L, NH, DH, scale=scale,
+                                    bias_u=u.cuda() if rel else None, bias_v=vb.cuda() if rel else None,
+                                    rel_table=table.cuda() if rel else None, want_split=True)
+    sh = lambda t: t.double().view(B, L, NH, DH).permute(0, 2, 1, 3)
+    Q, K, V = sh(q), sh(k), sh(v)
+    if rel:
+        AC = torch.einsum('bnqd,bnkd->bnqk', Q + u.double()[:, None, :], K)
+        BD = otf.shift(torch.einsum('bnqd,ld->bnql', Q + vb.double()[:, None, :], table.double()))
+        s = AC + BD
+    else:
+        s = Q @ K.transpose(-1, -2) * scale
+    mask = (torch.arange(L)[None, :] < lens.long()[:, None])
+    s = s + (~mask)[:, None, None, :].double() * otf.MASK_ADD
+    ref = (torch.softmax(s, -1) @ V).permute(0, 2, 1, 3).reshape(B, L, d)
+    o = out.cpu().double().view(B, L, d)
+    for b in range(B):
+        n = int(lens[b])
+        assert (o[b, :n] - ref[b, :n]).abs().max() < 2e-5
+        assert (o[b, n:] == 0).all()
+    torch.testing.assert_close((hi.float() + lo.float()).cpu(), out.cpu(), rtol=2e-5, atol=1e-6)
+
+
+def test_tener_plugin_matches_oracle_at_fp32_accuracy():
+    """BASELINE config 5 shape (reduced batch): logits within 1e-3 of the float64 oracle (the
+    north-star tolerance for fp32 emission logits), pred_ids equal wherever margins allow."""
+    B, L, V, VB = 6, 256, 3000, 5000
+    feats = synthetic.msra_batch(B, L, vocab=V, seed=9)
+    g = torch.Generator().manual_seed(2)
+    feats['bichar_ids'] = torch.randint(0, VB, (B, L), generator=g, dtype=torch.int32)
+    emb = torch.nn.functional.normalize(torch.randn(V, 50, generator=g), dim=1).numpy()
+    bemb = torch.nn.functional.normalize(torch.randn(VB, 50, generator=g), dim=1).numpy()
+    params = dict(synthetic.data_params(L), embedding=emb, bichar_embedding=bemb)
+    est = engine.Estimator("transformer_tener_crf_bichar", params)
+    est.evaluate(feats)
+    est.store.vars["logits/kernel"].mul_(4.0)
+    est.store.touch()
+    out = est.evaluate(feats)
+    w = est.store.state_dict()
+    ref = omodels.transformer_tener_crf_bichar(w, feats, est.params, dtype=torch.float64)
+    # emission logits through the public layer API
+    from chinesener_b200 import variables
+    from chinesener_b200.tools import layer
+    from chinesener_b200.tools.transformer.encoder import tener_encoder
+    from chinesener_b200.tools.transformer.modules import embedding_project
+    dev = est.to_device(feats)
+    with variables.use_store(est.store):
+        e = torch.empty((B * L, 100), dtype=torch.float32, device="cuda")
+        ops.embedding_lookup(torch.from_numpy(emb).cuda(), dev['token_ids'], out=e)
+        ops.embedding_lookup(torch.from_numpy(bemb).cuda(), dev['bichar_ids'], out=e, col_offset=50)
+        x = tener_encoder(embedding_project(e, 160).view(B, L, -1), dev['seq_len'], L, 2, 8, 0.2, 320, False)
+        logits = layer.dense(x, 10, 'logits')
+    valid = torch.arange(L)[None, :] < feats['seq_len'][:, None]
+    err = (logits.cpu().double() - ref['logits'])[valid].abs().max().item()
+    print(f"tener: max|logit - fp64 oracle| = {err:.2e} (max |logit| {ref['logits'][valid].abs().max().item():.2f})")
+    assert err < 1e-3
+    assert abs(out['loss'] - ref['loss']) < 1e-3 * max(1.0, abs(ref['loss']))
+    agree = (out['pred_ids'].numpy() == ref['pred_ids']).mean()
+    assert agree > 0.999, agree
+    assert (out['pred_ids'].numpy()[feats['mask'].numpy() == 0] == 0).all()
