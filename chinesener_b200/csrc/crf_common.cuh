@@ -87,6 +87,14 @@ __device__ __forceinline__ void load_group(float* xs, const float* rowp, int g) 
 
 }  // namespace crf
 
+// Small-batch (lane-per-tag) variants, crf_small.cu.  Chosen by the C-ABI entry points when
+// B <= NER_CRF_SMALL_B: few sequences -> optimise the per-step critical path, not HBM throughput.
+#define NER_CRF_SMALL_B 4096
+int ner_crf_viterbi_small(const float* logits, const int32_t* seq_len, const float* trans, int32_t* tags_out,
+                          float* best_score, int B, int L, int K, cudaStream_t st);
+int ner_crf_loglik_fwd_small(const float* logits, const int32_t* tags, const int32_t* seq_len, const float* trans,
+                             float* ll, float* logz, float* alpha_ws, int B, int L, int K, cudaStream_t st);
+
 // Dispatch a runtime K in [1,32] onto `template <int K> run<K>(args...)`.
 #define NER_CRF_DISPATCH_K(K_, CALL)                                                     \
   switch (K_) {                                                                          \

@@ -269,6 +269,10 @@ extern "C" int ner_crf_loglik_fwd(const float* logits, const int32_t* tags, cons
   if (!logits || !tags || !seq_len || !trans || !ll) return NER_ERR_INVALID_ARG;
   if (K > NER_MAX_TAGS) return NER_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B <= NER_CRF_SMALL_B && !(flags & 2)) {  // flags bit1: force the throughput kernel (tests / benches)
+    const int rc = ner_crf_loglik_fwd_small(logits, tags, seq_len, trans, ll, logz_out, alpha_ws, B, L, K, st);
+    if (rc != NER_ERR_UNSUPPORTED) return rc;
+  }
 #define CALL(KK) return launch_fwd<KK>(logits, tags, seq_len, trans, ll, logz_out, alpha_ws, B, L, flags, st)
   NER_CRF_DISPATCH_K(K, CALL)
 #undef CALL

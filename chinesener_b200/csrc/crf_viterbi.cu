@@ -213,6 +213,10 @@ extern "C" int ner_crf_viterbi(const float* logits, const int32_t* seq_len, cons
   if (!logits || !seq_len || !trans || !tags_out) return NER_ERR_INVALID_ARG;
   if (K > NER_MAX_TAGS) return NER_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B <= NER_CRF_SMALL_B) {
+    const int rc = ner_crf_viterbi_small(logits, seq_len, trans, tags_out, best_score, B, L, K, st);
+    if (rc != NER_ERR_UNSUPPORTED) return rc;
+  }
 #define CALL(KK) return launch_viterbi<KK>(logits, seq_len, trans, tags_out, best_score, B, L, st)
   NER_CRF_DISPATCH_K(K, CALL)
 #undef CALL

@@ -49,6 +49,14 @@ def test_viterbi_ties_resolve_to_lowest_index():
     np.testing.assert_array_equal(tags.cpu().numpy(), ref_tags)
 
 
+def test_viterbi_mid_batch_uses_thread_per_sequence_kernel():
+    B, L, K = 5000, 40, 10                              # above the lane-per-tag threshold, NT=32 CTAs
+    x, tr, lens, _ = _case(B, L, K, seed=17)
+    ref_tags, _ = crf.crf_decode(x, tr, lens, dtype=np.float32)
+    tags = ops.crf_viterbi(torch.from_numpy(x).cuda(), torch.from_numpy(lens).cuda(), torch.from_numpy(tr).cuda())
+    np.testing.assert_array_equal(tags.cpu().numpy(), ref_tags)
+
+
 def test_viterbi_large_batch_uses_128_thread_ctas():
     B, L, K = 148 * 64 + 77, 128, 10                    # > big-batch threshold, ragged tail CTA
     x, tr, lens, _ = _case(B, L, K, seed=11)
@@ -58,7 +66,7 @@ def test_viterbi_large_batch_uses_128_thread_ctas():
 
 
 @pytest.mark.parametrize("B,L,K", [(64, 128, 10), (8, 64, 10), (37, 150, 7), (5, 1, 4), (3, 17, 1), (130, 33, 13),
-                                   (9, 50, 20), (4, 40, 32), (19000, 24, 10), (6, 256, 10), (33, 10, 16)])
+                                   (9, 50, 20), (4, 40, 32), (19000, 24, 10), (6, 256, 10), (33, 10, 16), (5000, 16, 10)])
 @pytest.mark.parametrize("exact", [False, True])
 def test_loglik_forward(B, L, K, exact):
     x, tr, lens, tags = _case(B, L, K, seed=B + L + K)
