@@ -35,7 +35,8 @@ template <int R, int ACT, int H4REG>
 __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(const float* __restrict__ xproj, const float* __restrict__ wh_fw,
                                   const float* __restrict__ wh_bw, const int32_t* __restrict__ seq_len,
                                   float* __restrict__ out, int B, int L, int H, int C, float forget_bias,
-                                  const int32_t* __restrict__ cu_seqlens) {
+                                  const int32_t* __restrict__ cu_seqlens, float* __restrict__ gates_out,
+                                  float* __restrict__ cstate_out) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int HU = H / C;       // hidden units owned by this CTA
@@ -172,10 +173,19 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
         const float zj = zbuf[cr * NC + 1 * HU + cu];
         const float zf = zbuf[cr * NC + 2 * HU + cu];
         const float zo = zbuf[cr * NC + 3 * HU + cu];
-        c_state = sigmoidf_(zf + forget_bias) * c_state + sigmoidf_(zi) * actf<ACT>(zj);
-        h_state = sigmoidf_(zo) * actf<ACT>(c_state);
+        const float i_s = sigmoidf_(zi), j_a = actf<ACT>(zj), f_s = sigmoidf_(zf + forget_bias), o_s = sigmoidf_(zo);
+        c_state = f_s * c_state + i_s * j_a;
+        h_state = o_s * actf<ACT>(c_state);
         const int pos = dir == 0 ? s : len - 1 - s;
         out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = h_state;
+        if (gates_out != nullptr) {  // saved for back-propagation through time (bilstm_bwd.cu)
+          const size_t gi = ((size_t)b * L + pos) * 8 * H + (size_t)dir * 4 * H;
+          gates_out[gi + 0 * H + ug] = i_s;
+          gates_out[gi + 1 * H + ug] = j_a;
+          gates_out[gi + 2 * H + ug] = f_s;
+          gates_out[gi + 3 * H + ug] = o_s;
+          cstate_out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = c_state;
+        }
       } else if (b < B) {
         out[((size_t)b * L + s) * 2 * H + (size_t)dir * H + ug] = 0.f;
       }
@@ -208,7 +218,8 @@ int pick_cluster(int H) {
 
 template <int R, int ACT, int H4REG>
 int launch_rec(const float* xproj, const float* wh_fw, const float* wh_bw, const int32_t* seq_len, float* out, int B,
-               int L, int H, int C, float forget_bias, const int32_t* cu_seqlens, cudaStream_t st) {
+               int L, int H, int C, float forget_bias, const int32_t* cu_seqlens, float* gates_out, float* cstate_out,
+               cudaStream_t st) {
   const int HU = H / C, NC = 4 * HU;
   const size_t smem = ((H4REG > 0 ? 0 : (size_t)H * NC) + 2 * R * H + (size_t)R * NC + 32) * 4;
   auto kern = bilstm_rec_kernel<R, ACT, H4REG>;
@@ -227,7 +238,8 @@ int launch_rec(const float* xproj, const float* wh_fw, const float* wh_bw, const
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kern, xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, cu_seqlens);
+  e = cudaLaunchKernelEx(&cfg, kern, xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, cu_seqlens, gates_out,
+                         cstate_out);
   if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   return ner_launch_status();
 }
@@ -236,10 +248,12 @@ int launch_rec(const float* xproj, const float* wh_fw, const float* wh_bw, const
 
 extern "C" int ner_bilstm_recurrence(const float* xproj, const float* wh_fw, const float* wh_bw,
                                      const int32_t* seq_len, float* out, int B, int L, int H, int activation,
-                                     float forget_bias, const int32_t* cu_seqlens, ner_stream_t stream) {
+                                     float forget_bias, const int32_t* cu_seqlens, float* gates_out,
+                                     float* cstate_out, ner_stream_t stream) {
   if (B < 0 || L < 1 || H < 1) return NER_ERR_INVALID_ARG;
   if (B == 0) return NER_OK;
   if (!xproj || !wh_fw || !wh_bw || !seq_len || !out) return NER_ERR_INVALID_ARG;
+  if ((gates_out == nullptr) != (cstate_out == nullptr)) return NER_ERR_INVALID_ARG;
   if (activation != 0 && activation != 1) return NER_ERR_INVALID_ARG;
   if (H % 4 != 0) return NER_ERR_UNSUPPORTED;
   const int C = pick_cluster(H);
@@ -250,8 +264,8 @@ extern "C" int ner_bilstm_recurrence(const float* xproj, const float* wh_fw, con
   if ((long)2 * B * C > 148) R = 2;
   if ((long)2 * ((B + 1) / 2) * C > 2 * 148) R = 4;
 #define GO(RR, HR)                                                                                          \
-  return activation == 1 ? launch_rec<RR, 1, HR>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, cu_seqlens, st) \
-                         : launch_rec<RR, 0, HR>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, cu_seqlens, st)
+  return activation == 1 ? launch_rec<RR, 1, HR>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, cu_seqlens, gates_out, cstate_out, st) \
+                         : launch_rec<RR, 0, HR>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, cu_seqlens, gates_out, cstate_out, st)
   if (H == 128 && 4 * (H / C) <= 256) {  // register-resident W_h (the bert_bilstm_crf / bilstm_crf shape)
     if (R == 4) GO(4, 32);
     if (R == 2) GO(2, 32);

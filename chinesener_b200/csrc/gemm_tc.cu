@@ -12,8 +12,8 @@
 //   warp 1    MMA issuer   : one thread issues tcgen05.mma.kind::f16 x4 per k-block;
 //                            tcgen05.commit releases smem slots / publishes the accumulator
 //   warps 2-9 epilogue     : tcgen05.ld 32x32b (TMEM lane quarter = warp%4, two warps per quarter
-//                            on alternating 32-column chunks) -> bias / GELU / residual ->
-//                            16-byte global stores
+//                            on alternating 128-byte column groups) -> bias / GELU / residual ->
+//                            swizzled smem staging tile -> cp.async.bulk.tensor (TMA) store
 // Two TMEM accumulator stages (2*BN columns) let the epilogue of tile i overlap the main loop
 // of tile i+1.
 //
@@ -44,7 +44,8 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int TMEM_COLS = tmem_cols_for(2 * BN);
-  static constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + B_BYTES) + 256 /*barriers*/ + 2 * BN * 4 /*bias*/ + 1024 /*align slack*/;
+  // ring + 8 x 4 KB epilogue staging + barriers + bias; the dynamic smem base is 1024-aligned (checked in-kernel)
+  static constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + B_BYTES) + NUM_EPI_WARPS * 4096 + 256 + 2 * BN * 4;
 };
 
 template <int BN>
@@ -53,7 +54,7 @@ struct Cfg2 {  // per CTA of the pair
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;
   static constexpr int TMEM_COLS = tmem_cols_for(2 * BN);
-  static constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + B_BYTES) + 256 + 2 * BN * 4 + 1024;
+  static constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + B_BYTES) + NUM_EPI_WARPS * 4096 + 256 + 2 * BN * 4;
 };
 
 struct EpiArgs {
@@ -77,11 +78,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// One 32-column chunk of one accumulator row: TMEM registers -> fused epilogue -> global.
+// Fused epilogue math on one 32-column chunk of one accumulator row (values in registers).
 // `sbias` = this chunk's 32 bias values in shared memory (broadcast LDS.128), staged once per tile.
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const EpiArgs& ep, const float* sbias, int row,
-                                               int col0, int N) {
-  float v[32];
+__device__ __forceinline__ void epilogue_math(float (&v)[32], const uint32_t (&r)[32], const EpiArgs& ep,
+                                              const float* sbias, int row, int col0, int M, int N) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
   {
@@ -95,10 +95,9 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ep
       v[4 * i + 3] += b.w;
     }
   }
-  const size_t off = (size_t)row * N + col0;
-  if (ep.mode == NER_EPI_F32 || ep.mode == NER_EPI_RES_F32 || ep.mode == NER_EPI_RES_RELU_F32) {
-    if (ep.mode != NER_EPI_F32) {
-      const float4* r4 = reinterpret_cast<const float4*>(ep.residual + off);
+  if (ep.mode == NER_EPI_RES_F32 || ep.mode == NER_EPI_RES_RELU_F32) {
+    if (row < M && col0 < N) {
+      const float4* r4 = reinterpret_cast<const float4*>(ep.residual + (size_t)row * N + col0);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 b = __ldg(r4 + i);
@@ -112,25 +111,15 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ep
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
     }
-    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off);
+  } else if (ep.mode == NER_EPI_GELU_TANH_BF16) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  } else {
-    if (ep.mode == NER_EPI_GELU_TANH_BF16) {
+    for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+  } else if (ep.mode == NER_EPI_GELU_ERF_BF16) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
-    } else if (ep.mode == NER_EPI_GELU_ERF_BF16) {
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+  } else if (ep.mode == NER_EPI_RELU_BF16) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-    } else if (ep.mode == NER_EPI_RELU_BF16) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-    }
-    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + off);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      o4[i] = make_uint4(pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                         pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
   }
 }
 
@@ -150,31 +139,62 @@ __device__ __forceinline__ void epilogue_stage_bias(float* sbias, const EpiArgs&
   epi_bar_sync();
 }
 
-// Epilogue of one 128 x BN accumulator (this warp's lane quarter, its half of the column chunks).
-// TMEM loads are software-pipelined: the tcgen05.ld of chunk c+1 is in flight while chunk c is
-// converted and stored.
-template <int BN>
+// Epilogue of one 128 x BN accumulator.  Each epilogue warp owns a TMEM lane quarter (32 rows) and
+// every other 128-byte column group (64 bf16 or 32 fp32 columns).  Per group: tcgen05.ld -> fused
+// math -> the warp's 32 x 128 B staging tile in shared memory (SWIZZLE_128B: chunk ^ (row & 7),
+// conflict-free STS.128) -> ONE cp.async.bulk.tensor store by lane 0.  The store writes full
+// 128-byte lines and clips rows >= M / columns >= N by itself; direct per-thread stores wrote
+// 16-byte fragments of 32 different lines per instruction and were L2-transaction-bound.
+template <int BN, bool OUT_F32>
 __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int warp, int lane, const EpiArgs& ep,
-                                              const float* sbias, int row0, int n0, int M, int N) {
-  constexpr int NCH = BN / 64;         // chunks per warp (two warps share a lane quarter)
-  const int q = warp & 3;              // TMEM lane quarter this warp may access
-  const int half = (warp - 2) >> 2;    // 0: even chunks, 1: odd chunks
+                                              const CUtensorMap* tma_c, uint8_t* stage, const float* sbias, int row0,
+                                              int n0, int M, int N) {
+  constexpr int GC = OUT_F32 ? 32 : 64;  // columns per 128-byte group
+  constexpr int NG = BN / GC;            // groups per tile
+  const int q = warp & 3;                // TMEM lane quarter this warp may access
+  const int half = (warp - 2) >> 2;      // 0: even groups, 1: odd groups
   const int row = row0 + q * 32 + lane;
   const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16);
-  uint32_t ra[32], rb[32];
-  tmem_ld_32x32(tbase + (uint32_t)(half * 32), ra);
-#pragma unroll
-  for (int i = 0; i < NCH; ++i) {
-    const int c = half + 2 * i;
+  uint8_t* my = stage + lane * 128;
+  const int sw = lane & 7;
+#pragma unroll 1
+  for (int g = half; g < NG; g += 2) {
+    const int col0 = n0 + g * GC;
+    uint32_t ra[32];
+    float v[32];
+    uint4 pk[8];
+    tmem_ld_32x32(tbase + (uint32_t)(g * GC), ra);
     tmem_ld_wait();
-    if (i + 1 < NCH) {
-      if (i & 1) tmem_ld_32x32(tbase + (uint32_t)((c + 2) * 32), ra);
-      else tmem_ld_32x32(tbase + (uint32_t)((c + 2) * 32), rb);
+    epilogue_math(v, ra, ep, sbias + g * GC, row, col0, M, N);
+    if constexpr (OUT_F32) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        pk[i] = make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]),
+                           __float_as_uint(v[4 * i + 3]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        pk[i] = make_uint4(pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                           pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+      tmem_ld_32x32(tbase + (uint32_t)(g * GC + 32), ra);
+      tmem_ld_wait();
+      epilogue_math(v, ra, ep, sbias + g * GC + 32, row, col0 + 32, M, N);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        pk[4 + i] = make_uint4(pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                               pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
     }
-    const int col0 = n0 + c * 32;
-    if (ep.mode != NER_EPI_DIAG_DISCARD && row < M && col0 < N) {
-      if (i & 1) epilogue_chunk(rb, ep, sbias + c * 32, row, col0, N);
-      else epilogue_chunk(ra, ep, sbias + c * 32, row, col0, N);
+    if (ep.mode == NER_EPI_DIAG_DISCARD) continue;  // diagnostic: drain TMEM, store nothing
+    // the previous bulk store of this warp must have finished reading the staging tile
+    if (lane == 0) tma_store_wait_read<0>();
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(my + ((i ^ sw) << 4)) = pk[i];
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0 && col0 < N && row0 + q * 32 < M) {
+      tma_store_2d(tma_c, stage, col0, row0 + q * 32);
+      tma_store_commit();
     }
   }
 }
@@ -183,16 +203,17 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int warp, int l
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    EpiArgs ep, int M, int N, int K) {
+                    const __grid_constant__ CUtensorMap tma_c, EpiArgs ep, int M, int N, int K) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
 
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);  // SWIZZLE_128B needs 1024-B alignment
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;  // SWIZZLE_128B tiles need 1024-B alignment
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * C::A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (C::A_BYTES + C::B_BYTES));
+  uint8_t* epi_stage = smem + STAGES * (C::A_BYTES + C::B_BYTES);  // [NUM_EPI_WARPS][32 rows][128 B], 1024-aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + NUM_EPI_WARPS * 4096);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -210,6 +231,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_c);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -290,7 +312,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       epilogue_stage_bias<BN>(sbias + acc * BN, ep, n_blk * BN, N);
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      epilogue_tile<BN>(tmem_base + (uint32_t)(acc * BN), warp, lane, ep, sbias + acc * BN, m_blk * BM, n_blk * BN, M, N);
+      if (ep.mode == NER_EPI_F32 || ep.mode == NER_EPI_RES_F32 || ep.mode == NER_EPI_RES_RELU_F32)
+        epilogue_tile<BN, true>(tmem_base + (uint32_t)(acc * BN), warp, lane, ep, &tma_c, epi_stage + (warp - 2) * 4096,
+                                sbias + acc * BN, m_blk * BM, n_blk * BN, M, N);
+      else
+        epilogue_tile<BN, false>(tmem_base + (uint32_t)(acc * BN), warp, lane, ep, &tma_c, epi_stage + (warp - 2) * 4096,
+                                 sbias + acc * BN, m_blk * BM, n_blk * BN, M, N);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -301,6 +328,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   }
 
+  if (warp >= 2 && lane == 0) tma_store_wait_read<0>();  // staging tiles fully read before the CTA exits
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -320,16 +348,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                     EpiArgs ep, int M, int N, int K) {
+                     const __grid_constant__ CUtensorMap tma_c, EpiArgs ep, int M, int N, int K) {
   using C = Cfg2<BN>;
   constexpr int STAGES = C::STAGES;
 
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * C::A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (C::A_BYTES + C::B_BYTES));
+  uint8_t* epi_stage = smem + STAGES * (C::A_BYTES + C::B_BYTES);  // [NUM_EPI_WARPS][32 rows][128 B], 1024-aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + NUM_EPI_WARPS * 4096);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -350,6 +379,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_c);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -435,8 +465,12 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       epilogue_stage_bias<BN>(sbias + acc * BN, ep, n_blk * BN, N);
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      epilogue_tile<BN>(tmem_base + (uint32_t)(acc * BN), warp, lane, ep, sbias + acc * BN,
-                        m_blk * 2 * BM + (int)rank * BM, n_blk * BN, M, N);
+      if (ep.mode == NER_EPI_F32 || ep.mode == NER_EPI_RES_F32 || ep.mode == NER_EPI_RES_RELU_F32)
+        epilogue_tile<BN, true>(tmem_base + (uint32_t)(acc * BN), warp, lane, ep, &tma_c, epi_stage + (warp - 2) * 4096,
+                                sbias + acc * BN, m_blk * 2 * BM + (int)rank * BM, n_blk * BN, M, N);
+      else
+        epilogue_tile<BN, false>(tmem_base + (uint32_t)(acc * BN), warp, lane, ep, &tma_c, epi_stage + (warp - 2) * 4096,
+                                 sbias + acc * BN, m_blk * 2 * BM + (int)rank * BM, n_blk * BN, M, N);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc == 0 ? empty_remote0 : empty_remote1);
@@ -447,6 +481,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     }
   }
 
+  if (warp >= 2 && lane == 0) tma_store_wait_read<0>();
   tcgen05_fence_before();
   cluster_sync_all();  // both CTAs done with TMEM / remote barriers
   if (warp == 1) {
@@ -489,6 +524,22 @@ int make_map_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t 
   return r == CUDA_SUCCESS ? NER_OK : NER_ERR_INVALID_ARG;
 }
 
+// output [M, N] (bf16 or f32) with a {128 bytes of columns, 32 rows} box, 128-byte swizzle
+int make_map_out(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, bool f32) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return NER_ERR_NO_DRIVER;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {(cuuint32_t)(f32 ? 32 : 64), 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? NER_OK : NER_ERR_INVALID_ARG;
+}
+
+bool epi_is_f32(int mode) { return mode == NER_EPI_F32 || mode == NER_EPI_RES_F32 || mode == NER_EPI_RES_RELU_F32; }
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -507,13 +558,16 @@ int launch_gemm(const void* A, const void* Wt, EpiArgs ep, int M, int N, int K, 
   if (rc != NER_OK) return rc;
   rc = make_map_bf16_2d(&mb, Wt, (uint64_t)N, (uint64_t)K, BN);
   if (rc != NER_OK) return rc;
+  CUtensorMap mc;
+  rc = make_map_out(&mc, ep.out, (uint64_t)M, (uint64_t)N, epi_is_f32(ep.mode));
+  if (rc != NER_OK) return rc;
   auto kern = gemm_bf16_tc_kernel<BN>;
   const size_t smem = Cfg<BN>::SMEM;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, NUM_THREADS, smem, st>>>(ma, mb, ep, M, N, K);
+  kern<<<grid, NUM_THREADS, smem, st>>>(ma, mb, mc, ep, M, N, K);
   return ner_launch_status();
 }
 
@@ -524,6 +578,9 @@ int launch_gemm2(const void* A, const void* Wt, EpiArgs ep, int M, int N, int K,
   if (rc != NER_OK) return rc;
   rc = make_map_bf16_2d(&mb, Wt, (uint64_t)N, (uint64_t)K, BN / 2);
   if (rc != NER_OK) return rc;
+  CUtensorMap mc;
+  rc = make_map_out(&mc, ep.out, (uint64_t)M, (uint64_t)N, epi_is_f32(ep.mode));
+  if (rc != NER_OK) return rc;
   auto kern = gemm_bf16_tc2_kernel<BN>;
   const size_t smem = Cfg2<BN>::SMEM;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -531,7 +588,7 @@ int launch_gemm2(const void* A, const void* Wt, EpiArgs ep, int M, int N, int K,
   const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   const int max_pairs = sm_count() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  kern<<<2 * pairs, NUM_THREADS, smem, st>>>(ma, mb, ep, M, N, K);
+  kern<<<2 * pairs, NUM_THREADS, smem, st>>>(ma, mb, mc, ep, M, N, K);
   return ner_launch_status();
 }
 

@@ -1,0 +1,231 @@
+// Training-side HBM-bound kernels (sm_100a): operand transposes for the weight-gradient GEMMs,
+// bias gradients, label-projection backward, dropout, and the two optimizer steps of the reference
+// (tools/train_utils.py:246-390): AdamWeightDecayOptimizer (no bias correction, decoupled weight
+// decay, global-norm clipping) and tf.train.AdamOptimizer (bias-corrected, clip-by-value).
+#include "common.cuh"
+
+namespace {
+
+using namespace nerdev;
+
+// src f32 [M,N] (row stride ld) -> dst bf16 [N, Mp] (Mp >= M, zero padded): the K-major operand of a
+// weight-gradient GEMM  dW[K,N] = X^T dY  (reduction over the M rows).
+__global__ void __launch_bounds__(256)
+transpose_cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int M, int N, int Mp, int ld) {
+  __shared__ float tile[32][33];
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int m = m0 + i, n = n0 + tx;
+    tile[i][tx] = (m < M && n < N) ? src[(size_t)m * ld + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int n = n0 + i, m = m0 + tx;
+    if (n < N && m < Mp) dst[(size_t)n * Mp + m] = __float2bfloat16_rn(tile[tx][i]);
+  }
+}
+
+// out[n] (+)= scale * sum_m x[m, n]   (bias gradients)
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N, int ld, float scale) {
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ty = threadIdx.x >> 5;
+  __shared__ float part[8][33];
+  float acc = 0.f;
+  if (n < N)
+    for (int m = blockIdx.y * 8 + ty; m < M; m += gridDim.y * 8) acc += x[(size_t)m * ld + n];
+  part[ty][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += part[i][threadIdx.x & 31];
+    atomicAdd(out + n, scale * s);
+  }
+}
+
+// label projection backward:  dW[F,N] += x^T dy,  db[N] += colsum(dy),  dx[M,F] = dy W^T   (N <= 32)
+template <int NMAX>
+__global__ void __launch_bounds__(256)
+dense_small_n_bwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ dy,
+                         float* __restrict__ dW, float* __restrict__ db, float* __restrict__ dx, int M, int F, int N) {
+  extern __shared__ float sm[];
+  float* s_w = sm;            // [F][N]
+  float* s_dw = sm + F * N;   // [F][N] CTA partial
+  for (int e = threadIdx.x; e < F * N; e += blockDim.x) {
+    s_w[e] = W[e];
+    s_dw[e] = 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float dbacc = 0.f;  // lane n accumulates db[n]
+  for (int row = blockIdx.x * nw + warp; row < M; row += gridDim.x * nw) {
+    float g[NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) g[n] = (n < N) ? dy[(size_t)row * N + n] : 0.f;
+    if (lane < N) dbacc += dy[(size_t)row * N + lane];
+    for (int f = lane; f < F; f += 32) {
+      const float xv = x[(size_t)row * F + f];
+      float d = 0.f;
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n)
+        if (n < N) {
+          d = fmaf(g[n], s_w[f * N + n], d);
+          atomicAdd(&s_dw[f * N + n], xv * g[n]);
+        }
+      if (dx != nullptr) dx[(size_t)row * F + f] = d;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < F * N; e += blockDim.x) {
+    const float v = s_dw[e];
+    if (v != 0.f) atomicAdd(dW + e, v);
+  }
+  if (db != nullptr && lane < N && dbacc != 0.f) atomicAdd(db + lane, dbacc);
+}
+
+// Counter-based dropout (Philox-like integer hash of (seed, element index)): the same (seed, i)
+// gives the same keep decision in forward and backward, so no mask tensor is stored.
+__device__ __forceinline__ uint32_t hash3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t x = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du;
+  x ^= x >> 16;
+  x *= 0x7FEB352Du;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x;
+}
+__global__ void __launch_bounds__(256)
+dropout_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n, float keep, uint32_t seed_lo, uint32_t seed_hi) {
+  const float inv = 1.f / keep;
+  const uint32_t thr = (uint32_t)fminf(keep * 4294967296.f, 4294967295.f);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t r = hash3(seed_lo, seed_hi ^ (uint32_t)(i >> 32), (uint32_t)i);
+    y[i] = (r < thr) ? x[i] * inv : 0.f;
+  }
+}
+
+// sum of squares of a flat buffer -> out[0] (atomic), for clip_by_global_norm
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
+  float acc = 0.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc = fmaf(g[i], g[i], acc);
+  acc = warp_sum(acc);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += part[i];
+    atomicAdd(out, s);
+  }
+}
+
+// mode 0: AdamWeightDecayOptimizer (bert optimization.py): m,v update, upd = m/(sqrt(v)+eps) (+ wd*p), p -= lr*upd.
+//         gradient pre-scaled by clip = clip_norm / max(global_norm, clip_norm) read from gnorm_sq.
+// mode 1: tf.train.AdamOptimizer: g clipped to [-clip_value, clip_value], bias-corrected step size `lr`
+//         (caller passes lr_t = lr*sqrt(1-b2^t)/(1-b1^t)), p -= lr_t * m / (sqrt(v) + eps).
+__global__ void __launch_bounds__(256)
+adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 size_t n, float lr, float b1, float b2, float eps, float wd, int mode, float clip,
+                 const float* __restrict__ gnorm_sq, float grad_scale) {
+  float gs = grad_scale;
+  if (mode == 0 && gnorm_sq != nullptr && clip > 0.f) {
+    const float gn = sqrtf(*gnorm_sq) * grad_scale;
+    gs *= clip / fmaxf(gn, clip);
+  }
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float gi = g[i] * gs;
+    if (mode == 1 && clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float upd = mi / (sqrtf(vi) + eps);
+    if (mode == 0) upd += wd * p[i];
+    p[i] -= lr * upd;
+  }
+}
+
+int flat_grid(size_t n) {
+  size_t g = (n + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+extern "C" int ner_transpose_cast_bf16(const float* src, void* dst_bf16, int M, int N, int Mp, int ld_src,
+                                       ner_stream_t stream) {
+  if (M < 1 || N < 1 || Mp < M || ld_src < N || !src || !dst_bf16) return NER_ERR_INVALID_ARG;
+  dim3 grid((N + 31) / 32, (Mp + 31) / 32);
+  transpose_cast_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst_bf16), M, N, Mp, ld_src);
+  return ner_launch_status();
+}
+
+extern "C" int ner_colsum_add(const float* x, float* out, int M, int N, int ld, float scale, ner_stream_t stream) {
+  if (M < 0 || N < 1 || ld < N || !x || !out) return NER_ERR_INVALID_ARG;
+  if (M == 0) return NER_OK;
+  dim3 grid((N + 31) / 32, M >= 4096 ? 32 : (M >= 256 ? 8 : 1));
+  colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, M, N, ld, scale);
+  return ner_launch_status();
+}
+
+extern "C" int ner_dense_small_n_bwd(const float* x, const float* W, const float* dy, float* dW, float* db, float* dx,
+                                     int M, int F, int N, ner_stream_t stream) {
+  if (M < 0 || F < 1 || N < 1) return NER_ERR_INVALID_ARG;
+  if (M == 0) return NER_OK;
+  if (!x || !W || !dy || !dW) return NER_ERR_INVALID_ARG;
+  if (N > 32 || (size_t)2 * F * N * 4 > 200 * 1024) return NER_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)2 * F * N * 4;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long g = ((long)M + 63) / 64;
+  if (g > 148 * 2) g = 148 * 2;
+  cudaError_t e;
+  if (N <= 16) {
+    auto kern = dense_small_n_bwd_kernel<16>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
+    kern<<<(int)g, 256, smem, st>>>(x, W, dy, dW, db, dx, M, F, N);
+  } else {
+    auto kern = dense_small_n_bwd_kernel<32>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
+    kern<<<(int)g, 256, smem, st>>>(x, W, dy, dW, db, dx, M, F, N);
+  }
+  return ner_launch_status();
+}
+
+extern "C" int ner_dropout(const float* x, float* y, size_t n, float keep_prob, uint64_t seed, ner_stream_t stream) {
+  if (!x || !y) return n == 0 ? NER_OK : NER_ERR_INVALID_ARG;
+  if (!(keep_prob > 0.f) || keep_prob > 1.f) return NER_ERR_INVALID_ARG;
+  if (n == 0) return NER_OK;
+  dropout_kernel<<<flat_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n, keep_prob, (uint32_t)seed,
+                                                                             (uint32_t)(seed >> 32));
+  return ner_launch_status();
+}
+
+extern "C" int ner_sumsq_add(const float* g, size_t n, float* out, ner_stream_t stream) {
+  if (!g || !out) return n == 0 ? NER_OK : NER_ERR_INVALID_ARG;
+  if (n == 0) return NER_OK;
+  sumsq_kernel<<<flat_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, n, out);
+  return ner_launch_status();
+}
+
+extern "C" int ner_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, int mode, float clip,
+                             const float* gnorm_sq, float grad_scale, ner_stream_t stream) {
+  if (!p || !g || !m || !v) return n == 0 ? NER_OK : NER_ERR_INVALID_ARG;
+  if (mode != 0 && mode != 1) return NER_ERR_INVALID_ARG;
+  if (n == 0) return NER_OK;
+  adam_step_kernel<<<flat_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps,
+                                                                               weight_decay, mode, clip, gnorm_sq,
+                                                                               grad_scale);
+  return ner_launch_status();
+}

@@ -219,11 +219,23 @@ int ner_bert_encoder_fwd(const ner_bert_config* cfg, const float* word_emb, cons
  * + [bias_fw | bias_bw] (one ner_gemm_bf16 call, NER_EPI_F32); wh_fw / wh_bw = kernel[D:, :]
  * [H,4H] f32 with TF's gate order (i, j, f, o).  out [B,L,2H] f32 = concat(fw, bw), zero for
  * t >= seq_len.  activation: 0 tanh, 1 relu (params['rnn_activation']).  H % 4 == 0.
- * cu_seqlens: NULL (xproj row of (b,t) = b*L+t) or [B+1] (packed xproj: row = cu[b]+t). */
+ * cu_seqlens: NULL (xproj row of (b,t) = b*L+t) or [B+1] (packed xproj: row = cu[b]+t).
+ * gates_out [B*L, 8H] / cstate_out [B,L,2H]: both NULL (inference) or both given (training):
+ * post-activation gates (sigmoid(i), act(j), sigmoid(f+forget_bias), sigmoid(o)) and cell states. */
 int ner_bilstm_recurrence(const float* xproj, const float* wh_fw, const float* wh_bw,
                           const int32_t* seq_len, float* out, int B, int L, int H,
                           int activation, float forget_bias, const int32_t* cu_seqlens,
-                          ner_stream_t stream);
+                          float* gates_out, float* cstate_out, ner_stream_t stream);
+
+/* Back-propagation through time of ner_bilstm_recurrence (padded layout).  d_out [B,L,2H] f32;
+ * gates [B*L, 8H] / cstate [B,L,2H] saved by the forward call.  Writes d_xproj [B*L, 8H] f32 =
+ * gradient w.r.t. the hoisted input projection (zeros for t >= seq_len).  The caller finishes
+ * with plain GEMMs / reductions over it: dW_x = x^T d_xproj, d_bias = colsum(d_xproj),
+ * dx = d_xproj W_x^T, dW_h = h_prev^T d_xproj (per direction). */
+int ner_bilstm_recurrence_bwd(const float* d_out, const float* gates, const float* cstate,
+                              const float* wh_fw, const float* wh_bw, const int32_t* seq_len,
+                              float* d_xproj, int B, int L, int H, int activation,
+                              ner_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
  * SoftLexicon gather-and-pool — model/bilstm_crf_softlexicon.py:37-44
@@ -239,6 +251,39 @@ int ner_softlexicon_pool_fwd(const float* table, const int32_t* ids, const float
 int ner_softlexicon_pool_bwd(float* d_table, const int32_t* ids, const float* weights,
                              const float* d_out, int n_tok, int G, int S, int E, int V,
                              ner_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * Training-side kernels — gradients of the layers above and the two optimizer steps of
+ * tools/train_utils.py:246-390
+ * ------------------------------------------------------------------------ */
+
+/* src f32 [M,N] (row stride ld_src) -> bf16 [N,Mp] zero-padded: K-major operand of a
+ * weight-gradient GEMM dW[K,N] = X^T dY (the reduction runs over the M rows). */
+int ner_transpose_cast_bf16(const float* src, void* dst_bf16, int M, int N, int Mp, int ld_src,
+                            ner_stream_t stream);
+/* out[n] += scale * sum_m x[m,n]  (bias gradients). */
+int ner_colsum_add(const float* x, float* out, int M, int N, int ld, float scale,
+                   ner_stream_t stream);
+/* Gradient of ner_dense_small_n (f32 x): dW [F,N] += x^T dy, db [N] += colsum(dy) (db may be
+ * NULL), dx [M,F] = dy W^T (dx may be NULL).  dW/db are accumulated into (caller zeroes). */
+int ner_dense_small_n_bwd(const float* x, const float* W, const float* dy, float* dW, float* db,
+                          float* dx, int M, int F, int N, ner_stream_t stream);
+/* tf.layers.dropout: y[i] = keep(seed, i) ? x[i]/keep_prob : 0.  Counter-based: the same
+ * (seed, i) reproduces the mask, so the backward pass is the same call on the gradient. */
+int ner_dropout(const float* x, float* y, size_t n, float keep_prob, uint64_t seed,
+                ner_stream_t stream);
+/* out[0] += sum(g^2)  (tf.clip_by_global_norm, tools/train_utils.py:315). */
+int ner_sumsq_add(const float* g, size_t n, float* out, ner_stream_t stream);
+/* One optimizer step over a flat parameter buffer.
+ * mode 0 = AdamWeightDecayOptimizer (bert optimization.py; tools/train_utils.py:276-282):
+ *   g *= grad_scale * clip / max(sqrt(*gnorm_sq) * grad_scale, clip)  (gnorm_sq NULL / clip 0: no clip);
+ *   m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr * (m / (sqrt(v) + eps) + weight_decay * p).
+ * mode 1 = tf.train.AdamOptimizer (tools/train_utils.py:340-350,365-390): g clipped to
+ *   [-clip, clip] (clip 0: none), p -= lr * m / (sqrt(v) + eps) with lr the bias-corrected step
+ *   lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) computed by the caller. */
+int ner_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int mode, float clip,
+                  const float* gnorm_sq, float grad_scale, ner_stream_t stream);
 
 #ifdef __cplusplus
 }
