@@ -6,8 +6,10 @@
 // transition matrix spans < 30 nats): the K*K logsumexp of one step is evaluated in the
 // scaled-probability domain,
 //     m = max_i alpha[i];  p[i] = 2^((alpha[i]-m)*log2e);
-//     alpha'[j] = x[j] + m + cmax[j] + ln2*lg2( sum_i p[i] * E[i][j] ),  E = exp(trans - cmax[j])
-// i.e. K ex2 + K lg2 + K*K FFMA per step instead of K*K exp.  The exact path (flags bit0, or
+//     alpha'[j] = x[j] + (m + tmax) + ln2*lg2( sum_i p[i] * E[i][j] ),  E = exp(trans - tmax)
+// (tmax = max of the whole transition matrix), i.e. K ex2 + K lg2 + K*K FFMA per step instead of
+// K*K exp.  Chunks that lie completely inside a sequence (the common case) run a branch-free
+// unrolled body; only the first and the ragged last chunk take the checked path.  The exact path (flags bit0, or
 // chosen automatically for wide/inf transition matrices) evaluates every logsumexp with its
 // own max, exactly as the reference's reduce_logsumexp does.
 #include "crf_common.cuh"
@@ -89,6 +91,7 @@ crf_loglik_fwd_kernel(const float* __restrict__ logits, const int32_t* __restric
   }
   __syncthreads();
   bool fast = !force_exact;
+  float tmax = 0.f;
   {
     float lo = INFINITY, hi = -INFINITY;
     for (int e = 0; e < K * K; ++e) {
@@ -97,11 +100,9 @@ crf_loglik_fwd_kernel(const float* __restrict__ logits, const int32_t* __restric
       hi = fmaxf(hi, v);
     }
     if (!(hi - lo < 30.f) || !(fabsf(hi) < 1e30f) || !(fabsf(lo) < 1e30f)) fast = false;  // also NaN/inf
+    tmax = fast ? hi : 0.f;
   }
-  for (int e = tid; e < K * K; e += NT) {
-    const int j = e % K;
-    s_E[e] = fast ? expf(s_tr[e] - s_cmax[j]) : 0.f;
-  }
+  for (int e = tid; e < K * K; e += NT) s_E[e] = fast ? expf(s_tr[e] - tmax) : 0.f;
   __syncthreads();
 
   const float* gbase = logits + (size_t)row0 * LK;
@@ -118,17 +119,32 @@ crf_loglik_fwd_kernel(const float* __restrict__ logits, const int32_t* __restric
   }
 
   float E[E_REGS ? K * K : 1];
-  float cmx[K];
   if (E_REGS) {
 #pragma unroll
     for (int e = 0; e < K * K; ++e) E[e] = s_E[e];
   }
-#pragma unroll UNR
-  for (int j = 0; j < K; ++j) cmx[j] = s_cmax[j];
-
   float a[K];
 #pragma unroll UNR
   for (int j = 0; j < K; ++j) a[j] = 0.f;
+  // one forward-alpha step in the scaled-probability domain (no length checks)
+  auto fast_step = [&](const float* x) {
+    float m = a[0];
+#pragma unroll UNR
+    for (int i = 1; i < K; ++i) m = fmaxf(m, a[i]);
+    const float nm2 = -m * kLog2e;
+    float p[K];
+#pragma unroll UNR
+    for (int i = 0; i < K; ++i) p[i] = fast_ex2(fmaf(a[i], kLog2e, nm2));
+    const float mt = m + tmax;
+#pragma unroll UNR
+    for (int j = 0; j < K; ++j) {
+      float sum = 0.f;
+#pragma unroll UNR
+      for (int i = 0; i < K; ++i) sum = fmaf(p[i], E_REGS ? E[i * K + j] : s_E[i * K + j], sum);
+      a[j] = fmaf(kLn2, fast_lg2(sum), x[j] + mt);
+    }
+  };
+
   float score = 0.f;
   int prev = 0;
   float* aws = (alpha_ws != nullptr && tid < nv) ? alpha_ws + (size_t)(row0 + tid) * LK : nullptr;
@@ -158,6 +174,26 @@ crf_loglik_fwd_kernel(const float* __restrict__ logits, const int32_t* __restric
           tg[4 * q + 3] = v.w;
         }
       }
+      if (fast && t0 > 0 && t0 + T <= mylen) {
+        // ---- whole chunk inside the sequence: branch-free body
+#pragma unroll
+        for (int g = 0; g < T / G; ++g) {
+          float xs[G * K];
+          load_group<K>(xs, rowp, g);
+#pragma unroll
+          for (int gg = 0; gg < G; ++gg) {
+            const int tt = g * G + gg;
+            const int tag = min(max(tg[tt], 0), K - 1);
+            score += rowp[tt * K + tag] + s_tr[prev * K + tag];
+            prev = tag;
+            fast_step(xs + gg * K);
+            if (aws != nullptr) {
+#pragma unroll UNR
+              for (int j = 0; j < K; ++j) aws[(size_t)(t0 + tt) * K + j] = a[j];
+            }
+          }
+        }
+      } else
 #pragma unroll
       for (int g = 0; g < T / G; ++g) {
         if (t0 + g * G < mylen) {
@@ -178,19 +214,7 @@ crf_loglik_fwd_kernel(const float* __restrict__ logits, const int32_t* __restric
 #pragma unroll UNR
                 for (int j = 0; j < K; ++j) a[j] = xs[gg * K + j];
               } else if (fast) {
-                float m = a[0];
-#pragma unroll UNR
-                for (int i = 1; i < K; ++i) m = fmaxf(m, a[i]);
-                float p[K];
-#pragma unroll UNR
-                for (int i = 0; i < K; ++i) p[i] = fast_ex2((a[i] - m) * kLog2e);
-#pragma unroll UNR
-                for (int j = 0; j < K; ++j) {
-                  float sum = 0.f;
-#pragma unroll UNR
-                  for (int i = 0; i < K; ++i) sum = fmaf(p[i], E_REGS ? E[i * K + j] : s_E[i * K + j], sum);
-                  a[j] = xs[gg * K + j] + (m + cmx[j]) + kLn2 * fast_lg2(sum);
-                }
+                fast_step(xs + gg * K);
               } else {
                 float na[K];
 #pragma unroll UNR

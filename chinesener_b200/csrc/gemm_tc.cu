@@ -40,7 +40,7 @@ constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 1
 
 template <int BN>
 struct Cfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192) ? 4 : ((BN == 128) ? 6 : 8);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int TMEM_COLS = tmem_cols_for(2 * BN);
@@ -608,9 +608,27 @@ extern "C" int ner_gemm_bf16(const void* A, const void* Wt, const float* bias, c
   EpiArgs ep{bias, residual, out, epilogue};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int bn = tile_n;
-  if (bn == 0) bn = (N % 256 == 0 && ((M + BM - 1) / BM) * (N / 256) >= sm_count()) ? 256 : 128;
+  if (bn == 0) {
+    // Wave-quantisation cost model: time ~ ceil(tiles / SMs) * (relative cost of one 128 x BN tile).
+    // Relative costs measured on B200 (profiles/): the 128-wide tile is smem-bandwidth-bound.
+    const int mt = (M + BM - 1) / BM, sms = sm_count();
+    const int cand[3] = {256, 192, 128};
+    const float cost[3] = {1.00f, 0.80f, 0.64f};
+    float best = 1e30f;
+    bn = 128;
+    for (int i = 0; i < 3; ++i) {
+      if (N % cand[i] != 0) continue;
+      const int tiles = mt * (N / cand[i]);
+      const float t = (float)((tiles + sms - 1) / sms) * cost[i];
+      if (t < best - 1e-6f) {
+        best = t;
+        bn = cand[i];
+      }
+    }
+  }
   switch (bn) {
     case 256: return launch_gemm<256>(A, Wt, ep, M, N, K, st);
+    case 192: return launch_gemm<192>(A, Wt, ep, M, N, K, st);
     case 128: return launch_gemm<128>(A, Wt, ep, M, N, K, st);
     case 64: return launch_gemm<64>(A, Wt, ep, M, N, K, st);
     case NER_TILE_2CTA_256: return launch_gemm2<256>(A, Wt, ep, M, N, K, st);

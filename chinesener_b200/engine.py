@@ -10,7 +10,7 @@ import importlib
 
 import torch
 
-from . import variables
+from . import autodiff, variables
 
 _DEVICE_KEYS = ('token_ids', 'mask', 'segment_ids', 'label_ids', 'seq_len', 'softlexicon_ids', 'softlexicon_weights',
                 'bichar_ids', 'softword_ids', 'ex_softword_ids', 'task_ids')
@@ -54,6 +54,24 @@ class Estimator:
         dev = self.to_device(features)
         _, pred_ids = self.forward_device(dev, False)
         return {'pred_ids': pred_ids.cpu(), 'label_ids': features.get('label_ids'), 'tokens': features.get('tokens')}
+
+    def train_step(self, features):
+        """TRAIN mode of model_fn (reference tools/train_utils.py:151-168): forward with the tape,
+        backward, then the train op the reference picks by model name (:156-164).  -> loss (float)."""
+        from .tools import train_utils
+        dev = features if all(not torch.is_tensor(v) or v.is_cuda for v in features.values()) else self.to_device(features)
+        self.store.dropout_calls = 0
+        with variables.use_store(self.store), autodiff.recording(self.store) as tape:
+            loss, _ = self.build_graph(dev, None, self.params, True)
+            tape.backward()
+            p = self.params
+            if 'bert' in self.model_name:
+                train_utils.bert_train_op(loss, p['lr'], p['num_train_steps'], p['warmup_ratio'], p['diff_lr_times'])
+            elif 'transformer' in self.model_name:
+                raise NotImplementedError("transformer_train_op (Adam + Noam) is not built yet")
+            else:
+                train_utils.custom_train_op(loss, p['lr'], p['step_per_epoch'], p['decay_rate'])
+        return loss
 
     def evaluate(self, features):
         dev = self.to_device(features)

@@ -4,7 +4,7 @@ import torch
 
 from .. import ops
 from ..config import TRAIN_PARAMS as _BASE
-from ..tools.layer import bilstm, crf_decode, crf_layer, dense, _no_training
+from ..tools.layer import bilstm, crf_decode, crf_layer, dense, dropout
 
 
 def _const_table(params, key):
@@ -21,18 +21,20 @@ def build_graph(features, labels, params, is_training):
     """
     Use pretrain character embedding + bilstm + crf
     """
-    _no_training(is_training, "bilstm_crf")
     input_ids = features['token_ids']
     label_ids = features['label_ids']
     seq_len = features['seq_len']
 
     embedding = ops.embedding_lookup(_const_table(params, 'embedding'), input_ids)
+    embedding = dropout(embedding, rate=params['embedding_dropout'], is_training=is_training, seed=1234)
 
     lstm_output = bilstm(embedding, params['cell_type'], params['rnn_activation'],
                          params['hidden_units_list'], params['keep_prob_list'],
                          params['cell_size'], seq_len, params['dtype'], is_training)
 
-    logits = dense(lstm_output, units=params['label_size'], name='logits')
+    lstm_output = dropout(lstm_output, rate=params['embedding_dropout'], is_training=is_training, seed=1234)
+
+    logits = dense(lstm_output, units=params['label_size'], name='logits', is_training=is_training)
 
     trans, log_likelihood = crf_layer(logits, label_ids, seq_len, params['label_size'], is_training)
     pred_ids = crf_decode(logits, trans, seq_len, params['idx2tag'], is_training)

@@ -159,16 +159,34 @@ def bert_attention(qkv, mask, B, L, num_heads, head_dim=64, scale=None, mask_add
 
 
 # --------------------------------------------------------------------------- BiLSTM
-def bilstm_recurrence(xproj, wh_fw, wh_bw, seq_len, B, L, H, activation="tanh", forget_bias=1.0, cu_seqlens=None):
+def bilstm_recurrence(xproj, wh_fw, wh_bw, seq_len, B, L, H, activation="tanh", forget_bias=1.0, cu_seqlens=None,
+                      save_for_backward=False):
+    """-> out [B,L,2H]; with save_for_backward also (gates [B*L,8H], cstate [B,L,2H]) for bilstm_recurrence_bwd."""
     require_cuda(xproj, wh_fw, wh_bw, seq_len, cu_seqlens)
     assert xproj.dtype == torch.float32 and xproj.shape[1] == 8 * H
     assert cu_seqlens is not None or xproj.shape[0] == B * L
     assert wh_fw.shape == (H, 4 * H) and wh_bw.shape == (H, 4 * H)
     act = {"tanh": 0, "relu": 1}[activation]
     out = torch.empty((B, L, 2 * H), dtype=torch.float32, device=xproj.device)
+    gates = cst = None
+    if save_for_backward:
+        assert cu_seqlens is None, "training runs on the padded layout"
+        gates = torch.zeros((B * L, 8 * H), dtype=torch.float32, device=xproj.device)
+        cst = torch.zeros((B, L, 2 * H), dtype=torch.float32, device=xproj.device)
     check(lib().ner_bilstm_recurrence(ptr(xproj), ptr(wh_fw), ptr(wh_bw), ptr(_i32(seq_len)), ptr(out), B, L, H, act,
-                                      forget_bias, ptr(cu_seqlens), stream()))
-    return out
+                                      forget_bias, ptr(cu_seqlens), ptr(gates), ptr(cst), stream()))
+    return (out, gates, cst) if save_for_backward else out
+
+
+def bilstm_recurrence_bwd(d_out, gates, cstate, wh_fw, wh_bw, seq_len, B, L, H, activation="tanh"):
+    """-> d_xproj [B*L, 8H] f32 (gradient of the hoisted input projection)."""
+    require_cuda(d_out, gates, cstate, wh_fw, wh_bw, seq_len)
+    assert d_out.shape == (B, L, 2 * H) and d_out.dtype == torch.float32
+    act = {"tanh": 0, "relu": 1}[activation]
+    d_xproj = torch.empty((B * L, 8 * H), dtype=torch.float32, device=d_out.device)
+    check(lib().ner_bilstm_recurrence_bwd(ptr(d_out), ptr(gates), ptr(cstate), ptr(wh_fw), ptr(wh_bw), ptr(_i32(seq_len)),
+                                          ptr(d_xproj), B, L, H, act, stream()))
+    return d_xproj
 
 
 # --------------------------------------------------------------------------- SoftLexicon
@@ -271,3 +289,75 @@ def attention_f32(q, k, v, seq_len, B, L, num_heads, head_dim, scale=1.0, bias_u
                                   ptr(bias_u), ptr(bias_v), ptr(rel_table), ptr(_i32(seq_len)), scale, ptr(of), ptr(hi), ptr(lo),
                                   B, L, num_heads, head_dim, stream()))
     return of, hi, lo
+
+
+# --------------------------------------------------------------------------- training-side kernels
+def transpose_cast_bf16(x2d, Mp=None):
+    """f32 [M,N] -> bf16 [N,Mp]: K-major operand of a weight-gradient GEMM (reduction over the M rows)."""
+    require_cuda(x2d)
+    assert x2d.dtype == torch.float32 and x2d.dim() == 2 and x2d.stride(1) == 1
+    M, N = x2d.shape
+    Mp = Mp or (M + 7) // 8 * 8
+    out = torch.empty((N, Mp), dtype=torch.bfloat16, device=x2d.device)
+    check(lib().ner_transpose_cast_bf16(ptr(x2d), ptr(out), M, N, Mp, x2d.stride(0), stream()))
+    return out
+
+
+def wgrad_gemm(x2d, dy2d, out=None):
+    """dW [K,N] f32 = x^T [K,M] · dy [M,N] on the tensor cores (bf16 operands, fp32 accumulate)."""
+    M = x2d.shape[0]
+    Mp = (M + 7) // 8 * 8
+    xt = transpose_cast_bf16(x2d, Mp)        # [K, Mp]
+    dyt = transpose_cast_bf16(dy2d, Mp)      # [N, Mp]
+    N = dyt.shape[0]
+    if N % 32 != 0:                          # pad the output columns to the GEMM's 32-column granule
+        Np = (N + 31) // 32 * 32
+        dyt = torch.nn.functional.pad(dyt, (0, 0, 0, Np - N))
+    res = gemm_bf16(xt, dyt.contiguous(), None, epilogue=EPI_F32)
+    res = res[:, :N] if res.shape[1] != N else res
+    if out is not None:
+        out.add_(res)
+        return out
+    return res.contiguous()
+
+
+def colsum_add(x2d, out, scale=1.0):
+    require_cuda(x2d, out)
+    M, N = x2d.shape
+    check(lib().ner_colsum_add(ptr(x2d), ptr(out), M, N, x2d.stride(0), scale, stream()))
+    return out
+
+
+def dense_small_n_bwd(x2d, w, dy, dW, db=None, want_dx=True):
+    require_cuda(x2d, w, dy, dW, db)
+    assert x2d.dtype == torch.float32
+    M, F = x2d.shape
+    N = w.shape[1]
+    dx = torch.empty((M, F), dtype=torch.float32, device=x2d.device) if want_dx else None
+    check(lib().ner_dense_small_n_bwd(ptr(x2d), ptr(w), ptr(dy), ptr(dW), ptr(db), ptr(dx), M, F, N, stream()))
+    return dx
+
+
+def dropout(x, keep_prob, seed):
+    """tf.layers.dropout forward (and backward: same call on the gradient with the same seed)."""
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    y = torch.empty_like(x)
+    check(lib().ner_dropout(ptr(x), ptr(y), x.numel(), float(keep_prob), int(seed) & 0xFFFFFFFFFFFFFFFF, stream()))
+    return y
+
+
+def sumsq_add(g, out):
+    require_cuda(g, out)
+    check(lib().ner_sumsq_add(ptr(g), g.numel(), ptr(out), stream()))
+    return out
+
+
+def adam_step(p, g, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, mode=1, clip=0.0, gnorm_sq=None,
+              grad_scale=1.0):
+    """mode 0: AdamWeightDecayOptimizer (bert), mode 1: tf.train.AdamOptimizer; flat f32 buffers."""
+    require_cuda(p, g, m, v, gnorm_sq)
+    n = p.numel()
+    assert g.numel() == n and m.numel() == n and v.numel() == n
+    check(lib().ner_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), n, lr, beta1, beta2, eps, weight_decay, mode, clip,
+                              ptr(gnorm_sq), grad_scale, stream()))

@@ -6,6 +6,7 @@ import os
 
 import torch
 
+from .. import autodiff
 from .. import bert as _bert
 from .. import ops, variables
 
@@ -44,6 +45,30 @@ def pretrain_bert_embedding(input_ids, input_mask, segment_ids, pretrain_dir, dr
     return emb
 
 
+def dropout(inputs, rate, is_training, seed=1234):
+    """tf.layers.dropout(inputs, rate=rate, seed=seed, training=is_training) — identity in eval mode.
+
+    The mask is a counter-based hash of (seed, global_step, call index, element index): the backward
+    pass regenerates it instead of storing it.  (TF's own RNG stream cannot be reproduced; the
+    reference's seed=1234 only fixes ITS stream.)
+    """
+    if not is_training or rate <= 0.0:
+        return inputs
+    store = variables.default_store()
+    store.dropout_calls += 1
+    s = (int(seed) * 1000003 + store.global_step) * 1009 + store.dropout_calls
+    keep = 1.0 - rate
+    x = inputs.contiguous()
+    y = ops.dropout(x, keep, s)
+    tape = autodiff.current()
+    if tape is not None and tape.needs_grad(inputs):
+        def bwd(g):
+            if g is not None:
+                tape.add_grad(inputs, ops.dropout(g.contiguous(), keep, s))
+        tape.record(y, bwd)
+    return y
+
+
 def _lstm_pack(store, D, H, scope):
     """bf16 [8H, Dp] input-projection pack (fw | bw), fused bias [8H], fp32 recurrent matrices."""
     Dp = (D + 7) // 8 * 8
@@ -61,7 +86,8 @@ def _lstm_pack(store, D, H, scope):
 
 def bilstm(embedding, cell_type, activation, hidden_units_list, keep_prob_list, cell_size, seq_len, dtype, is_training):
     """reference tools/layer.py:27-41 — bidirectional_dynamic_rnn over LSTMCell; -> [B,L,2H] f32."""
-    _no_training(is_training, "bilstm")
+    if is_training:
+        return _bilstm_train(embedding, activation, hidden_units_list, keep_prob_list, cell_size, seq_len)
     if cell_type.lower() != 'lstm':
         raise Exception('Only lstm is built on the sm_100a path (reference models all use cell_type=lstm)')
     if cell_size != 1:
@@ -88,12 +114,82 @@ def bilstm(embedding, cell_type, activation, hidden_units_list, keep_prob_list, 
                                  cu_seqlens=pack.cu_seqlens if pack is not None else None)
 
 
-def dense(inputs, units, name='logits'):
+def _bilstm_train(embedding, activation, hidden_units_list, keep_prob_list, cell_size, seq_len):
+    """Training-mode bilstm(): same kernels on the padded layout, saves gates / cell states and
+    records the BPTT closure.  DropoutWrapper with keep_prob < 1 (state + output dropout inside the
+    recurrence) is not built yet."""
+    if cell_size != 1:
+        raise Exception('cell_size must be 1')
+    if float(keep_prob_list[0]) != 1.0:
+        raise TrainingPathNotBuilt("bilstm: DropoutWrapper keep_prob < 1 in training (recurrent dropout kernel)")
+    B, L, D = embedding.shape
+    H = hidden_units_list[0]
+    store = variables.default_store()
+    scope = "bilstm_layer/bidirectional_rnn"
+    names = {}
+    for d in ("fw", "bw"):
+        names[d] = (f"{scope}/{d}/multi_rnn_cell/cell_0/lstm_cell/kernel", f"{scope}/{d}/multi_rnn_cell/cell_0/lstm_cell/bias")
+        store.get_variable(names[d][0], (D + H, 4 * H), variables.glorot_uniform)
+        store.get_variable(names[d][1], (4 * H,), variables.zeros)
+    pk = _lstm_pack(store, D, H, scope)
+    x2d = embedding.reshape(B * L, D).contiguous()
+    x16 = ops.cast_pad_bf16(x2d, pk["Dp"])
+    xproj = ops.gemm_bf16(x16, pk["wx"], pk["bias"], epilogue=ops.EPI_F32)
+    out, gates, cst = ops.bilstm_recurrence(xproj, pk["wh_fw"], pk["wh_bw"], seq_len, B, L, H, activation=activation,
+                                            forget_bias=1.0, save_for_backward=True)
+    tape = autodiff.current()
+    if tape is not None:
+        need_dx = tape.needs_grad(embedding)
+
+        def bwd(g):
+            if g is None:
+                return
+            dxp = ops.bilstm_recurrence_bwd(g.contiguous(), gates, cst, pk["wh_fw"], pk["wh_bw"], seq_len, B, L, H,
+                                            activation=activation)
+            dwx = ops.wgrad_gemm(x2d, dxp)                                   # [D, 8H] = x^T d_xproj
+            for di, d in enumerate(("fw", "bw")):
+                gk, gb = store.grad(names[d][0]), store.grad(names[d][1])
+                dz = dxp[:, di * 4 * H:(di + 1) * 4 * H]
+                gk[:D] += dwx[:, di * 4 * H:(di + 1) * 4 * H]
+                ops.colsum_add(dz, gb, 1.0)
+                hprev = torch.zeros((B, L, H), dtype=torch.float32, device=out.device)
+                if di == 0:
+                    hprev[:, 1:] = out[:, :-1, :H]
+                else:
+                    hprev[:, :-1] = out[:, 1:, H:]
+                gk[D:] += ops.wgrad_gemm(hprev.view(B * L, H), dz)            # dW_h = h_prev^T dz
+            if need_dx:
+                wx = torch.cat([store.vars[names[d][0]][:D] for d in ("fw", "bw")], dim=1)   # [D, 8H]: K-major for dx
+                Dn = (D + 31) // 32 * 32
+                wxp = torch.nn.functional.pad(wx, (0, 0, 0, Dn - D)).to(torch.bfloat16).contiguous()
+                dx = ops.gemm_bf16(ops.cast_bf16(dxp), wxp, None, epilogue=ops.EPI_F32)[:, :D]
+                tape.add_grad(embedding, dx.reshape(B, L, D).contiguous())
+        tape.record(out, bwd)
+    return out
+
+
+def dense(inputs, units, name='logits', is_training=False):
     """tf.layers.dense(inputs, units, activation=None, use_bias=True, name=name) for units <= 32."""
     F = inputs.shape[-1]
     lead = inputs.shape[:-1]
     w = variables.get_variable(f"{name}/kernel", (F, units), variables.glorot_uniform)
     b = variables.get_variable(f"{name}/bias", (units,), variables.zeros)
+    tape = autodiff.current()
+    if is_training and tape is not None:
+        store = variables.default_store()
+        x2d = inputs.reshape(-1, F).contiguous()
+        out = ops.dense_small_n(x2d, w, b).view(*lead, units)
+        need_dx = tape.needs_grad(inputs)
+
+        def bwd(g):
+            if g is None:
+                return
+            dx = ops.dense_small_n_bwd(x2d, w, g.reshape(-1, units).contiguous(), store.grad(f"{name}/kernel"),
+                                       store.grad(f"{name}/bias"), want_dx=need_dx)
+            if need_dx:
+                tape.add_grad(inputs, dx.view(*lead, F))
+        tape.record(out, bwd)
+        return out
     x = getattr(inputs, "bf16", None)
     x = inputs if x is None else x
     pack = getattr(inputs, "pack", None)
@@ -111,6 +207,21 @@ def crf_layer(logits, label_ids, seq_len, label_size, is_training):
     trans = variables.get_variable("crf_layer/transitions", (label_size, label_size), variables.xavier)
     if label_ids is None:
         return trans, None
+    tape = autodiff.current()
+    if is_training and tape is not None:
+        store = variables.default_store()
+        lg = logits.contiguous()
+        ll, logz, alpha = ops.crf_loglik_fwd(lg, label_ids, seq_len, trans, want_alpha=True)
+
+        def bwd(g):
+            # g = d loss / d ll  [B]; the plugins use loss = mean(-ll)  ->  g = -1/B
+            B = lg.shape[0]
+            d_ll = g if g is not None else torch.full((B,), -1.0 / B, dtype=torch.float32, device=lg.device)
+            d_logits, d_trans = ops.crf_loglik_bwd(lg, label_ids, seq_len, trans, alpha, logz, d_ll.contiguous(), 1.0)
+            store.grad("crf_layer/transitions").add_(d_trans)
+            tape.add_grad(logits, d_logits)
+        tape.record(ll, bwd)
+        return trans, ll
     ll, _, _ = ops.crf_loglik_fwd(logits, label_ids, seq_len, trans)
     return trans, ll
 

@@ -1,0 +1,137 @@
+# -*-coding:utf-8 -*-
+"""Train ops with the reference's surface (reference tools/train_utils.py:246-390), run as fused
+kernels over ONE flat fp32 buffer per state (params / grads / m / v):
+
+  custom_train_op(loss, init_lr, step_per_epoch, decay_rate)   tf.train.AdamOptimizer + staircase
+        exponential decay + clip_by_value(+-5)                  (reference :340-350, 365-390)
+  bert_train_op(loss, init_lr, num_train_steps, warmup_ratio, diff_lr_times)
+        AdamWeightDecayOptimizer per LR group + clip_by_global_norm(1.0)   (reference :246-337)
+
+Data parallel: gradients live in one contiguous buffer, so a step issues exactly ONE NCCL
+all-reduce; the 1/world scaling is folded into the optimizer kernel.
+"""
+import torch
+
+from .. import ops, variables
+
+
+class FlatState:
+    """Re-homes every trainable variable (and its gradient) as a view of one flat buffer."""
+
+    def __init__(self, store, group_of=None):
+        self.store = store
+        names = store.trainable_names()
+        group_of = group_of or (lambda n: 0)
+        names.sort(key=lambda n: (group_of(n), ))           # stable: groups become contiguous ranges
+        self.names = names
+        self.group_ranges = {}                                # group -> [start, end)
+        total = sum(store.vars[n].numel() for n in names)
+        dev = store.device
+        self.params = torch.empty(total, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.slices = {}
+        off = 0
+        for n in names:
+            t = store.vars[n]
+            k = t.numel()
+            self.params[off:off + k].copy_(t.reshape(-1))
+            store.vars[n] = self.params[off:off + k].view(t.shape)
+            g_old = store.grads.get(n)
+            store.grads[n] = self.grads[off:off + k].view(t.shape)
+            if g_old is not None:
+                store.grads[n].copy_(g_old)
+            self.slices[n] = (off, off + k)
+            g = group_of(n)
+            s, e = self.group_ranges.get(g, (off, off))
+            self.group_ranges[g] = (min(s, off), off + k)
+            off += k
+        store.touch()
+
+    def zero_grads(self):
+        self.grads.zero_()
+
+
+def _flat(store, group_of=None):
+    fs = getattr(store, "_flat_state", None)
+    if fs is None or set(fs.names) != set(store.trainable_names()):
+        fs = FlatState(store, group_of)
+        store._flat_state = fs
+    return fs
+
+
+def allreduce_gradients(flat_grads):
+    """The single data-parallel exchange of a step: sum of the flat gradient buffer over ranks."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
+        return dist.get_world_size()
+    return 1
+
+
+def lr_decay(init_lr, global_step, step_per_epoch, decay_rate):
+    """tf.train.exponential_decay(..., staircase=True) (reference :365-376)."""
+    return init_lr * decay_rate ** (global_step // max(int(step_per_epoch), 1))
+
+
+def custom_train_op(loss, init_lr, step_per_epoch, decay_rate, store=None):
+    """Adam + exponential LR decay + clip_by_value(-5, 5) (reference :340-350, 378-390)."""
+    store = store or variables.default_store()
+    fs = _flat(store)
+    world = allreduce_gradients(fs.grads)
+    t = store.global_step + 1
+    lr = lr_decay(init_lr, store.global_step, step_per_epoch, decay_rate)
+    b1, b2 = 0.9, 0.999
+    lr_t = lr * (1 - b2 ** t) ** 0.5 / (1 - b1 ** t)
+    ops.adam_step(fs.params, fs.grads, fs.m, fs.v, lr=lr_t, beta1=b1, beta2=b2, eps=1e-8, mode=1, clip=5.0,
+                  grad_scale=1.0 / world)
+    store.global_step += 1
+    store.touch()
+    fs.zero_grads()
+    return lr
+
+
+def bert_lr(init_lr, global_step, num_train_steps, num_warmup_steps):
+    """create_optimizer's schedule (reference :252-274): linear warm-up, then linear decay to 0."""
+    lr = init_lr * max(0.0, 1.0 - min(global_step, num_train_steps) / float(num_train_steps))
+    if num_warmup_steps and global_step < num_warmup_steps:
+        lr = init_lr * global_step / float(num_warmup_steps)
+    return lr
+
+
+def bert_train_op(loss, init_lr, num_train_steps, warmup_ratio, diff_lr_times, verbose=False, store=None):
+    """AdamWeightDecayOptimizer with per-scope LR multipliers + clip_by_global_norm(1.0) (reference :287-337).
+
+    Groups are matched by substring of the variable name exactly like the reference (:300-303);
+    weight decay skips names containing LayerNorm / layer_norm / bias (:276-282)."""
+    store = store or variables.default_store()
+    keys = list((diff_lr_times or {}).keys())
+
+    def group_of(name):
+        for gi, k in enumerate(keys):
+            if k in name:
+                return (gi, 0 if _decays(name) else 1)
+        return (len(keys), 0 if _decays(name) else 1)
+
+    fs = _flat(store, group_of)
+    world = allreduce_gradients(fs.grads)
+    gsq = torch.zeros(1, dtype=torch.float32, device=fs.grads.device)
+    ops.sumsq_add(fs.grads, gsq)
+    num_warmup = int(num_train_steps * warmup_ratio)
+    lrs = {}
+    for g, (s, e) in fs.group_ranges.items():
+        gi, nodecay = g
+        mult = diff_lr_times[keys[gi]] if gi < len(keys) else 1
+        lr = bert_lr(init_lr * mult, store.global_step, num_train_steps, num_warmup)
+        lrs[g] = lr
+        ops.adam_step(fs.params[s:e], fs.grads[s:e], fs.m[s:e], fs.v[s:e], lr=lr, beta1=0.9, beta2=0.999, eps=1e-6,
+                      weight_decay=0.0 if nodecay else 0.01, mode=0, clip=1.0, gnorm_sq=gsq, grad_scale=1.0 / world)
+    store.global_step += 1
+    store.touch()
+    fs.zero_grads()
+    return lrs
+
+
+def _decays(name):
+    return not any(tok in name for tok in ("LayerNorm", "layer_norm", "bias"))

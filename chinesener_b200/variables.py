@@ -55,6 +55,9 @@ class VariableStore:
         self.gen = torch.Generator().manual_seed(seed)
         self.version = 0          # bumped whenever values change (invalidates packed-weight caches)
         self.caches = {}          # per-layer derived tensors (bf16 packs), keyed by the owning layer
+        self.grads = {}           # name -> gradient tensor (views of the optimizer's flat buffer once built)
+        self.global_step = 0
+        self.dropout_calls = 0    # per-step counter that decorrelates the dropout layers' seeds
 
     def get_variable(self, name, shape, initializer, trainable=True):
         v = self.vars.get(name)
@@ -84,6 +87,17 @@ class VariableStore:
 
     def touch(self):
         self.version += 1
+
+    def grad(self, name):
+        """Gradient accumulator of variable `name` (created zero on first use)."""
+        g = self.grads.get(name)
+        if g is None:
+            g = torch.zeros_like(self.vars[name])
+            self.grads[name] = g
+        return g
+
+    def trainable_names(self):
+        return [n for n in self.vars if self.trainable.get(n, True)]
 
     def cached(self, key, builder):
         ent = self.caches.get(key)

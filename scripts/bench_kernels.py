@@ -48,13 +48,14 @@ def bench_crf(B=262144, L=128, K=10):
 
 def bench_gemm():
     out = {}
-    for (M, N, K) in [(8192, 2304, 768), (8192, 768, 768), (8192, 3072, 768), (8192, 768, 3072), (8192, 1024, 768)]:
+    for (M, N, K) in [(8192, 2304, 768), (8192, 768, 768), (8192, 3072, 768), (8192, 768, 3072), (3150, 2304, 768),
+                      (3150, 768, 768), (3150, 3072, 768), (3150, 768, 3072), (3150, 1024, 768)]:
         a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
         w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
         bias = torch.randn(N, device="cuda")
         res = torch.randn(M, N, device="cuda")
-        for tn in (128, 256, ops.TILE_2CTA_128, ops.TILE_2CTA_256):
-            for epi, nm in ((ops.EPI_BF16, "bf16"), (ops.EPI_DIAG_DISCARD, "discard"), (ops.EPI_RES_F32, "resf32")):
+        for tn in (0, 128, 192, 256, ops.TILE_2CTA_256):
+            for epi, nm in ((ops.EPI_BF16, "bf16"), (ops.EPI_F32, "f32")):
                 o = torch.empty(M, N, device="cuda", dtype=torch.float32 if epi == ops.EPI_RES_F32 else torch.bfloat16)
                 med, best = timeit(lambda: ops.gemm_bf16(a, w, bias, residual=res if epi == ops.EPI_RES_F32 else None,
                                                          epilogue=epi, tile_n=tn, out=o), iters=20)

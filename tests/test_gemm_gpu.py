@@ -25,7 +25,7 @@ def _ref(a, wt, bias, residual, epi):
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 256, 128), (256, 128, 768), (8192, 768, 768),
                                    (8192, 2304, 768), (1000, 768, 3072), (77, 96, 200), (4096, 3072, 768),
                                    (300, 1024, 768)])
-@pytest.mark.parametrize("tile_n", [128, 256, ops.TILE_2CTA_128, ops.TILE_2CTA_256])
+@pytest.mark.parametrize("tile_n", [128, 192, 256, ops.TILE_2CTA_128, ops.TILE_2CTA_256])
 @pytest.mark.timeout(120)
 def test_gemm_matches_fp32_reference(M, N, K, tile_n):
     g = torch.Generator().manual_seed(M + N + K)
