@@ -1,0 +1,289 @@
+// Backward-pass HBM-bound kernels of the encoder (sm_100a): LayerNorm backward (with the residual
+// recomputed from the saved operands), bf16 transposes for the weight-gradient GEMMs, bias
+// gradients of bf16 tensors, GELU backward, and the embedding scatter-add.  Together with the
+// tcgen05 GEMM (gemm_tc.cu) and attention_bwd.cu they are the gradient that tf.gradients produces
+// for bert_base.bert.modeling.BertModel in the reference (tools/train_utils.py:314).
+#include "common.cuh"
+
+namespace {
+
+using namespace nerdev;
+
+constexpr int LN_MAXV = 8;
+
+__device__ __forceinline__ float4 ld_bf16x4(const __nv_bfloat16* p) {
+  const uint2 pk = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&pk.x);
+  const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&pk.y);
+  return make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+}
+__device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
+
+// z = y(bf16|f32) + residual(f32) is recomputed; out = LN(z)*gamma + beta.
+//   dz = rstd * (g*gamma - mean(g*gamma) - zhat * mean(g*gamma*zhat)),  dgamma += g*zhat,  dbeta += g
+// dz is written as f32 (the residual-branch gradient) and as bf16 (A operand of the dgrad GEMM).
+template <bool YBF16>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const void* __restrict__ yv, const float* __restrict__ residual, const float* __restrict__ gamma,
+                     const float* __restrict__ dout, float* __restrict__ dz_f32, __nv_bfloat16* __restrict__ dz_bf16,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int H, float eps) {
+  extern __shared__ float s_acc[];  // [2][H] CTA partials of dgamma / dbeta
+  for (int e = threadIdx.x; e < 2 * H; e += blockDim.x) s_acc[e] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int nv4 = (H / 4 + 31) / 32;
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += gridDim.x * (blockDim.x >> 5)) {
+    float4 z[LN_MAXV], g[LN_MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+      const int e = (lane + 32 * k) * 4;
+      if (k < nv4 && e < H) {
+        if constexpr (YBF16) z[k] = ld_bf16x4(static_cast<const __nv_bfloat16*>(yv) + (size_t)row * H + e);
+        else z[k] = *reinterpret_cast<const float4*>(static_cast<const float*>(yv) + (size_t)row * H + e);
+        if (residual != nullptr) {
+          const float4 r = *reinterpret_cast<const float4*>(residual + (size_t)row * H + e);
+          z[k].x += r.x; z[k].y += r.y; z[k].z += r.z; z[k].w += r.w;
+        }
+        g[k] = *reinterpret_cast<const float4*>(dout + (size_t)row * H + e);
+        s += z[k].x + z[k].y + z[k].z + z[k].w;
+      }
+    }
+    s = warp_sum(s);
+    const float mean = s / (float)H;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+      const int e = (lane + 32 * k) * 4;
+      if (k < nv4 && e < H) {
+        z[k].x -= mean; z[k].y -= mean; z[k].z -= mean; z[k].w -= mean;
+        q += z[k].x * z[k].x + z[k].y * z[k].y + z[k].z * z[k].z + z[k].w * z[k].w;
+      }
+    }
+    q = warp_sum(q);
+    const float rstd = rsqrtf(q / (float)H + eps);
+    float m1 = 0.f, m2 = 0.f;  // sum(g*gamma), sum(g*gamma*zhat)
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+      const int e = (lane + 32 * k) * 4;
+      if (k < nv4 && e < H) {
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + e));
+        // zhat
+        z[k].x *= rstd; z[k].y *= rstd; z[k].z *= rstd; z[k].w *= rstd;
+        atomicAdd(&s_acc[e + 0], g[k].x * z[k].x);
+        atomicAdd(&s_acc[e + 1], g[k].y * z[k].y);
+        atomicAdd(&s_acc[e + 2], g[k].z * z[k].z);
+        atomicAdd(&s_acc[e + 3], g[k].w * z[k].w);
+        atomicAdd(&s_acc[H + e + 0], g[k].x);
+        atomicAdd(&s_acc[H + e + 1], g[k].y);
+        atomicAdd(&s_acc[H + e + 2], g[k].z);
+        atomicAdd(&s_acc[H + e + 3], g[k].w);
+        g[k].x *= gm.x; g[k].y *= gm.y; g[k].z *= gm.z; g[k].w *= gm.w;
+        m1 += g[k].x + g[k].y + g[k].z + g[k].w;
+        m2 += g[k].x * z[k].x + g[k].y * z[k].y + g[k].z * z[k].z + g[k].w * z[k].w;
+      }
+    }
+    m1 = warp_sum(m1) / (float)H;
+    m2 = warp_sum(m2) / (float)H;
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+      const int e = (lane + 32 * k) * 4;
+      if (k < nv4 && e < H) {
+        float4 d;
+        d.x = rstd * (g[k].x - m1 - z[k].x * m2);
+        d.y = rstd * (g[k].y - m1 - z[k].y * m2);
+        d.z = rstd * (g[k].z - m1 - z[k].z * m2);
+        d.w = rstd * (g[k].w - m1 - z[k].w * m2);
+        if (dz_f32 != nullptr) *reinterpret_cast<float4*>(dz_f32 + (size_t)row * H + e) = d;
+        if (dz_bf16 != nullptr) st_bf16x4(dz_bf16 + (size_t)row * H + e, d);
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < H; e += blockDim.x) {
+    atomicAdd(dgamma + e, s_acc[e]);
+    atomicAdd(dbeta + e, s_acc[H + e]);
+  }
+}
+
+// bf16 [M,N] -> bf16 [N,Mp] (zero padded), 64x64 tiles through smem
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int M, int N, int Mp) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+  for (int i = ty; i < 64; i += 4) {
+    const int m = m0 + i, n = n0 + tx;
+    tile[i][tx] = (m < M && n < N) ? src[(size_t)m * N + n] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  for (int i = ty; i < 64; i += 4) {
+    const int n = n0 + i, m = m0 + tx;
+    if (n < N && m < Mp) dst[(size_t)n * Mp + m] = tile[tx][i];
+  }
+}
+
+// out[n] += sum_m x[m,n] for bf16 x (bias gradients of bf16 dense-output gradients)
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int M, int N) {
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ty = threadIdx.x >> 5;
+  __shared__ float part[8][33];
+  float acc = 0.f;
+  if (n < N)
+    for (int m = blockIdx.y * 8 + ty; m < M; m += gridDim.y * 8) acc += __bfloat162float(x[(size_t)m * N + n]);
+  part[ty][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += part[i][threadIdx.x & 31];
+    atomicAdd(out + n, s);
+  }
+}
+
+// d_pre = d_act * gelu'(pre)   (tanh approximation or erf), all bf16
+__global__ void __launch_bounds__(256)
+gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dact,
+                __nv_bfloat16* __restrict__ dpre, size_t n4, int erf_variant) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 x = ld_bf16x4(pre + 4 * i), g = ld_bf16x4(dact + 4 * i);
+    float xs[4] = {x.x, x.y, x.z, x.w}, gs[4] = {g.x, g.y, g.z, g.w}, o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float v = xs[k];
+      float d;
+      if (erf_variant) {
+        d = 0.5f * (1.f + erff(v * 0.7071067811865476f)) + v * 0.3989422804014327f * __expf(-0.5f * v * v);
+      } else {
+        const float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
+        const float t = tanhf(u);
+        d = 0.5f * (1.f + t) + 0.5f * v * (1.f - t * t) * 0.7978845608028654f * (1.f + 3.f * 0.044715f * v * v);
+      }
+      o[k] = gs[k] * d;
+    }
+    st_bf16x4(dpre + 4 * i, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// gelu forward on a bf16 pre-activation (training keeps `pre` for the backward pass)
+__global__ void __launch_bounds__(256)
+gelu_fwd_kernel(const __nv_bfloat16* __restrict__ pre, __nv_bfloat16* __restrict__ act, size_t n4, int erf_variant) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 x = ld_bf16x4(pre + 4 * i);
+    float xs[4] = {x.x, x.y, x.z, x.w}, o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float v = xs[k];
+      if (erf_variant) o[k] = 0.5f * v * (1.f + erff(v * 0.7071067811865476f));
+      else o[k] = 0.5f * v * (1.f + tanhf(0.7978845608028654f * (v + 0.044715f * v * v * v)));
+    }
+    st_bf16x4(act + 4 * i, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// embedding backward: d_word[ids[tok]] += dx[tok], d_type[seg[tok]] += dx[tok], d_pos[tok % L] += dx[tok]
+__global__ void __launch_bounds__(256)
+bert_embed_bwd_kernel(const float* __restrict__ dx, const int32_t* __restrict__ ids, const int32_t* __restrict__ seg,
+                      float* __restrict__ d_word, float* __restrict__ d_type, float* __restrict__ d_pos, int n_tok, int L,
+                      int H, int V, int n_type) {
+  const int lane = threadIdx.x & 31;
+  for (int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tok < n_tok; tok += gridDim.x * (blockDim.x >> 5)) {
+    const int id = min(max(ids[tok], 0), V - 1);
+    const int sg = seg ? min(max(seg[tok], 0), n_type - 1) : 0;
+    const int pos = tok % L;
+    const float* g = dx + (size_t)tok * H;
+    for (int e = lane; e < H; e += 32) {
+      const float v = g[e];
+      atomicAdd(d_word + (size_t)id * H + e, v);
+      atomicAdd(d_type + (size_t)sg * H + e, v);
+      atomicAdd(d_pos + (size_t)pos * H + e, v);
+    }
+  }
+}
+
+int rows_grid(int rows, int per_block) {
+  long g = ((long)rows + per_block - 1) / per_block;
+  if (g > 148L * 8) g = 148L * 8;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+int flat_grid(size_t n) {
+  size_t g = (n + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+extern "C" int ner_layernorm_bwd(const void* y, int y_is_bf16, const float* residual, const float* gamma,
+                                 const float* d_out, float* dz_f32, void* dz_bf16, float* d_gamma, float* d_beta, int M,
+                                 int H, float eps, ner_stream_t stream) {
+  if (M < 0 || H < 4) return NER_ERR_INVALID_ARG;
+  if (M == 0) return NER_OK;
+  if (!y || !gamma || !d_out || !d_gamma || !d_beta || (!dz_f32 && !dz_bf16)) return NER_ERR_INVALID_ARG;
+  if (H % 4 != 0 || H > 128 * LN_MAXV) return NER_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)2 * H * 4;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = rows_grid(M, 64);
+  if (y_is_bf16)
+    layernorm_bwd_kernel<true><<<grid, 256, smem, st>>>(y, residual, gamma, d_out, dz_f32,
+                                                        static_cast<__nv_bfloat16*>(dz_bf16), d_gamma, d_beta, M, H, eps);
+  else
+    layernorm_bwd_kernel<false><<<grid, 256, smem, st>>>(y, residual, gamma, d_out, dz_f32,
+                                                         static_cast<__nv_bfloat16*>(dz_bf16), d_gamma, d_beta, M, H, eps);
+  return ner_launch_status();
+}
+
+extern "C" int ner_transpose_bf16(const void* src_bf16, void* dst_bf16, int M, int N, int Mp, ner_stream_t stream) {
+  if (M < 1 || N < 1 || Mp < M || !src_bf16 || !dst_bf16) return NER_ERR_INVALID_ARG;
+  dim3 grid((N + 63) / 64, (Mp + 63) / 64);
+  transpose_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src_bf16), static_cast<__nv_bfloat16*>(dst_bf16), M, N, Mp);
+  return ner_launch_status();
+}
+
+extern "C" int ner_colsum_bf16_add(const void* x_bf16, float* out, int M, int N, ner_stream_t stream) {
+  if (M < 0 || N < 1 || !x_bf16 || !out) return NER_ERR_INVALID_ARG;
+  if (M == 0) return NER_OK;
+  dim3 grid((N + 31) / 32, M >= 4096 ? 32 : (M >= 256 ? 8 : 1));
+  colsum_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x_bf16), out, M, N);
+  return ner_launch_status();
+}
+
+extern "C" int ner_gelu_bf16(const void* pre_bf16, void* act_bf16, size_t n, int erf_variant, ner_stream_t stream) {
+  if (!pre_bf16 || !act_bf16 || (n % 4) != 0) return n == 0 ? NER_OK : NER_ERR_INVALID_ARG;
+  if (n == 0) return NER_OK;
+  gelu_fwd_kernel<<<flat_grid(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(pre_bf16), static_cast<__nv_bfloat16*>(act_bf16), n / 4, erf_variant);
+  return ner_launch_status();
+}
+
+extern "C" int ner_gelu_bwd_bf16(const void* pre_bf16, const void* dact_bf16, void* dpre_bf16, size_t n, int erf_variant,
+                                 ner_stream_t stream) {
+  if (!pre_bf16 || !dact_bf16 || !dpre_bf16 || (n % 4) != 0) return n == 0 ? NER_OK : NER_ERR_INVALID_ARG;
+  if (n == 0) return NER_OK;
+  gelu_bwd_kernel<<<flat_grid(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(pre_bf16), static_cast<const __nv_bfloat16*>(dact_bf16),
+      static_cast<__nv_bfloat16*>(dpre_bf16), n / 4, erf_variant);
+  return ner_launch_status();
+}
+
+extern "C" int ner_bert_embed_bwd(const float* dx, const int32_t* ids, const int32_t* seg, float* d_word, float* d_type,
+                                  float* d_pos, int B, int L, int H, int vocab, int n_type, ner_stream_t stream) {
+  if (B < 0 || L < 1 || H < 1) return NER_ERR_INVALID_ARG;
+  if (B == 0) return NER_OK;
+  if (!dx || !ids || !d_word || !d_type || !d_pos) return NER_ERR_INVALID_ARG;
+  bert_embed_bwd_kernel<<<rows_grid(B * L, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(dx, ids, seg, d_word, d_type,
+                                                                                          d_pos, B * L, L, H, vocab, n_type);
+  return ner_launch_status();
+}

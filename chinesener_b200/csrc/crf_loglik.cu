@@ -5,10 +5,10 @@
 // One thread per sequence; alpha[K] in registers.  Fast path (default, used when the
 // transition matrix spans < 30 nats): the K*K logsumexp of one step is evaluated in the
 // scaled-probability domain,
-//     m = max_i alpha[i];  p[i] = 2^((alpha[i]-m)*log2e);
-//     alpha'[j] = x[j] + (m + tmax) + ln2*lg2( sum_i p[i] * E[i][j] ),  E = exp(trans - tmax)
-// (tmax = max of the whole transition matrix), i.e. K ex2 + K lg2 + K*K FFMA per step instead of
-// K*K exp.  Chunks that lie completely inside a sequence (the common case) run a branch-free
+//     alpha_t[j] = lacc_t + ln p_t[j],   p_t[j] = (sum_i p_{t-1}[i] * E[i][j]) * exp(x_t[j] - max_j x_t[j]),
+//     E = exp(trans - tmax),  lacc_t = lacc_{t-1} + max_j x_t[j] + tmax,   p renormalised to max 1
+//     every other step (lacc += ln max p)
+// i.e. K*K FFMA + K ex2 per step (+ one rcp / lg2 per two steps) instead of K*K exp and K log.  Chunks that lie completely inside a sequence (the common case) run a branch-free
 // unrolled body; only the first and the ragged last chunk take the checked path.  The exact path (flags bit0, or
 // chosen automatically for wide/inf transition matrices) evaluates every logsumexp with its
 // own max, exactly as the reference's reduce_logsumexp does.
@@ -123,26 +123,52 @@ crf_loglik_fwd_kernel(const float* __restrict__ logits, const int32_t* __restric
 #pragma unroll
     for (int e = 0; e < K * K; ++e) E[e] = s_E[e];
   }
+  // Fast path state: alpha_j = lacc + ln(a[j]) with a[] kept in the PROBABILITY domain and
+  // renormalised (max -> 1) every other step; exact path state: a[j] = alpha_j.
   float a[K];
+  float lacc = 0.f;
 #pragma unroll UNR
   for (int j = 0; j < K; ++j) a[j] = 0.f;
-  // one forward-alpha step in the scaled-probability domain (no length checks)
-  auto fast_step = [&](const float* x) {
-    float m = a[0];
+  // a <- (a · E) * exp(x - max x);  lacc += max x + tmax   [+ renormalisation]
+  // per step: K*K FFMA + K ex2 (+ 1 rcp + 1 lg2 when renormalising) — no per-tag log
+  auto fast_step = [&](const float* x, bool renorm) {
+    float xm = x[0];
 #pragma unroll UNR
-    for (int i = 1; i < K; ++i) m = fmaxf(m, a[i]);
-    const float nm2 = -m * kLog2e;
-    float p[K];
-#pragma unroll UNR
-    for (int i = 0; i < K; ++i) p[i] = fast_ex2(fmaf(a[i], kLog2e, nm2));
-    const float mt = m + tmax;
+    for (int j = 1; j < K; ++j) xm = fmaxf(xm, x[j]);
+    const float nx2 = -xm * kLog2e;
+    float ns[K];
 #pragma unroll UNR
     for (int j = 0; j < K; ++j) {
       float sum = 0.f;
 #pragma unroll UNR
-      for (int i = 0; i < K; ++i) sum = fmaf(p[i], E_REGS ? E[i * K + j] : s_E[i * K + j], sum);
-      a[j] = fmaf(kLn2, fast_lg2(sum), x[j] + mt);
+      for (int i = 0; i < K; ++i) sum = fmaf(a[i], E_REGS ? E[i * K + j] : s_E[i * K + j], sum);
+      ns[j] = sum * fast_ex2(fmaf(x[j], kLog2e, nx2));
     }
+    lacc += xm + tmax;
+    if (renorm) {
+      float m = ns[0];
+#pragma unroll UNR
+      for (int j = 1; j < K; ++j) m = fmaxf(m, ns[j]);
+      const float r = __fdividef(1.f, m);
+#pragma unroll UNR
+      for (int j = 0; j < K; ++j) a[j] = ns[j] * r;
+      lacc = fmaf(kLn2, fast_lg2(m), lacc);
+    } else {
+#pragma unroll UNR
+      for (int j = 0; j < K; ++j) a[j] = ns[j];
+    }
+  };
+  auto fast_init = [&](const float* x) {
+    float xm = x[0];
+#pragma unroll UNR
+    for (int j = 1; j < K; ++j) xm = fmaxf(xm, x[j]);
+#pragma unroll UNR
+    for (int j = 0; j < K; ++j) a[j] = fast_ex2((x[j] - xm) * kLog2e);
+    lacc = xm;
+  };
+  auto store_alpha = [&](float* dst) {
+#pragma unroll UNR
+    for (int j = 0; j < K; ++j) dst[j] = fast ? fmaf(kLn2, fast_lg2(a[j]), lacc) : a[j];
   };
 
   float score = 0.f;
@@ -186,11 +212,8 @@ crf_loglik_fwd_kernel(const float* __restrict__ logits, const int32_t* __restric
             const int tag = min(max(tg[tt], 0), K - 1);
             score += rowp[tt * K + tag] + s_tr[prev * K + tag];
             prev = tag;
-            fast_step(xs + gg * K);
-            if (aws != nullptr) {
-#pragma unroll UNR
-              for (int j = 0; j < K; ++j) aws[(size_t)(t0 + tt) * K + j] = a[j];
-            }
+            fast_step(xs + gg * K, (tt & 1) != 0);
+            if (aws != nullptr) store_alpha(aws + (size_t)(t0 + tt) * K);
           }
         }
       } else
@@ -211,10 +234,14 @@ crf_loglik_fwd_kernel(const float* __restrict__ logits, const int32_t* __restric
               prev = tag;
               // ---- forward-alpha (crf_log_norm)
               if (t == 0) {
+                if (fast) {
+                  fast_init(xs + gg * K);
+                } else {
 #pragma unroll UNR
-                for (int j = 0; j < K; ++j) a[j] = xs[gg * K + j];
+                  for (int j = 0; j < K; ++j) a[j] = xs[gg * K + j];
+                }
               } else if (fast) {
-                fast_step(xs + gg * K);
+                fast_step(xs + gg * K, true);
               } else {
                 float na[K];
 #pragma unroll UNR
@@ -231,10 +258,7 @@ crf_loglik_fwd_kernel(const float* __restrict__ logits, const int32_t* __restric
 #pragma unroll UNR
                 for (int j = 0; j < K; ++j) a[j] = na[j];
               }
-              if (aws != nullptr) {
-#pragma unroll UNR
-                for (int j = 0; j < K; ++j) aws[(size_t)t * K + j] = a[j];
-              }
+              if (aws != nullptr) store_alpha(aws + (size_t)t * K);
             }
           }
         }
@@ -244,14 +268,22 @@ crf_loglik_fwd_kernel(const float* __restrict__ logits, const int32_t* __restric
   }
 
   if (tid < nv) {
-    float m = a[0];
+    float logz;
+    if (fast) {
+      float sum = 0.f;
 #pragma unroll UNR
-    for (int j = 1; j < K; ++j) m = fmaxf(m, a[j]);
-    const float mm = (fabsf(m) <= 3.0e38f) ? m : 0.f;
-    float sum = 0.f;
+      for (int j = 0; j < K; ++j) sum += a[j];
+      logz = lacc + logf(sum);
+    } else {
+      float m = a[0];
 #pragma unroll UNR
-    for (int j = 0; j < K; ++j) sum += expf(a[j] - mm);
-    float logz = logf(sum) + mm;
+      for (int j = 1; j < K; ++j) m = fmaxf(m, a[j]);
+      const float mm = (fabsf(m) <= 3.0e38f) ? m : 0.f;
+      float sum = 0.f;
+#pragma unroll UNR
+      for (int j = 0; j < K; ++j) sum += expf(a[j] - mm);
+      logz = logf(sum) + mm;
+    }
     if (rawlen <= 0) {  // crf_log_norm / crf_sequence_score: zero for empty sequences
       logz = 0.f;
       score = 0.f;

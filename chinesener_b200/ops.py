@@ -292,10 +292,16 @@ def attention_f32(q, k, v, seq_len, B, L, num_heads, head_dim, scale=1.0, bias_u
 
 
 # --------------------------------------------------------------------------- training-side kernels
+def _require_rows(x2d):
+    """CUDA f32 2-D tensor whose rows are contiguous (a column slice of a wider buffer is fine)."""
+    if not x2d.is_cuda:
+        raise _lib.NerB200Error("ner_b200 kernels take CUDA tensors (got a CPU tensor); there is no CPU path")
+    assert x2d.dtype == torch.float32 and x2d.dim() == 2 and x2d.stride(1) == 1
+
+
 def transpose_cast_bf16(x2d, Mp=None):
     """f32 [M,N] -> bf16 [N,Mp]: K-major operand of a weight-gradient GEMM (reduction over the M rows)."""
-    require_cuda(x2d)
-    assert x2d.dtype == torch.float32 and x2d.dim() == 2 and x2d.stride(1) == 1
+    _require_rows(x2d)
     M, N = x2d.shape
     Mp = Mp or (M + 7) // 8 * 8
     out = torch.empty((N, Mp), dtype=torch.bfloat16, device=x2d.device)
@@ -322,7 +328,8 @@ def wgrad_gemm(x2d, dy2d, out=None):
 
 
 def colsum_add(x2d, out, scale=1.0):
-    require_cuda(x2d, out)
+    _require_rows(x2d)
+    require_cuda(out)
     M, N = x2d.shape
     check(lib().ner_colsum_add(ptr(x2d), ptr(out), M, N, x2d.stride(0), scale, stream()))
     return out

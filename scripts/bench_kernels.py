@@ -56,7 +56,7 @@ def bench_gemm():
         res = torch.randn(M, N, device="cuda")
         for tn in (0, 128, 192, 256, ops.TILE_2CTA_256):
             for epi, nm in ((ops.EPI_BF16, "bf16"), (ops.EPI_F32, "f32")):
-                o = torch.empty(M, N, device="cuda", dtype=torch.float32 if epi == ops.EPI_RES_F32 else torch.bfloat16)
+                o = torch.empty(M, N, device="cuda", dtype=torch.float32 if epi in (ops.EPI_RES_F32, ops.EPI_F32) else torch.bfloat16)
                 med, best = timeit(lambda: ops.gemm_bf16(a, w, bias, residual=res if epi == ops.EPI_RES_F32 else None,
                                                          epilogue=epi, tile_n=tn, out=o), iters=20)
                 out[f"{M}x{N}x{K}_t{tn}_{nm}"] = dict(us=round(med * 1e3, 1), TFLOPs=round(2.0 * M * N * K / med / 1e9, 1))
