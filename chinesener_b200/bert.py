@@ -49,9 +49,10 @@ def create_bert_variables(cfg, store, scope="bert"):
         gv(f"{p}/output/dense/bias", (H,), variables.zeros)
         gv(f"{p}/output/LayerNorm/beta", (H,), variables.zeros)
         gv(f"{p}/output/LayerNorm/gamma", (H,), variables.ones)
-    # pooler exists in the checkpoint but is unused by the reference (only sequence_output)
-    gv(f"{scope}/pooler/dense/kernel", (H, H), tn)
-    gv(f"{scope}/pooler/dense/bias", (H,), variables.zeros)
+    # pooler exists in the checkpoint but is unused by the reference (only sequence_output): its
+    # gradients are None there, so apply_gradients never touches it -> not trainable here
+    gv(f"{scope}/pooler/dense/kernel", (H, H), tn, trainable=False)
+    gv(f"{scope}/pooler/dense/bias", (H,), variables.zeros, trainable=False)
 
 
 def _packed(store, cfg, scope):
@@ -172,3 +173,95 @@ def bert_forward(input_ids, input_mask, segment_ids, cfg, store=None, scope="ber
         y = ops.gemm_bf16(inter, w["wd"], w["bd"], epilogue=ops.EPI_BF16)
         x32, x16 = ops.layernorm(y, w["g2"], w["b2"], residual=x32, eps=1e-12)
     return x32, x16
+
+
+# =========================================================================== training
+def _tf_casts(store, cfg, scope):
+    """bf16 casts of the dense kernels in their TF layout [in, out]: the K-major B operand of the
+    data-gradient GEMMs (dX = dY · W^T)."""
+    def build():
+        v = store.vars
+        out = []
+        for l in range(cfg["num_hidden_layers"]):
+            p = f"{scope}/encoder/layer_{l}"
+            wqkv = torch.cat([v[f"{p}/attention/self/{n}/kernel"] for n in ("query", "key", "value")], dim=1).contiguous()
+            out.append(dict(wqkv=ops.cast_bf16(wqkv), wo=ops.cast_bf16(v[f"{p}/attention/output/dense/kernel"]),
+                            wi=ops.cast_bf16(v[f"{p}/intermediate/dense/kernel"]), wd=ops.cast_bf16(v[f"{p}/output/dense/kernel"])))
+        return out
+    return store.cached(("bert_tf_casts", scope), build)
+
+
+def bert_forward_train(input_ids, input_mask, segment_ids, cfg, store, tape, scope="bert", gelu="tanh"):
+    """Training-mode BertModel forward on the padded layout: same kernels, every intermediate the
+    backward pass needs is kept, and the backward closure is recorded on `tape`.
+    Dropout inside BertModel (hidden_dropout_prob / attention_probs_dropout_prob) is NOT applied
+    yet: the gradient path is otherwise complete."""
+    create_bert_variables(cfg, store, scope)
+    B, L = input_ids.shape
+    H, NH, I = cfg["hidden_size"], cfg["num_attention_heads"], cfg["intermediate_size"]
+    v = store.vars
+    layers = _packed(store, cfg, scope)
+    erf = gelu == "erf"
+    ids, seg, mask = ops._i32(input_ids), (None if segment_ids is None else ops._i32(segment_ids)), ops._i32(input_mask)
+    we, te, pe = (v[f"{scope}/embeddings/{n}"] for n in ("word_embeddings", "token_type_embeddings", "position_embeddings"))
+    ge, be = v[f"{scope}/embeddings/LayerNorm/gamma"], v[f"{scope}/embeddings/LayerNorm/beta"]
+    x32, x16 = ops.bert_embed_ln(we, te, pe, ge, be, ids, seg, eps=1e-12)
+    saved = []
+    for w in layers:
+        qkv = ops.gemm_bf16(x16, w["wqkv"], w["bqkv"], epilogue=ops.EPI_BF16)
+        ctx = ops.bert_attention(qkv, mask, B, L, NH, H // NH)
+        y1 = ops.gemm_bf16(ctx, w["wo"], w["bo"], epilogue=ops.EPI_BF16)
+        x1_32, x1_16 = ops.layernorm(y1, w["g1"], w["b1"], residual=x32, eps=1e-12)
+        pre = ops.gemm_bf16(x1_16, w["wi"], w["bi"], epilogue=ops.EPI_BF16)
+        inter = ops.gelu_bf16(pre, erf)
+        y2 = ops.gemm_bf16(inter, w["wd"], w["bd"], epilogue=ops.EPI_BF16)
+        x2_32, x2_16 = ops.layernorm(y2, w["g2"], w["b2"], residual=x1_32, eps=1e-12)
+        saved.append((x32, x16, qkv, ctx, y1, x1_32, x1_16, pre, inter, y2))
+        x32, x16 = x2_32, x2_16
+    out = x32.view(B, L, H)
+    out.bf16 = x16.view(B, L, H)
+
+    def bwd(g):
+        if g is None:
+            return
+        casts = _tf_casts(store, cfg, scope)
+        gr = store.grad
+        d = g.reshape(B * L, H).contiguous()
+        for li in reversed(range(len(layers))):
+            w, c = layers[li], casts[li]
+            x32_, x16_, qkv, ctx, y1, x1_32, x1_16, pre, inter, y2 = saved[li]
+            p = f"{scope}/encoder/layer_{li}"
+            # ---- output LayerNorm + FFN
+            dz2_32, dz2_16 = ops.layernorm_bwd(y2, w["g2"], d, gr(f"{p}/output/LayerNorm/gamma"), gr(f"{p}/output/LayerNorm/beta"),
+                                               residual=x1_32, eps=1e-12)
+            ops.colsum_bf16_add(dz2_16, gr(f"{p}/output/dense/bias"))
+            ops.wgrad_gemm_bf16(inter, dz2_16, gr(f"{p}/output/dense/kernel"))
+            dinter = ops.gemm_bf16(dz2_16, c["wd"], None, epilogue=ops.EPI_BF16)
+            dpre = ops.gelu_bwd_bf16(pre, dinter, erf)
+            ops.colsum_bf16_add(dpre, gr(f"{p}/intermediate/dense/bias"))
+            ops.wgrad_gemm_bf16(x1_16, dpre, gr(f"{p}/intermediate/dense/kernel"))
+            dx1 = ops.gemm_bf16(dpre, c["wi"], None, residual=dz2_32, epilogue=ops.EPI_RES_F32)
+            # ---- attention LayerNorm + output projection
+            dz1_32, dz1_16 = ops.layernorm_bwd(y1, w["g1"], dx1, gr(f"{p}/attention/output/LayerNorm/gamma"),
+                                               gr(f"{p}/attention/output/LayerNorm/beta"), residual=x32_, eps=1e-12)
+            ops.colsum_bf16_add(dz1_16, gr(f"{p}/attention/output/dense/bias"))
+            ops.wgrad_gemm_bf16(ctx, dz1_16, gr(f"{p}/attention/output/dense/kernel"))
+            dctx = ops.gemm_bf16(dz1_16, c["wo"], None, epilogue=ops.EPI_BF16)
+            # ---- attention core + fused QKV projection
+            dqkv = ops.bert_attention_bwd(qkv, mask, ctx, dctx, B, L, NH, H // NH)
+            dbqkv = torch.zeros(3 * H, dtype=torch.float32, device=d.device)
+            ops.colsum_bf16_add(dqkv, dbqkv)
+            dwqkv = ops.wgrad_gemm_bf16(x16_, dqkv)                       # [H, 3H]
+            for k, n in enumerate(("query", "key", "value")):
+                gr(f"{p}/attention/self/{n}/kernel").add_(dwqkv[:, k * H:(k + 1) * H])
+                gr(f"{p}/attention/self/{n}/bias").add_(dbqkv[k * H:(k + 1) * H])
+            d = ops.gemm_bf16(dqkv, c["wqkv"], None, residual=dz1_32, epilogue=ops.EPI_RES_F32)
+        # ---- embeddings: LayerNorm of (word + type + position)
+        segl = torch.zeros_like(ids) if seg is None else seg
+        emb_sum = (we[ids.long()] + te[segl.long()] + pe[:L][None]).reshape(B * L, H).contiguous()
+        dsum, _ = ops.layernorm_bwd(emb_sum, ge, d, gr(f"{scope}/embeddings/LayerNorm/gamma"), gr(f"{scope}/embeddings/LayerNorm/beta"),
+                                    eps=1e-12, want_bf16=False)
+        ops.bert_embed_bwd(dsum, ids, seg, gr(f"{scope}/embeddings/word_embeddings"), gr(f"{scope}/embeddings/token_type_embeddings"),
+                           gr(f"{scope}/embeddings/position_embeddings"))
+    tape.record(out, bwd)
+    return out

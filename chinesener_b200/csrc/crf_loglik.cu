@@ -136,14 +136,18 @@ crf_loglik_fwd_kernel(const float* __restrict__ logits, const int32_t* __restric
 #pragma unroll UNR
     for (int j = 1; j < K; ++j) xm = fmaxf(xm, x[j]);
     const float nx2 = -xm * kLog2e;
+    // i-outer order: K independent accumulators -> K-way ILP in the FFMA block (a j-outer loop is
+    // K dependent FFMAs per tag and leaves the pipe waiting on the 4-cycle accumulate latency)
     float ns[K];
 #pragma unroll UNR
-    for (int j = 0; j < K; ++j) {
-      float sum = 0.f;
+    for (int j = 0; j < K; ++j) ns[j] = a[0] * (E_REGS ? E[j] : s_E[j]);
 #pragma unroll UNR
-      for (int i = 0; i < K; ++i) sum = fmaf(a[i], E_REGS ? E[i * K + j] : s_E[i * K + j], sum);
-      ns[j] = sum * fast_ex2(fmaf(x[j], kLog2e, nx2));
+    for (int i = 1; i < K; ++i) {
+#pragma unroll UNR
+      for (int j = 0; j < K; ++j) ns[j] = fmaf(a[i], E_REGS ? E[i * K + j] : s_E[i * K + j], ns[j]);
     }
+#pragma unroll UNR
+    for (int j = 0; j < K; ++j) ns[j] *= fast_ex2(fmaf(x[j], kLog2e, nx2));
     lacc += xm + tmax;
     if (renorm) {
       float m = ns[0];

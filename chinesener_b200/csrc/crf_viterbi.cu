@@ -105,27 +105,34 @@ crf_viterbi_kernel(const float* __restrict__ logits, const int32_t* __restrict__
 #pragma unroll UNR
               for (int j = 0; j < K; ++j) s[j] = xs[gg * K + j];
             } else {
-              float ns[K];
+              // i-outer order: K independent (best, arg) pairs -> K-way ILP; per (i,j) the fp32 ops and the
+              // strict '>' (first max wins) are exactly those of the reference recursion
+              float best[K];
+              int arg[K];
               uint32_t bpw[W];
 #pragma unroll
               for (int w = 0; w < W; ++w) bpw[w] = 0u;
 #pragma unroll UNR
               for (int j = 0; j < K; ++j) {
-                float best = s[0] + (TR_REGS ? tr[j * K] : s_trT[j * K]);
-                int arg = 0;
-#pragma unroll UNR
-                for (int i = 1; i < K; ++i) {
-                  const float v = s[i] + (TR_REGS ? tr[j * K + i] : s_trT[j * K + i]);
-                  if (v > best) {
-                    best = v;
-                    arg = i;
-                  }
-                }
-                ns[j] = xs[gg * K + j] + best;
-                bpw[j / Bp::PER] |= (uint32_t)arg << ((j % Bp::PER) * Bp::NIB);
+                best[j] = s[0] + (TR_REGS ? tr[j * K] : s_trT[j * K]);
+                arg[j] = 0;
               }
 #pragma unroll UNR
-              for (int j = 0; j < K; ++j) s[j] = ns[j];
+              for (int i = 1; i < K; ++i) {
+#pragma unroll UNR
+                for (int j = 0; j < K; ++j) {
+                  const float v = s[i] + (TR_REGS ? tr[j * K + i] : s_trT[j * K + i]);
+                  if (v > best[j]) {
+                    best[j] = v;
+                    arg[j] = i;
+                  }
+                }
+              }
+#pragma unroll UNR
+              for (int j = 0; j < K; ++j) {
+                s[j] = xs[gg * K + j] + best[j];
+                bpw[j / Bp::PER] |= (uint32_t)arg[j] << ((j % Bp::PER) * Bp::NIB);
+              }
 #pragma unroll
               for (int w = 0; w < W; ++w) s_bp[(t * W + w) * NTP + tid] = bpw[w];
             }

@@ -21,7 +21,7 @@ def build_graph(features, labels, params, is_training):
                          params['hidden_units_list'], params['keep_prob_list'],
                          params['cell_size'], seq_len, params['dtype'], is_training)
 
-    logits = dense(lstm_output, units=params['label_size'], name='logits')
+    logits = dense(lstm_output, units=params['label_size'], name='logits', is_training=is_training)
 
     trans, log_likelihood = crf_layer(logits, label_ids, seq_len, params['label_size'], is_training)
     pred_ids = crf_decode(logits, trans, seq_len, params['idx2tag'], is_training)

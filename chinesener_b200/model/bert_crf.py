@@ -16,7 +16,7 @@ def build_graph(features, labels, params, is_training):
     embedding = pretrain_bert_embedding(input_ids, input_mask, segment_ids, params['pretrain_dir'],
                                         params['embedding_dropout'], is_training)
 
-    logits = dense(embedding, units=params['label_size'], name='logits')
+    logits = dense(embedding, units=params['label_size'], name='logits', is_training=is_training)
 
     trans, log_likelihood = crf_layer(logits, label_ids, seq_len, params['label_size'], is_training)
     pred_ids = crf_decode(logits, trans, seq_len, params['idx2tag'], is_training)

@@ -368,3 +368,74 @@ def adam_step(p, g, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0
     assert g.numel() == n and m.numel() == n and v.numel() == n
     check(lib().ner_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), n, lr, beta1, beta2, eps, weight_decay, mode, clip,
                               ptr(gnorm_sq), grad_scale, stream()))
+
+
+# --------------------------------------------------------------------------- encoder backward
+def layernorm_bwd(y, gamma, d_out, d_gamma, d_beta, residual=None, eps=1e-12, want_f32=True, want_bf16=True):
+    require_cuda(y, gamma, d_out, d_gamma, d_beta, residual)
+    M, H = y.shape
+    dz32 = torch.empty((M, H), dtype=torch.float32, device=y.device) if want_f32 else None
+    dz16 = torch.empty((M, H), dtype=torch.bfloat16, device=y.device) if want_bf16 else None
+    check(lib().ner_layernorm_bwd(ptr(y), 1 if y.dtype == torch.bfloat16 else 0, ptr(residual), ptr(gamma), ptr(d_out),
+                                  ptr(dz32), ptr(dz16), ptr(d_gamma), ptr(d_beta), M, H, eps, stream()))
+    return dz32, dz16
+
+
+def transpose_bf16(x, Mp=None):
+    require_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2
+    M, N = x.shape
+    Mp = Mp or (M + 7) // 8 * 8
+    out = torch.empty((N, Mp), dtype=torch.bfloat16, device=x.device)
+    check(lib().ner_transpose_bf16(ptr(x), ptr(out), M, N, Mp, stream()))
+    return out
+
+
+def wgrad_gemm_bf16(x16, dy16, out_f32=None):
+    """dW [K,N] f32 (+)= x^T · dy for bf16 activations x [M,K], dy [M,N] (tensor cores, fp32 accumulate)."""
+    M = x16.shape[0]
+    Mp = (M + 7) // 8 * 8
+    xt, dyt = transpose_bf16(x16, Mp), transpose_bf16(dy16, Mp)
+    if out_f32 is None:
+        return gemm_bf16(xt, dyt, None, epilogue=EPI_F32)
+    return gemm_bf16(xt, dyt, None, residual=out_f32, epilogue=EPI_RES_F32, out=out_f32)
+
+
+def colsum_bf16_add(x16, out):
+    require_cuda(x16, out)
+    M, N = x16.shape
+    check(lib().ner_colsum_bf16_add(ptr(x16), ptr(out), M, N, stream()))
+    return out
+
+
+def gelu_bf16(pre, erf=False):
+    require_cuda(pre)
+    out = torch.empty_like(pre)
+    check(lib().ner_gelu_bf16(ptr(pre), ptr(out), pre.numel(), 1 if erf else 0, stream()))
+    return out
+
+
+def gelu_bwd_bf16(pre, dact, erf=False):
+    require_cuda(pre, dact)
+    out = torch.empty_like(pre)
+    check(lib().ner_gelu_bwd_bf16(ptr(pre), ptr(dact), ptr(out), pre.numel(), 1 if erf else 0, stream()))
+    return out
+
+
+def bert_embed_bwd(dx, ids, seg, d_word, d_type, d_pos):
+    require_cuda(dx, ids, seg, d_word, d_type, d_pos)
+    B, L = ids.shape
+    H = dx.shape[-1]
+    check(lib().ner_bert_embed_bwd(ptr(dx), ptr(_i32(ids)), ptr(None if seg is None else _i32(seg)), ptr(d_word), ptr(d_type),
+                                   ptr(d_pos), B, L, H, d_word.shape[0], d_type.shape[0], stream()))
+
+
+def bert_attention_bwd(qkv, mask, ctx, dctx, B, L, num_heads, head_dim=64, scale=None, mask_add=-10000.0):
+    require_cuda(qkv, mask, ctx, dctx)
+    assert qkv.dtype == torch.bfloat16 and ctx.dtype == torch.bfloat16 and dctx.dtype == torch.bfloat16
+    dqkv = torch.empty_like(qkv)
+    if scale is None:
+        scale = 1.0 / (head_dim ** 0.5)
+    check(lib().ner_bert_attention_bwd(ptr(qkv), ptr(_i32(mask)), ptr(ctx), ptr(dctx), ptr(dqkv), B, L, num_heads, head_dim,
+                                       scale, mask_add, stream()))
+    return dqkv

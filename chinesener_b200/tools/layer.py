@@ -30,9 +30,14 @@ def pretrain_bert_embedding(input_ids, input_mask, segment_ids, pretrain_dir, dr
     Returns sequence_output [B,L,H] f32; its bf16 copy (what the next GEMM consumes) rides along
     as attribute `.bf16`.
     """
-    _no_training(is_training, "pretrain_bert_embedding")
     cfg = _bert.load_bert_config(pretrain_dir)
     B, L = input_ids.shape
+    if is_training:
+        tape = autodiff.current()
+        if tape is None:
+            raise TrainingPathNotBuilt("pretrain_bert_embedding(is_training=True) needs an autodiff tape (engine.train_step)")
+        emb = _bert.bert_forward_train(input_ids, input_mask, segment_ids, cfg, variables.default_store(), tape)
+        return dropout(emb, rate=drop_out, is_training=True, seed=1234)
     if PACK_SEQUENCES:
         pack = _bert.make_pack(input_mask)
         x32, x16 = _bert.bert_forward(input_ids, input_mask, segment_ids, cfg, pack=pack)

@@ -25,9 +25,11 @@ class FlatState:
         names.sort(key=lambda n: (group_of(n), ))           # stable: groups become contiguous ranges
         self.names = names
         self.group_ranges = {}                                # group -> [start, end)
-        total = sum(store.vars[n].numel() for n in names)
+        ALIGN = 64   # floats: every variable starts 256-byte aligned (TMA / 16-byte vector accesses on grads)
+        pad = lambda k: (k + ALIGN - 1) // ALIGN * ALIGN
+        total = sum(pad(store.vars[n].numel()) for n in names)
         dev = store.device
-        self.params = torch.empty(total, dtype=torch.float32, device=dev)
+        self.params = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grads = torch.zeros(total, dtype=torch.float32, device=dev)
         self.m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.v = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -45,8 +47,8 @@ class FlatState:
             self.slices[n] = (off, off + k)
             g = group_of(n)
             s, e = self.group_ranges.get(g, (off, off))
-            self.group_ranges[g] = (min(s, off), off + k)
-            off += k
+            self.group_ranges[g] = (min(s, off), off + pad(k))
+            off += pad(k)
         store.touch()
 
     def zero_grads(self):

@@ -285,6 +285,35 @@ int ner_adam_step(float* p, const float* g, float* m, float* v, size_t n, float 
                   float beta2, float eps, float weight_decay, int mode, float clip,
                   const float* gnorm_sq, float grad_scale, ner_stream_t stream);
 
+/* ---- encoder backward (gradient of BertModel, tools/train_utils.py:314) ---- */
+
+/* Backward of ner_layernorm: z = y (+ residual) is recomputed from the saved operands.
+ * dz = dL/dz written as f32 (residual-branch gradient) and/or bf16 (A operand of the next dgrad
+ * GEMM); d_gamma / d_beta [H] are accumulated into (caller zeroes). */
+int ner_layernorm_bwd(const void* y, int y_is_bf16, const float* residual, const float* gamma,
+                      const float* d_out, float* dz_f32, void* dz_bf16, float* d_gamma,
+                      float* d_beta, int M, int H, float eps, ner_stream_t stream);
+/* bf16 [M,N] -> bf16 [N,Mp] zero padded (K-major operands of weight-gradient GEMMs). */
+int ner_transpose_bf16(const void* src_bf16, void* dst_bf16, int M, int N, int Mp,
+                       ner_stream_t stream);
+/* out[n] += sum_m x[m,n], x bf16 [M,N]  (bias gradients). */
+int ner_colsum_bf16_add(const void* x_bf16, float* out, int M, int N, ner_stream_t stream);
+/* GELU on a saved bf16 pre-activation (training forward) and its backward d_pre = d_act * gelu'(pre).
+ * n % 4 == 0.  erf_variant: 0 tanh approximation, 1 erf. */
+int ner_gelu_bf16(const void* pre_bf16, void* act_bf16, size_t n, int erf_variant, ner_stream_t stream);
+int ner_gelu_bwd_bf16(const void* pre_bf16, const void* dact_bf16, void* dpre_bf16, size_t n,
+                      int erf_variant, ner_stream_t stream);
+/* Embedding backward: scatter-add dx [B*L,H] f32 into d_word [vocab,H], d_type [n_type,H],
+ * d_pos [>=L,H] (all accumulated into). */
+int ner_bert_embed_bwd(const float* dx, const int32_t* ids, const int32_t* seg, float* d_word,
+                       float* d_type, float* d_pos, int B, int L, int H, int vocab, int n_type,
+                       ner_stream_t stream);
+/* Backward of ner_bert_attention (padded layout, head_dim 64): qkv / ctx from the forward pass,
+ * dctx = dL/dctx; writes d_qkv (bf16, layout of qkv).  Scores are recomputed, nothing L x L is stored. */
+int ner_bert_attention_bwd(const void* qkv_bf16, const int32_t* mask, const void* ctx_bf16,
+                           const void* dctx_bf16, void* dqkv_bf16, int B, int L, int num_heads,
+                           int head_dim, float scale, float mask_add, ner_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,101 @@
+"""GPU: encoder backward kernels vs torch autograd (float64) of the same op."""
+import math
+
+import pytest
+import torch
+
+from chinesener_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _ln(z, g, b, eps):
+    m = z.mean(-1, keepdim=True)
+    v = ((z - m) ** 2).mean(-1, keepdim=True)
+    return (z - m) * torch.rsqrt(v + eps) * g + b
+
+
+@pytest.mark.parametrize("M,H,ybf16", [(200, 768, True), (77, 768, False), (33, 160, False)])
+def test_layernorm_backward(M, H, ybf16):
+    g = torch.Generator().manual_seed(M + H)
+    y = torch.randn(M, H, generator=g)
+    if ybf16:
+        y = y.to(torch.bfloat16).float()
+    r = torch.randn(M, H, generator=g)
+    gam = 1 + 0.1 * torch.randn(H, generator=g)
+    bet = 0.1 * torch.randn(H, generator=g)
+    dout = torch.randn(M, H, generator=g)
+    yd, rd, gd, bd = (t.double().requires_grad_(True) for t in (y, r, gam, bet))
+    (_ln(yd + rd, gd, bd, 1e-12) * dout.double()).sum().backward()
+    dgam = torch.zeros(H, device="cuda")
+    dbet = torch.zeros(H, device="cuda")
+    ycu = y.cuda().to(torch.bfloat16) if ybf16 else y.cuda()
+    dz32, dz16 = ops.layernorm_bwd(ycu, gam.cuda(), dout.cuda(), dgam, dbet, residual=r.cuda(), eps=1e-12)
+    torch.testing.assert_close(dz32.cpu().double(), yd.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dz32.cpu().double(), rd.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dz16.float().cpu().double(), yd.grad, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(dgam.cpu().double(), gd.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dbet.cpu().double(), bd.grad, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("erf", [False, True])
+def test_gelu_forward_backward(erf):
+    g = torch.Generator().manual_seed(1)
+    pre = (torch.randn(64, 3072, generator=g) * 2).to(torch.bfloat16)
+    dact = torch.randn(64, 3072, generator=g).to(torch.bfloat16)
+    x = pre.double().requires_grad_(True)
+    act = torch.nn.functional.gelu(x, approximate="none" if erf else "tanh")
+    (act * dact.double()).sum().backward()
+    a = ops.gelu_bf16(pre.cuda(), erf=erf)
+    d = ops.gelu_bwd_bf16(pre.cuda(), dact.cuda(), erf=erf)
+    torch.testing.assert_close(a.float().cpu().double(), act.detach(), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(d.float().cpu().double(), x.grad, rtol=1e-2, atol=1e-2)
+
+
+def test_transpose_colsum_embed_bwd():
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(1000, 200, generator=g).to(torch.bfloat16).cuda()
+    t = ops.transpose_bf16(x)
+    assert t.shape == (200, 1000) and torch.equal(t, x.t().contiguous())
+    cs = torch.zeros(200, device="cuda")
+    ops.colsum_bf16_add(x, cs)
+    torch.testing.assert_close(cs, x.float().sum(0), rtol=1e-4, atol=1e-3)
+    # weight gradient on tensor cores from bf16 activations
+    dy = torch.randn(1000, 96, generator=g).to(torch.bfloat16).cuda()
+    dw = ops.wgrad_gemm_bf16(x, dy)
+    ref = x.double().t() @ dy.double()
+    assert (dw.double() - ref).abs().max() < 1e-3 * ref.abs().max() + 1e-3
+    # embedding scatter-add
+    B, L, H, V = 3, 7, 64, 50
+    ids = torch.randint(0, V, (B, L), generator=g, dtype=torch.int32)
+    seg = torch.randint(0, 2, (B, L), generator=g, dtype=torch.int32)
+    dx = torch.randn(B * L, H, generator=g)
+    dw_, dt_, dp_ = torch.zeros(V, H, device="cuda"), torch.zeros(2, H, device="cuda"), torch.zeros(16, H, device="cuda")
+    ops.bert_embed_bwd(dx.cuda(), ids.cuda(), seg.cuda(), dw_, dt_, dp_)
+    rw = torch.zeros(V, H).index_add_(0, ids.view(-1).long(), dx)
+    rt = torch.zeros(2, H).index_add_(0, seg.view(-1).long(), dx)
+    rp = torch.zeros(16, H).index_add_(0, torch.arange(L).repeat(B), dx)
+    torch.testing.assert_close(dw_.cpu(), rw, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(dt_.cpu(), rt, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(dp_.cpu(), rp, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,L,NH", [(2, 128, 12), (3, 64, 4), (2, 150, 2), (1, 37, 3)])
+def test_attention_backward(B, L, NH):
+    D = 64
+    g = torch.Generator().manual_seed(B * L + NH)
+    qkv = (torch.randn(B * L, 3 * NH * D, generator=g) * 0.7).to(torch.bfloat16)
+    dctx = torch.randn(B * L, NH * D, generator=g).to(torch.bfloat16)
+    lens = torch.randint(1, L + 1, (B,), generator=g)
+    lens[0] = L
+    mask = (torch.arange(L)[None, :] < lens[:, None]).to(torch.int32)
+    x = qkv.double().requires_grad_(True)
+    q, k, v = x.view(B, L, 3, NH, D).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) / math.sqrt(D) + (1.0 - mask.double())[:, None, None, :] * -10000.0
+    ctx_ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, NH * D)
+    (ctx_ref * dctx.double()).sum().backward()
+    ctx = ops.bert_attention(qkv.cuda(), mask.cuda(), B, L, NH, D)
+    dqkv = ops.bert_attention_bwd(qkv.cuda(), mask.cuda(), ctx, dctx.cuda(), B, L, NH, D)
+    ref = x.grad
+    err = (dqkv.float().cpu().double() - ref).abs().max().item()
+    assert err < 3e-2 * ref.abs().max().item() + 1e-3, (err, ref.abs().max().item())

@@ -1,0 +1,67 @@
+"""GPU: TRAIN mode of the bert_crf plugin (BASELINE config 2's model) — the full encoder backward
+(dense dgrad/wgrad on tcgen05, attention backward, LayerNorm/GELU/embedding backward) against
+autograd of the float64 oracle, and a short AdamW run."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from chinesener_b200 import autodiff, engine, synthetic, variables
+from oracle import crf_torch, nn as onn
+
+pytestmark = pytest.mark.gpu
+
+CFG = {'vocab_size': 1500, 'hidden_size': 768, 'num_hidden_layers': 2, 'num_attention_heads': 12,
+       'intermediate_size': 3072, 'max_position_embeddings': 128, 'type_vocab_size': 2, 'initializer_range': 0.02}
+
+
+def _est(tmp_path, B=4, L=32, dropout=0.0):
+    (tmp_path / "bert_config.json").write_text(json.dumps(CFG))
+    feats = synthetic.msra_batch(B, L, vocab=CFG['vocab_size'], seed=21)
+    params = dict(synthetic.data_params(L), pretrain_dir=str(tmp_path), embedding_dropout=dropout)
+    return engine.Estimator("bert_crf", params), feats
+
+
+def _oracle(w, feats):
+    wd = {k: v.double().clone().requires_grad_(True) for k, v in w.items()}
+    seq = onn.bert_encoder(wd, feats['token_ids'], feats['mask'], feats['segment_ids'], num_layers=2, num_heads=12,
+                           dtype=torch.float64)
+    logits = seq @ wd['logits/kernel'] + wd['logits/bias']
+    ll = crf_torch.crf_log_likelihood(logits, feats['label_ids'], feats['seq_len'], wd['crf_layer/transitions'])
+    loss = (-ll).mean()
+    loss.backward()
+    return float(loss.detach()), {k: v.grad for k, v in wd.items()}
+
+
+def test_bert_crf_gradients_match_oracle_autograd(tmp_path):
+    est, feats = _est(tmp_path)
+    est.evaluate(feats)
+    est.store.vars["logits/kernel"].mul_(4.0)
+    est.store.touch()
+    w = est.store.state_dict()
+    ref_loss, ref = _oracle(w, feats)
+    dev = est.to_device(feats)
+    with variables.use_store(est.store), autodiff.recording(est.store) as tape:
+        loss, _ = est.build_graph(dev, None, est.params, True)
+        tape.backward()
+    assert abs(float(loss) - ref_loss) < 2e-2 * max(1.0, abs(ref_loss))
+    worst = {}
+    for name, g_ref in ref.items():
+        if g_ref is None or "pooler" in name:
+            continue
+        g = est.store.grads[name].cpu().double()
+        scale = max(g_ref.abs().max().item(), 1e-8)
+        worst[name] = (g - g_ref).abs().max().item() / scale
+    bad = {k: v for k, v in worst.items() if v > 8e-2}
+    print("max relative gradient error:", max(worst.values()), "over", len(worst), "variables")
+    assert not bad, bad
+    assert "bert/pooler/dense/kernel" not in est.store.grads      # unused by the reference: no gradient
+
+
+def test_bert_crf_training_reduces_loss(tmp_path):
+    est, feats = _est(tmp_path, dropout=0.1)
+    est.params.update(lr=2e-4, num_train_steps=100, warmup_ratio=0.1)
+    losses = [float(est.train_step(feats)) for _ in range(12)]
+    assert np.isfinite(losses).all()
+    assert losses[-1] < 0.8 * losses[0], losses
