@@ -31,7 +31,7 @@ def _worker(rank, world, port, q):
         for n in fs.names:
             store.grads[n].fill_(float(rank + 1))
         w = train_utils.allreduce_gradients(fs.grads)
-        ok = (w == world) and bool(torch.all(fs.grads == 3.0))
+        ok = (w == world) and float(fs.grads.max()) == 3.0       # (alignment padding between variables stays 0)
         # views stayed views: the per-variable gradient tensors see the reduced values
         ok = ok and all(bool(torch.all(store.grads[n] == 3.0)) for n in fs.names)
         ok = ok and fs.names[0] == "crf_layer/transitions"        # group 0 sorted first
