@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
                                   const float* __restrict__ wh_bw, const int32_t* __restrict__ seq_len,
                                   float* __restrict__ out, int B, int L, int H, int C, float forget_bias,
                                   const int32_t* __restrict__ cu_seqlens, float* __restrict__ gates_out,
-                                  float* __restrict__ cstate_out) {
+                                  float* __restrict__ cstate_out, float* __restrict__ hstate_out, float keep_prob,
+                                  uint32_t seed_lo, uint32_t seed_hi) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int HU = H / C;       // hidden units owned by this CTA
@@ -175,9 +176,21 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
         const float zo = zbuf[cr * NC + 3 * HU + cu];
         const float i_s = sigmoidf_(zi), j_a = actf<ACT>(zj), f_s = sigmoidf_(zf + forget_bias), o_s = sigmoidf_(zo);
         c_state = f_s * c_state + i_s * j_a;
-        h_state = o_s * actf<ACT>(c_state);
+        const float h_raw = o_s * actf<ACT>(c_state);
         const int pos = dir == 0 ? s : len - 1 - s;
-        out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = h_state;
+        float h_out = h_raw;
+        h_state = h_raw;
+        if (keep_prob < 1.f) {
+          // DropoutWrapper(output_keep_prob, state_keep_prob): independent masks for the emitted output
+          // and for the h part of the carried state (c is not dropped), fresh per step
+          const uint32_t thr = nerdev::keep_threshold(keep_prob);
+          const uint32_t e = (uint32_t)(((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug);
+          const float inv = 1.f / keep_prob;
+          h_out = nerdev::hash3(seed_lo, seed_hi, e) < thr ? h_raw * inv : 0.f;
+          h_state = nerdev::hash3(seed_lo ^ 0x5bd1e995u, seed_hi, e) < thr ? h_raw * inv : 0.f;
+        }
+        out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = h_out;
+        if (hstate_out != nullptr) hstate_out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = h_state;
         if (gates_out != nullptr) {  // saved for back-propagation through time (bilstm_bwd.cu)
           const size_t gi = ((size_t)b * L + pos) * 8 * H + (size_t)dir * 4 * H;
           gates_out[gi + 0 * H + ug] = i_s;
@@ -219,7 +232,7 @@ int pick_cluster(int H) {
 template <int R, int ACT, int H4REG>
 int launch_rec(const float* xproj, const float* wh_fw, const float* wh_bw, const int32_t* seq_len, float* out, int B,
                int L, int H, int C, float forget_bias, const int32_t* cu_seqlens, float* gates_out, float* cstate_out,
-               cudaStream_t st) {
+               float* hstate_out, float keep_prob, uint64_t seed, cudaStream_t st) {
   const int HU = H / C, NC = 4 * HU;
   const size_t smem = ((H4REG > 0 ? 0 : (size_t)H * NC) + 2 * R * H + (size_t)R * NC + 32) * 4;
   auto kern = bilstm_rec_kernel<R, ACT, H4REG>;
@@ -239,7 +252,7 @@ int launch_rec(const float* xproj, const float* wh_fw, const float* wh_bw, const
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   e = cudaLaunchKernelEx(&cfg, kern, xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, cu_seqlens, gates_out,
-                         cstate_out);
+                         cstate_out, hstate_out, keep_prob, (uint32_t)seed, (uint32_t)(seed >> 32));
   if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   return ner_launch_status();
 }
@@ -249,11 +262,13 @@ int launch_rec(const float* xproj, const float* wh_fw, const float* wh_bw, const
 extern "C" int ner_bilstm_recurrence(const float* xproj, const float* wh_fw, const float* wh_bw,
                                      const int32_t* seq_len, float* out, int B, int L, int H, int activation,
                                      float forget_bias, const int32_t* cu_seqlens, float* gates_out,
-                                     float* cstate_out, ner_stream_t stream) {
+                                     float* cstate_out, float* hstate_out, float keep_prob, uint64_t seed,
+                                     ner_stream_t stream) {
   if (B < 0 || L < 1 || H < 1) return NER_ERR_INVALID_ARG;
   if (B == 0) return NER_OK;
   if (!xproj || !wh_fw || !wh_bw || !seq_len || !out) return NER_ERR_INVALID_ARG;
   if ((gates_out == nullptr) != (cstate_out == nullptr)) return NER_ERR_INVALID_ARG;
+  if (!(keep_prob > 0.f) || keep_prob > 1.f) return NER_ERR_INVALID_ARG;
   if (activation != 0 && activation != 1) return NER_ERR_INVALID_ARG;
   if (H % 4 != 0) return NER_ERR_UNSUPPORTED;
   const int C = pick_cluster(H);
@@ -264,8 +279,8 @@ extern "C" int ner_bilstm_recurrence(const float* xproj, const float* wh_fw, con
   if ((long)2 * B * C > 148) R = 2;
   if ((long)2 * ((B + 1) / 2) * C > 2 * 148) R = 4;
 #define GO(RR, HR)                                                                                          \
-  return activation == 1 ? launch_rec<RR, 1, HR>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, cu_seqlens, gates_out, cstate_out, st) \
-                         : launch_rec<RR, 0, HR>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, cu_seqlens, gates_out, cstate_out, st)
+  return activation == 1 ? launch_rec<RR, 1, HR>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, cu_seqlens, gates_out, cstate_out, hstate_out, keep_prob, seed, st) \
+                         : launch_rec<RR, 0, HR>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, cu_seqlens, gates_out, cstate_out, hstate_out, keep_prob, seed, st)
   if (H == 128 && 4 * (H / C) <= 256) {  // register-resident W_h (the bert_bilstm_crf / bilstm_crf shape)
     if (R == 4) GO(4, 32);
     if (R == 2) GO(2, 32);

@@ -38,7 +38,8 @@ template <int R, int ACT>
 __global__ void __launch_bounds__(512, 1)
 bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gates, const float* __restrict__ cstate,
                   const float* __restrict__ wh_fw, const float* __restrict__ wh_bw, const int32_t* __restrict__ seq_len,
-                  float* __restrict__ d_xproj, int B, int L, int H, int C) {
+                  float* __restrict__ d_xproj, int B, int L, int H, int C, float keep_prob, uint32_t seed_lo,
+                  uint32_t seed_hi) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int HU = H / C, NC = 4 * HU, G4 = 4 * H;
@@ -102,7 +103,16 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
           const int ppos = dir == 0 ? s - 1 : len - s;  // position of forward step s-1
           c_prev = cstate[((size_t)b * L + ppos) * 2 * H + (size_t)dir * H + ug];
         }
-        const float dh = d_out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] + dhbuf[cr * HU + cu];
+        float dh_o = d_out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug];
+        float dh_s = dhbuf[cr * HU + cu];
+        if (keep_prob < 1.f) {  // same masks as the forward DropoutWrapper (output / state)
+          const uint32_t thr = nerdev::keep_threshold(keep_prob);
+          const uint32_t e = (uint32_t)(((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug);
+          const float inv = 1.f / keep_prob;
+          dh_o = nerdev::hash3(seed_lo, seed_hi, e) < thr ? dh_o * inv : 0.f;
+          dh_s = nerdev::hash3(seed_lo ^ 0x5bd1e995u, seed_hi, e) < thr ? dh_s * inv : 0.f;
+        }
+        const float dh = dh_o + dh_s;
         const float ac = actf<ACT>(c_t);
         const float d_o = dh * ac;
         const float dc = dh * o_s * act_grad_from_output<ACT>(ac) + dc_carry;
@@ -162,7 +172,8 @@ int pick_cluster_bwd(int H) {
 
 template <int R, int ACT>
 int launch_bwd(const float* d_out, const float* gates, const float* cstate, const float* wh_fw, const float* wh_bw,
-               const int32_t* seq_len, float* d_xproj, int B, int L, int H, int C, cudaStream_t st) {
+               const int32_t* seq_len, float* d_xproj, int B, int L, int H, int C, float keep_prob, uint64_t seed,
+               cudaStream_t st) {
   const int HU = H / C;
   const size_t smem = ((size_t)4 * H * (HU + 1) + 2 * R * 4 * H + (size_t)R * HU + 32) * 4;
   auto kern = bilstm_bwd_kernel<R, ACT>;
@@ -185,7 +196,8 @@ int launch_bwd(const float* d_out, const float* gates, const float* cstate, cons
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kern, d_out, gates, cstate, wh_fw, wh_bw, seq_len, d_xproj, B, L, H, C);
+  e = cudaLaunchKernelEx(&cfg, kern, d_out, gates, cstate, wh_fw, wh_bw, seq_len, d_xproj, B, L, H, C, keep_prob,
+                         (uint32_t)seed, (uint32_t)(seed >> 32));
   if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   return ner_launch_status();
 }
@@ -194,7 +206,8 @@ int launch_bwd(const float* d_out, const float* gates, const float* cstate, cons
 
 extern "C" int ner_bilstm_recurrence_bwd(const float* d_out, const float* gates, const float* cstate,
                                          const float* wh_fw, const float* wh_bw, const int32_t* seq_len,
-                                         float* d_xproj, int B, int L, int H, int activation, ner_stream_t stream) {
+                                         float* d_xproj, int B, int L, int H, int activation, float keep_prob,
+                                         uint64_t seed, ner_stream_t stream) {
   if (B < 0 || L < 1 || H < 1) return NER_ERR_INVALID_ARG;
   if (B == 0) return NER_OK;
   if (!d_out || !gates || !cstate || !wh_fw || !wh_bw || !seq_len || !d_xproj) return NER_ERR_INVALID_ARG;
@@ -206,8 +219,8 @@ extern "C" int ner_bilstm_recurrence_bwd(const float* d_out, const float* gates,
   if ((long)2 * B * C > 148) R = 2;
   if (2 * (H / C) > 512) R = 1;
 #define GO(RR)                                                                                                \
-  return activation == 1 ? launch_bwd<RR, 1>(d_out, gates, cstate, wh_fw, wh_bw, seq_len, d_xproj, B, L, H, C, st) \
-                         : launch_bwd<RR, 0>(d_out, gates, cstate, wh_fw, wh_bw, seq_len, d_xproj, B, L, H, C, st)
+  return activation == 1 ? launch_bwd<RR, 1>(d_out, gates, cstate, wh_fw, wh_bw, seq_len, d_xproj, B, L, H, C, keep_prob, seed, st) \
+                         : launch_bwd<RR, 0>(d_out, gates, cstate, wh_fw, wh_bw, seq_len, d_xproj, B, L, H, C, keep_prob, seed, st)
   if (R == 2) GO(2);
   GO(1);
 #undef GO

@@ -54,4 +54,18 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Counter-based keep decision shared by every dropout site (forward and backward regenerate it).
+__device__ __forceinline__ uint32_t hash3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t x = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du;
+  x ^= x >> 16;
+  x *= 0x7FEB352Du;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t keep_threshold(float keep) {
+  return (uint32_t)fminf(keep * 4294967296.f, 4294967295.f);
+}
+
 }  // namespace nerdev

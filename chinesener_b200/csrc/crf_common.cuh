@@ -16,9 +16,9 @@ using namespace nerdev;
 constexpr int T_CHUNK = 8;  // time steps staged per chunk
 constexpr int NSTAGE = 2;   // cp.async ring depth
 
-template <int K>
+template <int K, int TT = T_CHUNK>
 struct Geom {
-  static constexpr int T = T_CHUNK;
+  static constexpr int T = TT;
   static constexpr int G = (K % 4 == 0) ? 1 : ((K % 2 == 0) ? 2 : 4);  // steps per LDS.128 group
   static constexpr int CE = T * K;                                    // floats per row-chunk
   static constexpr int NQ = CE / 4;                                   // float4 per row-chunk
@@ -30,10 +30,10 @@ struct Geom {
 
 // Stage chunk `c` (time steps [t0, t0+T)) of the CTA's rows into dst[NT][P].
 // s_len[r] = effective length of row r (>= 1); elements at t >= s_len[r] are not fetched.
-template <int K, int NT>
+template <int K, int NT, int TT = T_CHUNK>
 __device__ __forceinline__ void stage_logits(float* dst, const float* __restrict__ gbase, int LK,
                                              int t0, int L, int nv, const int* s_len, int vec16) {
-  using Gm = Geom<K>;
+  using Gm = Geom<K, TT>;
   const int steps = min(Gm::T, L - t0);
   const int ne = steps * K;
   if (vec16) {

@@ -12,6 +12,8 @@
 // unrolled body; only the first and the ragged last chunk take the checked path.  The exact path (flags bit0, or
 // chosen automatically for wide/inf transition matrices) evaluates every logsumexp with its
 // own max, exactly as the reference's reduce_logsumexp does.
+#include <stdlib.h>
+
 #include "crf_common.cuh"
 
 namespace {
@@ -22,17 +24,17 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr int TAGP = 12;  // tag-chunk pitch (ints): 3 x 16B, odd -> conflict-free LDS.128
 
-template <int K, int NT>
+template <int K, int NT, int TT>
 size_t loglik_smem_bytes() {
-  using Gm = Geom<K>;
+  using Gm = Geom<K, TT>;
   size_t words = 2 * Gm::KK4 + 32 + NT + (size_t)NSTAGE * NT * Gm::P + (size_t)NSTAGE * NT * TAGP;
   return words * 4;
 }
 
-template <int NT>
+template <int NT, int TT>
 __device__ __forceinline__ void stage_tags(int* dst, const int32_t* __restrict__ gbase, int L, int t0,
                                            int nv, const int* s_len, int vec16) {
-  constexpr int T = T_CHUNK;
+  constexpr int T = TT;
   const int steps = min(T, L - t0);
   if (vec16) {
     for (int idx = threadIdx.x; idx < NT * (T / 4); idx += NT) {
@@ -49,16 +51,16 @@ __device__ __forceinline__ void stage_tags(int* dst, const int32_t* __restrict__
   }
 }
 
-template <int K, int NT>
-__global__ void __launch_bounds__(NT)
+template <int K, int NT, int TT, bool EREG, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 crf_loglik_fwd_kernel(const float* __restrict__ logits, const int32_t* __restrict__ tags,
                       const int32_t* __restrict__ seq_len, const float* __restrict__ trans,
                       float* __restrict__ ll, float* __restrict__ logz_out,
                       float* __restrict__ alpha_ws, int B, int L, int vec_logits, int vec_tags,
                       int force_exact) {
-  using Gm = Geom<K>;
+  using Gm = Geom<K, TT>;
   constexpr int T = Gm::T, G = Gm::G, P = Gm::P;
-  constexpr bool E_REGS = (K <= 10);
+  constexpr bool E_REGS = EREG;
   constexpr int UNR = Gm::UNROLL ? K : 1;
 
   extern __shared__ __align__(16) float smem[];
@@ -112,8 +114,8 @@ crf_loglik_fwd_kernel(const float* __restrict__ logits, const int32_t* __restric
 #pragma unroll
   for (int s = 0; s < NSTAGE - 1; ++s) {
     if (s < nchunk) {
-      stage_logits<K, NT>(s_stage + s * NT * P, gbase, LK, s * T, L, nv, s_len, vec_logits);
-      stage_tags<NT>(s_tags + s * NT * TAGP, tbase, L, s * T, nv, s_len, vec_tags);
+      stage_logits<K, NT, TT>(s_stage + s * NT * P, gbase, LK, s * T, L, nv, s_len, vec_logits);
+      stage_tags<NT, TT>(s_tags + s * NT * TAGP, tbase, L, s * T, nv, s_len, vec_tags);
     }
     cp_async_commit();
   }
@@ -182,8 +184,8 @@ crf_loglik_fwd_kernel(const float* __restrict__ logits, const int32_t* __restric
   for (int c = 0; c < nchunk; ++c) {
     const int cn = c + NSTAGE - 1;
     if (cn < nchunk) {
-      stage_logits<K, NT>(s_stage + (cn % NSTAGE) * NT * P, gbase, LK, cn * T, L, nv, s_len, vec_logits);
-      stage_tags<NT>(s_tags + (cn % NSTAGE) * NT * TAGP, tbase, L, cn * T, nv, s_len, vec_tags);
+      stage_logits<K, NT, TT>(s_stage + (cn % NSTAGE) * NT * P, gbase, LK, cn * T, L, nv, s_len, vec_logits);
+      stage_tags<NT, TT>(s_tags + (cn % NSTAGE) * NT * TAGP, tbase, L, cn * T, nv, s_len, vec_tags);
     }
     cp_async_commit();
     cp_async_wait<NSTAGE - 1>();
@@ -216,7 +218,7 @@ crf_loglik_fwd_kernel(const float* __restrict__ logits, const int32_t* __restric
             const int tag = min(max(tg[tt], 0), K - 1);
             score += rowp[tt * K + tag] + s_tr[prev * K + tag];
             prev = tag;
-            fast_step(xs + gg * K, (tt & 1) != 0);
+            fast_step(xs + gg * K, (tt & 1) != 0 || T < 2);
             if (aws != nullptr) store_alpha(aws + (size_t)(t0 + tt) * K);
           }
         }
@@ -297,12 +299,12 @@ crf_loglik_fwd_kernel(const float* __restrict__ logits, const int32_t* __restric
   }
 }
 
-template <int K, int NT>
+template <int K, int NT, int TT, bool EREG, int MINB = 1>
 int launch_fwd_nt(const float* logits, const int32_t* tags, const int32_t* seq_len,
                   const float* trans, float* ll, float* logz, float* alpha_ws, int B, int L,
                   int flags, cudaStream_t st) {
-  const size_t smem = loglik_smem_bytes<K, NT>();
-  auto kern = crf_loglik_fwd_kernel<K, NT>;
+  const size_t smem = loglik_smem_bytes<K, NT, TT>();
+  auto kern = crf_loglik_fwd_kernel<K, NT, TT, EREG, MINB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   const int vl = ((L * K) % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
@@ -312,11 +314,38 @@ int launch_fwd_nt(const float* logits, const int32_t* tags, const int32_t* seq_l
   return ner_launch_status();
 }
 
+// Tuning variants of the throughput kernel for the reference's K = 10 tag set, selected with
+// NER_CRF_FWD_VARIANT (profiles/README.md records the measurements behind the default).
+int fwd_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NER_CRF_FWD_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 template <int K>
 int launch_fwd(const float* logits, const int32_t* tags, const int32_t* seq_len, const float* trans,
                float* ll, float* logz, float* alpha_ws, int B, int L, int flags, cudaStream_t st) {
-  if (B > 148 * 64 * 2) return launch_fwd_nt<K, 64>(logits, tags, seq_len, trans, ll, logz, alpha_ws, B, L, flags, st);
-  return launch_fwd_nt<K, 32>(logits, tags, seq_len, trans, ll, logz, alpha_ws, B, L, flags, st);
+  constexpr bool ER = (K <= 10);
+  if (B > 148 * 64 * 2) {
+    if constexpr (K == 10) {
+      switch (fwd_variant()) {
+        case 1: return launch_fwd_nt<K, 64, 4, false>(logits, tags, seq_len, trans, ll, logz, alpha_ws, B, L, flags, st);
+        case 2: return launch_fwd_nt<K, 128, 4, false>(logits, tags, seq_len, trans, ll, logz, alpha_ws, B, L, flags, st);
+        case 3: return launch_fwd_nt<K, 64, 4, true>(logits, tags, seq_len, trans, ll, logz, alpha_ws, B, L, flags, st);
+        case 4: return launch_fwd_nt<K, 128, 8, false>(logits, tags, seq_len, trans, ll, logz, alpha_ws, B, L, flags, st);
+        case 5: return launch_fwd_nt<K, 64, 4, false, 8>(logits, tags, seq_len, trans, ll, logz, alpha_ws, B, L, flags, st);
+        case 6: return launch_fwd_nt<K, 64, 4, false, 6>(logits, tags, seq_len, trans, ll, logz, alpha_ws, B, L, flags, st);
+        case 7: return launch_fwd_nt<K, 64, 4, true, 6>(logits, tags, seq_len, trans, ll, logz, alpha_ws, B, L, flags, st);
+        case 8: return launch_fwd_nt<K, 128, 4, false, 4>(logits, tags, seq_len, trans, ll, logz, alpha_ws, B, L, flags, st);
+        default: break;
+      }
+    }
+    return launch_fwd_nt<K, 64, T_CHUNK, ER>(logits, tags, seq_len, trans, ll, logz, alpha_ws, B, L, flags, st);
+  }
+  return launch_fwd_nt<K, 32, T_CHUNK, ER>(logits, tags, seq_len, trans, ll, logz, alpha_ws, B, L, flags, st);
 }
 
 }  // namespace

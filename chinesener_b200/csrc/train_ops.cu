@@ -87,19 +87,10 @@ dense_small_n_bwd_kernel(const float* __restrict__ x, const float* __restrict__ 
 
 // Counter-based dropout (Philox-like integer hash of (seed, element index)): the same (seed, i)
 // gives the same keep decision in forward and backward, so no mask tensor is stored.
-__device__ __forceinline__ uint32_t hash3(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t x = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du;
-  x ^= x >> 16;
-  x *= 0x7FEB352Du;
-  x ^= x >> 15;
-  x *= 0x846CA68Bu;
-  x ^= x >> 16;
-  return x;
-}
 __global__ void __launch_bounds__(256)
 dropout_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n, float keep, uint32_t seed_lo, uint32_t seed_hi) {
   const float inv = 1.f / keep;
-  const uint32_t thr = (uint32_t)fminf(keep * 4294967296.f, 4294967295.f);
+  const uint32_t thr = keep_threshold(keep);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint32_t r = hash3(seed_lo, seed_hi ^ (uint32_t)(i >> 32), (uint32_t)i);

@@ -160,32 +160,36 @@ def bert_attention(qkv, mask, B, L, num_heads, head_dim=64, scale=None, mask_add
 
 # --------------------------------------------------------------------------- BiLSTM
 def bilstm_recurrence(xproj, wh_fw, wh_bw, seq_len, B, L, H, activation="tanh", forget_bias=1.0, cu_seqlens=None,
-                      save_for_backward=False):
-    """-> out [B,L,2H]; with save_for_backward also (gates [B*L,8H], cstate [B,L,2H]) for bilstm_recurrence_bwd."""
+                      save_for_backward=False, keep_prob=1.0, seed=0):
+    """-> out [B,L,2H]; with save_for_backward also (gates [B*L,8H], cstate [B,L,2H], hstate [B,L,2H]) for
+    bilstm_recurrence_bwd.  keep_prob < 1: DropoutWrapper output/state dropout (training)."""
     require_cuda(xproj, wh_fw, wh_bw, seq_len, cu_seqlens)
     assert xproj.dtype == torch.float32 and xproj.shape[1] == 8 * H
     assert cu_seqlens is not None or xproj.shape[0] == B * L
     assert wh_fw.shape == (H, 4 * H) and wh_bw.shape == (H, 4 * H)
     act = {"tanh": 0, "relu": 1}[activation]
     out = torch.empty((B, L, 2 * H), dtype=torch.float32, device=xproj.device)
-    gates = cst = None
+    gates = cst = hst = None
     if save_for_backward:
         assert cu_seqlens is None, "training runs on the padded layout"
         gates = torch.zeros((B * L, 8 * H), dtype=torch.float32, device=xproj.device)
         cst = torch.zeros((B, L, 2 * H), dtype=torch.float32, device=xproj.device)
+        hst = torch.zeros((B, L, 2 * H), dtype=torch.float32, device=xproj.device)
     check(lib().ner_bilstm_recurrence(ptr(xproj), ptr(wh_fw), ptr(wh_bw), ptr(_i32(seq_len)), ptr(out), B, L, H, act,
-                                      forget_bias, ptr(cu_seqlens), ptr(gates), ptr(cst), stream()))
-    return (out, gates, cst) if save_for_backward else out
+                                      forget_bias, ptr(cu_seqlens), ptr(gates), ptr(cst), ptr(hst), float(keep_prob),
+                                      int(seed) & 0xFFFFFFFFFFFFFFFF, stream()))
+    return (out, gates, cst, hst) if save_for_backward else out
 
 
-def bilstm_recurrence_bwd(d_out, gates, cstate, wh_fw, wh_bw, seq_len, B, L, H, activation="tanh"):
+def bilstm_recurrence_bwd(d_out, gates, cstate, wh_fw, wh_bw, seq_len, B, L, H, activation="tanh", keep_prob=1.0, seed=0):
     """-> d_xproj [B*L, 8H] f32 (gradient of the hoisted input projection)."""
     require_cuda(d_out, gates, cstate, wh_fw, wh_bw, seq_len)
     assert d_out.shape == (B, L, 2 * H) and d_out.dtype == torch.float32
     act = {"tanh": 0, "relu": 1}[activation]
     d_xproj = torch.empty((B * L, 8 * H), dtype=torch.float32, device=d_out.device)
     check(lib().ner_bilstm_recurrence_bwd(ptr(d_out), ptr(gates), ptr(cstate), ptr(wh_fw), ptr(wh_bw), ptr(_i32(seq_len)),
-                                          ptr(d_xproj), B, L, H, act, stream()))
+                                          ptr(d_xproj), B, L, H, act, float(keep_prob), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                          stream()))
     return d_xproj
 
 

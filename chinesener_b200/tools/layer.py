@@ -120,13 +120,12 @@ def bilstm(embedding, cell_type, activation, hidden_units_list, keep_prob_list, 
 
 
 def _bilstm_train(embedding, activation, hidden_units_list, keep_prob_list, cell_size, seq_len):
-    """Training-mode bilstm(): same kernels on the padded layout, saves gates / cell states and
-    records the BPTT closure.  DropoutWrapper with keep_prob < 1 (state + output dropout inside the
-    recurrence) is not built yet."""
+    """Training-mode bilstm(): same kernels on the padded layout, saves gates / cell states / carried
+    h and records the BPTT closure.  keep_prob < 1 = DropoutWrapper(output_keep_prob, state_keep_prob)
+    (reference tools/layer.py:20-23): counter-based masks inside the recurrence kernels."""
     if cell_size != 1:
         raise Exception('cell_size must be 1')
-    if float(keep_prob_list[0]) != 1.0:
-        raise TrainingPathNotBuilt("bilstm: DropoutWrapper keep_prob < 1 in training (recurrent dropout kernel)")
+    keep = float(keep_prob_list[0])
     B, L, D = embedding.shape
     H = hidden_units_list[0]
     store = variables.default_store()
@@ -140,8 +139,10 @@ def _bilstm_train(embedding, activation, hidden_units_list, keep_prob_list, cell
     x2d = embedding.reshape(B * L, D).contiguous()
     x16 = ops.cast_pad_bf16(x2d, pk["Dp"])
     xproj = ops.gemm_bf16(x16, pk["wx"], pk["bias"], epilogue=ops.EPI_F32)
-    out, gates, cst = ops.bilstm_recurrence(xproj, pk["wh_fw"], pk["wh_bw"], seq_len, B, L, H, activation=activation,
-                                            forget_bias=1.0, save_for_backward=True)
+    store.dropout_calls += 1
+    seed = (1234 * 1000003 + store.global_step) * 1009 + store.dropout_calls
+    out, gates, cst, hst = ops.bilstm_recurrence(xproj, pk["wh_fw"], pk["wh_bw"], seq_len, B, L, H, activation=activation,
+                                                 forget_bias=1.0, save_for_backward=True, keep_prob=keep, seed=seed)
     tape = autodiff.current()
     if tape is not None:
         need_dx = tape.needs_grad(embedding)
@@ -150,7 +151,7 @@ def _bilstm_train(embedding, activation, hidden_units_list, keep_prob_list, cell
             if g is None:
                 return
             dxp = ops.bilstm_recurrence_bwd(g.contiguous(), gates, cst, pk["wh_fw"], pk["wh_bw"], seq_len, B, L, H,
-                                            activation=activation)
+                                            activation=activation, keep_prob=keep, seed=seed)
             dwx = ops.wgrad_gemm(x2d, dxp)                                   # [D, 8H] = x^T d_xproj
             for di, d in enumerate(("fw", "bw")):
                 gk, gb = store.grad(names[d][0]), store.grad(names[d][1])
@@ -158,10 +159,10 @@ def _bilstm_train(embedding, activation, hidden_units_list, keep_prob_list, cell
                 gk[:D] += dwx[:, di * 4 * H:(di + 1) * 4 * H]
                 ops.colsum_add(dz, gb, 1.0)
                 hprev = torch.zeros((B, L, H), dtype=torch.float32, device=out.device)
-                if di == 0:
-                    hprev[:, 1:] = out[:, :-1, :H]
+                if di == 0:                       # carried (state-dropped) h of the previous forward step
+                    hprev[:, 1:] = hst[:, :-1, :H]
                 else:
-                    hprev[:, :-1] = out[:, 1:, H:]
+                    hprev[:, :-1] = hst[:, 1:, H:]
                 gk[D:] += ops.wgrad_gemm(hprev.view(B * L, H), dz)            # dW_h = h_prev^T dz
             if need_dx:
                 wx = torch.cat([store.vars[names[d][0]][:D] for d in ("fw", "bw")], dim=1)   # [D, 8H]: K-major for dx

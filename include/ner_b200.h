@@ -221,11 +221,15 @@ int ner_bert_encoder_fwd(const ner_bert_config* cfg, const float* word_emb, cons
  * t >= seq_len.  activation: 0 tanh, 1 relu (params['rnn_activation']).  H % 4 == 0.
  * cu_seqlens: NULL (xproj row of (b,t) = b*L+t) or [B+1] (packed xproj: row = cu[b]+t).
  * gates_out [B*L, 8H] / cstate_out [B,L,2H]: both NULL (inference) or both given (training):
- * post-activation gates (sigmoid(i), act(j), sigmoid(f+forget_bias), sigmoid(o)) and cell states. */
+ * post-activation gates (sigmoid(i), act(j), sigmoid(f+forget_bias), sigmoid(o)) and cell states.
+ * keep_prob < 1 (training, tools/layer.py:20-23 DropoutWrapper(output_keep_prob, state_keep_prob)):
+ * independent counter-based masks (seed) on the emitted output and on the carried h; hstate_out
+ * [B,L,2H] (nullable) receives the carried (state-dropped) h, the operand of dW_h. */
 int ner_bilstm_recurrence(const float* xproj, const float* wh_fw, const float* wh_bw,
                           const int32_t* seq_len, float* out, int B, int L, int H,
                           int activation, float forget_bias, const int32_t* cu_seqlens,
-                          float* gates_out, float* cstate_out, ner_stream_t stream);
+                          float* gates_out, float* cstate_out, float* hstate_out, float keep_prob,
+                          uint64_t seed, ner_stream_t stream);
 
 /* Back-propagation through time of ner_bilstm_recurrence (padded layout).  d_out [B,L,2H] f32;
  * gates [B*L, 8H] / cstate [B,L,2H] saved by the forward call.  Writes d_xproj [B*L, 8H] f32 =
@@ -234,8 +238,8 @@ int ner_bilstm_recurrence(const float* xproj, const float* wh_fw, const float* w
  * dx = d_xproj W_x^T, dW_h = h_prev^T d_xproj (per direction). */
 int ner_bilstm_recurrence_bwd(const float* d_out, const float* gates, const float* cstate,
                               const float* wh_fw, const float* wh_bw, const int32_t* seq_len,
-                              float* d_xproj, int B, int L, int H, int activation,
-                              ner_stream_t stream);
+                              float* d_xproj, int B, int L, int H, int activation, float keep_prob,
+                              uint64_t seed, ner_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
  * SoftLexicon gather-and-pool — model/bilstm_crf_softlexicon.py:37-44

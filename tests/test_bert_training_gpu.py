@@ -47,11 +47,14 @@ def test_bert_crf_gradients_match_oracle_autograd(tmp_path):
         tape.backward()
     assert abs(float(loss) - ref_loss) < 2e-2 * max(1.0, abs(ref_loss))
     worst = {}
+    gscale = max(g.abs().max().item() for n, g in ref.items() if g is not None and "pooler" not in n)
     for name, g_ref in ref.items():
         if g_ref is None or "pooler" in name:
             continue
         g = est.store.grads[name].cpu().double()
-        scale = max(g_ref.abs().max().item(), 1e-8)
+        # key biases have an analytically ZERO gradient (softmax is shift-invariant along the keys), so
+        # every variable is measured against max(its own scale, 1e-3 of the largest gradient)
+        scale = max(g_ref.abs().max().item(), 1e-3 * gscale)
         worst[name] = (g - g_ref).abs().max().item() / scale
     bad = {k: v for k, v in worst.items() if v > 8e-2}
     print("max relative gradient error:", max(worst.values()), "over", len(worst), "variables")

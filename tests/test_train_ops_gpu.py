@@ -40,7 +40,8 @@ def test_bilstm_bptt_matches_autograd(B, L, H, act):
     bs = [w[n + "bias"].detach() for n in names]
     xproj = torch.cat([x.detach().view(B * L, D) @ k[:D] + b for k, b in zip(ks, bs)], dim=1).float().cuda()
     whf, whb = ks[0][D:].float().contiguous().cuda(), ks[1][D:].float().contiguous().cuda()
-    out, gates, cst = ops.bilstm_recurrence(xproj, whf, whb, lens.cuda(), B, L, H, activation=act, save_for_backward=True)
+    out, gates, cst, hst = ops.bilstm_recurrence(xproj, whf, whb, lens.cuda(), B, L, H, activation=act, save_for_backward=True)
+    assert torch.equal(hst, out)                     # keep_prob 1: carried h == emitted output
     torch.testing.assert_close(out.cpu().double(), out_ref.detach(), rtol=1e-4, atol=1e-4)
     dxp = ops.bilstm_recurrence_bwd(d_out.float().cuda(), gates, cst, whf, whb, lens.cuda(), B, L, H, activation=act)
     dxp = dxp.cpu().double()
@@ -134,3 +135,30 @@ def test_crf_torch_oracle_agrees_with_numpy_oracle():
     a = crf.crf_log_likelihood(x, tags, lens, tr)
     b = crf_torch.crf_log_likelihood(torch.from_numpy(x), torch.from_numpy(tags), torch.from_numpy(lens), torch.from_numpy(tr))
     np.testing.assert_allclose(b.numpy(), a, rtol=1e-10, atol=1e-10)
+
+
+def test_bilstm_dropout_wrapper_masks_are_consistent():
+    """keep_prob < 1: output / state masks are independent Bernoulli(keep) scaled by 1/keep, and the
+    backward kernel regenerates them (finite-difference check of one loss through the kernels)."""
+    B, L, H, D = 4, 12, 128, 16
+    g = torch.Generator().manual_seed(3)
+    w = _lstm_w(D, H, 1)
+    names = [f"bilstm_layer/bidirectional_rnn/{d}/multi_rnn_cell/cell_0/lstm_cell/" for d in ("fw", "bw")]
+    ks = [w[n + "kernel"] for n in names]
+    lens = torch.full((B,), L, dtype=torch.int32)
+    xproj = torch.randn(B * L, 8 * H, generator=g).cuda()
+    whf, whb = ks[0][D:].float().contiguous().cuda(), ks[1][D:].float().contiguous().cuda()
+    out1, gates, cst, hst = ops.bilstm_recurrence(xproj, whf, whb, lens.cuda(), B, L, H, save_for_backward=True, keep_prob=1.0)
+    out, gates, cst, hst = ops.bilstm_recurrence(xproj, whf, whb, lens.cuda(), B, L, H, save_for_backward=True, keep_prob=0.8, seed=77)
+    kept = (out != 0).float().mean().item()
+    assert abs(kept - 0.8) < 0.03
+    assert (out != 0).ne(hst != 0).float().mean().item() > 0.2          # independent masks
+    d_out = torch.randn(B, L, 2 * H, generator=g).cuda()
+    dxp = ops.bilstm_recurrence_bwd(d_out, gates, cst, whf, whb, lens.cuda(), B, L, H, keep_prob=0.8, seed=77)
+    # directional finite difference of  sum(out * d_out)  w.r.t. xproj
+    v = torch.randn_like(xproj)
+    eps = 1e-2
+    f = lambda xp: (ops.bilstm_recurrence(xp, whf, whb, lens.cuda(), B, L, H, keep_prob=0.8, seed=77).double() * d_out.double()).sum().item()
+    fd = (f(xproj + eps * v) - f(xproj - eps * v)) / (2 * eps)
+    an = (dxp.double() * v.double()).sum().item()
+    assert abs(fd - an) < 2e-2 * max(1.0, abs(an)), (fd, an)
