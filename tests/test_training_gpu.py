@@ -10,11 +10,11 @@ from oracle import crf_torch, nn as onn, optim
 pytestmark = pytest.mark.gpu
 
 
-def _setup(B=8, L=64, V=2000, seed=3, dropout=0.0):
+def _setup(B=8, L=64, V=2000, seed=3, dropout=0.0, keep=1.0):
     feats = synthetic.msra_batch(B, L, vocab=V, seed=seed)
     g = torch.Generator().manual_seed(0)
     emb = torch.nn.functional.normalize(torch.randn(V, 50, generator=g), dim=1).numpy()
-    params = dict(synthetic.data_params(L), embedding=emb, embedding_dropout=dropout)
+    params = dict(synthetic.data_params(L), embedding=emb, embedding_dropout=dropout, keep_prob_list=[keep])
     est = engine.Estimator("bilstm_crf", params)
     return est, feats, emb
 
@@ -65,7 +65,7 @@ def test_one_train_step_equals_reference_adam():
 
 
 def test_training_reduces_the_loss_with_dropout_on():
-    est, feats, emb = _setup(dropout=0.3)
+    est, feats, emb = _setup(dropout=0.3, keep=0.8)      # embedding dropout + DropoutWrapper(0.8)
     losses = [float(est.train_step(feats)) for _ in range(25)]
     assert losses[-1] < 0.7 * losses[0], losses
     ev = est.evaluate(feats)
