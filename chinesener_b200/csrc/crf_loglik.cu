@@ -120,11 +120,19 @@ crf_loglik_fwd_kernel(const float* __restrict__ logits, const int32_t* __restric
     cp_async_commit();
   }
 
-  float E[E_REGS ? K * K : 1];
+  // E as packed column pairs: E2[i][q] = (E[i][2q], E[i][2q+1]) (hi lane 0 for the pad column of an odd K)
+  constexpr int KP = (K + 1) / 2;
+  f32x2 E2[E_REGS ? K * KP : 1];
   if (E_REGS) {
 #pragma unroll
-    for (int e = 0; e < K * K; ++e) E[e] = s_E[e];
+    for (int i = 0; i < K; ++i)
+#pragma unroll
+      for (int q = 0; q < KP; ++q) E2[i * KP + q] = pk2(s_E[i * K + 2 * q], 2 * q + 1 < K ? s_E[i * K + 2 * q + 1] : 0.f);
   }
+  auto e2 = [&](int i, int q) -> f32x2 {
+    if (E_REGS) return E2[i * KP + q];
+    return pk2(s_E[i * K + 2 * q], 2 * q + 1 < K ? s_E[i * K + 2 * q + 1] : 0.f);
+  };
   // Fast path state: alpha_j = lacc + ln(a[j]) with a[] kept in the PROBABILITY domain and
   // renormalised (max -> 1) every other step; exact path state: a[j] = alpha_j.
   float a[K];
@@ -132,36 +140,52 @@ crf_loglik_fwd_kernel(const float* __restrict__ logits, const int32_t* __restric
 #pragma unroll UNR
   for (int j = 0; j < K; ++j) a[j] = 0.f;
   // a <- (a · E) * exp(x - max x);  lacc += max x + tmax   [+ renormalisation]
-  // per step: K*K FFMA + K ex2 (+ 1 rcp + 1 lg2 when renormalising) — no per-tag log
+  // per step: K*K/2 FFMA2 (a_i broadcast x column pair) + K ex2 (+ 1 rcp + 1 lg2 when renormalising)
   auto fast_step = [&](const float* x, bool renorm) {
     float xm = x[0];
+    if (K > 1) {
 #pragma unroll UNR
-    for (int j = 1; j < K; ++j) xm = fmaxf(xm, x[j]);
+      for (int j = 1; j + 1 < K; j += 2) xm = max3(xm, x[j], x[j + 1]);
+      if (K % 2 == 0) xm = fmaxf(xm, x[K - 1]);
+    }
     const float nx2 = -xm * kLog2e;
-    // i-outer order: K independent accumulators -> K-way ILP in the FFMA block (a j-outer loop is
-    // K dependent FFMAs per tag and leaves the pipe waiting on the 4-cycle accumulate latency)
-    float ns[K];
+    // K/2 independent packed accumulators, i-outer: K/2-way ILP in the FFMA2 block
+    f32x2 ns[KP];
 #pragma unroll UNR
-    for (int j = 0; j < K; ++j) ns[j] = a[0] * (E_REGS ? E[j] : s_E[j]);
+    for (int q = 0; q < KP; ++q) ns[q] = mul2(pk2(a[0], a[0]), e2(0, q));
 #pragma unroll UNR
     for (int i = 1; i < K; ++i) {
 #pragma unroll UNR
-      for (int j = 0; j < K; ++j) ns[j] = fmaf(a[i], E_REGS ? E[i * K + j] : s_E[i * K + j], ns[j]);
+      for (int q = 0; q < KP; ++q) ns[q] = fma2(pk2(a[i], a[i]), e2(i, q), ns[q]);
+    }
+    lacc += xm + tmax;
+    float n[2 * KP];
+#pragma unroll UNR
+    for (int q = 0; q < KP; ++q) {
+      const f32x2 arg = fma2(pk2(x[2 * q], 2 * q + 1 < K ? x[2 * q + 1] : 0.f), pk2(kLog2e, kLog2e), pk2(nx2, nx2));
+      float lo, hi;
+      upk2(arg, lo, hi);
+      ns[q] = mul2(ns[q], pk2(fast_ex2(lo), fast_ex2(hi)));
+      if (renorm) upk2(ns[q], n[2 * q], n[2 * q + 1]);
+    }
+    if (renorm) {
+      float m = n[0];
+      if (K > 1) {
+#pragma unroll UNR
+        for (int j = 1; j + 1 < K; j += 2) m = max3(m, n[j], n[j + 1]);
+        if (K % 2 == 0) m = fmaxf(m, n[K - 1]);
+      }
+      const float r = __fdividef(1.f, m);
+      lacc = fmaf(kLn2, fast_lg2(m), lacc);
+#pragma unroll UNR
+      for (int q = 0; q < KP; ++q) ns[q] = mul2(ns[q], pk2(r, r));
     }
 #pragma unroll UNR
-    for (int j = 0; j < K; ++j) ns[j] *= fast_ex2(fmaf(x[j], kLog2e, nx2));
-    lacc += xm + tmax;
-    if (renorm) {
-      float m = ns[0];
-#pragma unroll UNR
-      for (int j = 1; j < K; ++j) m = fmaxf(m, ns[j]);
-      const float r = __fdividef(1.f, m);
-#pragma unroll UNR
-      for (int j = 0; j < K; ++j) a[j] = ns[j] * r;
-      lacc = fmaf(kLn2, fast_lg2(m), lacc);
-    } else {
-#pragma unroll UNR
-      for (int j = 0; j < K; ++j) a[j] = ns[j];
+    for (int q = 0; q < KP; ++q) {
+      float lo, hi;
+      upk2(ns[q], lo, hi);
+      a[2 * q] = lo;
+      if (2 * q + 1 < K) a[2 * q + 1] = hi;
     }
   };
   auto fast_init = [&](const float* x) {
@@ -317,12 +341,8 @@ int launch_fwd_nt(const float* logits, const int32_t* tags, const int32_t* seq_l
 // Tuning variants of the throughput kernel for the reference's K = 10 tag set, selected with
 // NER_CRF_FWD_VARIANT (profiles/README.md records the measurements behind the default).
 int fwd_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("NER_CRF_FWD_VARIANT");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
+  const char* e = getenv("NER_CRF_FWD_VARIANT");   // tuning / test hook, read per call
+  return e ? atoi(e) : 0;
 }
 
 template <int K>

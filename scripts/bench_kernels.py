@@ -37,6 +37,7 @@ def bench_crf(B=262144, L=128, K=10):
     out["viterbi"] = dict(ms=med, best_ms=best, GBps=byts / med / 1e6, bytes=byts)
     import os
     out["fwd_variant"] = os.environ.get("NER_CRF_FWD_VARIANT", "0")
+    out["vit_variant"] = os.environ.get("NER_CRF_VIT_VARIANT", "0")
     for exact in (False, True):
         med, best = timeit(lambda: ops.crf_loglik_fwd(x, tags, lens, tr, exact=exact))
         byts = B * L * (4 * K + 4) + 8 * B + 4 * K * K

@@ -103,3 +103,30 @@ def test_loglik_alpha_workspace():
     for b in range(B):
         n = int(lens[b])
         np.testing.assert_allclose(a[b, :n], alphas[b, :n], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("B,L,K", [(148 * 64 + 77, 128, 10), (9600, 37, 7), (9500, 50, 16), (9601, 21, 12), (9490, 9, 3)])
+def test_viterbi_parked_backpointer_kernel_bit_exact(monkeypatch, variant, B, L, K):
+    """The occupancy-first kernel (low backpointer nibbles parked in the tags_out slab): every tuning
+    variant must reproduce the oracle's tags and scores, ragged lengths and a partial tail CTA included."""
+    monkeypatch.setenv("NER_CRF_VIT_VARIANT", str(variant))
+    x, tr, lens, _ = _case(B, L, K, seed=variant * 100 + K)
+    lens[0], lens[1], lens[2] = L, 1, 0
+    x[5] = np.round(x[5])                                # a row with many exact ties
+    ref_tags, ref_best = crf.crf_decode(x, tr, lens, dtype=np.float32)
+    tags, best = ops.crf_viterbi(torch.from_numpy(x).cuda(), torch.from_numpy(lens).cuda(),
+                                 torch.from_numpy(tr).cuda(), return_score=True)
+    np.testing.assert_array_equal(tags.cpu().numpy(), ref_tags)
+    np.testing.assert_array_equal(best.cpu().numpy(), ref_best.astype(np.float32))
+
+
+@pytest.mark.parametrize("variant", [1, 3, 6, 7])
+def test_loglik_tuning_variants(monkeypatch, variant):
+    monkeypatch.setenv("NER_CRF_FWD_VARIANT", str(variant))
+    B, L, K = 19000, 40, 10
+    x, tr, lens, tags = _case(B, L, K, seed=variant)
+    ref = crf.crf_log_likelihood(x, tags, lens, tr, dtype=np.float64)
+    ll, _, _ = ops.crf_loglik_fwd(torch.from_numpy(x).cuda(), torch.from_numpy(tags).cuda(),
+                                  torch.from_numpy(lens).cuda(), torch.from_numpy(tr).cuda())
+    np.testing.assert_allclose(ll.cpu().numpy(), ref, rtol=1e-4, atol=1e-4)
