@@ -39,29 +39,71 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle-reason sampling DURING the timed regions (B200_PROFILING.md recipe).  NVML is polled
+    from a thread every ~2 ms (the timed regions last tens of ms, shorter than one `nvidia-smi -lms` period);
+    `nvidia-smi` is the fallback when the NVML binding is unavailable."""
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.h, self.stop_flag = index, [], None, None, False
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
 
     def start(self):
+        try:
+            self.nv, self.h = self._nvml_handle()
+            self.mx = float(self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.h = None
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nv
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"), (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"), (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                self.rows.append((sm, [n for b, n in bits if r & b], util))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.h is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            sm = [r[0] for r in self.rows]
+            reasons = sorted({n for r in self.rows for n in r[1]})
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml, 2 ms poll over the device-resident and e2e timed regions"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -72,7 +114,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 def make_estimator():
@@ -279,12 +321,34 @@ def run_ours(args):
         evs.append((s, e))
     barrier()
     t_e2e = sum(s.elapsed_time(e) for s, e in evs) / 1e3
+
+    # ---- TRAIN step (SURVEY 8(d)(i) second figure): forward with the tape + backward + one NCCL all-reduce of the
+    #      flat gradient buffer (N>1) + AdamW, device-resident batches; reported beside the PREDICT headline
+    t_train = None
+    if not args.no_train:
+        est_t = make_estimator()
+        est_t.params.update(num_train_steps=10000, warmup_ratio=0.1)
+        for i in range(3):
+            est_t.train_step(dev_batches[i % nb])
+        evs = []
+        barrier()
+        for i in range(args.steps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            est_t.train_step(dev_batches[i % nb])
+            e.record()
+            evs.append((s, e))
+        barrier()
+        t_train = sum(s.elapsed_time(e) for s, e in evs) / 1e3
+        del est_t
     clocks = sampler.stop() if rank == 0 else None
 
     if dist is not None:
-        t = torch.tensor([t_res, t_e2e], device="cuda", dtype=torch.float64)
+        t = torch.tensor([t_res, t_e2e, t_train or 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_res, t_e2e = float(t[0]), float(t[1])
+        t_train = float(t[2]) if t_train is not None else None
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM), instrumented pass on rank 0
     roof = cpu = None
@@ -327,6 +391,11 @@ def run_ours(args):
                     "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
         }
+        if t_train is not None:
+            line["train"] = {"value": sent / t_train, "unit": "sentences/sec", "ms_per_step": 1e3 * t_train / args.steps,
+                             "what": "TRAIN step of the same plugin: forward (padded layout, dropout on) + backward + "
+                                     + ("one NCCL all-reduce of the flat fp32 gradient buffer + " if world > 1 else "")
+                                     + "global-norm clip + AdamW (bert_train_op); device-resident batches"}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
@@ -341,6 +410,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-train", dest="no_train", action="store_true", help="skip the TRAIN-step figure")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

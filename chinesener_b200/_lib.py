@@ -29,13 +29,14 @@ SIGNATURES = {
     "ner_seq_pack_plan": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "ner_bert_embed_ln": (_i, [_vp] * 9 + [_i] * 6 + [_c.c_float, _vp, _i, _vp]),
     "ner_layernorm": (_i, [_vp, _i] + [_vp] * 5 + [_i, _i, _c.c_float, _vp]),
-    "ner_bert_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _c.c_float, _c.c_float, _vp, _vp]),
+    "ner_bert_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _c.c_float, _c.c_float, _vp, _c.c_float, _c.c_uint64, _vp]),
     "ner_bilstm_recurrence": (_i, [_vp] * 5 + [_i, _i, _i, _i, _c.c_float, _vp, _vp, _vp, _vp, _c.c_float, _c.c_uint64, _vp]),
     "ner_bilstm_recurrence_bwd": (_i, [_vp] * 7 + [_i, _i, _i, _i, _c.c_float, _c.c_uint64, _vp]),
     "ner_transpose_cast_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "ner_colsum_add": (_i, [_vp, _vp, _i, _i, _i, _c.c_float, _vp]),
     "ner_dense_small_n_bwd": (_i, [_vp] * 6 + [_i, _i, _i, _vp]),
     "ner_dropout": (_i, [_vp, _vp, _c.c_size_t, _c.c_float, _c.c_uint64, _vp]),
+    "ner_dropout_bf16": (_i, [_vp, _vp, _c.c_size_t, _c.c_float, _c.c_uint64, _vp]),
     "ner_sumsq_add": (_i, [_vp, _c.c_size_t, _vp, _vp]),
     "ner_layernorm_bwd": (_i, [_vp, _i] + [_vp] * 7 + [_i, _i, _c.c_float, _vp]),
     "ner_transpose_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
@@ -43,7 +44,7 @@ SIGNATURES = {
     "ner_gelu_bf16": (_i, [_vp, _vp, _c.c_size_t, _i, _vp]),
     "ner_gelu_bwd_bf16": (_i, [_vp, _vp, _vp, _c.c_size_t, _i, _vp]),
     "ner_bert_embed_bwd": (_i, [_vp] * 6 + [_i] * 5 + [_vp]),
-    "ner_bert_attention_bwd": (_i, [_vp] * 5 + [_i] * 4 + [_c.c_float, _c.c_float, _vp]),
+    "ner_bert_attention_bwd": (_i, [_vp] * 5 + [_i] * 4 + [_c.c_float, _c.c_float, _c.c_float, _c.c_uint64, _vp]),
     "ner_adam_step": (_i, [_vp] * 4 + [_c.c_size_t] + [_c.c_float] * 5 + [_i, _c.c_float, _vp, _c.c_float, _vp]),
     "ner_softlexicon_pool_fwd": (_i, [_vp] * 4 + [_i] * 6 + [_vp]),
     "ner_embedding_lookup": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

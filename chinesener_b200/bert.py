@@ -194,9 +194,17 @@ def _tf_casts(store, cfg, scope):
 def bert_forward_train(input_ids, input_mask, segment_ids, cfg, store, tape, scope="bert", gelu="tanh"):
     """Training-mode BertModel forward on the padded layout: same kernels, every intermediate the
     backward pass needs is kept, and the backward closure is recorded on `tape`.
-    Dropout inside BertModel (hidden_dropout_prob / attention_probs_dropout_prob) is NOT applied
-    yet: the gradient path is otherwise complete."""
+    BertModel(is_training=True) dropout (bert modeling.py: hidden_dropout_prob after the embedding
+    LayerNorm and after the attention-output / FFN-output dense layers, attention_probs_dropout_prob
+    on the softmax output; both 0.1 in bert_config.json) uses the same counter-based masks as every
+    other dropout site: the backward pass regenerates them from (seed, element)."""
     create_bert_variables(cfg, store, scope)
+    keep_h = 1.0 - float(cfg.get("hidden_dropout_prob", 0.1))
+    keep_a = 1.0 - float(cfg.get("attention_probs_dropout_prob", 0.1))
+
+    def next_seed():
+        store.dropout_calls += 1
+        return (4321 * 1000003 + store.global_step) * 1009 + store.dropout_calls
     B, L = input_ids.shape
     H, NH, I = cfg["hidden_size"], cfg["num_attention_heads"], cfg["intermediate_size"]
     v = store.vars
@@ -206,17 +214,26 @@ def bert_forward_train(input_ids, input_mask, segment_ids, cfg, store, tape, sco
     we, te, pe = (v[f"{scope}/embeddings/{n}"] for n in ("word_embeddings", "token_type_embeddings", "position_embeddings"))
     ge, be = v[f"{scope}/embeddings/LayerNorm/gamma"], v[f"{scope}/embeddings/LayerNorm/beta"]
     x32, x16 = ops.bert_embed_ln(we, te, pe, ge, be, ids, seg, eps=1e-12)
+    seed_e = next_seed()
+    if keep_h < 1.0:
+        x32 = ops.dropout(x32, keep_h, seed_e)
+        x16 = ops.cast_bf16(x32)
     saved = []
     for w in layers:
+        sa, s1, s2 = next_seed(), next_seed(), next_seed()
         qkv = ops.gemm_bf16(x16, w["wqkv"], w["bqkv"], epilogue=ops.EPI_BF16)
-        ctx = ops.bert_attention(qkv, mask, B, L, NH, H // NH)
+        ctx = ops.bert_attention(qkv, mask, B, L, NH, H // NH, keep_prob=keep_a, seed=sa)
         y1 = ops.gemm_bf16(ctx, w["wo"], w["bo"], epilogue=ops.EPI_BF16)
+        if keep_h < 1.0:
+            ops.dropout(y1, keep_h, s1, inplace=True)
         x1_32, x1_16 = ops.layernorm(y1, w["g1"], w["b1"], residual=x32, eps=1e-12)
         pre = ops.gemm_bf16(x1_16, w["wi"], w["bi"], epilogue=ops.EPI_BF16)
         inter = ops.gelu_bf16(pre, erf)
         y2 = ops.gemm_bf16(inter, w["wd"], w["bd"], epilogue=ops.EPI_BF16)
+        if keep_h < 1.0:
+            ops.dropout(y2, keep_h, s2, inplace=True)
         x2_32, x2_16 = ops.layernorm(y2, w["g2"], w["b2"], residual=x1_32, eps=1e-12)
-        saved.append((x32, x16, qkv, ctx, y1, x1_32, x1_16, pre, inter, y2))
+        saved.append((x32, x16, qkv, ctx, y1, x1_32, x1_16, pre, inter, y2, sa, s1, s2))
         x32, x16 = x2_32, x2_16
     out = x32.view(B, L, H)
     out.bf16 = x16.view(B, L, H)
@@ -229,11 +246,13 @@ def bert_forward_train(input_ids, input_mask, segment_ids, cfg, store, tape, sco
         d = g.reshape(B * L, H).contiguous()
         for li in reversed(range(len(layers))):
             w, c = layers[li], casts[li]
-            x32_, x16_, qkv, ctx, y1, x1_32, x1_16, pre, inter, y2 = saved[li]
+            x32_, x16_, qkv, ctx, y1, x1_32, x1_16, pre, inter, y2, sa, s1, s2 = saved[li]
             p = f"{scope}/encoder/layer_{li}"
             # ---- output LayerNorm + FFN
             dz2_32, dz2_16 = ops.layernorm_bwd(y2, w["g2"], d, gr(f"{p}/output/LayerNorm/gamma"), gr(f"{p}/output/LayerNorm/beta"),
                                                residual=x1_32, eps=1e-12)
+            if keep_h < 1.0:                      # dz2_32 feeds the residual path, dz2_16 the dropped dense output
+                ops.dropout(dz2_16, keep_h, s2, inplace=True)
             ops.colsum_bf16_add(dz2_16, gr(f"{p}/output/dense/bias"))
             ops.wgrad_gemm_bf16(inter, dz2_16, gr(f"{p}/output/dense/kernel"))
             dinter = ops.gemm_bf16(dz2_16, c["wd"], None, epilogue=ops.EPI_BF16)
@@ -244,11 +263,13 @@ def bert_forward_train(input_ids, input_mask, segment_ids, cfg, store, tape, sco
             # ---- attention LayerNorm + output projection
             dz1_32, dz1_16 = ops.layernorm_bwd(y1, w["g1"], dx1, gr(f"{p}/attention/output/LayerNorm/gamma"),
                                                gr(f"{p}/attention/output/LayerNorm/beta"), residual=x32_, eps=1e-12)
+            if keep_h < 1.0:
+                ops.dropout(dz1_16, keep_h, s1, inplace=True)
             ops.colsum_bf16_add(dz1_16, gr(f"{p}/attention/output/dense/bias"))
             ops.wgrad_gemm_bf16(ctx, dz1_16, gr(f"{p}/attention/output/dense/kernel"))
             dctx = ops.gemm_bf16(dz1_16, c["wo"], None, epilogue=ops.EPI_BF16)
             # ---- attention core + fused QKV projection
-            dqkv = ops.bert_attention_bwd(qkv, mask, ctx, dctx, B, L, NH, H // NH)
+            dqkv = ops.bert_attention_bwd(qkv, mask, ctx, dctx, B, L, NH, H // NH, keep_prob=keep_a, seed=sa)
             dbqkv = torch.zeros(3 * H, dtype=torch.float32, device=d.device)
             ops.colsum_bf16_add(dqkv, dbqkv)
             dwqkv = ops.wgrad_gemm_bf16(x16_, dqkv)                       # [H, 3H]
@@ -256,7 +277,9 @@ def bert_forward_train(input_ids, input_mask, segment_ids, cfg, store, tape, sco
                 gr(f"{p}/attention/self/{n}/kernel").add_(dwqkv[:, k * H:(k + 1) * H])
                 gr(f"{p}/attention/self/{n}/bias").add_(dbqkv[k * H:(k + 1) * H])
             d = ops.gemm_bf16(dqkv, c["wqkv"], None, residual=dz1_32, epilogue=ops.EPI_RES_F32)
-        # ---- embeddings: LayerNorm of (word + type + position)
+        # ---- embeddings: dropout, then LayerNorm of (word + type + position)
+        if keep_h < 1.0:
+            d = ops.dropout(d.contiguous(), keep_h, seed_e)
         segl = torch.zeros_like(ids) if seg is None else seg
         emb_sum = (we[ids.long()] + te[segl.long()] + pe[:L][None]).reshape(B * L, H).contiguous()
         dsum, _ = ops.layernorm_bwd(emb_sum, ge, d, gr(f"{scope}/embeddings/LayerNorm/gamma"), gr(f"{scope}/embeddings/LayerNorm/beta"),

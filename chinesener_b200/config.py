@@ -31,4 +31,5 @@ BERT_BASE_CHINESE = {
     'vocab_size': 21128, 'hidden_size': 768, 'num_hidden_layers': 12, 'num_attention_heads': 12,
     'intermediate_size': 3072, 'max_position_embeddings': 512, 'type_vocab_size': 2,
     'hidden_act': 'gelu', 'initializer_range': 0.02,
+    'hidden_dropout_prob': 0.1, 'attention_probs_dropout_prob': 0.1,   # applied by BertModel(is_training=True) only
 }

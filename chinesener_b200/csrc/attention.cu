@@ -34,10 +34,17 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// attention_probs dropout (training): z(b,h,q,k) in {0, 1/keep} from the shared counter hash; the
+// row sums keep the undropped probabilities (dropout follows the softmax in attention_layer()).
+__device__ __forceinline__ float attn_drop(uint32_t sa, uint32_t sb, int q, int k, uint32_t thr, float inv_keep) {
+  return hash3(sa, (uint32_t)q, (uint32_t)k ^ sb) < thr ? inv_keep : 0.f;
+}
+
+template <bool DROP>
 __global__ void __launch_bounds__(128)
 bert_attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ mask,
                       __nv_bfloat16* __restrict__ ctx, int Lpad, int NH, int Lp_max, float scale, float mask_add,
-                      const int32_t* __restrict__ cu_seqlens) {
+                      const int32_t* __restrict__ cu_seqlens, float keep, uint32_t seed_lo, uint32_t seed_hi) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __nv_bfloat16* Vs = Ks + (size_t)Lp_max * PITCH;
@@ -140,6 +147,18 @@ bert_attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __re
       }
       l0 = l0 * c0 + ps0;
       l1 = l1 * c1 + ps1;
+      if (DROP) {
+        const uint32_t sa = seed_lo ^ ((uint32_t)(b * NH + h) * 0x9E3779B1u), thr = keep_threshold(keep);
+        const float ik = 1.f / keep;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const int k = kb + nt * 8 + cq;
+          s[nt][0] *= attn_drop(sa, seed_hi, r0, k, thr, ik);
+          s[nt][1] *= attn_drop(sa, seed_hi, r0, k + 1, thr, ik);
+          s[nt][2] *= attn_drop(sa, seed_hi, r1, k, thr, ik);
+          s[nt][3] *= attn_drop(sa, seed_hi, r1, k + 1, thr, ik);
+        }
+      }
 #pragma unroll
       for (int dt = 0; dt < 8; ++dt) {
         o[dt][0] *= c0;
@@ -180,19 +199,20 @@ bert_attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __re
 
 extern "C" int ner_bert_attention(const void* qkv_bf16, const int32_t* mask, void* ctx_bf16, int B, int L,
                                   int num_heads, int head_dim, float scale, float mask_add,
-                                  const int32_t* cu_seqlens, ner_stream_t stream) {
-  if (B < 0 || L < 1 || num_heads < 1) return NER_ERR_INVALID_ARG;
+                                  const int32_t* cu_seqlens, float keep_prob, uint64_t seed, ner_stream_t stream) {
+  if (B < 0 || L < 1 || num_heads < 1 || !(keep_prob > 0.f)) return NER_ERR_INVALID_ARG;
   if (B == 0) return NER_OK;
   if (!qkv_bf16 || (!mask && !cu_seqlens) || !ctx_bf16) return NER_ERR_INVALID_ARG;
   if (head_dim != D) return NER_ERR_UNSUPPORTED;
   const int Lp = (L + KB - 1) / KB * KB;
   const size_t smem = (size_t)2 * Lp * PITCH * 2 + (size_t)Lp * 4;
   if (smem > 227 * 1024) return NER_ERR_UNSUPPORTED;  // L <= ~780
-  cudaError_t e = cudaFuncSetAttribute(bert_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = keep_prob < 1.f ? bert_attention_kernel<true> : bert_attention_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   dim3 grid((L + QT - 1) / QT, num_heads, B);
-  bert_attention_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+  kern<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv_bf16), mask, static_cast<__nv_bfloat16*>(ctx_bf16), L, num_heads, Lp, scale,
-      mask_add, cu_seqlens);
+      mask_add, cu_seqlens, keep_prob, (uint32_t)seed, (uint32_t)(seed >> 32));
   return ner_launch_status();
 }

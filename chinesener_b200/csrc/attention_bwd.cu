@@ -77,10 +77,20 @@ __device__ __forceinline__ void mma_p_b(float (&out)[8][4], const float (&p)[8][
   }
 }
 
+// Same attention_probs dropout factor as the forward kernel (attention.cu): z in {0, 1/keep}.
+// With O = (P o z) V:  dV = (P o z)^T dO,  dS = P o (z o dP - D),  D = rowsum(dO o O) unchanged.
+__device__ __forceinline__ float attn_drop(uint32_t sa, uint32_t sb, int q, int k, uint32_t thr, float inv_keep) {
+  return hash3(sa, (uint32_t)q, (uint32_t)k ^ sb) < thr ? inv_keep : 0.f;
+}
+
+template <bool DROP>
 __global__ void __launch_bounds__(NW * 32)
 bert_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ mask,
                           const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ dctx,
-                          __nv_bfloat16* __restrict__ dqkv, int L, int NH, int Lp, float scale, float mask_add) {
+                          __nv_bfloat16* __restrict__ dqkv, int L, int NH, int Lp, float scale, float mask_add,
+                          float keep, uint32_t seed_lo, uint32_t seed_hi) {
+  const uint32_t dsa = seed_lo ^ ((uint32_t)(blockIdx.y * NH + blockIdx.x) * 0x9E3779B1u), dthr = keep_threshold(keep);
+  const float dik = 1.f / keep;
   extern __shared__ __align__(16) uint8_t smraw[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smraw);
   __nv_bfloat16* Ks = Qs + (size_t)Lp * PITCH;
@@ -211,6 +221,13 @@ bert_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* 
         const float p01 = exp2f((s[nt][1] * scale + a1 - m0) * kLog2e) * li0;
         const float p10 = exp2f((s[nt][2] * scale + a0 - m1) * kLog2e) * li1;
         const float p11 = exp2f((s[nt][3] * scale + a1 - m1) * kLog2e) * li1;
+        if (DROP) {
+          const int k = kb + nt * 8 + cq;
+          dp[nt][0] *= attn_drop(dsa, seed_hi, r0, k, dthr, dik);
+          dp[nt][1] *= attn_drop(dsa, seed_hi, r0, k + 1, dthr, dik);
+          dp[nt][2] *= attn_drop(dsa, seed_hi, r1, k, dthr, dik);
+          dp[nt][3] *= attn_drop(dsa, seed_hi, r1, k + 1, dthr, dik);
+        }
         s[nt][0] = p00 * (dp[nt][0] - d0);
         s[nt][1] = p01 * (dp[nt][1] - d0);
         s[nt][2] = p10 * (dp[nt][2] - d1);
@@ -252,14 +269,21 @@ bert_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* 
         const float p01 = exp2f((st[nt][1] * scale + ma0 - mq1) * kLog2e) * lq1;
         const float p10 = exp2f((st[nt][2] * scale + ma1 - mq0) * kLog2e) * lq0;
         const float p11 = exp2f((st[nt][3] * scale + ma1 - mq1) * kLog2e) * lq1;
-        st[nt][0] = p00;
-        st[nt][1] = p01;
-        st[nt][2] = p10;
-        st[nt][3] = p11;
-        dpt[nt][0] = p00 * (dpt[nt][0] - dq0);
-        dpt[nt][1] = p01 * (dpt[nt][1] - dq1);
-        dpt[nt][2] = p10 * (dpt[nt][2] - dq0);
-        dpt[nt][3] = p11 * (dpt[nt][3] - dq1);
+        float z00 = 1.f, z01 = 1.f, z10 = 1.f, z11 = 1.f;
+        if (DROP) {
+          z00 = attn_drop(dsa, seed_hi, q0, k0, dthr, dik);
+          z01 = attn_drop(dsa, seed_hi, q1, k0, dthr, dik);
+          z10 = attn_drop(dsa, seed_hi, q0, k1, dthr, dik);
+          z11 = attn_drop(dsa, seed_hi, q1, k1, dthr, dik);
+        }
+        st[nt][0] = p00 * z00;
+        st[nt][1] = p01 * z01;
+        st[nt][2] = p10 * z10;
+        st[nt][3] = p11 * z11;
+        dpt[nt][0] = p00 * (z00 * dpt[nt][0] - dq0);
+        dpt[nt][1] = p01 * (z01 * dpt[nt][1] - dq1);
+        dpt[nt][2] = p10 * (z10 * dpt[nt][2] - dq0);
+        dpt[nt][3] = p11 * (z11 * dpt[nt][3] - dq1);
       }
       mma_p_b(dv, st, Os, qb, lane);   // dV += P^T dO
       mma_p_b(dk, dpt, Qs, qb, lane);  // dK += dS^T Q
@@ -284,20 +308,22 @@ bert_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* 
 
 extern "C" int ner_bert_attention_bwd(const void* qkv_bf16, const int32_t* mask, const void* ctx_bf16,
                                       const void* dctx_bf16, void* dqkv_bf16, int B, int L, int num_heads,
-                                      int head_dim, float scale, float mask_add, ner_stream_t stream) {
-  if (B < 0 || L < 1 || num_heads < 1) return NER_ERR_INVALID_ARG;
+                                      int head_dim, float scale, float mask_add, float keep_prob, uint64_t seed,
+                                      ner_stream_t stream) {
+  if (B < 0 || L < 1 || num_heads < 1 || !(keep_prob > 0.f)) return NER_ERR_INVALID_ARG;
   if (B == 0) return NER_OK;
   if (!qkv_bf16 || !mask || !ctx_bf16 || !dctx_bf16 || !dqkv_bf16) return NER_ERR_INVALID_ARG;
   if (head_dim != D) return NER_ERR_UNSUPPORTED;
   const int Lp = (L + 63) / 64 * 64;
   const size_t smem = (size_t)4 * Lp * PITCH * 2 + (size_t)4 * Lp * 4;
   if (smem > 227 * 1024) return NER_ERR_UNSUPPORTED;  // L <= ~380
-  cudaError_t e = cudaFuncSetAttribute(bert_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = keep_prob < 1.f ? bert_attention_bwd_kernel<true> : bert_attention_bwd_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   dim3 grid(num_heads, B);
-  bert_attention_bwd_kernel<<<grid, NW * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+  kern<<<grid, NW * 32, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv_bf16), mask, static_cast<const __nv_bfloat16*>(ctx_bf16),
       static_cast<const __nv_bfloat16*>(dctx_bf16), static_cast<__nv_bfloat16*>(dqkv_bf16), L, num_heads, Lp, scale,
-      mask_add);
+      mask_add, keep_prob, (uint32_t)seed, (uint32_t)(seed >> 32));
   return ner_launch_status();
 }

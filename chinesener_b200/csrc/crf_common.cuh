@@ -37,12 +37,32 @@ __device__ __forceinline__ void stage_logits(float* dst, const float* __restrict
   const int steps = min(Gm::T, L - t0);
   const int ne = steps * K;
   if (vec16) {
-    for (int idx = threadIdx.x; idx < NT * Gm::NQ; idx += NT) {
-      const int r = idx / Gm::NQ, q = idx - r * Gm::NQ;
-      if (r < nv) {
-        const int rem = min(ne, (s_len[r] - t0) * K);
-        if (4 * q < rem)
-          cp_async16(dst + r * Gm::P + 4 * q, gbase + (size_t)r * LK + (size_t)t0 * K + 4 * q);
+    if constexpr (Gm::NQ <= NT) {
+      // Fixed (row-in-group, 16-byte column) per thread: every index below except t0 is loop-invariant,
+      // so one request costs a length compare and a pointer add (the flat idx -> (row, column) split
+      // this replaces cost more instructions per step than the DP itself).  NQ consecutive lanes
+      // fetch one row's contiguous T*K*4-byte piece.
+      constexpr int RPI = NT / Gm::NQ, NIT = (NT + RPI - 1) / RPI;
+      const int rr = threadIdx.x / Gm::NQ, q = threadIdx.x - rr * Gm::NQ;
+      if (rr < RPI) {
+        const int e = t0 * K + 4 * q;           // element offset inside the row
+        const int lim_c = (t0 + steps) * K;     // end of this chunk
+        const float* g = gbase + (size_t)rr * LK + e;
+        float* d = dst + rr * Gm::P + 4 * q;
+#pragma unroll(NIT <= 16 ? NIT : 1)
+        for (int it = 0; it < NIT; ++it) {
+          const int r = rr + it * RPI;
+          if (r < nv && e < min(lim_c, s_len[r] * K)) cp_async16(d + it * RPI * Gm::P, g + (size_t)it * RPI * LK);
+        }
+      }
+    } else {
+      for (int idx = threadIdx.x; idx < NT * Gm::NQ; idx += NT) {
+        const int r = idx / Gm::NQ, q = idx - r * Gm::NQ;
+        if (r < nv) {
+          const int rem = min(ne, (s_len[r] - t0) * K);
+          if (4 * q < rem)
+            cp_async16(dst + r * Gm::P + 4 * q, gbase + (size_t)r * LK + (size_t)t0 * K + 4 * q);
+        }
       }
     }
   } else {

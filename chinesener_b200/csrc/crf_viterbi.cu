@@ -430,17 +430,8 @@ int launch_viterbi(const float* logits, const int32_t* seq_len, const float* tra
   // spread over more SMs with 32-sequence CTAs.
   const bool big = B > 148 * 32 * 2;
   if constexpr (K <= 16) {
-    if (big) {
-      int rc = NER_ERR_UNSUPPORTED;
-      switch (vit_variant()) {
-        case 1: rc = launch_viterbi_gs<K, 64, 4, 1>(logits, seq_len, trans, tags_out, best_score, B, L, st); break;
-        case 2: rc = launch_viterbi_gs<K, 64, 4, 6>(logits, seq_len, trans, tags_out, best_score, B, L, st); break;
-        case 3: rc = launch_viterbi_gs<K, 128, 4, 3>(logits, seq_len, trans, tags_out, best_score, B, L, st); break;
-        case 4: rc = launch_viterbi_gs<K, 64, 8, 1>(logits, seq_len, trans, tags_out, best_score, B, L, st); break;
-        case 5: rc = launch_viterbi_gs<K, 128, 8, 1>(logits, seq_len, trans, tags_out, best_score, B, L, st); break;
-        case 6: rc = launch_viterbi_gs<K, 64, 4, 8>(logits, seq_len, trans, tags_out, best_score, B, L, st); break;
-        default: break;
-      }
+    if (big && vit_variant() != 1) {   // NER_CRF_VIT_VARIANT=1: time the all-on-chip kernel instead
+      const int rc = launch_viterbi_gs<K, 64, 4, 6>(logits, seq_len, trans, tags_out, best_score, B, L, st);
       if (rc != NER_ERR_UNSUPPORTED) return rc;
     }
   }

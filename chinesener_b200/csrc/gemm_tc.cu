@@ -24,6 +24,8 @@
 //                              stages its own 128 A rows and HALF of the B tile, so the L2->smem
 //                              bytes per FLOP drop by 1.5x vs the 128x256 single-CTA tile (the
 //                              single-CTA kernel is L2-feed-bound at ~9-10 TB/s).
+#include <mutex>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -34,6 +36,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 8;
+constexpr float kSkFixupCost = 3.0f;  // stream-K: park + re-read of one partial accumulator, in k-block times (measured, profiles/)
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
 constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
@@ -123,6 +126,63 @@ __device__ __forceinline__ void epilogue_math(float (&v)[32], const uint32_t (&r
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stream-K work split.  With SK the M x N x K iteration space is cut into tiles * num_kb k-block
+// units and CTA c owns the contiguous unit range [c*U/G, (c+1)*U/G): every SM gets the same number
+// of k-blocks whatever tiles/SMs is (the packed M of an MSRA batch gives 1.5 / 2.03 / 0.5 waves on
+// the encoder's GEMMs, i.e. 25-50 % idle SMs with whole-tile scheduling).  A CTA's range is
+//   [tail piece of a tile]  [whole tiles]  [head piece of a tile]
+// The CTA holding a tile's HEAD (kb0 == 0) finishes that tile: it adds the fp32 partial sums that
+// the CTAs holding the later k-blocks parked in their workspace slot and runs the normal epilogue.
+// A tail piece is always the FIRST thing its CTA does and the head piece the LAST, so a finisher
+// never waits in practice and no wait cycle can form (all CTAs are co-resident: grid <= #SMs).
+struct SkArgs {
+  float4* ws;   // [grid][BN/32 chunks][8][128 rows] float4: slot c = partial accumulator of CTA c's first segment
+  int* flags;   // [grid] 0 / 1 = slot c published; reset to 0 by the finisher (all zero between launches)
+};
+
+struct SegIter {
+  int num_kb, num_tiles, tile, stride;
+  long long u, u1;
+  bool sk;
+  __device__ SegIter(bool sk_, int num_tiles_, int num_kb_) : num_kb(num_kb_), num_tiles(num_tiles_), sk(sk_) {
+    if (sk) {
+      const long long U = (long long)num_tiles * num_kb;
+      u = (long long)blockIdx.x * U / gridDim.x;
+      u1 = (long long)(blockIdx.x + 1) * U / gridDim.x;
+    } else {
+      tile = blockIdx.x;
+      stride = gridDim.x;
+    }
+  }
+  __device__ bool next(int& t, int& kb0, int& kb1) {
+    if (sk) {
+      if (u >= u1) return false;
+      t = (int)(u / num_kb);
+      kb0 = (int)(u - (long long)t * num_kb);
+      const long long rem = u1 - u;
+      kb1 = (rem < (long long)(num_kb - kb0)) ? kb0 + (int)rem : num_kb;
+      u += kb1 - kb0;
+      return true;
+    }
+    if (tile >= num_tiles) return false;
+    t = tile;
+    kb0 = 0;
+    kb1 = num_kb;
+    tile += stride;
+    return true;
+  }
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ void epi_bar_sync() {  // named barrier 1 over the 8 epilogue warps only
   asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
 }
@@ -145,10 +205,48 @@ __device__ __forceinline__ void epilogue_stage_bias(float* sbias, const EpiArgs&
 // conflict-free STS.128) -> ONE cp.async.bulk.tensor store by lane 0.  The store writes full
 // 128-byte lines and clips rows >= M / columns >= N by itself; direct per-thread stores wrote
 // 16-byte fragments of 32 different lines per instruction and were L2-transaction-bound.
+// Finisher side of a split tile: add the parked partial sums of CTAs [c_first, c_first + n_part) to
+// one 32-column chunk held in registers (same (chunk, i, row) layout the contributors wrote).
+template <int BN>
+__device__ __forceinline__ void add_partials(uint32_t (&r)[32], const float4* ws, int c_first, int n_part, int chunk,
+                                             int row_in_tile) {
+  constexpr size_t SLOT = (size_t)(BN / 32) * 8 * 128;
+  for (int c = 0; c < n_part; ++c) {
+    const float4* p = ws + (size_t)(c_first + c) * SLOT + (size_t)chunk * 8 * 128 + row_in_tile;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 v = __ldcg(p + i * 128);
+      r[4 * i + 0] = __float_as_uint(__uint_as_float(r[4 * i + 0]) + v.x);
+      r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + v.y);
+      r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + v.z);
+      r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + v.w);
+    }
+  }
+}
+
+// Contributor side: park the raw fp32 accumulator of this CTA's (partial) first segment in its slot.
+template <int BN>
+__device__ __forceinline__ void park_partial(uint32_t tmem_acc, int warp, int lane, float4* slot) {
+  const int q = warp & 3, half = (warp - 2) >> 2;
+  const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+  for (int ch = half; ch < BN / 32; ch += 2) {
+    uint32_t ra[32];
+    tmem_ld_32x32(tbase + (uint32_t)(ch * 32), ra);
+    tmem_ld_wait();
+    float4* p = slot + (size_t)ch * 8 * 128 + q * 32 + lane;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      __stcg(p + i * 128, make_float4(__uint_as_float(ra[4 * i]), __uint_as_float(ra[4 * i + 1]),
+                                      __uint_as_float(ra[4 * i + 2]), __uint_as_float(ra[4 * i + 3])));
+  }
+}
+
 template <int BN, bool OUT_F32>
 __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int warp, int lane, const EpiArgs& ep,
                                               const CUtensorMap* tma_c, uint8_t* stage, const float* sbias, int row0,
-                                              int n0, int M, int N) {
+                                              int n0, int M, int N, const float4* ws = nullptr, int c_first = 0,
+                                              int n_part = 0) {
   constexpr int GC = OUT_F32 ? 32 : 64;  // columns per 128-byte group
   constexpr int NG = BN / GC;            // groups per tile
   const int q = warp & 3;                // TMEM lane quarter this warp may access
@@ -165,6 +263,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int warp, int l
     uint4 pk[8];
     tmem_ld_32x32(tbase + (uint32_t)(g * GC), ra);
     tmem_ld_wait();
+    if (n_part > 0) add_partials<BN>(ra, ws, c_first, n_part, g * GC / 32, q * 32 + lane);
     epilogue_math(v, ra, ep, sbias + g * GC, row, col0, M, N);
     if constexpr (OUT_F32) {
 #pragma unroll
@@ -178,6 +277,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int warp, int l
                            pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
       tmem_ld_32x32(tbase + (uint32_t)(g * GC + 32), ra);
       tmem_ld_wait();
+      if (n_part > 0) add_partials<BN>(ra, ws, c_first, n_part, g * GC / 32 + 1, q * 32 + lane);
       epilogue_math(v, ra, ep, sbias + g * GC + 32, row, col0 + 32, M, N);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -200,10 +300,10 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int warp, int l
 }
 
 // ===================================================================== cta_group::1
-template <int BN>
+template <int BN, bool SK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    const __grid_constant__ CUtensorMap tma_c, EpiArgs ep, int M, int N, int K) {
+                    const __grid_constant__ CUtensorMap tma_c, EpiArgs ep, int M, int N, int K, SkArgs skargs) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
 
@@ -253,9 +353,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      SegIter it(SK, num_tiles, num_kb);
+      int tile, kb0, kb1;
+      while (it.next(tile, kb0, kb1)) {
         const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full_bar[stage], C::A_BYTES + C::B_BYTES);
           tma_load_2d(smem_a + stage * C::A_BYTES, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
@@ -275,11 +377,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      SegIter it(SK, num_tiles, num_kb);
+      int tile, kb0, kb1;
+      while (it.next(tile, kb0, kb1)) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + stage * C::A_BYTES);
@@ -288,7 +392,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t da = make_smem_desc_sw128(a_addr + k * UMMA_K * 2);
             const uint64_t db = make_smem_desc_sw128(b_addr + k * UMMA_K * 2);
-            umma_f16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
           if (++stage == STAGES) {
@@ -307,17 +411,53 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     // ===================== epilogue warps (2..9) =====================
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    constexpr size_t SLOT = (size_t)(BN / 32) * 8 * 128;
+    SegIter it(SK, num_tiles, num_kb);
+    int tile, kb0, kb1;
+    while (it.next(tile, kb0, kb1)) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
-      epilogue_stage_bias<BN>(sbias + acc * BN, ep, n_blk * BN, N);
+      const bool contributor = SK && kb0 > 0;
+      if (!contributor) epilogue_stage_bias<BN>(sbias + acc * BN, ep, n_blk * BN, N);
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      if (ep.mode == NER_EPI_F32 || ep.mode == NER_EPI_RES_F32 || ep.mode == NER_EPI_RES_RELU_F32)
-        epilogue_tile<BN, true>(tmem_base + (uint32_t)(acc * BN), warp, lane, ep, &tma_c, epi_stage + (warp - 2) * 4096,
-                                sbias + acc * BN, m_blk * BM, n_blk * BN, M, N);
-      else
-        epilogue_tile<BN, false>(tmem_base + (uint32_t)(acc * BN), warp, lane, ep, &tma_c, epi_stage + (warp - 2) * 4096,
-                                 sbias + acc * BN, m_blk * BM, n_blk * BN, M, N);
+      if (contributor) {
+        park_partial<BN>(tmem_base + (uint32_t)(acc * BN), warp, lane, skargs.ws + (size_t)blockIdx.x * SLOT);
+        __threadfence();
+        epi_bar_sync();
+        if (warp == 2 && lane == 0) st_release_gpu(skargs.flags + blockIdx.x, 1);
+      } else {
+        int c_first = 0, n_part = 0;
+        if (SK && kb1 < num_kb) {
+          // finisher: the following CTAs whose ranges start inside this tile hold its later k-blocks
+          const long long U = (long long)num_tiles * num_kb, tile_end = (long long)(tile + 1) * num_kb;
+          c_first = blockIdx.x + 1;
+          for (int c = c_first; c < (int)gridDim.x; ++c) {
+            const long long c0 = (long long)c * U / gridDim.x, c1 = (long long)(c + 1) * U / gridDim.x;
+            if (c0 >= tile_end) break;
+            if (c1 > c0) ++n_part; else if (n_part == 0) ++c_first;   // (empty ranges only occur when U < grid)
+          }
+          if (warp == 2 && lane == 0) {
+            for (int c = 0; c < n_part; ++c) {
+              unsigned spins = 0;
+              while (ld_acquire_gpu(skargs.flags + c_first + c) == 0)
+                if (++spins > (1u << 28)) __trap();   // never hang the GPU on a protocol bug
+            }
+          }
+          epi_bar_sync();
+          __threadfence();
+        }
+        if (ep.mode == NER_EPI_F32 || ep.mode == NER_EPI_RES_F32 || ep.mode == NER_EPI_RES_RELU_F32)
+          epilogue_tile<BN, true>(tmem_base + (uint32_t)(acc * BN), warp, lane, ep, &tma_c, epi_stage + (warp - 2) * 4096,
+                                  sbias + acc * BN, m_blk * BM, n_blk * BN, M, N, skargs.ws, c_first, n_part);
+        else
+          epilogue_tile<BN, false>(tmem_base + (uint32_t)(acc * BN), warp, lane, ep, &tma_c, epi_stage + (warp - 2) * 4096,
+                                   sbias + acc * BN, m_blk * BM, n_blk * BN, M, N, skargs.ws, c_first, n_part);
+        if (n_part > 0) {
+          epi_bar_sync();   // every epilogue thread has consumed the parked partials
+          if (warp == 2)
+            for (int c = lane; c < n_part; c += 32) skargs.flags[c_first + c] = 0;
+        }
+      }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -551,8 +691,57 @@ int sm_count() {
   return n;
 }
 
+// Stream-K scratch: one slot of 128 x 256 fp32 per CTA + one flag per CTA, per (device, stream) so
+// that GEMMs running concurrently on different streams never share slots.  Allocated on first use
+// (the only memory this library owns), never freed, flags zeroed once (the kernel restores them).
+struct SkScratch {
+  int dev;
+  cudaStream_t st;
+  float4* ws;
+  int* flags;
+};
+constexpr int kMaxSkScratch = 16;
+SkScratch g_sk[kMaxSkScratch];
+int g_sk_n = 0;
+std::mutex g_sk_mu;
+
+bool sk_scratch(cudaStream_t st, SkArgs* out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  std::lock_guard<std::mutex> lk(g_sk_mu);
+  for (int i = 0; i < g_sk_n; ++i)
+    if (g_sk[i].dev == dev && g_sk[i].st == st) {
+      out->ws = g_sk[i].ws;
+      out->flags = g_sk[i].flags;
+      return true;
+    }
+  if (g_sk_n == kMaxSkScratch) return false;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+    (void)cudaGetLastError();
+    return false;   // no allocation inside a graph capture: the caller falls back to whole-tile scheduling
+  }
+  const size_t slot = (size_t)(256 / 32) * 8 * 128 * sizeof(float4);
+  float4* ws = nullptr;
+  int* flags = nullptr;
+  if (cudaMalloc(&ws, slot * sm_count()) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  if (cudaMalloc(&flags, sizeof(int) * sm_count()) != cudaSuccess || cudaMemset(flags, 0, sizeof(int) * sm_count()) != cudaSuccess) {
+    (void)cudaGetLastError();
+    cudaFree(ws);
+    return false;
+  }
+  cudaDeviceSynchronize();
+  g_sk[g_sk_n++] = SkScratch{dev, st, ws, flags};
+  out->ws = ws;
+  out->flags = flags;
+  return true;
+}
+
 template <int BN>
-int launch_gemm(const void* A, const void* Wt, EpiArgs ep, int M, int N, int K, cudaStream_t st) {
+int launch_gemm(const void* A, const void* Wt, EpiArgs ep, int M, int N, int K, cudaStream_t st, bool sk = false) {
   CUtensorMap ma, mb;
   int rc = make_map_bf16_2d(&ma, A, (uint64_t)M, (uint64_t)K, BM);
   if (rc != NER_OK) return rc;
@@ -561,13 +750,24 @@ int launch_gemm(const void* A, const void* Wt, EpiArgs ep, int M, int N, int K, 
   CUtensorMap mc;
   rc = make_map_out(&mc, ep.out, (uint64_t)M, (uint64_t)N, epi_is_f32(ep.mode));
   if (rc != NER_OK) return rc;
-  auto kern = gemm_bf16_tc_kernel<BN>;
   const size_t smem = Cfg<BN>::SMEM;
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int num_kb = (K + BK - 1) / BK;
+  SkArgs ska{nullptr, nullptr};
+  // stream-K needs every CTA co-resident (grid = #SMs) and at least one k-block unit per CTA
+  sk = sk && (long long)tiles * num_kb >= sm_count() && ep.mode != NER_EPI_DIAG_DISCARD && sk_scratch(st, &ska);
+  if (sk) {
+    auto kern = gemm_bf16_tc_kernel<BN, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
+    kern<<<sm_count(), NUM_THREADS, smem, st>>>(ma, mb, mc, ep, M, N, K, ska);
+    return ner_launch_status();
+  }
+  auto kern = gemm_bf16_tc_kernel<BN, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, NUM_THREADS, smem, st>>>(ma, mb, mc, ep, M, N, K);
+  kern<<<grid, NUM_THREADS, smem, st>>>(ma, mb, mc, ep, M, N, K, ska);
   return ner_launch_status();
 }
 
@@ -608,10 +808,16 @@ extern "C" int ner_gemm_bf16(const void* A, const void* Wt, const float* bias, c
   EpiArgs ep{bias, residual, out, epilogue};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int bn = tile_n;
-  if (bn == 0) {
-    // Wave-quantisation cost model: time ~ ceil(tiles / SMs) * (relative cost of one 128 x BN tile).
-    // Relative costs measured on B200 (profiles/): the 128-wide tile is smem-bandwidth-bound.
-    const int mt = (M + BM - 1) / BM, sms = sm_count();
+  bool sk = false;
+  if (bn == NER_TILE_SK_256 || bn == NER_TILE_SK_128) {
+    sk = true;
+    bn = (bn == NER_TILE_SK_256) ? 256 : 128;
+  } else if (bn == 0) {
+    // Cost model in units of one 128x256 k-block per CTA.  Whole-tile scheduling: ceil(tiles/SMs) waves
+    // of num_kb k-blocks, the relative tile costs measured on B200 (profiles/): the 128-wide tile is
+    // smem-bandwidth-bound.  Stream-K (128x256 tiles): every CTA gets ceil(tiles*num_kb/SMs) k-blocks
+    // plus a fixed charge for parking / adding one partial accumulator.
+    const int mt = (M + BM - 1) / BM, sms = sm_count(), num_kb = (K + BK - 1) / BK;
     const int cand[3] = {256, 192, 128};
     const float cost[3] = {1.00f, 0.80f, 0.64f};
     float best = 1e30f;
@@ -619,17 +825,25 @@ extern "C" int ner_gemm_bf16(const void* A, const void* Wt, const float* bias, c
     for (int i = 0; i < 3; ++i) {
       if (N % cand[i] != 0) continue;
       const int tiles = mt * (N / cand[i]);
-      const float t = (float)((tiles + sms - 1) / sms) * cost[i];
+      const float t = (float)((tiles + sms - 1) / sms) * cost[i] * (float)num_kb;
       if (t < best - 1e-6f) {
         best = t;
         bn = cand[i];
       }
     }
+    if (N % 256 == 0) {
+      const long long units = (long long)mt * (N / 256) * num_kb;
+      const float t_sk = (float)((units + sms - 1) / sms) + kSkFixupCost;
+      if (units >= sms && t_sk < 0.9f * best) {
+        sk = true;
+        bn = 256;
+      }
+    }
   }
   switch (bn) {
-    case 256: return launch_gemm<256>(A, Wt, ep, M, N, K, st);
+    case 256: return launch_gemm<256>(A, Wt, ep, M, N, K, st, sk);
     case 192: return launch_gemm<192>(A, Wt, ep, M, N, K, st);
-    case 128: return launch_gemm<128>(A, Wt, ep, M, N, K, st);
+    case 128: return launch_gemm<128>(A, Wt, ep, M, N, K, st, sk);
     case 64: return launch_gemm<64>(A, Wt, ep, M, N, K, st);
     case NER_TILE_2CTA_256: return launch_gemm2<256>(A, Wt, ep, M, N, K, st);
     case NER_TILE_2CTA_128: return launch_gemm2<128>(A, Wt, ep, M, N, K, st);

@@ -98,6 +98,18 @@ dropout_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n, flo
   }
 }
 
+__global__ void __launch_bounds__(256)
+dropout_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n, float keep, uint32_t seed_lo,
+                    uint32_t seed_hi) {
+  const float inv = 1.f / keep;
+  const uint32_t thr = keep_threshold(keep);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t r = hash3(seed_lo, seed_hi ^ (uint32_t)(i >> 32), (uint32_t)i);
+    y[i] = (r < thr) ? __float2bfloat16(__bfloat162float(x[i]) * inv) : __float2bfloat16(0.f);
+  }
+}
+
 // sum of squares of a flat buffer -> out[0] (atomic), for clip_by_global_norm
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
@@ -190,6 +202,15 @@ extern "C" int ner_dense_small_n_bwd(const float* x, const float* W, const float
     if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
     kern<<<(int)g, 256, smem, st>>>(x, W, dy, dW, db, dx, M, F, N);
   }
+  return ner_launch_status();
+}
+
+extern "C" int ner_dropout_bf16(const void* x, void* y, size_t n, float keep_prob, uint64_t seed, ner_stream_t stream) {
+  if (!x || !y) return n == 0 ? NER_OK : NER_ERR_INVALID_ARG;
+  if (!(keep_prob > 0.f) || keep_prob > 1.f) return NER_ERR_INVALID_ARG;
+  if (n == 0) return NER_OK;
+  dropout_bf16_kernel<<<flat_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, keep_prob, (uint32_t)seed, (uint32_t)(seed >> 32));
   return ner_launch_status();
 }
 

@@ -11,6 +11,7 @@ from ._lib import check, lib, ptr, require_cuda, stream
 EPI_F32, EPI_BF16, EPI_GELU_TANH_BF16, EPI_GELU_ERF_BF16, EPI_RELU_BF16, EPI_RES_F32, EPI_RES_RELU_F32 = range(7)
 EPI_DIAG_DISCARD = 99
 TILE_2CTA_128, TILE_2CTA_256 = 1128, 1256   # CTA-pair (cta_group::2) tiles of ner_gemm_bf16
+TILE_SK_128, TILE_SK_256 = 2128, 2256       # stream-K scheduling of 128 x {128,256} tiles
 
 
 def _i32(t):
@@ -144,8 +145,10 @@ def layernorm(y, gamma, beta, residual=None, eps=1e-12, want_f32=True, want_bf16
     return of, ob
 
 
-def bert_attention(qkv, mask, B, L, num_heads, head_dim=64, scale=None, mask_add=-10000.0, cu_seqlens=None):
-    """Padded mode: qkv [B*L, 3HD] + mask.  Packed mode: qkv [T, 3HD] + cu_seqlens [B+1] (L = max length)."""
+def bert_attention(qkv, mask, B, L, num_heads, head_dim=64, scale=None, mask_add=-10000.0, cu_seqlens=None, keep_prob=1.0,
+                   seed=0):
+    """Padded mode: qkv [B*L, 3HD] + mask.  Packed mode: qkv [T, 3HD] + cu_seqlens [B+1] (L = max length).
+    keep_prob < 1: attention_probs dropout (training)."""
     require_cuda(qkv, mask, cu_seqlens)
     assert qkv.dtype == torch.bfloat16 and qkv.shape[1] == 3 * num_heads * head_dim
     assert cu_seqlens is not None or qkv.shape[0] == B * L
@@ -154,7 +157,7 @@ def bert_attention(qkv, mask, B, L, num_heads, head_dim=64, scale=None, mask_add
     if scale is None:
         scale = 1.0 / (head_dim ** 0.5)
     check(lib().ner_bert_attention(ptr(qkv), ptr(mask), ptr(ctx), B, L, num_heads, head_dim, scale, mask_add,
-                                   ptr(cu_seqlens), stream()))
+                                   ptr(cu_seqlens), float(keep_prob), int(seed) & 0xFFFFFFFFFFFFFFFF, stream()))
     return ctx
 
 
@@ -349,12 +352,13 @@ def dense_small_n_bwd(x2d, w, dy, dW, db=None, want_dx=True):
     return dx
 
 
-def dropout(x, keep_prob, seed):
-    """tf.layers.dropout forward (and backward: same call on the gradient with the same seed)."""
+def dropout(x, keep_prob, seed, inplace=False):
+    """tf.layers.dropout forward (and backward: same call on the gradient with the same seed); f32 or bf16."""
     require_cuda(x)
-    assert x.dtype == torch.float32 and x.is_contiguous()
-    y = torch.empty_like(x)
-    check(lib().ner_dropout(ptr(x), ptr(y), x.numel(), float(keep_prob), int(seed) & 0xFFFFFFFFFFFFFFFF, stream()))
+    assert x.dtype in (torch.float32, torch.bfloat16) and x.is_contiguous()
+    y = x if inplace else torch.empty_like(x)
+    fn = lib().ner_dropout if x.dtype == torch.float32 else lib().ner_dropout_bf16
+    check(fn(ptr(x), ptr(y), x.numel(), float(keep_prob), int(seed) & 0xFFFFFFFFFFFFFFFF, stream()))
     return y
 
 
@@ -434,12 +438,12 @@ def bert_embed_bwd(dx, ids, seg, d_word, d_type, d_pos):
                                    ptr(d_pos), B, L, H, d_word.shape[0], d_type.shape[0], stream()))
 
 
-def bert_attention_bwd(qkv, mask, ctx, dctx, B, L, num_heads, head_dim=64, scale=None, mask_add=-10000.0):
+def bert_attention_bwd(qkv, mask, ctx, dctx, B, L, num_heads, head_dim=64, scale=None, mask_add=-10000.0, keep_prob=1.0, seed=0):
     require_cuda(qkv, mask, ctx, dctx)
     assert qkv.dtype == torch.bfloat16 and ctx.dtype == torch.bfloat16 and dctx.dtype == torch.bfloat16
     dqkv = torch.empty_like(qkv)
     if scale is None:
         scale = 1.0 / (head_dim ** 0.5)
     check(lib().ner_bert_attention_bwd(ptr(qkv), ptr(_i32(mask)), ptr(ctx), ptr(dctx), ptr(dqkv), B, L, num_heads, head_dim,
-                                       scale, mask_add, stream()))
+                                       scale, mask_add, float(keep_prob), int(seed) & 0xFFFFFFFFFFFFFFFF, stream()))
     return dqkv

@@ -87,10 +87,14 @@ int ner_crf_loglik_bwd(const float* logits, const int32_t* tags, const int32_t* 
 #define NER_EPI_RES_RELU_F32 6   /* out f32  = relu(acc + bias + residual)   */
 #define NER_EPI_DIAG_DISCARD 99  /* diagnostic only: accumulate, drain TMEM, store nothing */
 
-/* tile_n selectors of ner_gemm_bf16: 64/128/256 = one CTA per 128 x tile_n tile
- * (cta_group::1); the 2CTA values = a CTA pair per 256 x N tile (cta_group::2). */
+/* tile_n selectors of ner_gemm_bf16: 64/128/192/256 = one CTA per 128 x tile_n tile
+ * (cta_group::1), whole tiles round-robin over the SMs; the 2CTA values = a CTA pair per 256 x N
+ * tile (cta_group::2); the SK values = 128 x tile_n tiles with stream-K scheduling (every SM gets
+ * the same number of k-blocks; split tiles are summed through an internal fp32 scratch). */
 #define NER_TILE_2CTA_128 1128
 #define NER_TILE_2CTA_256 1256
+#define NER_TILE_SK_128 2128
+#define NER_TILE_SK_256 2256
 
 /* out[M,N] = epilogue(A[M,K] · Wt[N,K]^T + bias[N]).  A and Wt are bf16,
  * K contiguous (Wt is the TF kernel [K,N] transposed once by
@@ -174,10 +178,12 @@ int ner_layernorm(const void* y, int y_is_bf16, const float* residual, const flo
  * qkv bf16 [B*L, 3*num_heads*head_dim] (Q | K | V blocks, heads contiguous inside each),
  * mask [B,L] i32 (1 = keep), ctx bf16 [B*L, num_heads*head_dim].  head_dim must be 64.
  * BERT: scale = 1/sqrt(64), mask_add = -10000.  Packed mode: cu_seqlens [B+1] non-NULL — sequence b
- * occupies rows [cu[b], cu[b+1]) of qkv/ctx, every key is valid, mask is ignored. */
+ * occupies rows [cu[b], cu[b+1]) of qkv/ctx, every key is valid, mask is ignored.
+ * keep_prob < 1: attention_probs dropout of BertModel in training (probabilities scaled by
+ * keep(seed; b, head, q, k) / keep_prob after the softmax); keep_prob = 1: inference. */
 int ner_bert_attention(const void* qkv_bf16, const int32_t* mask, void* ctx_bf16, int B, int L,
                        int num_heads, int head_dim, float scale, float mask_add,
-                       const int32_t* cu_seqlens, ner_stream_t stream);
+                       const int32_t* cu_seqlens, float keep_prob, uint64_t seed, ner_stream_t stream);
 
 /* Whole BertModel forward in one call (what tools/layer.py:68-77 gets from
  * modeling.BertModel(...).get_sequence_output()).  `layers` is a HOST array of per-layer
@@ -276,6 +282,9 @@ int ner_dense_small_n_bwd(const float* x, const float* W, const float* dy, float
  * (seed, i) reproduces the mask, so the backward pass is the same call on the gradient. */
 int ner_dropout(const float* x, float* y, size_t n, float keep_prob, uint64_t seed,
                 ner_stream_t stream);
+/* Same on bf16 tensors (BertModel's hidden dropout on the bf16 dense outputs; y may alias x). */
+int ner_dropout_bf16(const void* x_bf16, void* y_bf16, size_t n, float keep_prob, uint64_t seed,
+                     ner_stream_t stream);
 /* out[0] += sum(g^2)  (tf.clip_by_global_norm, tools/train_utils.py:315). */
 int ner_sumsq_add(const float* g, size_t n, float* out, ner_stream_t stream);
 /* One optimizer step over a flat parameter buffer.
@@ -313,10 +322,12 @@ int ner_bert_embed_bwd(const float* dx, const int32_t* ids, const int32_t* seg, 
                        float* d_type, float* d_pos, int B, int L, int H, int vocab, int n_type,
                        ner_stream_t stream);
 /* Backward of ner_bert_attention (padded layout, head_dim 64): qkv / ctx from the forward pass,
- * dctx = dL/dctx; writes d_qkv (bf16, layout of qkv).  Scores are recomputed, nothing L x L is stored. */
+ * dctx = dL/dctx; writes d_qkv (bf16, layout of qkv).  Scores are recomputed, nothing L x L is stored;
+ * (keep_prob, seed) must be the forward call's so the dropout mask is regenerated. */
 int ner_bert_attention_bwd(const void* qkv_bf16, const int32_t* mask, const void* ctx_bf16,
                            const void* dctx_bf16, void* dqkv_bf16, int B, int L, int num_heads,
-                           int head_dim, float scale, float mask_add, ner_stream_t stream);
+                           int head_dim, float scale, float mask_add, float keep_prob, uint64_t seed,
+                           ner_stream_t stream);
 
 #ifdef __cplusplus
 }

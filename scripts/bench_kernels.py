@@ -57,7 +57,7 @@ def bench_gemm():
         w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
         bias = torch.randn(N, device="cuda")
         res = torch.randn(M, N, device="cuda")
-        for tn in (0, 128, 192, 256, ops.TILE_2CTA_256):
+        for tn in (0, 128, 192, 256, ops.TILE_2CTA_256, ops.TILE_SK_256, ops.TILE_SK_128):
             for epi, nm in ((ops.EPI_BF16, "bf16"), (ops.EPI_F32, "f32")):
                 o = torch.empty(M, N, device="cuda", dtype=torch.float32 if epi in (ops.EPI_RES_F32, ops.EPI_F32) else torch.bfloat16)
                 med, best = timeit(lambda: ops.gemm_bf16(a, w, bias, residual=res if epi == ops.EPI_RES_F32 else None,

@@ -99,3 +99,45 @@ def test_attention_backward(B, L, NH):
     ref = x.grad
     err = (dqkv.float().cpu().double() - ref).abs().max().item()
     assert err < 3e-2 * ref.abs().max().item() + 1e-3, (err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,L,NH", [(2, 128, 12), (2, 70, 3)])
+def test_attention_probs_dropout_forward_and_backward(B, L, NH):
+    """BertModel(is_training=True): dropout on the softmax output.  The kernels' counter-based mask is
+    rebuilt on the host (tests/_masks.py) and fed to the float64 autograd reference."""
+    from _masks import attention_keep
+    D, keep, seed = 64, 0.9, (77 << 32) | 123456789
+    g = torch.Generator().manual_seed(B * L + NH + 1)
+    qkv = (torch.randn(B * L, 3 * NH * D, generator=g) * 0.7).to(torch.bfloat16)
+    dctx = torch.randn(B * L, NH * D, generator=g).to(torch.bfloat16)
+    lens = torch.randint(1, L + 1, (B,), generator=g)
+    lens[0] = L
+    mask = (torch.arange(L)[None, :] < lens[:, None]).to(torch.int32)
+    z = torch.from_numpy(attention_keep(B, NH, L, keep, seed)).double() / keep
+    assert 0.85 < float((z > 0).double().mean()) < 0.95
+    x = qkv.double().requires_grad_(True)
+    q, k, v = x.view(B, L, 3, NH, D).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) / math.sqrt(D) + (1.0 - mask.double())[:, None, None, :] * -10000.0
+    ctx_ref = ((torch.softmax(s, -1) * z) @ v).permute(0, 2, 1, 3).reshape(B * L, NH * D)
+    (ctx_ref * dctx.double()).sum().backward()
+    ctx = ops.bert_attention(qkv.cuda(), mask.cuda(), B, L, NH, D, keep_prob=keep, seed=seed)
+    err = (ctx.float().cpu().double() - ctx_ref.detach()).abs().max().item()
+    assert err < 2e-2 * ctx_ref.abs().max().item() + 1e-3, err
+    dqkv = ops.bert_attention_bwd(qkv.cuda(), mask.cuda(), ctx, dctx.cuda(), B, L, NH, D, keep_prob=keep, seed=seed)
+    ref = x.grad
+    err = (dqkv.float().cpu().double() - ref).abs().max().item()
+    assert err < 3e-2 * ref.abs().max().item() + 1e-3, (err, ref.abs().max().item())
+
+
+def test_bf16_dropout_matches_host_mask_and_is_its_own_backward():
+    from _masks import elementwise_keep
+    n, keep, seed = 100003, 0.9, 987654321012
+    x = torch.randn(n).to(torch.bfloat16)
+    y = ops.dropout(x.cuda(), keep, seed)
+    m = torch.from_numpy(elementwise_keep(n, keep, seed))
+    ref = torch.where(m, (x.float() / keep).to(torch.bfloat16), torch.zeros((), dtype=torch.bfloat16))
+    assert torch.equal(y.cpu(), ref)
+    y32 = ops.dropout(x.float().cuda(), keep, seed)                # the f32 kernel shares the decisions
+    assert torch.equal((y32 != 0).cpu() | (x.float() == 0), m | (x.float() == 0))
+    xi = x.cuda().clone()
+    assert ops.dropout(xi, keep, seed, inplace=True).data_ptr() == xi.data_ptr() and torch.equal(xi, y)

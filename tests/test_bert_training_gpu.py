@@ -16,8 +16,9 @@ CFG = {'vocab_size': 1500, 'hidden_size': 768, 'num_hidden_layers': 2, 'num_atte
        'intermediate_size': 3072, 'max_position_embeddings': 128, 'type_vocab_size': 2, 'initializer_range': 0.02}
 
 
-def _est(tmp_path, B=4, L=32, dropout=0.0, model="bert_crf", keep=1.0):
-    (tmp_path / "bert_config.json").write_text(json.dumps(CFG))
+def _est(tmp_path, B=4, L=32, dropout=0.0, model="bert_crf", keep=1.0, bert_dropout=0.0):
+    cfg = dict(CFG, hidden_dropout_prob=bert_dropout, attention_probs_dropout_prob=bert_dropout)
+    (tmp_path / "bert_config.json").write_text(json.dumps(cfg))
     feats = synthetic.msra_batch(B, L, vocab=CFG['vocab_size'], seed=21)
     params = dict(synthetic.data_params(L), pretrain_dir=str(tmp_path), embedding_dropout=dropout, keep_prob_list=[keep])
     return engine.Estimator(model, params), feats
@@ -68,7 +69,7 @@ def test_bert_gradients_match_oracle_autograd(tmp_path, model):
 
 @pytest.mark.parametrize("model", ["bert_crf", "bert_bilstm_crf"])
 def test_bert_training_reduces_loss(tmp_path, model):
-    est, feats = _est(tmp_path, dropout=0.1, model=model, keep=0.8)
+    est, feats = _est(tmp_path, dropout=0.1, model=model, keep=0.8, bert_dropout=0.1)   # every dropout site on
     # bert_bilstm_crf multiplies lr by 100 (lstm) / 500 (crf, logits) (diff_lr_times, reference
     # model/bert_bilstm_crf.py:45-47): its ReLU cells diverge at the lr bert_crf tolerates
     est.params.update(lr=2e-4 if model == "bert_crf" else 1e-5, num_train_steps=100, warmup_ratio=0.1)

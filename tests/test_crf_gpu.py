@@ -105,11 +105,12 @@ def test_loglik_alpha_workspace():
         np.testing.assert_allclose(a[b, :n], alphas[b, :n], rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("B,L,K", [(148 * 64 + 77, 128, 10), (9600, 37, 7), (9500, 50, 16), (9601, 21, 12), (9490, 9, 3)])
-def test_viterbi_parked_backpointer_kernel_bit_exact(monkeypatch, variant, B, L, K):
-    """The occupancy-first kernel (low backpointer nibbles parked in the tags_out slab): every tuning
-    variant must reproduce the oracle's tags and scores, ragged lengths and a partial tail CTA included."""
+def test_viterbi_large_batch_kernels_bit_exact(monkeypatch, variant, B, L, K):
+    """variant 0 = the occupancy-first kernel (low backpointer nibbles parked in the tags_out slab),
+    variant 1 = the all-on-chip kernel it replaced (still the fallback for K > 16): both must reproduce the
+    oracle's tags and scores, ragged lengths and a partial tail CTA included."""
     monkeypatch.setenv("NER_CRF_VIT_VARIANT", str(variant))
     x, tr, lens, _ = _case(B, L, K, seed=variant * 100 + K)
     lens[0], lens[1], lens[2] = L, 1, 0
@@ -121,11 +122,12 @@ def test_viterbi_parked_backpointer_kernel_bit_exact(monkeypatch, variant, B, L,
     np.testing.assert_array_equal(best.cpu().numpy(), ref_best.astype(np.float32))
 
 
-@pytest.mark.parametrize("variant", [1, 3, 6, 7])
-def test_loglik_tuning_variants(monkeypatch, variant):
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("K", [10, 7, 13])
+def test_loglik_large_batch_configurations(monkeypatch, variant, K):
     monkeypatch.setenv("NER_CRF_FWD_VARIANT", str(variant))
-    B, L, K = 19000, 40, 10
-    x, tr, lens, tags = _case(B, L, K, seed=variant)
+    B, L = 19000, 40
+    x, tr, lens, tags = _case(B, L, K, seed=variant + K)
     ref = crf.crf_log_likelihood(x, tags, lens, tr, dtype=np.float64)
     ll, _, _ = ops.crf_loglik_fwd(torch.from_numpy(x).cuda(), torch.from_numpy(tags).cuda(),
                                   torch.from_numpy(lens).cuda(), torch.from_numpy(tr).cuda())

@@ -63,3 +63,41 @@ def test_gemm_auto_tile_and_no_bias():
     wt = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).cuda()
     out = ops.gemm_bf16(a, wt, None, epilogue=ops.EPI_F32)
     torch.testing.assert_close(out, a.float() @ wt.float().t(), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(3150, 2304, 768), (3150, 768, 768), (3150, 3072, 768), (3150, 768, 3072), (1000, 768, 3072),
+                                   (8192, 2304, 768), (128, 256, 128), (2500, 256, 3072), (3195, 1024, 64)])
+@pytest.mark.parametrize("tile_n", [ops.TILE_SK_256, ops.TILE_SK_128, 0])
+@pytest.mark.timeout(120)
+def test_gemm_stream_k_matches_fp32_reference(M, N, K, tile_n):
+    """Stream-K scheduling (split tiles summed through the fp32 scratch): same result as whole-tile
+    scheduling, call after call (the finisher restores the flags), fp32 and bf16 outputs."""
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+    wt = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    res = torch.randn(M, N, generator=g).cuda()
+    ref = _ref(a, wt, bias, None, ops.EPI_F32)
+    for _ in range(3):
+        out = ops.gemm_bf16(a, wt, bias, epilogue=ops.EPI_F32, tile_n=tile_n)
+        torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-3)
+    out = ops.gemm_bf16(a, wt, bias, residual=res, epilogue=ops.EPI_RES_F32, tile_n=tile_n)
+    torch.testing.assert_close(out, ref + res, rtol=1e-4, atol=1e-3)
+    out = ops.gemm_bf16(a, wt, bias, epilogue=ops.EPI_GELU_TANH_BF16, tile_n=tile_n)
+    torch.testing.assert_close(out.float(), _ref(a, wt, bias, None, ops.EPI_GELU_TANH_BF16), rtol=1e-2, atol=1e-2)
+
+
+def test_gemm_stream_k_on_a_second_stream():
+    M, N, K = 3150, 768, 3072
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+    wt = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).cuda()
+    ref = a.float() @ wt.float().t()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        o2 = ops.gemm_bf16(a, wt, None, epilogue=ops.EPI_F32, tile_n=ops.TILE_SK_256)
+    o1 = ops.gemm_bf16(a, wt, None, epilogue=ops.EPI_F32, tile_n=ops.TILE_SK_256)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(o1, ref, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(o2, ref, rtol=1e-4, atol=1e-3)
