@@ -350,6 +350,15 @@ def run_ours(args):
         t_res, t_e2e = float(t[0]), float(t[1])
         t_train = float(t[2]) if t_train is not None else None
 
+    # ---- host enqueue time of one step (GPU parked behind a spin kernel): says whether the step is launch-bound
+    torch.cuda.synchronize()
+    torch.cuda._sleep(40_000_000)
+    h0 = time.perf_counter()
+    for i in range(5):
+        step_resident(i)
+    host_ms = (time.perf_counter() - h0) * 1e3 / 5
+    torch.cuda.synchronize()
+
     # ---- roofline of the dominant kernel (tcgen05 GEMM), instrumented pass on rank 0
     roof = cpu = None
     if rank == 0:
@@ -359,7 +368,11 @@ def run_ours(args):
         _lib._HOOK = timer
         _bert.PER_KERNEL = True          # same kernels, one C-ABI call each, so every GEMM launch gets its own events
         for i in range(min(args.steps, 5)):
+            # per-kernel calls come from Python (~20 us of host time each): hold the GPU behind a ~10 ms spin
+            # kernel so the whole step is enqueued first and the event pairs bracket execution, not launch latency
+            torch.cuda._sleep(20_000_000)
             step_resident(i)
+            torch.cuda.synchronize()
         _bert.PER_KERNEL = False
         _lib._HOOK = None
         ms, fl, n = timer.summary()
@@ -389,7 +402,7 @@ def run_ours(args):
                        "lengths": "MSRA-shaped (mean fill ~0.39)"},
             "e2e": {"value": sent / t_e2e, "unit": "sentences/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * t_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+            "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "clocks": clocks, "roofline": roof,
         }
         if t_train is not None:
             line["train"] = {"value": sent / t_train, "unit": "sentences/sec", "ms_per_step": 1e3 * t_train / args.steps,

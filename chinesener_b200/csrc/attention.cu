@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(128)
 bert_attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ mask,
                       __nv_bfloat16* __restrict__ ctx, int Lpad, int NH, int Lp_max, float scale, float mask_add,
                       const int32_t* __restrict__ cu_seqlens, float keep, uint32_t seed_lo, uint32_t seed_hi) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __nv_bfloat16* Vs = Ks + (size_t)Lp_max * PITCH;
@@ -211,8 +213,9 @@ extern "C" int ner_bert_attention(const void* qkv_bf16, const int32_t* mask, voi
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   dim3 grid((L + QT - 1) / QT, num_heads, B);
-  kern<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(qkv_bf16), mask, static_cast<__nv_bfloat16*>(ctx_bf16), L, num_heads, Lp, scale,
-      mask_add, cu_seqlens, keep_prob, (uint32_t)seed, (uint32_t)(seed >> 32));
+  e = ner_launch_pdl(kern, grid, dim3(128), smem, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(qkv_bf16),
+                     mask, static_cast<__nv_bfloat16*>(ctx_bf16), L, num_heads, Lp, scale, mask_add, cu_seqlens, keep_prob,
+                     (uint32_t)seed, (uint32_t)(seed >> 32));
+  if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   return ner_launch_status();
 }

@@ -97,6 +97,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ yv, const float* __restrict__ residual, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
                  int M, int H, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int nv4 = (H / 4 + 31) / 32;
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += gridDim.x * (blockDim.x >> 5)) {
@@ -292,12 +294,10 @@ extern "C" int ner_layernorm(const void* y, int y_is_bf16, const float* residual
   if (M == 0) return NER_OK;
   if (!y || !gamma || !beta || (!out_f32 && !out_bf16)) return NER_ERR_INVALID_ARG;
   if (H % 4 != 0 || H > 128 * LN_MAXV) return NER_ERR_UNSUPPORTED;
-  if (y_is_bf16)
-    layernorm_kernel<true><<<grid_for_rows(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        y, residual, gamma, beta, out_f32, static_cast<__nv_bfloat16*>(out_bf16), M, H, eps);
-  else
-    layernorm_kernel<false><<<grid_for_rows(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        y, residual, gamma, beta, out_f32, static_cast<__nv_bfloat16*>(out_bf16), M, H, eps);
+  cudaError_t e = ner_launch_pdl(y_is_bf16 ? layernorm_kernel<true> : layernorm_kernel<false>, dim3(grid_for_rows(M, 8)),
+                                 dim3(256), 0, static_cast<cudaStream_t>(stream), y, residual, gamma, beta, out_f32,
+                                 static_cast<__nv_bfloat16*>(out_bf16), M, H, eps);
+  if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   return ner_launch_status();
 }
 

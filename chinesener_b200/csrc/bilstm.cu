@@ -21,12 +21,14 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// ex2.approx-based forms (abs. error ~1e-7, far inside the 1e-4 parity bar of tests/test_bilstm_gpu.py):
+// the activations sit on the per-step critical path of the recurrence.
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 template <int ACT>
 __device__ __forceinline__ float actf(float x) {
   if (ACT == 1) return fmaxf(x, 0.f);
-  return tanhf(x);
+  return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x));   // tanh(x); saturates correctly for |x| large
 }
 
 // H4REG > 0: this thread's gate column of W_h (H4REG float4 = H fp32 values) is register-resident
@@ -53,14 +55,13 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
   constexpr bool WREG = H4REG > 0;
   float4* Ws4 = reinterpret_cast<float4*>(smem);                 // [H4][NC] float4 (4 consecutive k), smem path only
   float* hbuf = smem + (WREG ? 0 : (size_t)H * NC);              // [2][R][H]
-  float* zbuf = hbuf + 2 * R * H;                                // [R][NC]
-  int* s_len = reinterpret_cast<int*>(zbuf + R * NC);            // [R]
+  int* s_len = reinterpret_cast<int*>(hbuf + 2 * R * H);         // [R]
 
   const float* wh = dir == 0 ? wh_fw : wh_bw;                    // [H][4H], columns (i,j,f,o) x H
   float4 wreg[WREG ? H4REG : 1];
   if constexpr (WREG) {
     if (tid < NC) {
-      const int g0 = tid / HU, u0 = tid - g0 * HU;
+      const int g0 = tid & 3, u0 = tid >> 2;   // unit-major: the 4 gates of a hidden unit sit in 4 adjacent lanes
       const size_t gc = (size_t)g0 * H + rank * HU + u0;
 #pragma unroll
       for (int k4 = 0; k4 < H4REG; ++k4) {
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
   } else {
     for (int idx = tid; idx < H4 * NC; idx += blockDim.x) {
       const int k4 = idx / NC, col = idx - k4 * NC;
-      const int g = col / HU, u = col - g * HU;
+      const int g = col & 3, u = col >> 2;
       const size_t gc = (size_t)g * H + rank * HU + u;
       float4 w;
       w.x = wh[(size_t)(4 * k4 + 0) * 4 * H + gc];
@@ -91,14 +92,17 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
   for (int r = 0; r < R; ++r) maxlen = max(maxlen, s_len[r]);
   cluster.sync();  // every CTA's hbuf is zeroed before anyone writes remotely
 
-  // gate-column role
+  // Thread t < NC owns gate g = t & 3 of hidden unit u = t >> 2 (of this CTA's slice): the four
+  // pre-activations of a unit live in four adjacent lanes, so the cell update gathers them with
+  // three shuffles — no shared-memory round trip and no CTA barrier between the dot products and
+  // the cell; the only synchronisation per time step is the (cluster) barrier that publishes h.
   const bool col_ok = tid < NC;
-  const int g = col_ok ? tid / HU : 0, u = col_ok ? tid - g * HU : 0;
-  const size_t xcol = (size_t)dir * 4 * H + (size_t)g * H + rank * HU + u;
-  // cell role: thread (r,u2)
-  const bool cell_ok = tid < R * HU;
-  const int cr = cell_ok ? tid / HU : 0, cu = cell_ok ? tid - cr * HU : 0;
-  float c_state = 0.f, h_state = 0.f;
+  const int g = tid & 3, u = tid >> 2;
+  const int ug = rank * HU + u;
+  const size_t xcol = (size_t)dir * 4 * H + (size_t)g * H + ug;
+  // cell role: lane g of a unit's quad updates row r = g (R <= 4), so the R cell updates run in parallel
+  const bool cell_ok = col_ok && g < R;
+  float c_state = 0.f;
 
   // xproj row of (row r, position pos): padded layout b*L + pos, or packed layout cu_seqlens[b] + pos
   size_t xrow0[R];
@@ -115,14 +119,21 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
       xp[r] = xproj[(xrow0[r] + pos) * 8 * H + xcol];
     }
   }
+  const uint32_t thr = nerdev::keep_threshold(keep_prob);
+  const float inv_keep = 1.f / keep_prob;
 
   for (int s = 0; s < maxlen; ++s) {
     const float* hcur = hbuf + (s & 1) * R * H;
     float* hnxt = hbuf + ((s + 1) & 1) * R * H;
-    if (col_ok) {
-      float acc[R];
+    // packed fp32 pairs (FFMA2): (w_k, w_k+1) x (h_k, h_k+1) halves the FMA issue slots of the dot
+    // products, the per-step throughput bound of this kernel; two chains per row for latency
+    nerdev::f32x2 pa[R], pb[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = xp[r];
+    for (int r = 0; r < R; ++r) {
+      pa[r] = nerdev::pk2(xp[r], 0.f);
+      pb[r] = nerdev::pk2(0.f, 0.f);
+    }
+    if (col_ok) {
       // prefetch next step's input projection while the dot products run
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -141,10 +152,8 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             const float4 hv = hc4[r * H4 + k4];
-            acc[r] = fmaf(w.x, hv.x, acc[r]);
-            acc[r] = fmaf(w.y, hv.y, acc[r]);
-            acc[r] = fmaf(w.z, hv.z, acc[r]);
-            acc[r] = fmaf(w.w, hv.w, acc[r]);
+            pa[r] = nerdev::fma2(nerdev::pk2(w.x, w.y), nerdev::pk2(hv.x, hv.y), pa[r]);
+            pb[r] = nerdev::fma2(nerdev::pk2(w.z, w.w), nerdev::pk2(hv.z, hv.w), pb[r]);
           }
         }
       } else {
@@ -154,26 +163,38 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             const float4 hv = hc4[r * H4 + k4];
-            acc[r] = fmaf(w.x, hv.x, acc[r]);
-            acc[r] = fmaf(w.y, hv.y, acc[r]);
-            acc[r] = fmaf(w.z, hv.z, acc[r]);
-            acc[r] = fmaf(w.w, hv.w, acc[r]);
+            pa[r] = nerdev::fma2(nerdev::pk2(w.x, w.y), nerdev::pk2(hv.x, hv.y), pa[r]);
+            pb[r] = nerdev::fma2(nerdev::pk2(w.z, w.w), nerdev::pk2(hv.z, hv.w), pb[r]);
           }
         }
       }
-#pragma unroll
-      for (int r = 0; r < R; ++r) zbuf[r * NC + tid] = acc[r];
     }
-    __syncthreads();
+    // quad transpose: lane r of the quad receives (z_i, z_j, z_f, z_o) of row r
+    float zi = 0.f, zj = 0.f, zf = 0.f, zo = 0.f;
+    const int qb = (tid & 31) & ~3;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float z0, z1, z2, z3;
+      nerdev::upk2(pa[r], z0, z1);
+      nerdev::upk2(pb[r], z2, z3);
+      const float z = (z0 + z1) + (z2 + z3);
+      const float a0 = __shfl_sync(0xffffffffu, z, qb + 0);
+      const float a1 = __shfl_sync(0xffffffffu, z, qb + 1);
+      const float a2 = __shfl_sync(0xffffffffu, z, qb + 2);
+      const float a3 = __shfl_sync(0xffffffffu, z, qb + 3);
+      if (g == r) {
+        zi = a0;
+        zj = a1;
+        zf = a2;
+        zo = a3;
+      }
+    }
     if (cell_ok) {
-      const int len = s_len[cr];
-      const int b = b0 + cr;
-      const int ug = rank * HU + cu;
+      const int r = g;
+      const int len = s_len[r];
+      const int b = b0 + r;
+      float h_state = 0.f;
       if (s < len) {
-        const float zi = zbuf[cr * NC + 0 * HU + cu];
-        const float zj = zbuf[cr * NC + 1 * HU + cu];
-        const float zf = zbuf[cr * NC + 2 * HU + cu];
-        const float zo = zbuf[cr * NC + 3 * HU + cu];
         const float i_s = sigmoidf_(zi), j_a = actf<ACT>(zj), f_s = sigmoidf_(zf + forget_bias), o_s = sigmoidf_(zo);
         c_state = f_s * c_state + i_s * j_a;
         const float h_raw = o_s * actf<ACT>(c_state);
@@ -183,11 +204,9 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
         if (keep_prob < 1.f) {
           // DropoutWrapper(output_keep_prob, state_keep_prob): independent masks for the emitted output
           // and for the h part of the carried state (c is not dropped), fresh per step
-          const uint32_t thr = nerdev::keep_threshold(keep_prob);
           const uint32_t e = (uint32_t)(((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug);
-          const float inv = 1.f / keep_prob;
-          h_out = nerdev::hash3(seed_lo, seed_hi, e) < thr ? h_raw * inv : 0.f;
-          h_state = nerdev::hash3(seed_lo ^ 0x5bd1e995u, seed_hi, e) < thr ? h_raw * inv : 0.f;
+          h_out = nerdev::hash3(seed_lo, seed_hi, e) < thr ? h_raw * inv_keep : 0.f;
+          h_state = nerdev::hash3(seed_lo ^ 0x5bd1e995u, seed_hi, e) < thr ? h_raw * inv_keep : 0.f;
         }
         out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = h_out;
         if (hstate_out != nullptr) hstate_out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = h_state;
@@ -199,15 +218,20 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
           gates_out[gi + 3 * H + ug] = o_s;
           cstate_out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = c_state;
         }
-      } else if (b < B) {
-        out[((size_t)b * L + s) * 2 * H + (size_t)dir * H + ug] = 0.f;
+      } else {
+        // past this row's end: dynamic_rnn emits zeros and carries the state; h of a finished row is
+        // never read again (its own recurrence has stopped), so 0 is as good as the carried value
+        if (b < B) out[((size_t)b * L + s) * 2 * H + (size_t)dir * H + ug] = 0.f;
       }
       for (int dst = 0; dst < C; ++dst) {
         float* remote = cluster.map_shared_rank(hnxt, dst);
-        remote[cr * H + ug] = h_state;
+        remote[r * H + ug] = h_state;
       }
     }
-    cluster.sync();
+    if (C == 1)
+      __syncthreads();
+    else
+      cluster.sync();
   }
 
   // positions past the longest row of this cluster: zeros
@@ -234,7 +258,7 @@ int launch_rec(const float* xproj, const float* wh_fw, const float* wh_bw, const
                int L, int H, int C, float forget_bias, const int32_t* cu_seqlens, float* gates_out, float* cstate_out,
                float* hstate_out, float keep_prob, uint64_t seed, cudaStream_t st) {
   const int HU = H / C, NC = 4 * HU;
-  const size_t smem = ((H4REG > 0 ? 0 : (size_t)H * NC) + 2 * R * H + (size_t)R * NC + 32) * 4;
+  const size_t smem = ((H4REG > 0 ? 0 : (size_t)H * NC) + 2 * R * H + 32) * 4;
   auto kern = bilstm_rec_kernel<R, ACT, H4REG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;

@@ -15,7 +15,30 @@ static inline int ner_launch_status() {
   return NER_ERR_CUDA_BASE - (int)e;
 }
 
+// Launch with programmatic dependent launch (PDL): the grid may be scheduled while the previous
+// kernel of the stream is still draining, runs its prologue, and blocks in pdl_wait() until that
+// kernel has completed and flushed.  Kernels launched this way call pdl_launch_dependents() at
+// entry and pdl_wait() before their first global-memory access.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ner_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                         Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 namespace nerdev {
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);

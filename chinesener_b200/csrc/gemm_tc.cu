@@ -36,7 +36,10 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 8;
-constexpr float kSkFixupCost = 3.0f;  // stream-K: park + re-read of one partial accumulator, in k-block times (measured, profiles/)
+// stream-K fixed charge in k-block times: parking + re-reading a 128 KB partial accumulator and the
+// exposed finisher epilogue cost ~6 us (trip 16/17: SK loses on the encoder's forward shapes at M ~ 3150,
+// 24.9 vs 18.8 us for 3150x2304x768); it pays when tiles << SMs and K is long (weight gradients, K = tokens).
+constexpr float kSkFixupCost = 10.0f;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
 constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
@@ -306,6 +309,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                     const __grid_constant__ CUtensorMap tma_c, EpiArgs ep, int M, int N, int K, SkArgs skargs) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
+  nerdev::pdl_launch_dependents();   // the next kernel of the stream may start its prologue while this one runs
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;  // SWIZZLE_128B tiles need 1024-B alignment
@@ -347,6 +351,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // barriers, TMEM and descriptor prefetch are set up: everything below touches global memory and must
+  // wait for the previous kernel of the stream (no-op unless launched with the PDL attribute)
+  nerdev::pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -760,14 +767,16 @@ int launch_gemm(const void* A, const void* Wt, EpiArgs ep, int M, int N, int K, 
     auto kern = gemm_bf16_tc_kernel<BN, true>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
-    kern<<<sm_count(), NUM_THREADS, smem, st>>>(ma, mb, mc, ep, M, N, K, ska);
+    e = ner_launch_pdl(kern, dim3(sm_count()), dim3(NUM_THREADS), smem, st, ma, mb, mc, ep, M, N, K, ska);
+    if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
     return ner_launch_status();
   }
   auto kern = gemm_bf16_tc_kernel<BN, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, NUM_THREADS, smem, st>>>(ma, mb, mc, ep, M, N, K, ska);
+  e = ner_launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), smem, st, ma, mb, mc, ep, M, N, K, ska);
+  if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   return ner_launch_status();
 }
 
