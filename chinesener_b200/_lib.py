@@ -67,6 +67,21 @@ class BertLayerWeights(_c.Structure):
                                    "ln2_gamma", "ln2_beta")]
 
 
+class BertLayerGrads(_c.Structure):
+    _fields_ = [(n, _vp) for n in ("wqkv_kn", "wo_kn", "wi_kn", "wd_kn", "d_wq", "d_wk", "d_wv", "d_bq", "d_bk", "d_bv",
+                                   "d_wo", "d_bo", "d_ln1_gamma", "d_ln1_beta", "d_wi", "d_bi", "d_wd", "d_bd",
+                                   "d_ln2_gamma", "d_ln2_beta")]
+
+
+SIGNATURES["ner_bert_train_saved_bytes"] = (_c.c_size_t, [_c.POINTER(BertConfig), _i])
+SIGNATURES["ner_bert_train_scratch_bytes"] = (_c.c_size_t, [_c.POINTER(BertConfig), _i])
+SIGNATURES["ner_bert_encoder_train_fwd"] = (_i, [_c.POINTER(BertConfig)] + [_vp] * 5 + [_c.POINTER(BertLayerWeights)] + [_vp] * 3
+                                            + [_i, _i, _c.c_float, _c.c_float, _c.c_uint64, _vp, _vp, _vp, _c.c_size_t, _vp])
+SIGNATURES["ner_bert_encoder_train_bwd"] = (_i, [_c.POINTER(BertConfig), _vp, _c.POINTER(BertLayerWeights), _c.POINTER(BertLayerGrads)]
+                                            + [_vp] * 5 + [_vp] * 3 + [_i, _i, _c.c_float, _c.c_float, _c.c_uint64, _vp, _vp,
+                                                                       _c.c_size_t, _vp, _c.c_size_t, _vp])
+SIGNATURES["ner_bert_embed_sum"] = (_i, [_vp] * 6 + [_i] * 6 + [_vp])
+SIGNATURES["ner_axpy_f32"] = (_i, [_vp, _vp, _c.c_size_t, _c.c_float, _vp])
 SIGNATURES["ner_bert_encoder_workspace_bytes"] = (_c.c_size_t, [_c.POINTER(BertConfig), _i])
 SIGNATURES["ner_bert_encoder_fwd"] = (_i, [_c.POINTER(BertConfig)] + [_vp] * 5 + [_c.POINTER(BertLayerWeights)] + [_vp] * 3
                                       + [_i, _i, _vp, _vp, _i, _vp, _vp, _vp, _c.c_size_t, _vp])

@@ -38,6 +38,12 @@ layernorm_bwd_kernel(const void* __restrict__ yv, const float* __restrict__ resi
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int nv4 = (H / 4 + 31) / 32;
+  // a lane owns the same columns in every row: d_gamma / d_beta partials stay in registers across the
+  // warp's rows and reach shared memory once per warp (per-element shared atomics per row made this
+  // kernel 4x slower than its HBM time)
+  float4 ag[LN_MAXV], ab[LN_MAXV];
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k) ag[k] = ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += gridDim.x * (blockDim.x >> 5)) {
     float4 z[LN_MAXV], g[LN_MAXV];
     float s = 0.f;
@@ -76,14 +82,14 @@ layernorm_bwd_kernel(const void* __restrict__ yv, const float* __restrict__ resi
         const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + e));
         // zhat
         z[k].x *= rstd; z[k].y *= rstd; z[k].z *= rstd; z[k].w *= rstd;
-        atomicAdd(&s_acc[e + 0], g[k].x * z[k].x);
-        atomicAdd(&s_acc[e + 1], g[k].y * z[k].y);
-        atomicAdd(&s_acc[e + 2], g[k].z * z[k].z);
-        atomicAdd(&s_acc[e + 3], g[k].w * z[k].w);
-        atomicAdd(&s_acc[H + e + 0], g[k].x);
-        atomicAdd(&s_acc[H + e + 1], g[k].y);
-        atomicAdd(&s_acc[H + e + 2], g[k].z);
-        atomicAdd(&s_acc[H + e + 3], g[k].w);
+        ag[k].x = fmaf(g[k].x, z[k].x, ag[k].x);
+        ag[k].y = fmaf(g[k].y, z[k].y, ag[k].y);
+        ag[k].z = fmaf(g[k].z, z[k].z, ag[k].z);
+        ag[k].w = fmaf(g[k].w, z[k].w, ag[k].w);
+        ab[k].x += g[k].x;
+        ab[k].y += g[k].y;
+        ab[k].z += g[k].z;
+        ab[k].w += g[k].w;
         g[k].x *= gm.x; g[k].y *= gm.y; g[k].z *= gm.z; g[k].w *= gm.w;
         m1 += g[k].x + g[k].y + g[k].z + g[k].w;
         m2 += g[k].x * z[k].x + g[k].y * z[k].y + g[k].z * z[k].z + g[k].w * z[k].w;
@@ -103,6 +109,20 @@ layernorm_bwd_kernel(const void* __restrict__ yv, const float* __restrict__ resi
         if (dz_f32 != nullptr) *reinterpret_cast<float4*>(dz_f32 + (size_t)row * H + e) = d;
         if (dz_bf16 != nullptr) st_bf16x4(dz_bf16 + (size_t)row * H + e, d);
       }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k) {
+    const int e = (lane + 32 * k) * 4;
+    if (k < nv4 && e < H) {
+      atomicAdd(&s_acc[e + 0], ag[k].x);
+      atomicAdd(&s_acc[e + 1], ag[k].y);
+      atomicAdd(&s_acc[e + 2], ag[k].z);
+      atomicAdd(&s_acc[e + 3], ag[k].w);
+      atomicAdd(&s_acc[H + e + 0], ab[k].x);
+      atomicAdd(&s_acc[H + e + 1], ab[k].y);
+      atomicAdd(&s_acc[H + e + 2], ab[k].z);
+      atomicAdd(&s_acc[H + e + 3], ab[k].w);
     }
   }
   __syncthreads();
@@ -145,6 +165,40 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += part[i][threadIdx.x & 31];
     atomicAdd(out + n, s);
+  }
+}
+
+// Same for N % 8 == 0: a thread owns 8 adjacent columns (one 16-byte load per row), a warp 256 columns,
+// the 8 warps of a CTA stride over rows; shared-memory reduction over the warps, one atomic per column per CTA.
+__global__ void __launch_bounds__(256)
+colsum_bf16_v8_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int M, int N) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  __shared__ float part[8][256 + 8];
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c0 < N) {
+    for (int m = blockIdx.y * 8 + warp; m < M; m += gridDim.y * 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(x + (size_t)m * N + c0);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[w][threadIdx.x];
+    atomicAdd(out + c, s);
   }
 }
 
@@ -255,6 +309,14 @@ extern "C" int ner_transpose_bf16(const void* src_bf16, void* dst_bf16, int M, i
 extern "C" int ner_colsum_bf16_add(const void* x_bf16, float* out, int M, int N, ner_stream_t stream) {
   if (M < 0 || N < 1 || !x_bf16 || !out) return NER_ERR_INVALID_ARG;
   if (M == 0) return NER_OK;
+  if (N % 8 == 0 && (reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0) {
+    const int cb = (N + 255) / 256;
+    int gy = (2 * 148 + cb - 1) / cb;          // ~2 CTAs per SM in total
+    if (gy > (M + 7) / 8) gy = (M + 7) / 8;
+    colsum_bf16_v8_kernel<<<dim3(cb, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x_bf16),
+                                                                                        out, M, N);
+    return ner_launch_status();
+  }
   dim3 grid((N + 31) / 32, M >= 4096 ? 32 : (M >= 256 ? 8 : 1));
   colsum_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x_bf16), out, M, N);
   return ner_launch_status();

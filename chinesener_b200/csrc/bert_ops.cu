@@ -91,6 +91,27 @@ bert_embed_ln_kernel(const float* __restrict__ word_emb, const float* __restrict
   }
 }
 
+// word + token_type + position, no LayerNorm (the pre-LN sum the embedding LayerNorm backward needs)
+__global__ void __launch_bounds__(256)
+bert_embed_sum_kernel(const float* __restrict__ word_emb, const float* __restrict__ type_emb,
+                      const float* __restrict__ pos_emb, const int32_t* __restrict__ ids, const int32_t* __restrict__ seg,
+                      float* __restrict__ out, int n_tok, int L, int H, int V, int n_type) {
+  const int lane = threadIdx.x & 31;
+  for (int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tok < n_tok; tok += gridDim.x * (blockDim.x >> 5)) {
+    const int id = min(max(ids[tok], 0), V - 1);
+    const int sg = min(max(seg != nullptr ? seg[tok] : 0, 0), n_type - 1);
+    const float* w = word_emb + (size_t)id * H;
+    const float* ty = type_emb + (size_t)sg * H;
+    const float* po = pos_emb + (size_t)(tok % L) * H;
+    for (int e = lane * 4; e < H; e += 128) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(w + e));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ty + e));
+      const float4 c = __ldg(reinterpret_cast<const float4*>(po + e));
+      *reinterpret_cast<float4*>(out + (size_t)tok * H + e) = make_float4(a.x + b.x + c.x, a.y + b.y + c.y, a.z + b.z + c.z, a.w + b.w + c.w);
+    }
+  }
+}
+
 // y (+ optional residual) -> LayerNorm -> fp32 and/or bf16.  y is fp32 or (YBF16) bf16.
 template <bool YBF16>
 __global__ void __launch_bounds__(256)
@@ -284,6 +305,17 @@ extern "C" int ner_bert_embed_ln(const float* word_emb, const float* type_emb, c
   bert_embed_ln_kernel<<<grid_for_rows(n_tok, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       word_emb, type_emb, pos_emb, gamma, beta, ids, seg, out_f32, static_cast<__nv_bfloat16*>(out_bf16), n_tok, L, H,
       vocab, n_type, eps, tok_src);
+  return ner_launch_status();
+}
+
+extern "C" int ner_bert_embed_sum(const float* word_emb, const float* type_emb, const float* pos_emb, const int32_t* ids,
+                                  const int32_t* seg, float* out, int B, int L, int H, int vocab, int n_type, int max_pos,
+                                  ner_stream_t stream) {
+  if (B < 0 || L < 1 || H < 4 || H % 4 != 0) return NER_ERR_INVALID_ARG;
+  if (B == 0) return NER_OK;
+  if (!word_emb || !type_emb || !pos_emb || !ids || !out || L > max_pos) return NER_ERR_INVALID_ARG;
+  bert_embed_sum_kernel<<<grid_for_rows(B * L, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(word_emb, type_emb, pos_emb, ids,
+                                                                                             seg, out, B * L, L, H, vocab, n_type);
   return ner_launch_status();
 }
 

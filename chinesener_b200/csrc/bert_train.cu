@@ -1,0 +1,232 @@
+// TRAIN-mode BertModel forward and backward as two C-ABI calls (bert_base.bert.modeling.BertModel
+// with is_training=True as driven from reference tools/layer.py:63-81, gradients as tf.gradients
+// derives them at tools/train_utils.py:314).  The host loops below only enqueue kernels (≈11 per
+// layer forward, ≈27 per layer backward) on the caller's stream: issued from Python the same
+// sequence costs ~20 us of host time per launch and the TRAIN step was launch-bound (19 ms of host
+// time for ~7 ms of device work, profiles/README.md trip 19).
+//
+// Saved activations (padded layout, rows = B*L), one block per layer:
+//   x32 f32 | x16 bf16 (layer input) | qkv bf16 | ctx bf16 | y1 bf16 (dropped) | x1_32 f32 | x1_16 bf16 |
+//   pre bf16 | inter bf16 | y2 bf16 (dropped);    the encoder output is the caller's out_f32 / out_bf16.
+// Dropout seeds: every site draws seed = base + index (embedding 0; layer l: 1+3l attention probs,
+// 2+3l attention-output dense, 3+3l FFN-output dense); the backward call regenerates the masks.
+#include "common.cuh"
+
+namespace {
+
+inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct LayerSaved {
+  float* x32;
+  void* x16;
+  void* qkv;
+  void* ctx;
+  void* y1;
+  float* x1_32;
+  void* x1_16;
+  void* pre;
+  void* inter;
+  void* y2;
+};
+
+size_t layer_saved_bytes(size_t R, size_t H, size_t I) {
+  return al(R * H * 4) + al(R * H * 2) + al(R * 3 * H * 2) + al(R * H * 2) + al(R * H * 2) + al(R * H * 4) + al(R * H * 2) +
+         al(R * I * 2) + al(R * I * 2) + al(R * H * 2);
+}
+
+LayerSaved carve(uint8_t* p, size_t R, size_t H, size_t I) {
+  LayerSaved s;
+  s.x32 = reinterpret_cast<float*>(p);   p += al(R * H * 4);
+  s.x16 = p;                             p += al(R * H * 2);
+  s.qkv = p;                             p += al(R * 3 * H * 2);
+  s.ctx = p;                             p += al(R * H * 2);
+  s.y1 = p;                              p += al(R * H * 2);
+  s.x1_32 = reinterpret_cast<float*>(p); p += al(R * H * 4);
+  s.x1_16 = p;                           p += al(R * H * 2);
+  s.pre = p;                             p += al(R * I * 2);
+  s.inter = p;                           p += al(R * I * 2);
+  s.y2 = p;
+  return s;
+}
+
+#define NER_TRY(call)              \
+  do {                             \
+    const int rc_ = (call);        \
+    if (rc_ != NER_OK) return rc_; \
+  } while (0)
+
+// dW [K_in, N_out] f32 += x^T · dy   (x [R, K_in], dy [R, N_out] bf16): both operands transposed to K-major
+// (K = tokens) and multiplied on the tensor cores with the accumulate-into-residual epilogue.
+int wgrad(const void* x, int k_in, const void* dy_t /* [N_out, Rp] or null */, const void* dy, int n_out, float* dw, int R,
+          int Rp, void* xt, void* dyt, cudaStream_t st) {
+  NER_TRY(ner_transpose_bf16(x, xt, R, k_in, Rp, st));
+  const void* b = dy_t;
+  if (b == nullptr) {
+    NER_TRY(ner_transpose_bf16(dy, dyt, R, n_out, Rp, st));
+    b = dyt;
+  }
+  return ner_gemm_bf16(xt, b, nullptr, dw, dw, k_in, n_out, Rp, NER_EPI_RES_F32, 0, st);
+}
+
+}  // namespace
+
+extern "C" size_t ner_bert_train_saved_bytes(const ner_bert_config* cfg, int rows) {
+  if (!cfg || rows < 0) return 0;
+  const size_t R = (size_t)rows, H = (size_t)cfg->hidden_size, I = (size_t)cfg->intermediate_size;
+  return (size_t)cfg->num_layers * layer_saved_bytes(R, H, I) + al(R * H * 4) /* embedding sum */;
+}
+
+extern "C" size_t ner_bert_train_scratch_bytes(const ner_bert_config* cfg, int rows) {
+  if (!cfg || rows < 0) return 0;
+  const size_t R = (size_t)rows, Rp = (R + 7) / 8 * 8, H = (size_t)cfg->hidden_size, I = (size_t)cfg->intermediate_size;
+  const size_t W = I > 3 * H ? I : 3 * H;
+  return 2 * al(R * H * 4)      // d ping-pong (f32)
+         + al(R * H * 4)        // dz f32 (residual-path gradient)
+         + al(R * H * 2)        // dz bf16
+         + 2 * al(R * I * 2)    // dinter, dpre
+         + al(R * H * 2)        // dctx
+         + al(R * 3 * H * 2)    // dqkv
+         + 2 * al(W * Rp * 2)   // transposed operands of the weight-gradient GEMMs
+         + al(3 * H * 4);       // fused QKV bias gradient
+}
+
+extern "C" int ner_bert_encoder_train_fwd(const ner_bert_config* cfg, const float* word_emb, const float* type_emb,
+                                          const float* pos_emb, const float* emb_ln_gamma, const float* emb_ln_beta,
+                                          const ner_bert_layer_weights* layers, const int32_t* ids, const int32_t* mask,
+                                          const int32_t* seg, int B, int L, float hidden_keep, float attn_keep,
+                                          uint64_t seed, float* out_f32, void* out_bf16, void* saved, size_t saved_bytes,
+                                          ner_stream_t stream) {
+  if (!cfg || !layers || !out_f32 || !out_bf16 || !ids || !mask || !saved) return NER_ERR_INVALID_ARG;
+  if (B < 0 || L < 1 || !(hidden_keep > 0.f) || hidden_keep > 1.f || !(attn_keep > 0.f) || attn_keep > 1.f)
+    return NER_ERR_INVALID_ARG;
+  if (B == 0) return NER_OK;
+  const int rows = B * L, H = cfg->hidden_size, NH = cfg->num_heads, I = cfg->intermediate_size;
+  if (H % NH != 0) return NER_ERR_INVALID_ARG;
+  if (saved_bytes < ner_bert_train_saved_bytes(cfg, rows)) return NER_ERR_WORKSPACE;
+  const size_t R = (size_t)rows, lb = layer_saved_bytes(R, H, I);
+  uint8_t* base = static_cast<uint8_t*>(saved);
+  float* emb_sum = reinterpret_cast<float*>(base + (size_t)cfg->num_layers * lb);
+  const int gelu_erf = cfg->gelu_erf ? 1 : 0;
+  const float scale = 1.0f / sqrtf((float)(H / NH));
+
+  // embeddings: sum -> LayerNorm -> dropout   (layer_norm_and_dropout of embedding_postprocessor)
+  LayerSaved s0 = carve(base, R, H, I);
+  NER_TRY(ner_bert_embed_sum(word_emb, type_emb, pos_emb, ids, seg, emb_sum, B, L, H, cfg->vocab_size, cfg->type_vocab_size,
+                             cfg->max_position, stream));
+  NER_TRY(ner_layernorm(emb_sum, 0, nullptr, emb_ln_gamma, emb_ln_beta, s0.x32, s0.x16, rows, H, cfg->ln_eps, stream));
+  if (hidden_keep < 1.f) {
+    NER_TRY(ner_dropout(s0.x32, s0.x32, R * H, hidden_keep, seed, stream));
+    NER_TRY(ner_cast_bf16(s0.x32, s0.x16, R * H, stream));
+  }
+  for (int l = 0; l < cfg->num_layers; ++l) {
+    const ner_bert_layer_weights& w = layers[l];
+    LayerSaved s = carve(base + (size_t)l * lb, R, H, I);
+    const bool last = l + 1 == cfg->num_layers;
+    LayerSaved nx = last ? s : carve(base + (size_t)(l + 1) * lb, R, H, I);
+    float* o32 = last ? out_f32 : nx.x32;
+    void* o16 = last ? out_bf16 : nx.x16;
+    const uint64_t sa = seed + 1 + 3 * (uint64_t)l, s1 = sa + 1, s2 = sa + 2;
+    NER_TRY(ner_gemm_bf16(s.x16, w.wqkv, w.bqkv, nullptr, s.qkv, rows, 3 * H, H, NER_EPI_BF16, 0, stream));
+    NER_TRY(ner_bert_attention(s.qkv, mask, s.ctx, B, L, NH, H / NH, scale, -10000.0f, nullptr, attn_keep, sa, stream));
+    NER_TRY(ner_gemm_bf16(s.ctx, w.wo, w.bo, nullptr, s.y1, rows, H, H, NER_EPI_BF16, 0, stream));
+    if (hidden_keep < 1.f) NER_TRY(ner_dropout_bf16(s.y1, s.y1, R * H, hidden_keep, s1, stream));
+    NER_TRY(ner_layernorm(s.y1, 1, s.x32, w.ln1_gamma, w.ln1_beta, s.x1_32, s.x1_16, rows, H, cfg->ln_eps, stream));
+    NER_TRY(ner_gemm_bf16(s.x1_16, w.wi, w.bi, nullptr, s.pre, rows, I, H, NER_EPI_BF16, 0, stream));
+    NER_TRY(ner_gelu_bf16(s.pre, s.inter, R * I, gelu_erf, stream));
+    NER_TRY(ner_gemm_bf16(s.inter, w.wd, w.bd, nullptr, s.y2, rows, H, I, NER_EPI_BF16, 0, stream));
+    if (hidden_keep < 1.f) NER_TRY(ner_dropout_bf16(s.y2, s.y2, R * H, hidden_keep, s2, stream));
+    NER_TRY(ner_layernorm(s.y2, 1, s.x1_32, w.ln2_gamma, w.ln2_beta, o32, o16, rows, H, cfg->ln_eps, stream));
+  }
+  return NER_OK;
+}
+
+extern "C" int ner_bert_encoder_train_bwd(const ner_bert_config* cfg, const float* emb_ln_gamma,
+                                          const ner_bert_layer_weights* layers, const ner_bert_layer_grads* grads,
+                                          float* d_word_emb, float* d_type_emb, float* d_pos_emb, float* d_emb_ln_gamma,
+                                          float* d_emb_ln_beta, const int32_t* ids, const int32_t* mask,
+                                          const int32_t* seg, int B, int L, float hidden_keep, float attn_keep,
+                                          uint64_t seed, const float* d_out, const void* saved, size_t saved_bytes,
+                                          void* scratch, size_t scratch_bytes, ner_stream_t stream) {
+  if (!cfg || !layers || !grads || !d_out || !saved || !scratch || !ids || !mask || !emb_ln_gamma) return NER_ERR_INVALID_ARG;
+  if (!d_word_emb || !d_type_emb || !d_pos_emb || !d_emb_ln_gamma || !d_emb_ln_beta) return NER_ERR_INVALID_ARG;
+  if (B < 0 || L < 1) return NER_ERR_INVALID_ARG;
+  if (B == 0) return NER_OK;
+  const int rows = B * L, H = cfg->hidden_size, NH = cfg->num_heads, I = cfg->intermediate_size;
+  if (saved_bytes < ner_bert_train_saved_bytes(cfg, rows) || scratch_bytes < ner_bert_train_scratch_bytes(cfg, rows))
+    return NER_ERR_WORKSPACE;
+  const size_t R = (size_t)rows, lb = layer_saved_bytes(R, H, I);
+  const int Rp = (rows + 7) / 8 * 8;
+  const size_t W = (size_t)(I > 3 * H ? I : 3 * H);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* base = const_cast<uint8_t*>(static_cast<const uint8_t*>(saved));
+  const float* emb_sum = reinterpret_cast<const float*>(base + (size_t)cfg->num_layers * lb);
+
+  uint8_t* p = static_cast<uint8_t*>(scratch);
+  float* dA = reinterpret_cast<float*>(p);     p += al(R * H * 4);
+  float* dB = reinterpret_cast<float*>(p);     p += al(R * H * 4);
+  float* dz32 = reinterpret_cast<float*>(p);   p += al(R * H * 4);
+  void* dz16 = p;                              p += al(R * H * 2);
+  void* dinter = p;                            p += al(R * I * 2);
+  void* dpre = p;                              p += al(R * I * 2);
+  void* dctx = p;                              p += al(R * H * 2);
+  void* dqkv = p;                              p += al(R * 3 * H * 2);
+  void* xt = p;                                p += al(W * Rp * 2);
+  void* dyt = p;                               p += al(W * Rp * 2);
+  float* dbqkv = reinterpret_cast<float*>(p);
+  const int gelu_erf = cfg->gelu_erf ? 1 : 0;
+  const float scale = 1.0f / sqrtf((float)(H / NH));
+
+  const float* d = d_out;   // gradient w.r.t. the current layer's output (f32 [rows, H])
+  for (int l = cfg->num_layers - 1; l >= 0; --l) {
+    const ner_bert_layer_weights& w = layers[l];
+    const ner_bert_layer_grads& g = grads[l];
+    LayerSaved s = carve(base + (size_t)l * lb, R, H, I);
+    const uint64_t sa = seed + 1 + 3 * (uint64_t)l, s1 = sa + 1, s2 = sa + 2;
+    // ---- output LayerNorm + FFN
+    NER_TRY(ner_layernorm_bwd(s.y2, 1, s.x1_32, w.ln2_gamma, d, dz32, dz16, g.d_ln2_gamma, g.d_ln2_beta, rows, H, cfg->ln_eps,
+                              stream));
+    if (hidden_keep < 1.f) NER_TRY(ner_dropout_bf16(dz16, dz16, R * H, hidden_keep, s2, stream));   // dense-branch only
+    NER_TRY(ner_colsum_bf16_add(dz16, g.d_bd, rows, H, stream));
+    NER_TRY(wgrad(s.inter, I, nullptr, dz16, H, g.d_wd, rows, Rp, xt, dyt, st));
+    NER_TRY(ner_gemm_bf16(dz16, g.wd_kn, nullptr, nullptr, dinter, rows, I, H, NER_EPI_BF16, 0, stream));
+    NER_TRY(ner_gelu_bwd_bf16(s.pre, dinter, dpre, R * I, gelu_erf, stream));
+    NER_TRY(ner_colsum_bf16_add(dpre, g.d_bi, rows, I, stream));
+    NER_TRY(wgrad(s.x1_16, H, nullptr, dpre, I, g.d_wi, rows, Rp, xt, dyt, st));
+    float* dx1 = (d == dA) ? dB : dA;
+    NER_TRY(ner_gemm_bf16(dpre, g.wi_kn, nullptr, dz32, dx1, rows, H, I, NER_EPI_RES_F32, 0, stream));
+    // ---- attention LayerNorm + output projection
+    NER_TRY(ner_layernorm_bwd(s.y1, 1, s.x32, w.ln1_gamma, dx1, dz32, dz16, g.d_ln1_gamma, g.d_ln1_beta, rows, H, cfg->ln_eps,
+                              stream));
+    if (hidden_keep < 1.f) NER_TRY(ner_dropout_bf16(dz16, dz16, R * H, hidden_keep, s1, stream));
+    NER_TRY(ner_colsum_bf16_add(dz16, g.d_bo, rows, H, stream));
+    NER_TRY(wgrad(s.ctx, H, nullptr, dz16, H, g.d_wo, rows, Rp, xt, dyt, st));
+    NER_TRY(ner_gemm_bf16(dz16, g.wo_kn, nullptr, nullptr, dctx, rows, H, H, NER_EPI_BF16, 0, stream));
+    // ---- attention core + fused QKV projection
+    NER_TRY(ner_bert_attention_bwd(s.qkv, mask, s.ctx, dctx, dqkv, B, L, NH, H / NH, scale, -10000.0f, attn_keep, sa, stream));
+    if (cudaMemsetAsync(dbqkv, 0, (size_t)3 * H * 4, st) != cudaSuccess) return NER_ERR_CUDA_BASE - (int)cudaGetLastError();
+    NER_TRY(ner_colsum_bf16_add(dqkv, dbqkv, rows, 3 * H, stream));
+    NER_TRY(ner_axpy_f32(g.d_bq, dbqkv, H, 1.f, stream));
+    NER_TRY(ner_axpy_f32(g.d_bk, dbqkv + H, H, 1.f, stream));
+    NER_TRY(ner_axpy_f32(g.d_bv, dbqkv + 2 * H, H, 1.f, stream));
+    // dW_q | dW_k | dW_v: the transposed d_qkv [3H, Rp] is three contiguous [H, Rp] operands
+    NER_TRY(ner_transpose_bf16(s.x16, xt, rows, H, Rp, stream));
+    NER_TRY(ner_transpose_bf16(dqkv, dyt, rows, 3 * H, Rp, stream));
+    const uint8_t* dyt8 = static_cast<const uint8_t*>(dyt);
+    NER_TRY(ner_gemm_bf16(xt, dyt8, nullptr, g.d_wq, g.d_wq, H, H, Rp, NER_EPI_RES_F32, 0, stream));
+    NER_TRY(ner_gemm_bf16(xt, dyt8 + (size_t)H * Rp * 2, nullptr, g.d_wk, g.d_wk, H, H, Rp, NER_EPI_RES_F32, 0, stream));
+    NER_TRY(ner_gemm_bf16(xt, dyt8 + (size_t)2 * H * Rp * 2, nullptr, g.d_wv, g.d_wv, H, H, Rp, NER_EPI_RES_F32, 0, stream));
+    float* dprev = (dx1 == dA) ? dB : dA;
+    NER_TRY(ner_gemm_bf16(dqkv, g.wqkv_kn, nullptr, dz32, dprev, rows, H, 3 * H, NER_EPI_RES_F32, 0, stream));
+    d = dprev;
+  }
+  // ---- embeddings: dropout, LayerNorm of (word + type + position), scatter-add
+  float* de = (d == dA) ? dB : dA;
+  if (hidden_keep < 1.f) {
+    NER_TRY(ner_dropout(d, de, R * H, hidden_keep, seed, stream));
+    d = de;
+  }
+  NER_TRY(ner_layernorm_bwd(emb_sum, 0, nullptr, emb_ln_gamma, d, dz32, nullptr, d_emb_ln_gamma, d_emb_ln_beta, rows, H,
+                            cfg->ln_eps, stream));
+  return ner_bert_embed_bwd(dz32, ids, seg, d_word_emb, d_type_emb, d_pos_emb, B, L, H, cfg->vocab_size, cfg->type_vocab_size,
+                            stream);
+}

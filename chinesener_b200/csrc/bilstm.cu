@@ -189,49 +189,60 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
         zo = a3;
       }
     }
-    if (cell_ok) {
-      const int r = g;
-      const int len = s_len[r];
-      const int b = b0 + r;
-      float h_state = 0.f;
-      if (s < len) {
-        const float i_s = sigmoidf_(zi), j_a = actf<ACT>(zj), f_s = sigmoidf_(zf + forget_bias), o_s = sigmoidf_(zo);
-        c_state = f_s * c_state + i_s * j_a;
-        const float h_raw = o_s * actf<ACT>(c_state);
-        const int pos = dir == 0 ? s : len - 1 - s;
-        float h_out = h_raw;
-        h_state = h_raw;
-        if (keep_prob < 1.f) {
-          // DropoutWrapper(output_keep_prob, state_keep_prob): independent masks for the emitted output
-          // and for the h part of the carried state (c is not dropped), fresh per step
-          const uint32_t e = (uint32_t)(((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug);
-          h_out = nerdev::hash3(seed_lo, seed_hi, e) < thr ? h_raw * inv_keep : 0.f;
-          h_state = nerdev::hash3(seed_lo ^ 0x5bd1e995u, seed_hi, e) < thr ? h_raw * inv_keep : 0.f;
-        }
-        out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = h_out;
-        if (hstate_out != nullptr) hstate_out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = h_state;
-        if (gates_out != nullptr) {  // saved for back-propagation through time (bilstm_bwd.cu)
-          const size_t gi = ((size_t)b * L + pos) * 8 * H + (size_t)dir * 4 * H;
-          gates_out[gi + 0 * H + ug] = i_s;
-          gates_out[gi + 1 * H + ug] = j_a;
-          gates_out[gi + 2 * H + ug] = f_s;
-          gates_out[gi + 3 * H + ug] = o_s;
-          cstate_out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = c_state;
-        }
-      } else {
-        // past this row's end: dynamic_rnn emits zeros and carries the state; h of a finished row is
-        // never read again (its own recurrence has stopped), so 0 is as good as the carried value
-        if (b < B) out[((size_t)b * L + s) * 2 * H + (size_t)dir * H + ug] = 0.f;
+    // Publish h first, arrive on the cluster barrier, THEN issue this step's global stores: the release
+    // fence of the arrive then only has to cover the DSMEM stores (and last step's long-drained global
+    // stores).  With the global stores ahead of the barrier the fence stalled every step until they had
+    // all been acknowledged (ncu: 20 % of the kernel's samples on the barrier's ERRBAR).
+    float i_s = 0.f, j_a = 0.f, f_s = 0.f, o_s = 0.f, h_out = 0.f, h_state = 0.f;
+    const int r = g;
+    const int len = cell_ok ? s_len[r] : 0;
+    const int b = b0 + r;
+    const bool live = cell_ok && s < len;
+    const int pos = dir == 0 ? s : len - 1 - s;
+    if (live) {
+      i_s = sigmoidf_(zi);
+      j_a = actf<ACT>(zj);
+      f_s = sigmoidf_(zf + forget_bias);
+      o_s = sigmoidf_(zo);
+      c_state = f_s * c_state + i_s * j_a;
+      const float h_raw = o_s * actf<ACT>(c_state);
+      h_out = h_raw;
+      h_state = h_raw;
+      if (keep_prob < 1.f) {
+        // DropoutWrapper(output_keep_prob, state_keep_prob): independent masks for the emitted output
+        // and for the h part of the carried state (c is not dropped), fresh per step
+        const uint32_t e = (uint32_t)(((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug);
+        h_out = nerdev::hash3(seed_lo, seed_hi, e) < thr ? h_raw * inv_keep : 0.f;
+        h_state = nerdev::hash3(seed_lo ^ 0x5bd1e995u, seed_hi, e) < thr ? h_raw * inv_keep : 0.f;
       }
+    }
+    if (cell_ok) {
+      // (h of a finished row is never read again — its own recurrence has stopped — so 0 is as good as
+      // the carried value dynamic_rnn keeps)
       for (int dst = 0; dst < C; ++dst) {
         float* remote = cluster.map_shared_rank(hnxt, dst);
         remote[r * H + ug] = h_state;
       }
     }
-    if (C == 1)
-      __syncthreads();
+    if (C > 1) cluster.barrier_arrive();
+    if (live) {
+      out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = h_out;
+      if (hstate_out != nullptr) hstate_out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = h_state;
+      if (gates_out != nullptr) {  // saved for back-propagation through time (bilstm_bwd.cu)
+        const size_t gi = ((size_t)b * L + pos) * 8 * H + (size_t)dir * 4 * H;
+        gates_out[gi + 0 * H + ug] = i_s;
+        gates_out[gi + 1 * H + ug] = j_a;
+        gates_out[gi + 2 * H + ug] = f_s;
+        gates_out[gi + 3 * H + ug] = o_s;
+        cstate_out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = c_state;
+      }
+    } else if (cell_ok && b < B) {
+      out[((size_t)b * L + s) * 2 * H + (size_t)dir * H + ug] = 0.f;   // past this row's end: dynamic_rnn emits zeros
+    }
+    if (C > 1)
+      cluster.barrier_wait();
     else
-      cluster.sync();
+      __syncthreads();
   }
 
   // positions past the longest row of this cluster: zeros

@@ -205,6 +205,18 @@ extern "C" int ner_dense_small_n_bwd(const float* x, const float* W, const float
   return ner_launch_status();
 }
 
+__global__ void __launch_bounds__(256) axpy_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n, float a) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = fmaf(a, src[i], dst[i]);
+}
+
+extern "C" int ner_axpy_f32(float* dst, const float* src, size_t n, float a, ner_stream_t stream) {
+  if (!dst || !src) return n == 0 ? NER_OK : NER_ERR_INVALID_ARG;
+  if (n == 0) return NER_OK;
+  axpy_kernel<<<flat_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(dst, src, n, a);
+  return ner_launch_status();
+}
+
 extern "C" int ner_dropout_bf16(const void* x, void* y, size_t n, float keep_prob, uint64_t seed, ner_stream_t stream) {
   if (!x || !y) return n == 0 ? NER_OK : NER_ERR_INVALID_ARG;
   if (!(keep_prob > 0.f) || keep_prob > 1.f) return NER_ERR_INVALID_ARG;

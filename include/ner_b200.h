@@ -217,6 +217,44 @@ int ner_bert_encoder_fwd(const ner_bert_config* cfg, const float* word_emb, cons
                          float* out_f32, void* out_bf16, void* workspace, size_t workspace_bytes,
                          ner_stream_t stream);
 
+/* TRAIN-mode BertModel (is_training=True) as two calls: forward keeping every activation the backward
+ * pass needs, and backward accumulating into the caller's gradient tensors (tf.gradients of
+ * tools/train_utils.py:314 through the encoder).  Padded layout, rows = B*L.
+ * Dropout: hidden_keep = 1 - hidden_dropout_prob (embedding output, attention-output dense, FFN-output
+ * dense), attn_keep = 1 - attention_probs_dropout_prob; counter-based masks from `seed`, regenerated by
+ * the backward call (same seed).  `saved` (ner_bert_train_saved_bytes) carries the activations from
+ * forward to backward; `scratch` (ner_bert_train_scratch_bytes) is backward-only. */
+typedef struct {
+  /* TF-layout [K_in, N_out] bf16 casts of the dense kernels (ner_cast_bf16): B operands of the data-gradient GEMMs */
+  const void* wqkv_kn; const void* wo_kn; const void* wi_kn; const void* wd_kn;
+  /* gradient tensors, f32, accumulated into (TF shapes: kernels [in,out], biases [out]) */
+  float* d_wq; float* d_wk; float* d_wv; float* d_bq; float* d_bk; float* d_bv;
+  float* d_wo; float* d_bo; float* d_ln1_gamma; float* d_ln1_beta;
+  float* d_wi; float* d_bi; float* d_wd; float* d_bd; float* d_ln2_gamma; float* d_ln2_beta;
+} ner_bert_layer_grads;
+
+size_t ner_bert_train_saved_bytes(const ner_bert_config* cfg, int rows);
+size_t ner_bert_train_scratch_bytes(const ner_bert_config* cfg, int rows);
+int ner_bert_encoder_train_fwd(const ner_bert_config* cfg, const float* word_emb, const float* type_emb,
+                               const float* pos_emb, const float* emb_ln_gamma, const float* emb_ln_beta,
+                               const ner_bert_layer_weights* layers, const int32_t* ids,
+                               const int32_t* mask, const int32_t* seg, int B, int L,
+                               float hidden_keep, float attn_keep, uint64_t seed, float* out_f32,
+                               void* out_bf16, void* saved, size_t saved_bytes, ner_stream_t stream);
+int ner_bert_encoder_train_bwd(const ner_bert_config* cfg, const float* emb_ln_gamma,
+                               const ner_bert_layer_weights* layers, const ner_bert_layer_grads* grads,
+                               float* d_word_emb, float* d_type_emb, float* d_pos_emb,
+                               float* d_emb_ln_gamma, float* d_emb_ln_beta, const int32_t* ids,
+                               const int32_t* mask, const int32_t* seg, int B, int L,
+                               float hidden_keep, float attn_keep, uint64_t seed, const float* d_out,
+                               const void* saved, size_t saved_bytes, void* scratch,
+                               size_t scratch_bytes, ner_stream_t stream);
+/* word[ids] + type[seg] + pos[0:L] without the LayerNorm -> f32 [B*L,H] (operand of the embedding
+ * LayerNorm backward). */
+int ner_bert_embed_sum(const float* word_emb, const float* type_emb, const float* pos_emb,
+                       const int32_t* ids, const int32_t* seg, float* out, int B, int L, int H,
+                       int vocab, int n_type, int max_pos, ner_stream_t stream);
+
 /* ------------------------------------------------------------------------ *
  * BiLSTM — tools/layer.py:27-41 bilstm() -> bidirectional_dynamic_rnn(LSTMCell)
  * ------------------------------------------------------------------------ */
@@ -285,6 +323,8 @@ int ner_dropout(const float* x, float* y, size_t n, float keep_prob, uint64_t se
 /* Same on bf16 tensors (BertModel's hidden dropout on the bf16 dense outputs; y may alias x). */
 int ner_dropout_bf16(const void* x_bf16, void* y_bf16, size_t n, float keep_prob, uint64_t seed,
                      ner_stream_t stream);
+/* dst[i] += a * src[i]. */
+int ner_axpy_f32(float* dst, const float* src, size_t n, float a, ner_stream_t stream);
 /* out[0] += sum(g^2)  (tf.clip_by_global_norm, tools/train_utils.py:315). */
 int ner_sumsq_add(const float* g, size_t n, float* out, ner_stream_t stream);
 /* One optimizer step over a flat parameter buffer.

@@ -36,6 +36,17 @@ def main(steps=5, B=64, L=128):
         est.train_step(batches[i % 2])
     e2.record()
     torch.cuda.synchronize()
+    if os.environ.get("NER_PROF_HOST"):
+        import cProfile
+        import pstats
+        torch.cuda._sleep(60_000_000)
+        pr = cProfile.Profile()
+        pr.enable()
+        for i in range(3):
+            est.train_step(batches[i % 2])
+        pr.disable()
+        torch.cuda.synchronize()
+        pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
     print(json.dumps({"host_enqueue_ms_per_step": host_ms, "library_launches_per_step": (_lib.LAUNCHES - l0) / (2 * steps),
                       "ms_per_step_back_to_back": s2.elapsed_time(e2) / steps,
                       "note": "first figure = host time to enqueue one step while the GPU is parked"}))

@@ -37,9 +37,13 @@ def _oracle(w, feats, lstm_activation=None):
     return float(loss.detach()), {k: v.grad for k, v in wd.items()}
 
 
+@pytest.mark.parametrize("per_kernel", [False, True])
 @pytest.mark.parametrize("model", ["bert_crf", "bert_bilstm_crf"])
-def test_bert_gradients_match_oracle_autograd(tmp_path, model):
-    """bert_crf (config 2) and bert_bilstm_crf (the north-star plugin): d loss / d every variable."""
+def test_bert_gradients_match_oracle_autograd(tmp_path, model, per_kernel, monkeypatch):
+    """bert_crf (config 2) and bert_bilstm_crf (the north-star plugin): d loss / d every variable, through the
+    two-call C composite (ner_bert_encoder_train_fwd/_bwd) and through the one-call-per-kernel path."""
+    from chinesener_b200 import bert as _bert
+    monkeypatch.setattr(_bert, "PER_KERNEL", per_kernel)
     est, feats = _est(tmp_path, model=model)
     est.evaluate(feats)
     est.store.vars["logits/kernel"].mul_(4.0)
