@@ -27,7 +27,8 @@ sys.path.insert(0, ROOT)
 B_PER_GPU, SEQ_LEN, LABELS = 64, 128, 10
 METRIC = "sentences/sec bert_bilstm_crf MSRA L=128"
 WORKLOAD = ("bert_bilstm_crf msra seq_len=128 bs=64/GPU PREDICT step: BERT-base fwd (12L, H768) + BiLSTM(H128, relu) "
-            "+ logits + CRF log-lik + Viterbi; bf16 tcgen05 GEMM operands, fp32 residual/LSTM/CRF; MSRA-shaped lengths")
+            "+ logits + CRF Viterbi -> pred_ids (the log-likelihood is part of the graph but PREDICT does not fetch it, as "
+            "in the reference's Estimator); bf16 tcgen05 GEMM operands, fp32 residual/LSTM/CRF; MSRA-shaped lengths")
 
 
 def measured_peaks():
@@ -307,11 +308,25 @@ def run_ours(args):
     launches = _lib.LAUNCHES - l0
     t_res = sum(s.elapsed_time(e) for s, e in evs) / 1e3
 
-    # ---- end-to-end timing through Estimator.predict: pinned host batch -> H2D -> step -> D2H pred_ids
-    for i in range(2):
-        est.predict(batches[i % nb])
-    evs = []
+    # ---- end-to-end timing through the public PREDICT API, Estimator.predict_iter (the generator shape of
+    #      tf.estimator.Estimator.predict): every step copies its pinned host batch H2D and its pred_ids D2H inside
+    #      the timed region; the next batch is enqueued while the previous result is awaited.  One event pair around
+    #      the K steps (per-step brackets do not exist in a pipelined loop); no flush kernel here: the 170 MB of
+    #      bf16 weights streamed every step already exceed the 126 MB L2.
+    for _ in est.predict_iter(batches[i % nb] for i in range(3)):
+        pass
     barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    n_out = 0
+    for out in est.predict_iter(batches[i % nb] for i in range(args.steps)):
+        n_out += out['pred_ids'].shape[0]
+    e.record()
+    barrier()
+    assert n_out == B_PER_GPU * args.steps
+    t_e2e = s.elapsed_time(e) / 1e3
+    # unpipelined variant (one blocking Estimator.predict per batch), reported beside it
+    evs = []
     for i in range(args.steps):
         flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -320,7 +335,7 @@ def run_ours(args):
         e.record()
         evs.append((s, e))
     barrier()
-    t_e2e = sum(s.elapsed_time(e) for s, e in evs) / 1e3
+    t_e2e_blocking = sum(s.elapsed_time(e) for s, e in evs) / 1e3
 
     # ---- TRAIN step (SURVEY 8(d)(i) second figure): forward with the tape + backward + one NCCL all-reduce of the
     #      flat gradient buffer (N>1) + AdamW, device-resident batches; reported beside the PREDICT headline
@@ -401,7 +416,8 @@ def run_ours(args):
                              "untimed 256 MB write between timed steps",
                        "lengths": "MSRA-shaped (mean fill ~0.39)"},
             "e2e": {"value": sent / t_e2e, "unit": "sentences/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * t_e2e / args.steps},
+                    "ms_per_step": 1e3 * t_e2e / args.steps, "api": "Estimator.predict_iter (depth 2)",
+                    "blocking_predict_ms_per_step": 1e3 * t_e2e_blocking / args.steps},
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "clocks": clocks, "roofline": roof,
         }
         if t_train is not None:

@@ -21,6 +21,38 @@ namespace cg = cooperative_groups;
 
 namespace {
 
+// --- DSMEM signalling without a cluster barrier: a remote 4-byte store that completes transaction
+// bytes on the DESTINATION CTA's mbarrier (st.async), so publishing h needs no fence over this
+// thread's earlier global stores and no L1 invalidate (barrier.cluster costs both every step).
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+               "r"(__float_as_uint(v)), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init_(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nerdev::smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_(uint64_t* bar, uint32_t tx_bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nerdev::smem_u32(bar)), "r"(tx_bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(nerdev::smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
 // ex2.approx-based forms (abs. error ~1e-7, far inside the 1e-4 parity bar of tests/test_bilstm_gpu.py):
 // the activations sit on the per-step critical path of the recurrence.
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
@@ -55,7 +87,8 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
   constexpr bool WREG = H4REG > 0;
   float4* Ws4 = reinterpret_cast<float4*>(smem);                 // [H4][NC] float4 (4 consecutive k), smem path only
   float* hbuf = smem + (WREG ? 0 : (size_t)H * NC);              // [2][R][H]
-  int* s_len = reinterpret_cast<int*>(hbuf + 2 * R * H);         // [R]
+  int* s_len = reinterpret_cast<int*>(hbuf + 2 * R * H);         // [R] (8 ints reserved)
+  uint64_t* hbar = reinterpret_cast<uint64_t*>(s_len + 8);      // [2] one mbarrier per h buffer
 
   const float* wh = dir == 0 ? wh_fw : wh_bw;                    // [H][4H], columns (i,j,f,o) x H
   float4 wreg[WREG ? H4REG : 1];
@@ -86,6 +119,11 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
   }
   for (int idx = tid; idx < 2 * R * H; idx += blockDim.x) hbuf[idx] = 0.f;
   if (tid < R) s_len[tid] = (b0 + tid < B) ? min(max(seq_len[b0 + tid], 0), L) : 0;
+  if (tid == 0) {
+    mbar_init_(&hbar[0], 1);
+    mbar_init_(&hbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
   int maxlen = 0;
 #pragma unroll
@@ -122,9 +160,14 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
   const uint32_t thr = nerdev::keep_threshold(keep_prob);
   const float inv_keep = 1.f / keep_prob;
 
+  const uint32_t h_bytes = (uint32_t)(R * H * 4);   // every CTA receives the full h of its R rows each step
   for (int s = 0; s < maxlen; ++s) {
     const float* hcur = hbuf + (s & 1) * R * H;
     float* hnxt = hbuf + ((s + 1) & 1) * R * H;
+    if (C > 1) {
+      if (tid == 0) mbar_arrive_expect_tx_(&hbar[(s + 1) & 1], h_bytes);   // arm the buffer written this step
+      if (s > 0) mbar_wait_(&hbar[s & 1], (uint32_t)((s - 1) >> 1) & 1u);   // h of step s-1 has landed (k-th use of the buffer)
+    }
     // packed fp32 pairs (FFMA2): (w_k, w_k+1) x (h_k, h_k+1) halves the FMA issue slots of the dot
     // products, the per-step throughput bound of this kernel; two chains per row for latency
     nerdev::f32x2 pa[R], pb[R];
@@ -189,10 +232,10 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
         zo = a3;
       }
     }
-    // Publish h first, arrive on the cluster barrier, THEN issue this step's global stores: the release
-    // fence of the arrive then only has to cover the DSMEM stores (and last step's long-drained global
-    // stores).  With the global stores ahead of the barrier the fence stalled every step until they had
-    // all been acknowledged (ncu: 20 % of the kernel's samples on the barrier's ERRBAR).
+    // h is published with st.async + mbarrier transaction bytes (see the helpers above): with
+    // barrier.cluster the release fence of the arrive stalled every step until this thread's global stores
+    // had been acknowledged (ncu: 20 % of the kernel's samples on the barrier's ERRBAR) and the wait
+    // invalidated L1.
     float i_s = 0.f, j_a = 0.f, f_s = 0.f, o_s = 0.f, h_out = 0.f, h_state = 0.f;
     const int r = g;
     const int len = cell_ok ? s_len[r] : 0;
@@ -219,12 +262,13 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
     if (cell_ok) {
       // (h of a finished row is never read again — its own recurrence has stopped — so 0 is as good as
       // the carried value dynamic_rnn keeps)
-      for (int dst = 0; dst < C; ++dst) {
-        float* remote = cluster.map_shared_rank(hnxt, dst);
-        remote[r * H + ug] = h_state;
+      if (C > 1) {
+        const uint32_t la = nerdev::smem_u32(hnxt + r * H + ug), lb = nerdev::smem_u32(&hbar[(s + 1) & 1]);
+        for (int dst = 0; dst < C; ++dst) st_async_f32(mapa_u32(la, (uint32_t)dst), h_state, mapa_u32(lb, (uint32_t)dst));
+      } else {
+        hnxt[r * H + ug] = h_state;
       }
     }
-    if (C > 1) cluster.barrier_arrive();
     if (live) {
       out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = h_out;
       if (hstate_out != nullptr) hstate_out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = h_state;
@@ -239,11 +283,9 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
     } else if (cell_ok && b < B) {
       out[((size_t)b * L + s) * 2 * H + (size_t)dir * H + ug] = 0.f;   // past this row's end: dynamic_rnn emits zeros
     }
-    if (C > 1)
-      cluster.barrier_wait();
-    else
-      __syncthreads();
+    if (C == 1) __syncthreads();
   }
+  if (C > 1) cluster.sync();   // nobody exits while a peer may still be sending into its shared memory
 
   // positions past the longest row of this cluster: zeros
   for (int idx = tid; idx < R * HU; idx += blockDim.x) {
@@ -269,7 +311,7 @@ int launch_rec(const float* xproj, const float* wh_fw, const float* wh_bw, const
                int L, int H, int C, float forget_bias, const int32_t* cu_seqlens, float* gates_out, float* cstate_out,
                float* hstate_out, float keep_prob, uint64_t seed, cudaStream_t st) {
   const int HU = H / C, NC = 4 * HU;
-  const size_t smem = ((H4REG > 0 ? 0 : (size_t)H * NC) + 2 * R * H + 32) * 4;
+  const size_t smem = ((H4REG > 0 ? 0 : (size_t)H * NC) + 2 * R * H + 32) * 4;   // + s_len[8] + 2 mbarriers (16-B aligned: R*H even)
   auto kern = bilstm_rec_kernel<R, ACT, H4REG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;

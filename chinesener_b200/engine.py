@@ -55,6 +55,37 @@ class Estimator:
         _, pred_ids = self.forward_device(dev, False)
         return {'pred_ids': pred_ids.cpu(), 'label_ids': features.get('label_ids'), 'tokens': features.get('tokens')}
 
+    def predict_iter(self, batches, depth=2):
+        """Generator form of PREDICT — the shape of tf.estimator.Estimator.predict(input_fn), which the
+        reference drives at main.py:52-55: yields one result dict per host batch, in order.  The device work
+        of up to `depth` batches is in flight before the oldest result is awaited, so the host->device copy
+        of batch i+1 and the enqueue of its kernels overlap batch i on the GPU; results come back through
+        a small ring of pinned host buffers."""
+        ring, inflight = {}, []
+
+        def finish(item):
+            ev, buf, feats = item
+            ev.synchronize()
+            return {'pred_ids': buf.clone(), 'label_ids': feats.get('label_ids'), 'tokens': feats.get('tokens')}
+
+        k = 0
+        for feats in batches:
+            dev = self.to_device(feats)
+            _, pred_ids = self.forward_device(dev, False)
+            key = (tuple(pred_ids.shape), k % (depth + 1))
+            buf = ring.get(key)
+            if buf is None:
+                buf = ring[key] = torch.empty(pred_ids.shape, dtype=pred_ids.dtype, pin_memory=True)
+            buf.copy_(pred_ids, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            inflight.append((ev, buf, feats))
+            k += 1
+            if len(inflight) >= depth:
+                yield finish(inflight.pop(0))
+        while inflight:
+            yield finish(inflight.pop(0))
+
     def train_step(self, features):
         """TRAIN mode of model_fn (reference tools/train_utils.py:151-168): forward with the tape,
         backward, then the train op the reference picks by model name (:156-164).  -> loss (float)."""

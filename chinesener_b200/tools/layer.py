@@ -228,8 +228,8 @@ def crf_layer(logits, label_ids, seq_len, label_size, is_training):
             tape.add_grad(logits, d_logits)
         tape.record(ll, bwd)
         return trans, ll
-    ll, _, _ = ops.crf_loglik_fwd(logits, label_ids, seq_len, trans)
-    return trans, ll
+    # EVAL / PREDICT: built lazily — evaluated when the loss is fetched (EVAL), never in PREDICT
+    return trans, variables.Deferred(lambda: ops.crf_loglik_fwd(logits, label_ids, seq_len, trans)[0])
 
 
 def crf_decode(logits, trans, seq_len, idx2tag, is_training, mask=None):

@@ -139,3 +139,40 @@ def use_store(store):
 
 def get_variable(name, shape, initializer, trainable=True):
     return default_store().get_variable(name, shape, initializer, trainable)
+
+
+class Deferred:
+    """A graph tensor that is evaluated only when fetched.  The reference builds `loss` and `pred_ids` in one
+    TF graph and a session run computes only what the mode fetches: PREDICT never runs the log-likelihood
+    (tools/train_utils.py:181-185 exports pred_ids only).  Non-training crf_layer() returns one of these;
+    `float(x)` / `x.value()` is the fetch."""
+
+    def __init__(self, thunk):
+        self._thunk, self._val = thunk, None
+
+    def value(self):
+        if self._thunk is not None:
+            self._val, self._thunk = self._thunk(), None
+        return self._val
+
+    def mean(self):
+        return Deferred(lambda: self.value().mean())
+
+    def __neg__(self):
+        return Deferred(lambda: -self.value())
+
+    def __add__(self, other):
+        return Deferred(lambda: self.value() + (other.value() if isinstance(other, Deferred) else other))
+
+    __radd__ = __add__
+
+    def __mul__(self, other):
+        return Deferred(lambda: self.value() * (other.value() if isinstance(other, Deferred) else other))
+
+    __rmul__ = __mul__
+
+    def __float__(self):
+        return float(self.value())
+
+    def item(self):
+        return float(self)

@@ -166,3 +166,20 @@ def test_composite_encoder_call_equals_per_kernel_path(tmp_path):
         a32, a16 = bert.bert_forward(ids, mask, seg, cfg, store=store, pack=pack, per_kernel=False)
         b32, b16 = bert.bert_forward(ids, mask, seg, cfg, store=store, pack=pack, per_kernel=True)
         assert torch.equal(a32, b32) and torch.equal(a16, b16)
+
+
+def test_predict_iter_yields_what_predict_returns():
+    """The pipelined generator (tf.estimator.Estimator.predict's shape) returns, in order, exactly the
+    pred_ids of one blocking predict() per batch."""
+    B, L, V = 16, 64, 11329
+    g = torch.Generator().manual_seed(0)
+    emb = torch.nn.functional.normalize(torch.randn(V, 50, generator=g), dim=1).numpy()
+    est = engine.Estimator("bilstm_crf", dict(synthetic.data_params(L), embedding=emb))
+    batches = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in synthetic.msra_batch(B, L, vocab=V, seed=40 + i).items()}
+               for i in range(5)]
+    ref = [est.predict(b)['pred_ids'] for b in batches]
+    outs = list(est.predict_iter(iter(batches)))
+    assert len(outs) == len(batches)
+    for o, r, b in zip(outs, ref, batches):
+        assert torch.equal(o['pred_ids'], r)
+        assert o['label_ids'] is b['label_ids']
