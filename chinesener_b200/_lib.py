@@ -29,6 +29,7 @@ SIGNATURES = {
     "ner_seq_pack_plan": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "ner_bert_embed_ln": (_i, [_vp] * 9 + [_i] * 6 + [_c.c_float, _vp, _i, _vp]),
     "ner_layernorm": (_i, [_vp, _i] + [_vp] * 5 + [_i, _i, _c.c_float, _vp]),
+    "ner_layernorm_dropout": (_i, [_vp, _i] + [_vp] * 5 + [_i, _i, _c.c_float, _c.c_float, _c.c_uint64, _vp]),
     "ner_bert_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _c.c_float, _c.c_float, _vp, _c.c_float, _c.c_uint64, _vp]),
     "ner_bilstm_recurrence": (_i, [_vp] * 5 + [_i, _i, _i, _i, _c.c_float, _vp, _vp, _vp, _vp, _c.c_float, _c.c_uint64, _vp]),
     "ner_bilstm_recurrence_bwd": (_i, [_vp] * 7 + [_i, _i, _i, _i, _c.c_float, _c.c_uint64, _vp]),
@@ -39,6 +40,7 @@ SIGNATURES = {
     "ner_dropout_bf16": (_i, [_vp, _vp, _c.c_size_t, _c.c_float, _c.c_uint64, _vp]),
     "ner_sumsq_add": (_i, [_vp, _c.c_size_t, _vp, _vp]),
     "ner_layernorm_bwd": (_i, [_vp, _i] + [_vp] * 7 + [_i, _i, _c.c_float, _vp]),
+    "ner_layernorm_dropout_bwd": (_i, [_vp, _i] + [_vp] * 7 + [_i, _i, _c.c_float, _c.c_float, _c.c_uint64, _vp]),
     "ner_transpose_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "ner_colsum_bf16_add": (_i, [_vp, _vp, _i, _i, _vp]),
     "ner_gelu_bf16": (_i, [_vp, _vp, _c.c_size_t, _i, _vp]),

@@ -286,15 +286,11 @@ def bert_forward_train(input_ids, input_mask, segment_ids, cfg, store, tape, sco
         qkv = ops.gemm_bf16(x16, w["wqkv"], w["bqkv"], epilogue=ops.EPI_BF16)
         ctx = ops.bert_attention(qkv, mask, B, L, NH, H // NH, keep_prob=keep_a, seed=sa)
         y1 = ops.gemm_bf16(ctx, w["wo"], w["bo"], epilogue=ops.EPI_BF16)
-        if keep_h < 1.0:
-            ops.dropout(y1, keep_h, s1, inplace=True)
-        x1_32, x1_16 = ops.layernorm(y1, w["g1"], w["b1"], residual=x32, eps=1e-12)
+        x1_32, x1_16 = ops.layernorm(y1, w["g1"], w["b1"], residual=x32, eps=1e-12, keep_prob=keep_h, seed=s1)
         pre = ops.gemm_bf16(x1_16, w["wi"], w["bi"], epilogue=ops.EPI_BF16)
         inter = ops.gelu_bf16(pre, erf)
         y2 = ops.gemm_bf16(inter, w["wd"], w["bd"], epilogue=ops.EPI_BF16)
-        if keep_h < 1.0:
-            ops.dropout(y2, keep_h, s2, inplace=True)
-        x2_32, x2_16 = ops.layernorm(y2, w["g2"], w["b2"], residual=x1_32, eps=1e-12)
+        x2_32, x2_16 = ops.layernorm(y2, w["g2"], w["b2"], residual=x1_32, eps=1e-12, keep_prob=keep_h, seed=s2)
         saved.append((x32, x16, qkv, ctx, y1, x1_32, x1_16, pre, inter, y2, sa, s1, s2))
         x32, x16 = x2_32, x2_16
     out = x32.view(B, L, H)
@@ -312,9 +308,8 @@ def bert_forward_train(input_ids, input_mask, segment_ids, cfg, store, tape, sco
             p = f"{scope}/encoder/layer_{li}"
             # ---- output LayerNorm + FFN
             dz2_32, dz2_16 = ops.layernorm_bwd(y2, w["g2"], d, gr(f"{p}/output/LayerNorm/gamma"), gr(f"{p}/output/LayerNorm/beta"),
-                                               residual=x1_32, eps=1e-12)
-            if keep_h < 1.0:                      # dz2_32 feeds the residual path, dz2_16 the dropped dense output
-                ops.dropout(dz2_16, keep_h, s2, inplace=True)
+                                               residual=x1_32, eps=1e-12, keep_prob=keep_h, seed=s2)
+            # (dz2_32 feeds the residual path, dz2_16 — masked like the forward — the dense output)
             ops.colsum_bf16_add(dz2_16, gr(f"{p}/output/dense/bias"))
             ops.wgrad_gemm_bf16(inter, dz2_16, gr(f"{p}/output/dense/kernel"))
             dinter = ops.gemm_bf16(dz2_16, c["wd"], None, epilogue=ops.EPI_BF16)
@@ -324,9 +319,8 @@ def bert_forward_train(input_ids, input_mask, segment_ids, cfg, store, tape, sco
             dx1 = ops.gemm_bf16(dpre, c["wi"], None, residual=dz2_32, epilogue=ops.EPI_RES_F32)
             # ---- attention LayerNorm + output projection
             dz1_32, dz1_16 = ops.layernorm_bwd(y1, w["g1"], dx1, gr(f"{p}/attention/output/LayerNorm/gamma"),
-                                               gr(f"{p}/attention/output/LayerNorm/beta"), residual=x32_, eps=1e-12)
-            if keep_h < 1.0:
-                ops.dropout(dz1_16, keep_h, s1, inplace=True)
+                                               gr(f"{p}/attention/output/LayerNorm/beta"), residual=x32_, eps=1e-12,
+                                               keep_prob=keep_h, seed=s1)
             ops.colsum_bf16_add(dz1_16, gr(f"{p}/attention/output/dense/bias"))
             ops.wgrad_gemm_bf16(ctx, dz1_16, gr(f"{p}/attention/output/dense/kernel"))
             dctx = ops.gemm_bf16(dz1_16, c["wo"], None, epilogue=ops.EPI_BF16)

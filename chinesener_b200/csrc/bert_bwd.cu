@@ -28,11 +28,16 @@ __device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float4 v) {
 // z = y(bf16|f32) + residual(f32) is recomputed; out = LN(z)*gamma + beta.
 //   dz = rstd * (g*gamma - mean(g*gamma) - zhat * mean(g*gamma*zhat)),  dgamma += g*zhat,  dbeta += g
 // dz is written as f32 (the residual-branch gradient) and as bf16 (A operand of the dgrad GEMM).
-template <bool YBF16>
+// DROP: the forward was ner_layernorm_dropout — z is rebuilt as dropout(y) + residual from the UNdropped y and
+// the bf16 gradient (the dense-output branch) is masked the same way; dz_f32 (the residual branch) is not.
+template <bool YBF16, bool DROP>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const void* __restrict__ yv, const float* __restrict__ residual, const float* __restrict__ gamma,
                      const float* __restrict__ dout, float* __restrict__ dz_f32, __nv_bfloat16* __restrict__ dz_bf16,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int H, float eps) {
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int H, float eps, float keep,
+                     uint32_t seed_lo, uint32_t seed_hi) {
+  const uint32_t thr = keep_threshold(keep);
+  const float inv_keep = 1.f / keep;
   extern __shared__ float s_acc[];  // [2][H] CTA partials of dgamma / dbeta
   for (int e = threadIdx.x; e < 2 * H; e += blockDim.x) s_acc[e] = 0.f;
   __syncthreads();
@@ -46,6 +51,7 @@ layernorm_bwd_kernel(const void* __restrict__ yv, const float* __restrict__ resi
   for (int k = 0; k < LN_MAXV; ++k) ag[k] = ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += gridDim.x * (blockDim.x >> 5)) {
     float4 z[LN_MAXV], g[LN_MAXV];
+    float4 mk[DROP ? LN_MAXV : 1];
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < LN_MAXV; ++k) {
@@ -53,6 +59,15 @@ layernorm_bwd_kernel(const void* __restrict__ yv, const float* __restrict__ resi
       if (k < nv4 && e < H) {
         if constexpr (YBF16) z[k] = ld_bf16x4(static_cast<const __nv_bfloat16*>(yv) + (size_t)row * H + e);
         else z[k] = *reinterpret_cast<const float4*>(static_cast<const float*>(yv) + (size_t)row * H + e);
+        if constexpr (DROP) {
+          const size_t i = (size_t)row * H + e;
+          const uint32_t hi = seed_hi ^ (uint32_t)(i >> 32), lo = (uint32_t)i;
+          mk[k].x = hash3(seed_lo, hi, lo) < thr ? inv_keep : 0.f;
+          mk[k].y = hash3(seed_lo, hi, lo + 1) < thr ? inv_keep : 0.f;
+          mk[k].z = hash3(seed_lo, hi, lo + 2) < thr ? inv_keep : 0.f;
+          mk[k].w = hash3(seed_lo, hi, lo + 3) < thr ? inv_keep : 0.f;
+          z[k].x *= mk[k].x; z[k].y *= mk[k].y; z[k].z *= mk[k].z; z[k].w *= mk[k].w;
+        }
         if (residual != nullptr) {
           const float4 r = *reinterpret_cast<const float4*>(residual + (size_t)row * H + e);
           z[k].x += r.x; z[k].y += r.y; z[k].z += r.z; z[k].w += r.w;
@@ -107,6 +122,9 @@ layernorm_bwd_kernel(const void* __restrict__ yv, const float* __restrict__ resi
         d.z = rstd * (g[k].z - m1 - z[k].z * m2);
         d.w = rstd * (g[k].w - m1 - z[k].w * m2);
         if (dz_f32 != nullptr) *reinterpret_cast<float4*>(dz_f32 + (size_t)row * H + e) = d;
+        if constexpr (DROP) {
+          d.x *= mk[k].x; d.y *= mk[k].y; d.z *= mk[k].z; d.w *= mk[k].w;
+        }
         if (dz_bf16 != nullptr) st_bf16x4(dz_bf16 + (size_t)row * H + e, d);
       }
     }
@@ -279,23 +297,30 @@ int flat_grid(size_t n) {
 
 }  // namespace
 
-extern "C" int ner_layernorm_bwd(const void* y, int y_is_bf16, const float* residual, const float* gamma,
-                                 const float* d_out, float* dz_f32, void* dz_bf16, float* d_gamma, float* d_beta, int M,
-                                 int H, float eps, ner_stream_t stream) {
+extern "C" int ner_layernorm_dropout_bwd(const void* y, int y_is_bf16, const float* residual, const float* gamma,
+                                         const float* d_out, float* dz_f32, void* dz_bf16, float* d_gamma, float* d_beta,
+                                         int M, int H, float eps, float keep_prob, uint64_t seed, ner_stream_t stream) {
   if (M < 0 || H < 4) return NER_ERR_INVALID_ARG;
   if (M == 0) return NER_OK;
   if (!y || !gamma || !d_out || !d_gamma || !d_beta || (!dz_f32 && !dz_bf16)) return NER_ERR_INVALID_ARG;
+  if (!(keep_prob > 0.f) || keep_prob > 1.f) return NER_ERR_INVALID_ARG;
   if (H % 4 != 0 || H > 128 * LN_MAXV) return NER_ERR_UNSUPPORTED;
   const size_t smem = (size_t)2 * H * 4;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = rows_grid(M, 64);
-  if (y_is_bf16)
-    layernorm_bwd_kernel<true><<<grid, 256, smem, st>>>(y, residual, gamma, d_out, dz_f32,
-                                                        static_cast<__nv_bfloat16*>(dz_bf16), d_gamma, d_beta, M, H, eps);
-  else
-    layernorm_bwd_kernel<false><<<grid, 256, smem, st>>>(y, residual, gamma, d_out, dz_f32,
-                                                         static_cast<__nv_bfloat16*>(dz_bf16), d_gamma, d_beta, M, H, eps);
+  const bool drop = keep_prob < 1.f;
+  auto kern = y_is_bf16 ? (drop ? layernorm_bwd_kernel<true, true> : layernorm_bwd_kernel<true, false>)
+                        : (drop ? layernorm_bwd_kernel<false, true> : layernorm_bwd_kernel<false, false>);
+  kern<<<grid, 256, smem, st>>>(y, residual, gamma, d_out, dz_f32, static_cast<__nv_bfloat16*>(dz_bf16), d_gamma, d_beta, M, H,
+                                eps, keep_prob, (uint32_t)seed, (uint32_t)(seed >> 32));
   return ner_launch_status();
+}
+
+extern "C" int ner_layernorm_bwd(const void* y, int y_is_bf16, const float* residual, const float* gamma,
+                                 const float* d_out, float* dz_f32, void* dz_bf16, float* d_gamma, float* d_beta, int M,
+                                 int H, float eps, ner_stream_t stream) {
+  return ner_layernorm_dropout_bwd(y, y_is_bf16, residual, gamma, d_out, dz_f32, dz_bf16, d_gamma, d_beta, M, H, eps, 1.0f, 0,
+                                   stream);
 }
 
 extern "C" int ner_transpose_bf16(const void* src_bf16, void* dst_bf16, int M, int N, int Mp, ner_stream_t stream) {

@@ -113,15 +113,19 @@ bert_embed_sum_kernel(const float* __restrict__ word_emb, const float* __restric
 }
 
 // y (+ optional residual) -> LayerNorm -> fp32 and/or bf16.  y is fp32 or (YBF16) bf16.
-template <bool YBF16>
+// DROP: y is first passed through dropout (counter-based mask of ner_dropout: element index row*H + col) —
+// BertModel's hidden dropout in front of the residual add, fused so the dropped tensor is never written.
+template <bool YBF16, bool DROP>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ yv, const float* __restrict__ residual, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
-                 int M, int H, float eps) {
+                 int M, int H, float eps, float keep, uint32_t seed_lo, uint32_t seed_hi) {
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int nv4 = (H / 4 + 31) / 32;
+  const uint32_t thr = keep_threshold(keep);
+  const float inv_keep = 1.f / keep;
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += gridDim.x * (blockDim.x >> 5)) {
     const float* r = residual ? residual + (size_t)row * H : nullptr;
     float4 v[LN_MAXV];
@@ -136,6 +140,14 @@ layernorm_kernel(const void* __restrict__ yv, const float* __restrict__ residual
           v[k] = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
         } else {
           v[k] = *reinterpret_cast<const float4*>(static_cast<const float*>(yv) + (size_t)row * H + e);
+        }
+        if constexpr (DROP) {
+          const size_t i = (size_t)row * H + e;
+          const uint32_t hi = seed_hi ^ (uint32_t)(i >> 32), lo = (uint32_t)i;
+          v[k].x = hash3(seed_lo, hi, lo) < thr ? v[k].x * inv_keep : 0.f;
+          v[k].y = hash3(seed_lo, hi, lo + 1) < thr ? v[k].y * inv_keep : 0.f;
+          v[k].z = hash3(seed_lo, hi, lo + 2) < thr ? v[k].z * inv_keep : 0.f;
+          v[k].w = hash3(seed_lo, hi, lo + 3) < thr ? v[k].w * inv_keep : 0.f;
         }
         if (r != nullptr) {
           const float4 b = *reinterpret_cast<const float4*>(r + e);
@@ -319,18 +331,28 @@ extern "C" int ner_bert_embed_sum(const float* word_emb, const float* type_emb, 
   return ner_launch_status();
 }
 
-extern "C" int ner_layernorm(const void* y, int y_is_bf16, const float* residual, const float* gamma,
-                             const float* beta, float* out_f32, void* out_bf16, int M, int H, float eps,
-                             ner_stream_t stream) {
+extern "C" int ner_layernorm_dropout(const void* y, int y_is_bf16, const float* residual, const float* gamma,
+                                     const float* beta, float* out_f32, void* out_bf16, int M, int H, float eps,
+                                     float keep_prob, uint64_t seed, ner_stream_t stream) {
   if (M < 0 || H < 4) return NER_ERR_INVALID_ARG;
   if (M == 0) return NER_OK;
   if (!y || !gamma || !beta || (!out_f32 && !out_bf16)) return NER_ERR_INVALID_ARG;
+  if (!(keep_prob > 0.f) || keep_prob > 1.f) return NER_ERR_INVALID_ARG;
   if (H % 4 != 0 || H > 128 * LN_MAXV) return NER_ERR_UNSUPPORTED;
-  cudaError_t e = ner_launch_pdl(y_is_bf16 ? layernorm_kernel<true> : layernorm_kernel<false>, dim3(grid_for_rows(M, 8)),
-                                 dim3(256), 0, static_cast<cudaStream_t>(stream), y, residual, gamma, beta, out_f32,
-                                 static_cast<__nv_bfloat16*>(out_bf16), M, H, eps);
+  const bool drop = keep_prob < 1.f;
+  auto kern = y_is_bf16 ? (drop ? layernorm_kernel<true, true> : layernorm_kernel<true, false>)
+                        : (drop ? layernorm_kernel<false, true> : layernorm_kernel<false, false>);
+  cudaError_t e = ner_launch_pdl(kern, dim3(grid_for_rows(M, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), y, residual,
+                                 gamma, beta, out_f32, static_cast<__nv_bfloat16*>(out_bf16), M, H, eps, keep_prob,
+                                 (uint32_t)seed, (uint32_t)(seed >> 32));
   if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   return ner_launch_status();
+}
+
+extern "C" int ner_layernorm(const void* y, int y_is_bf16, const float* residual, const float* gamma,
+                             const float* beta, float* out_f32, void* out_bf16, int M, int H, float eps,
+                             ner_stream_t stream) {
+  return ner_layernorm_dropout(y, y_is_bf16, residual, gamma, beta, out_f32, out_bf16, M, H, eps, 1.0f, 0, stream);
 }
 
 extern "C" int ner_pack_weight_bf16(const float* w_kn, void* wt_nk_bf16, int K, int N, ner_stream_t stream) {

@@ -6,8 +6,8 @@
 // time for ~7 ms of device work, profiles/README.md trip 19).
 //
 // Saved activations (padded layout, rows = B*L), one block per layer:
-//   x32 f32 | x16 bf16 (layer input) | qkv bf16 | ctx bf16 | y1 bf16 (dropped) | x1_32 f32 | x1_16 bf16 |
-//   pre bf16 | inter bf16 | y2 bf16 (dropped);    the encoder output is the caller's out_f32 / out_bf16.
+//   x32 f32 | x16 bf16 (layer input) | qkv bf16 | ctx bf16 | y1 bf16 | x1_32 f32 | x1_16 bf16 |
+//   pre bf16 | inter bf16 | y2 bf16   (y1 / y2 are kept UNdropped: the LayerNorm kernels apply the hidden dropout);    the encoder output is the caller's out_f32 / out_bf16.
 // Dropout seeds: every site draws seed = base + index (embedding 0; layer l: 1+3l attention probs,
 // 2+3l attention-output dense, 3+3l FFN-output dense); the backward call regenerates the masks.
 #include "common.cuh"
@@ -129,13 +129,13 @@ extern "C" int ner_bert_encoder_train_fwd(const ner_bert_config* cfg, const floa
     NER_TRY(ner_gemm_bf16(s.x16, w.wqkv, w.bqkv, nullptr, s.qkv, rows, 3 * H, H, NER_EPI_BF16, 0, stream));
     NER_TRY(ner_bert_attention(s.qkv, mask, s.ctx, B, L, NH, H / NH, scale, -10000.0f, nullptr, attn_keep, sa, stream));
     NER_TRY(ner_gemm_bf16(s.ctx, w.wo, w.bo, nullptr, s.y1, rows, H, H, NER_EPI_BF16, 0, stream));
-    if (hidden_keep < 1.f) NER_TRY(ner_dropout_bf16(s.y1, s.y1, R * H, hidden_keep, s1, stream));
-    NER_TRY(ner_layernorm(s.y1, 1, s.x32, w.ln1_gamma, w.ln1_beta, s.x1_32, s.x1_16, rows, H, cfg->ln_eps, stream));
+    NER_TRY(ner_layernorm_dropout(s.y1, 1, s.x32, w.ln1_gamma, w.ln1_beta, s.x1_32, s.x1_16, rows, H, cfg->ln_eps, hidden_keep, s1,
+                                  stream));
     NER_TRY(ner_gemm_bf16(s.x1_16, w.wi, w.bi, nullptr, s.pre, rows, I, H, NER_EPI_BF16, 0, stream));
     NER_TRY(ner_gelu_bf16(s.pre, s.inter, R * I, gelu_erf, stream));
     NER_TRY(ner_gemm_bf16(s.inter, w.wd, w.bd, nullptr, s.y2, rows, H, I, NER_EPI_BF16, 0, stream));
-    if (hidden_keep < 1.f) NER_TRY(ner_dropout_bf16(s.y2, s.y2, R * H, hidden_keep, s2, stream));
-    NER_TRY(ner_layernorm(s.y2, 1, s.x1_32, w.ln2_gamma, w.ln2_beta, o32, o16, rows, H, cfg->ln_eps, stream));
+    NER_TRY(ner_layernorm_dropout(s.y2, 1, s.x1_32, w.ln2_gamma, w.ln2_beta, o32, o16, rows, H, cfg->ln_eps, hidden_keep, s2,
+                                  stream));
   }
   return NER_OK;
 }
@@ -183,9 +183,8 @@ extern "C" int ner_bert_encoder_train_bwd(const ner_bert_config* cfg, const floa
     LayerSaved s = carve(base + (size_t)l * lb, R, H, I);
     const uint64_t sa = seed + 1 + 3 * (uint64_t)l, s1 = sa + 1, s2 = sa + 2;
     // ---- output LayerNorm + FFN
-    NER_TRY(ner_layernorm_bwd(s.y2, 1, s.x1_32, w.ln2_gamma, d, dz32, dz16, g.d_ln2_gamma, g.d_ln2_beta, rows, H, cfg->ln_eps,
-                              stream));
-    if (hidden_keep < 1.f) NER_TRY(ner_dropout_bf16(dz16, dz16, R * H, hidden_keep, s2, stream));   // dense-branch only
+    NER_TRY(ner_layernorm_dropout_bwd(s.y2, 1, s.x1_32, w.ln2_gamma, d, dz32, dz16, g.d_ln2_gamma, g.d_ln2_beta, rows, H,
+                                      cfg->ln_eps, hidden_keep, s2, stream));   // mask applies to the dense branch (dz16) only
     NER_TRY(ner_colsum_bf16_add(dz16, g.d_bd, rows, H, stream));
     NER_TRY(wgrad(s.inter, I, nullptr, dz16, H, g.d_wd, rows, Rp, xt, dyt, st));
     NER_TRY(ner_gemm_bf16(dz16, g.wd_kn, nullptr, nullptr, dinter, rows, I, H, NER_EPI_BF16, 0, stream));
@@ -195,9 +194,8 @@ extern "C" int ner_bert_encoder_train_bwd(const ner_bert_config* cfg, const floa
     float* dx1 = (d == dA) ? dB : dA;
     NER_TRY(ner_gemm_bf16(dpre, g.wi_kn, nullptr, dz32, dx1, rows, H, I, NER_EPI_RES_F32, 0, stream));
     // ---- attention LayerNorm + output projection
-    NER_TRY(ner_layernorm_bwd(s.y1, 1, s.x32, w.ln1_gamma, dx1, dz32, dz16, g.d_ln1_gamma, g.d_ln1_beta, rows, H, cfg->ln_eps,
-                              stream));
-    if (hidden_keep < 1.f) NER_TRY(ner_dropout_bf16(dz16, dz16, R * H, hidden_keep, s1, stream));
+    NER_TRY(ner_layernorm_dropout_bwd(s.y1, 1, s.x32, w.ln1_gamma, dx1, dz32, dz16, g.d_ln1_gamma, g.d_ln1_beta, rows, H,
+                                      cfg->ln_eps, hidden_keep, s1, stream));
     NER_TRY(ner_colsum_bf16_add(dz16, g.d_bo, rows, H, stream));
     NER_TRY(wgrad(s.ctx, H, nullptr, dz16, H, g.d_wo, rows, Rp, xt, dyt, st));
     NER_TRY(ner_gemm_bf16(dz16, g.wo_kn, nullptr, nullptr, dctx, rows, H, H, NER_EPI_BF16, 0, stream));

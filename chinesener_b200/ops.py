@@ -134,14 +134,15 @@ def bert_embed_ln(word_emb, type_emb, pos_emb, gamma, beta, ids, seg, eps=1e-12,
     return of, ob
 
 
-def layernorm(y, gamma, beta, residual=None, eps=1e-12, want_f32=True, want_bf16=True):
+def layernorm(y, gamma, beta, residual=None, eps=1e-12, want_f32=True, want_bf16=True, keep_prob=1.0, seed=0):
+    """LN(dropout(y) + residual); keep_prob < 1 fuses BertModel's hidden dropout (training)."""
     require_cuda(y, gamma, beta, residual)
     assert y.dtype in (torch.float32, torch.bfloat16)
     M, H = y.shape
     of = torch.empty((M, H), dtype=torch.float32, device=y.device) if want_f32 else None
     ob = torch.empty((M, H), dtype=torch.bfloat16, device=y.device) if want_bf16 else None
-    check(lib().ner_layernorm(ptr(y), 1 if y.dtype == torch.bfloat16 else 0, ptr(residual), ptr(gamma), ptr(beta), ptr(of),
-                              ptr(ob), M, H, eps, stream()))
+    check(lib().ner_layernorm_dropout(ptr(y), 1 if y.dtype == torch.bfloat16 else 0, ptr(residual), ptr(gamma), ptr(beta),
+                                      ptr(of), ptr(ob), M, H, eps, float(keep_prob), int(seed) & 0xFFFFFFFFFFFFFFFF, stream()))
     return of, ob
 
 
@@ -379,13 +380,15 @@ def adam_step(p, g, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0
 
 
 # --------------------------------------------------------------------------- encoder backward
-def layernorm_bwd(y, gamma, d_out, d_gamma, d_beta, residual=None, eps=1e-12, want_f32=True, want_bf16=True):
+def layernorm_bwd(y, gamma, d_out, d_gamma, d_beta, residual=None, eps=1e-12, want_f32=True, want_bf16=True, keep_prob=1.0,
+                  seed=0):
     require_cuda(y, gamma, d_out, d_gamma, d_beta, residual)
     M, H = y.shape
     dz32 = torch.empty((M, H), dtype=torch.float32, device=y.device) if want_f32 else None
     dz16 = torch.empty((M, H), dtype=torch.bfloat16, device=y.device) if want_bf16 else None
-    check(lib().ner_layernorm_bwd(ptr(y), 1 if y.dtype == torch.bfloat16 else 0, ptr(residual), ptr(gamma), ptr(d_out),
-                                  ptr(dz32), ptr(dz16), ptr(d_gamma), ptr(d_beta), M, H, eps, stream()))
+    check(lib().ner_layernorm_dropout_bwd(ptr(y), 1 if y.dtype == torch.bfloat16 else 0, ptr(residual), ptr(gamma), ptr(d_out),
+                                          ptr(dz32), ptr(dz16), ptr(d_gamma), ptr(d_beta), M, H, eps, float(keep_prob),
+                                          int(seed) & 0xFFFFFFFFFFFFFFFF, stream()))
     return dz32, dz16
 
 

@@ -174,6 +174,13 @@ int ner_layernorm(const void* y, int y_is_bf16, const float* residual, const flo
                   const float* beta, float* out_f32, void* out_bf16, int M, int H, float eps,
                   ner_stream_t stream);
 
+/* ner_layernorm with BertModel's hidden dropout fused in front of the residual add:
+ * out = LN(dropout(y) + residual), mask = the counter-based decisions of ner_dropout (element = row*H + col).
+ * keep_prob = 1: identical to ner_layernorm. */
+int ner_layernorm_dropout(const void* y, int y_is_bf16, const float* residual, const float* gamma,
+                          const float* beta, float* out_f32, void* out_bf16, int M, int H, float eps,
+                          float keep_prob, uint64_t seed, ner_stream_t stream);
+
 /* attention_layer core: ctx = softmax(Q K^T * scale + (1-mask)*mask_add) V per head.
  * qkv bf16 [B*L, 3*num_heads*head_dim] (Q | K | V blocks, heads contiguous inside each),
  * mask [B,L] i32 (1 = keep), ctx bf16 [B*L, num_heads*head_dim].  head_dim must be 64.
@@ -346,6 +353,12 @@ int ner_adam_step(float* p, const float* g, float* m, float* v, size_t n, float 
 int ner_layernorm_bwd(const void* y, int y_is_bf16, const float* residual, const float* gamma,
                       const float* d_out, float* dz_f32, void* dz_bf16, float* d_gamma,
                       float* d_beta, int M, int H, float eps, ner_stream_t stream);
+/* Backward of ner_layernorm_dropout: y is the UNdropped forward input; dz_f32 = gradient of the residual
+ * branch, dz_bf16 = gradient w.r.t. y (masked like the forward). */
+int ner_layernorm_dropout_bwd(const void* y, int y_is_bf16, const float* residual, const float* gamma,
+                              const float* d_out, float* dz_f32, void* dz_bf16, float* d_gamma,
+                              float* d_beta, int M, int H, float eps, float keep_prob, uint64_t seed,
+                              ner_stream_t stream);
 /* bf16 [M,N] -> bf16 [N,Mp] zero padded (K-major operands of weight-gradient GEMMs). */
 int ner_transpose_bf16(const void* src_bf16, void* dst_bf16, int M, int N, int Mp,
                        ner_stream_t stream);

@@ -141,3 +141,27 @@ def test_bf16_dropout_matches_host_mask_and_is_its_own_backward():
     assert torch.equal((y32 != 0).cpu() | (x.float() == 0), m | (x.float() == 0))
     xi = x.cuda().clone()
     assert ops.dropout(xi, keep, seed, inplace=True).data_ptr() == xi.data_ptr() and torch.equal(xi, y)
+
+
+def test_layernorm_with_fused_hidden_dropout_forward_and_backward():
+    """ner_layernorm_dropout / _bwd: LN(dropout(y) + r) with the host-rebuilt mask, against float64 autograd."""
+    from _masks import elementwise_keep
+    M, H, keep, seed = 150, 768, 0.9, 424242
+    g = torch.Generator().manual_seed(7)
+    y = torch.randn(M, H, generator=g).to(torch.bfloat16)
+    r = torch.randn(M, H, generator=g)
+    gam, bet = 1 + 0.1 * torch.randn(H, generator=g), 0.1 * torch.randn(H, generator=g)
+    dout = torch.randn(M, H, generator=g)
+    z = torch.from_numpy(elementwise_keep(M * H, keep, seed)).view(M, H).double() / keep
+    yd, rd, gd, bd = (t.double().requires_grad_(True) for t in (y.float(), r, gam, bet))
+    ref = _ln(yd * z + rd, gd, bd, 1e-12)
+    (ref * dout.double()).sum().backward()
+    o32, o16 = ops.layernorm(y.cuda(), gam.cuda(), bet.cuda(), residual=r.cuda(), eps=1e-12, keep_prob=keep, seed=seed)
+    torch.testing.assert_close(o32.cpu().double(), ref.detach(), rtol=1e-4, atol=1e-4)
+    dgam, dbet = torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda")
+    dz32, dz16 = ops.layernorm_bwd(y.cuda(), gam.cuda(), dout.cuda(), dgam, dbet, residual=r.cuda(), eps=1e-12, keep_prob=keep,
+                                   seed=seed)
+    torch.testing.assert_close(dz32.cpu().double(), rd.grad, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(dz16.float().cpu().double(), yd.grad, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(dgam.cpu().double(), gd.grad, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(dbet.cpu().double(), bd.grad, rtol=1e-3, atol=1e-3)
