@@ -393,7 +393,12 @@ def run_ours(args):
         ms, fl, n = timer.summary()
         achieved = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (tcgen05.mma kind::f16, all dense layers)",
-                "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
+                "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                # DRAM bytes of one in-step launch of the dominant kernel from `ncu --set full` (trip 27,
+                # profiles/r01_ncu_gemm_in_step_trip27_details.txt: gemm_bf16_tc_kernel<256>, QKV projection of a packed
+                # batch, dram read 9.42 MB, write 0): below the 22.8 MB of algorithmic operand bytes because the A operand
+                # and the output stay in the 126 MB L2 between kernels; only the weights stream from HBM.
+                "traffic": 9418752, "traffic_unit": "bytes per launch (ncu, one launch)",
                 "peak_source": f"{how} bf16_tflops_sustained", "launches_timed": n,
                 "gemm_share_of_step": (ms / min(args.steps, 5)) / (1e3 * t_res / args.steps) if t_res > 0 else None}
         if world == 1 and not args.no_cpu_baseline:

@@ -150,9 +150,9 @@ layernorm_bwd_kernel(const void* __restrict__ yv, const float* __restrict__ resi
   }
 }
 
-// bf16 [M,N] -> bf16 [N,Mp] (zero padded), 64x64 tiles through smem
+// bf16 [M,N] -> bf16 [N,Mp] (zero padded), 64x64 tiles through smem — 2-byte accesses, any N (fallback)
 __global__ void __launch_bounds__(256)
-transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int M, int N, int Mp) {
+transpose_bf16_scalar_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int M, int N, int Mp) {
   __shared__ __nv_bfloat16 tile[64][66];
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
@@ -164,6 +164,39 @@ transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __re
   for (int i = ty; i < 64; i += 4) {
     const int n = n0 + i, m = m0 + tx;
     if (n < N && m < Mp) dst[(size_t)n * Mp + m] = tile[tx][i];
+  }
+}
+
+// Same for even N: 2x2 sub-blocks.  A thread loads the words (m, n..n+1) and (m+1, n..n+1), re-pairs them with two
+// PRMTs into (n; m..m+1) and (n+1; m..m+1) and parks those in a [64 n][32 m-pair] word tile (pitch 33: the 16-byte
+// output reads are conflict-free, the parking stores 2-way); output rows leave as 16-byte stores.  Half the
+// memory instructions of the scalar kernel and 4x wider ones on the store side (the wgrad operand transposes
+// were 2.2 ms of an 18 ms TRAIN step).
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int M, int N, int Mp) {
+  __shared__ uint32_t t[64][33];
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = n0 + 2 * lane;
+#pragma unroll
+  for (int rp = warp; rp < 32; rp += 8) {
+    const int m = m0 + 2 * rp;
+    uint32_t a = 0u, b = 0u;
+    if (n < N) {
+      if (m < M) a = *reinterpret_cast<const uint32_t*>(src + (size_t)m * N + n);
+      if (m + 1 < M) b = *reinterpret_cast<const uint32_t*>(src + (size_t)(m + 1) * N + n);
+    }
+    t[2 * lane][rp] = __byte_perm(a, b, 0x5410);      // column n   : (row m, row m+1)
+    t[2 * lane + 1][rp] = __byte_perm(a, b, 0x7632);  // column n+1 : (row m, row m+1)
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = threadIdx.x; c < 512; c += 256) {
+    const int nr = c >> 3, ch = c & 7;
+    if (n0 + nr < N && m0 + 8 * ch < Mp) {
+      const uint4 v = make_uint4(t[nr][4 * ch], t[nr][4 * ch + 1], t[nr][4 * ch + 2], t[nr][4 * ch + 3]);
+      *reinterpret_cast<uint4*>(dst + (size_t)(n0 + nr) * Mp + m0 + 8 * ch) = v;
+    }
   }
 }
 
@@ -326,8 +359,14 @@ extern "C" int ner_layernorm_bwd(const void* y, int y_is_bf16, const float* resi
 extern "C" int ner_transpose_bf16(const void* src_bf16, void* dst_bf16, int M, int N, int Mp, ner_stream_t stream) {
   if (M < 1 || N < 1 || Mp < M || !src_bf16 || !dst_bf16) return NER_ERR_INVALID_ARG;
   dim3 grid((N + 63) / 64, (Mp + 63) / 64);
-  transpose_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(src_bf16), static_cast<__nv_bfloat16*>(dst_bf16), M, N, Mp);
+  const bool vec = (N % 2 == 0) && (Mp % 8 == 0) && ((reinterpret_cast<uintptr_t>(src_bf16) & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(dst_bf16) & 15) == 0);
+  if (vec)
+    transpose_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(src_bf16), static_cast<__nv_bfloat16*>(dst_bf16), M, N, Mp);
+  else
+    transpose_bf16_scalar_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(src_bf16), static_cast<__nv_bfloat16*>(dst_bf16), M, N, Mp);
   return ner_launch_status();
 }
 

@@ -52,6 +52,19 @@ def test_gelu_forward_backward(erf):
     torch.testing.assert_close(d.float().cpu().double(), x.grad, rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize("M,N", [(1000, 200), (8192, 768), (333, 3072), (77, 51), (130, 66), (1, 8)])
+def test_transpose_and_colsum_shapes(M, N):
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, N, generator=g).to(torch.bfloat16).cuda()
+    Mp = (M + 7) // 8 * 8
+    t = ops.transpose_bf16(x)
+    assert t.shape == (N, Mp)
+    assert torch.equal(t[:, :M], x.t().contiguous()) and bool((t[:, M:] == 0).all())
+    cs = torch.zeros(N, device="cuda")
+    ops.colsum_bf16_add(x, cs)
+    torch.testing.assert_close(cs, x.float().sum(0), rtol=1e-4, atol=2e-3 * max(1.0, M ** 0.5))
+
+
 def test_transpose_colsum_embed_bwd():
     g = torch.Generator().manual_seed(2)
     x = torch.randn(1000, 200, generator=g).to(torch.bfloat16).cuda()
