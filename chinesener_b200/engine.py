@@ -6,6 +6,7 @@ and its PREDICT output dict carries the keys 'pred_ids', 'label_ids', 'tokens'
 (tools/train_utils.py:181-185).  Host batches come in as (pinned) CPU tensors and are copied
 to the device inside `predict` — that copy is part of the end-to-end number bench.py reports.
 """
+import contextlib
 import importlib
 
 import torch
@@ -55,13 +56,20 @@ class Estimator:
         _, pred_ids = self.forward_device(dev, False)
         return {'pred_ids': pred_ids.cpu(), 'label_ids': features.get('label_ids'), 'tokens': features.get('tokens')}
 
-    def predict_iter(self, batches, depth=2):
+    def predict_iter(self, batches, depth=2, streams=1):
         """Generator form of PREDICT — the shape of tf.estimator.Estimator.predict(input_fn), which the
         reference drives at main.py:52-55: yields one result dict per host batch, in order.  The device work
         of up to `depth` batches is in flight before the oldest result is awaited, so the host->device copy
         of batch i+1 and the enqueue of its kernels overlap batch i on the GPU; results come back through
-        a small ring of pinned host buffers."""
+        a small ring of pinned host buffers.
+        streams > 1: consecutive batches run on different CUDA streams (sentences are independent, SURVEY
+        8(e)), so the SMs a kernel of one batch leaves idle — the partial last wave of every encoder GEMM
+        at the packed M of a 64-sentence batch — are taken by the other batch's kernels."""
         ring, inflight = {}, []
+        depth = max(depth, streams)
+        side = [torch.cuda.Stream() for _ in range(streams)] if streams > 1 else None
+        if side is not None:
+            torch.cuda.synchronize()          # weight packs / caches built on the caller's stream are complete
 
         def finish(item):
             ev, buf, feats = item
@@ -70,21 +78,26 @@ class Estimator:
 
         k = 0
         for feats in batches:
-            dev = self.to_device(feats)
-            _, pred_ids = self.forward_device(dev, False)
-            key = (tuple(pred_ids.shape), k % (depth + 1))
-            buf = ring.get(key)
-            if buf is None:
-                buf = ring[key] = torch.empty(pred_ids.shape, dtype=pred_ids.dtype, pin_memory=True)
-            buf.copy_(pred_ids, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
+            ctx = torch.cuda.stream(side[k % streams]) if side is not None else contextlib.nullcontext()
+            with ctx:
+                dev = self.to_device(feats)
+                _, pred_ids = self.forward_device(dev, False)
+                key = (tuple(pred_ids.shape), k % (depth + 1))
+                buf = ring.get(key)
+                if buf is None:
+                    buf = ring[key] = torch.empty(pred_ids.shape, dtype=pred_ids.dtype, pin_memory=True)
+                buf.copy_(pred_ids, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
             inflight.append((ev, buf, feats))
             k += 1
             if len(inflight) >= depth:
                 yield finish(inflight.pop(0))
         while inflight:
             yield finish(inflight.pop(0))
+        if side is not None:
+            for st in side:
+                torch.cuda.current_stream().wait_stream(st)
 
     def train_step(self, features):
         """TRAIN mode of model_fn (reference tools/train_utils.py:151-168): forward with the tape,

@@ -178,8 +178,25 @@ def test_predict_iter_yields_what_predict_returns():
     batches = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in synthetic.msra_batch(B, L, vocab=V, seed=40 + i).items()}
                for i in range(5)]
     ref = [est.predict(b)['pred_ids'] for b in batches]
-    outs = list(est.predict_iter(iter(batches)))
-    assert len(outs) == len(batches)
-    for o, r, b in zip(outs, ref, batches):
+    for streams in (1, 2):
+        outs = list(est.predict_iter(iter(batches), streams=streams))
+        assert len(outs) == len(batches)
+        for o, r, b in zip(outs, ref, batches):
+            assert torch.equal(o['pred_ids'], r)
+            assert o['label_ids'] is b['label_ids']
+
+
+def test_two_stream_predict_iter_on_the_bert_plugin(tmp_path):
+    """Consecutive batches on two CUDA streams (per-stream encoder workspace, shared weight packs)."""
+    import json
+    (tmp_path / "bert_config.json").write_text(json.dumps(SMALL_BERT))
+    params = dict(synthetic.data_params(64), pretrain_dir=str(tmp_path))
+    est = engine.Estimator("bert_bilstm_crf", params)
+    batches = [{k: (v.pin_memory() if torch.is_tensor(v) else v)
+                for k, v in synthetic.msra_batch(16, 64, vocab=SMALL_BERT['vocab_size'], seed=90 + i).items()} for i in range(6)]
+    est.predict(batches[0])
+    _scale_up(est.store, ["logits/kernel"], 8.0)
+    ref = [est.predict(b)['pred_ids'] for b in batches]
+    outs = list(est.predict_iter(iter(batches), streams=2))
+    for o, r in zip(outs, ref):
         assert torch.equal(o['pred_ids'], r)
-        assert o['label_ids'] is b['label_ids']
