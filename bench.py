@@ -311,9 +311,10 @@ def run_ours(args):
     # ---- same K steps with consecutive batches on two CUDA streams (independent sentences): the SMs
     #      one batch's kernel leaves idle in its partial last wave run the other batch's kernels.  One event pair
     #      around the K steps; no flush kernel (the 170 MB of bf16 weights streamed per step exceed the 126 MB L2).
-    side = [torch.cuda.Stream(), torch.cuda.Stream()]
-    for i in range(4):
-        with torch.cuda.stream(side[i % 2]):
+    NS = max(2, args.streams)
+    side = [torch.cuda.Stream() for _ in range(NS)]
+    for i in range(2 * NS):
+        with torch.cuda.stream(side[i % NS]):
             step_resident(i)
     barrier()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -321,7 +322,7 @@ def run_ours(args):
     for st in side:
         st.wait_event(s)
     for i in range(args.steps):
-        with torch.cuda.stream(side[i % 2]):
+        with torch.cuda.stream(side[i % NS]):
             step_resident(i)
     for st in side:
         torch.cuda.current_stream().wait_stream(st)
@@ -334,13 +335,13 @@ def run_ours(args):
     #      the timed region; the next batch is enqueued while the previous result is awaited.  One event pair around
     #      the K steps (per-step brackets do not exist in a pipelined loop); no flush kernel here: the 170 MB of
     #      bf16 weights streamed every step already exceed the 126 MB L2.
-    for _ in est.predict_iter((batches[i % nb] for i in range(4)), streams=2):
+    for _ in est.predict_iter((batches[i % nb] for i in range(2 * NS)), depth=NS + 1, streams=NS):
         pass
     barrier()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     n_out = 0
-    for out in est.predict_iter((batches[i % nb] for i in range(args.steps)), streams=2):
+    for out in est.predict_iter((batches[i % nb] for i in range(args.steps)), depth=NS + 1, streams=NS):
         n_out += out['pred_ids'].shape[0]
     e.record()
     barrier()
@@ -442,11 +443,11 @@ def run_ours(args):
                        "l2": "working set/step > 126 MB L2 (170 MB bf16 weights + activations); L2 also flushed by an "
                              "untimed 256 MB write between timed steps",
                        "lengths": "MSRA-shaped (mean fill ~0.39)",
-                       "streams": ("2 CUDA streams per GPU, consecutive batches alternate" if t_res2 <= t_res else "1"),
+                       "streams": (f"{NS} CUDA streams per GPU, consecutive batches alternate" if t_res2 <= t_res else "1"),
                        "single_stream_ms_per_step": 1e3 * t_res / args.steps,
                        "two_stream_ms_per_step": 1e3 * t_res2 / args.steps},
             "e2e": {"value": sent / t_e2e, "unit": "sentences/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * t_e2e / args.steps, "api": "Estimator.predict_iter(depth=2, streams=2)",
+                    "ms_per_step": 1e3 * t_e2e / args.steps, "api": f"Estimator.predict_iter(depth={NS + 1}, streams={NS})",
                     "blocking_predict_ms_per_step": 1e3 * t_e2e_blocking / args.steps},
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "clocks": clocks, "roofline": roof,
         }
@@ -470,6 +471,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     ap.add_argument("--no-train", dest="no_train", action="store_true", help="skip the TRAIN-step figure")
+    ap.add_argument("--streams", type=int, default=3, help="CUDA streams per GPU that consecutive PREDICT batches alternate over")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -66,7 +66,7 @@ class Estimator:
         8(e)), so the SMs a kernel of one batch leaves idle — the partial last wave of every encoder GEMM
         at the packed M of a 64-sentence batch — are taken by the other batch's kernels."""
         ring, inflight = {}, []
-        depth = max(depth, streams)
+        depth = max(depth, streams + 1) if streams > 1 else depth
         side = [torch.cuda.Stream() for _ in range(streams)] if streams > 1 else None
         if side is not None:
             torch.cuda.synchronize()          # weight packs / caches built on the caller's stream are complete
