@@ -61,7 +61,7 @@ SIGNATURES = {
 class BertConfig(_c.Structure):
     _fields_ = [("hidden_size", _i), ("num_heads", _i), ("intermediate_size", _i), ("num_layers", _i),
                 ("vocab_size", _i), ("type_vocab_size", _i), ("max_position", _i), ("ln_eps", _c.c_float),
-                ("gelu_erf", _i)]
+                ("gelu_erf", _i), ("gemm_tile", _i)]
 
 
 class BertLayerWeights(_c.Structure):

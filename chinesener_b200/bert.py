@@ -101,7 +101,7 @@ def _c_tables(store, cfg, scope, gelu):
         from . import _lib
         c = _lib.BertConfig(cfg["hidden_size"], cfg["num_attention_heads"], cfg["intermediate_size"],
                             cfg["num_hidden_layers"], cfg["vocab_size"], cfg["type_vocab_size"],
-                            cfg["max_position_embeddings"], 1e-12, 1 if gelu == "erf" else 0)
+                            cfg["max_position_embeddings"], 1e-12, 1 if gelu == "erf" else 0, 0)
         arr = (_lib.BertLayerWeights * len(layers))()
         for i, w in enumerate(layers):
             arr[i] = _lib.BertLayerWeights(w["wqkv"].data_ptr(), w["bqkv"].data_ptr(), w["wo"].data_ptr(), w["bo"].data_ptr(),
@@ -132,6 +132,7 @@ def bert_forward(input_ids, input_mask, segment_ids, cfg, store=None, scope="ber
         H = cfg["hidden_size"]
         v = store.vars
         c, arr, _ = _c_tables(store, cfg, scope, gelu)
+        c.gemm_tile = ops.DEFAULT_TILE            # latency (0) or throughput tile policy, see ops.DEFAULT_TILE
         rows = pack.total if pack else B * L
         dev = input_ids.device
         of = torch.empty((rows, H), dtype=torch.float32, device=dev)

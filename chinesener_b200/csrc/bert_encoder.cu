@@ -57,17 +57,17 @@ extern "C" int ner_bert_encoder_fwd(const ner_bert_config* cfg, const float* wor
   const float scale = 1.0f / sqrtf((float)(H / NH));
   for (int l = 0; l < cfg->num_layers; ++l) {
     const ner_bert_layer_weights& w = layers[l];
-    rc = ner_gemm_bf16(out_bf16, w.wqkv, w.bqkv, nullptr, qkv, rows, 3 * H, H, NER_EPI_BF16, 0, stream);
+    rc = ner_gemm_bf16(out_bf16, w.wqkv, w.bqkv, nullptr, qkv, rows, 3 * H, H, NER_EPI_BF16, cfg->gemm_tile, stream);
     if (rc != NER_OK) return rc;
     rc = ner_bert_attention(qkv, mask, ctx, B, L, NH, H / NH, scale, -10000.0f, cu_seqlens, 1.0f, 0, stream);
     if (rc != NER_OK) return rc;
-    rc = ner_gemm_bf16(ctx, w.wo, w.bo, nullptr, y, rows, H, H, NER_EPI_BF16, 0, stream);
+    rc = ner_gemm_bf16(ctx, w.wo, w.bo, nullptr, y, rows, H, H, NER_EPI_BF16, cfg->gemm_tile, stream);
     if (rc != NER_OK) return rc;
     rc = ner_layernorm(y, 1, out_f32, w.ln1_gamma, w.ln1_beta, x1f, x1b, rows, H, cfg->ln_eps, stream);
     if (rc != NER_OK) return rc;
-    rc = ner_gemm_bf16(x1b, w.wi, w.bi, nullptr, inter, rows, I, H, gelu, 0, stream);
+    rc = ner_gemm_bf16(x1b, w.wi, w.bi, nullptr, inter, rows, I, H, gelu, cfg->gemm_tile, stream);
     if (rc != NER_OK) return rc;
-    rc = ner_gemm_bf16(inter, w.wd, w.bd, nullptr, y, rows, H, I, NER_EPI_BF16, 0, stream);
+    rc = ner_gemm_bf16(inter, w.wd, w.bd, nullptr, y, rows, H, I, NER_EPI_BF16, cfg->gemm_tile, stream);
     if (rc != NER_OK) return rc;
     rc = ner_layernorm(y, 1, x1f, w.ln2_gamma, w.ln2_beta, out_f32, out_bf16, rows, H, cfg->ln_eps, stream);
     if (rc != NER_OK) return rc;

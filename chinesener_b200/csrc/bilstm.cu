@@ -14,6 +14,7 @@
 // hidden units, applies the cell, and broadcasts the new h slice to every CTA of the cluster
 // through distributed shared memory; one cluster barrier per time step.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -355,6 +356,10 @@ extern "C" int ner_bilstm_recurrence(const float* xproj, const float* wh_fw, con
   int R = 1;
   if ((long)2 * B * C > 148) R = 2;
   if ((long)2 * ((B + 1) / 2) * C > 2 * 148) R = 4;
+  if (const char* e = getenv("NER_BILSTM_ROWS")) {   // tuning hook: rows per cluster (1, 2 or 4)
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) R = v;
+  }
 #define GO(RR, HR)                                                                                          \
   return activation == 1 ? launch_rec<RR, 1, HR>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, cu_seqlens, gates_out, cstate_out, hstate_out, keep_prob, seed, st) \
                          : launch_rec<RR, 0, HR>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, cu_seqlens, gates_out, cstate_out, hstate_out, keep_prob, seed, st)

@@ -85,47 +85,60 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
         d_xproj[((size_t)b * L + t) * 2 * G4 + (size_t)dir * G4 + g * H + rank * HU + u] = 0.f;
   }
 
+  // Per-step operands (saved gates, cell states, upstream gradient) do not depend on the recurrence: they are
+  // fetched one step ahead so their L2/HBM latency overlaps the previous step instead of heading its chain.
+  const int my_len = cell_ok ? s_len[cr] : 0;
+  const int my_b = b0 + cr;
+  const int ug = rank * HU + cu;
+  float n_i = 0.f, n_j = 0.f, n_f = 0.f, n_o = 0.f, n_c = 0.f, n_cp = 0.f, n_dho = 0.f;
+  auto fetch = [&](int s) {
+    if (cell_ok && s >= 0 && s < my_len) {
+      const int pos = dir == 0 ? s : my_len - 1 - s;
+      const size_t gi = ((size_t)my_b * L + pos) * 2 * G4 + (size_t)dir * G4;
+      n_i = gates[gi + 0 * H + ug];
+      n_j = gates[gi + 1 * H + ug];
+      n_f = gates[gi + 2 * H + ug];
+      n_o = gates[gi + 3 * H + ug];
+      n_c = cstate[((size_t)my_b * L + pos) * 2 * H + (size_t)dir * H + ug];
+      n_cp = 0.f;
+      if (s > 0) {
+        const int ppos = dir == 0 ? s - 1 : my_len - s;  // position of forward step s-1
+        n_cp = cstate[((size_t)my_b * L + ppos) * 2 * H + (size_t)dir * H + ug];
+      }
+      n_dho = d_out[((size_t)my_b * L + pos) * 2 * H + (size_t)dir * H + ug];
+    }
+  };
+  fetch(maxlen - 1);
+
   for (int s = maxlen - 1; s >= 0; --s) {
     float* dzcur = dzbuf + (s & 1) * R * G4;
-    if (cell_ok) {
-      const int len = s_len[cr];
-      const int b = b0 + cr;
-      const int ug = rank * HU + cu;
-      float dzi = 0.f, dzj = 0.f, dzf = 0.f, dzo = 0.f;
-      if (s < len) {
-        const int pos = dir == 0 ? s : len - 1 - s;
-        const size_t gi = ((size_t)b * L + pos) * 2 * G4 + (size_t)dir * G4;
-        const float i_s = gates[gi + 0 * H + ug], j_a = gates[gi + 1 * H + ug];
-        const float f_s = gates[gi + 2 * H + ug], o_s = gates[gi + 3 * H + ug];
-        const float c_t = cstate[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug];
-        float c_prev = 0.f;
-        if (s > 0) {
-          const int ppos = dir == 0 ? s - 1 : len - s;  // position of forward step s-1
-          c_prev = cstate[((size_t)b * L + ppos) * 2 * H + (size_t)dir * H + ug];
-        }
-        float dh_o = d_out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug];
-        float dh_s = dhbuf[cr * HU + cu];
-        if (keep_prob < 1.f) {  // same masks as the forward DropoutWrapper (output / state)
-          const uint32_t thr = nerdev::keep_threshold(keep_prob);
-          const uint32_t e = (uint32_t)(((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug);
-          const float inv = 1.f / keep_prob;
-          dh_o = nerdev::hash3(seed_lo, seed_hi, e) < thr ? dh_o * inv : 0.f;
-          dh_s = nerdev::hash3(seed_lo ^ 0x5bd1e995u, seed_hi, e) < thr ? dh_s * inv : 0.f;
-        }
-        const float dh = dh_o + dh_s;
-        const float ac = actf<ACT>(c_t);
-        const float d_o = dh * ac;
-        const float dc = dh * o_s * act_grad_from_output<ACT>(ac) + dc_carry;
-        dzi = dc * j_a * i_s * (1.f - i_s);
-        dzj = dc * i_s * act_grad_from_output<ACT>(j_a);
-        dzf = dc * c_prev * f_s * (1.f - f_s);
-        dzo = d_o * o_s * (1.f - o_s);
-        dc_carry = dc * f_s;
-        d_xproj[gi + 0 * H + ug] = dzi;
-        d_xproj[gi + 1 * H + ug] = dzj;
-        d_xproj[gi + 2 * H + ug] = dzf;
-        d_xproj[gi + 3 * H + ug] = dzo;
+    float dzi = 0.f, dzj = 0.f, dzf = 0.f, dzo = 0.f;
+    const bool live = cell_ok && s < my_len;
+    const float i_s = n_i, j_a = n_j, f_s = n_f, o_s = n_o, c_t = n_c, c_prev = n_cp;
+    float dh_o = n_dho;
+    fetch(s - 1);
+    const int pos = dir == 0 ? s : my_len - 1 - s;
+    const size_t gi = ((size_t)my_b * L + pos) * 2 * G4 + (size_t)dir * G4;
+    if (live) {
+      float dh_s = dhbuf[cr * HU + cu];
+      if (keep_prob < 1.f) {  // same masks as the forward DropoutWrapper (output / state)
+        const uint32_t thr = nerdev::keep_threshold(keep_prob);
+        const uint32_t e = (uint32_t)(((size_t)my_b * L + pos) * 2 * H + (size_t)dir * H + ug);
+        const float inv = 1.f / keep_prob;
+        dh_o = nerdev::hash3(seed_lo, seed_hi, e) < thr ? dh_o * inv : 0.f;
+        dh_s = nerdev::hash3(seed_lo ^ 0x5bd1e995u, seed_hi, e) < thr ? dh_s * inv : 0.f;
       }
+      const float dh = dh_o + dh_s;
+      const float ac = actf<ACT>(c_t);
+      const float d_o = dh * ac;
+      const float dc = dh * o_s * act_grad_from_output<ACT>(ac) + dc_carry;
+      dzi = dc * j_a * i_s * (1.f - i_s);
+      dzj = dc * i_s * act_grad_from_output<ACT>(j_a);
+      dzf = dc * c_prev * f_s * (1.f - f_s);
+      dzo = d_o * o_s * (1.f - o_s);
+      dc_carry = dc * f_s;
+    }
+    if (cell_ok) {
       // broadcast this unit's four gate gradients to every CTA (global column order g*H + ug)
       for (int dst = 0; dst < C; ++dst) {
         float* remote = cluster.map_shared_rank(dzcur, dst);
@@ -135,7 +148,15 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
         remote[cr * G4 + 3 * H + ug] = dzo;
       }
     }
-    cluster.sync();
+    // arrive before this step's global stores: the barrier's release fence then does not wait for them
+    cluster.barrier_arrive();
+    if (live) {
+      d_xproj[gi + 0 * H + ug] = dzi;
+      d_xproj[gi + 1 * H + ug] = dzj;
+      d_xproj[gi + 2 * H + ug] = dzf;
+      d_xproj[gi + 3 * H + ug] = dzo;
+    }
+    cluster.barrier_wait();
     // dh_prev[r][k] for owned k: split the 4H columns over the threads of a (r,k) team
     {
       const int teams = R * HU;

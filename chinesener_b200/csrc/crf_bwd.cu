@@ -351,6 +351,11 @@ extern "C" int ner_crf_loglik_bwd(const float* logits, const int32_t* tags, cons
   if (!logits || !tags || !seq_len || !trans || !alpha_ws || !logz || !d_logits || !d_trans) return NER_ERR_INVALID_ARG;
   if (K > NER_MAX_TAGS) return NER_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B <= NER_CRF_SMALL_B) {   // few sequences: the lane-per-tag kernel (crf_small.cu) walks a much shorter chain
+    const int rc = ner_crf_loglik_bwd_small(logits, tags, seq_len, trans, alpha_ws, logz, d_ll, scale, d_logits, d_trans, B, L,
+                                            K, st);
+    if (rc != NER_ERR_UNSUPPORTED) return rc;
+  }
 #define CALL(KK) \
   return launch_bwd<KK>(logits, tags, seq_len, trans, alpha_ws, logz, d_ll, scale, d_logits, d_trans, B, L, st)
   NER_CRF_DISPATCH_K(K, CALL)

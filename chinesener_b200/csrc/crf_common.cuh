@@ -114,6 +114,9 @@ int ner_crf_viterbi_small(const float* logits, const int32_t* seq_len, const flo
                           float* best_score, int B, int L, int K, cudaStream_t st);
 int ner_crf_loglik_fwd_small(const float* logits, const int32_t* tags, const int32_t* seq_len, const float* trans,
                              float* ll, float* logz, float* alpha_ws, int B, int L, int K, cudaStream_t st);
+int ner_crf_loglik_bwd_small(const float* logits, const int32_t* tags, const int32_t* seq_len, const float* trans,
+                             const float* alpha_ws, const float* logz, const float* d_ll, float scale, float* d_logits,
+                             float* d_trans, int B, int L, int K, cudaStream_t st);
 
 // Dispatch a runtime K in [1,32] onto `template <int K> run<K>(args...)`.
 #define NER_CRF_DISPATCH_K(K_, CALL)                                                     \

@@ -203,6 +203,123 @@ crf_loglik_lanes_kernel(const float* __restrict__ logits, const int32_t* __restr
   }
 }
 
+// Backward of the log-likelihood for small batches, lane i = tag i (see crf_bwd.cu for the closed form):
+//   w_j          = x_t[j] + beta_t[j]                                   (lane j; broadcast by shuffles)
+//   v_ij         = trans[i][j] + w_j                                    (lane i, all j)
+//   beta_{t-1}[i] = logsumexp_j v_ij                                    (own max, as reduce_logsumexp)
+//   M_t[i][j]    = exp(alpha_{t-1}[i] - logZ + v_ij)                    pair marginal, accumulated in registers
+//   d_x[t][i]    = g * (1[y_t = i] - exp(alpha_t[i] + beta_t[i] - logZ))
+// g = d_ll[b] * scale.  d_trans gets one atomic per (sequence, i, j) at the end.
+template <int K>
+__global__ void __launch_bounds__(32)
+crf_loglik_bwd_lanes_kernel(const float* __restrict__ logits, const int32_t* __restrict__ tags,
+                            const int32_t* __restrict__ seq_len, const float* __restrict__ trans,
+                            const float* __restrict__ alpha_ws, const float* __restrict__ logz,
+                            const float* __restrict__ d_ll, float scale, float* __restrict__ d_logits,
+                            float* __restrict__ d_trans, int B, int L) {
+  constexpr int GS = Lanes<K>::GS, SPW = Lanes<K>::SPW;
+  const int lane = threadIdx.x;
+  const int g = lane / GS, i = lane % GS;
+  const int b = blockIdx.x * SPW + g;
+  const bool seq_ok = b < B;
+  const bool tag_ok = i < K;
+  const int len = seq_ok ? min(max(seq_len[b], 0), L) : 0;
+  int wmax = len;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+
+  float tr[K];   // row i of the transition matrix
+#pragma unroll
+  for (int jj = 0; jj < K; ++jj) tr[jj] = tag_ok ? trans[i * K + jj] : 0.f;
+  float acc[K];  // sum_t (M_t[i][j] - 1[y_{t-1}=i, y_t=j])
+#pragma unroll
+  for (int jj = 0; jj < K; ++jj) acc[jj] = 0.f;
+
+  const size_t base = (size_t)(seq_ok ? b : 0) * L;
+  const float lz = seq_ok ? logz[b] : 0.f;
+  const float gco = seq_ok ? (d_ll != nullptr ? d_ll[b] : 1.f) * scale : 0.f;
+  const float* xp = logits + base * K + (tag_ok ? i : 0);
+  const float* ap = alpha_ws + base * K + (tag_ok ? i : 0);
+  const int32_t* tp = tags + base;
+  float* dp = d_logits + base * K + (tag_ok ? i : 0);
+  const bool io = seq_ok && tag_ok;
+  // zero fill past the sequence end
+  if (io)
+    for (int t = len; t < L; ++t) dp[(size_t)t * K] = 0.f;
+
+  auto ldx = [&](int t) -> float { return (io && t >= 0 && t < len) ? xp[(size_t)t * K] : 0.f; };
+  auto lda = [&](int t) -> float { return (io && t >= 0 && t < len) ? ap[(size_t)t * K] : 0.f; };
+  auto ldtag = [&](int t) -> int { return (seq_ok && t >= 0 && t < len) ? min(max(tp[t], 0), K - 1) : 0; };
+
+  // iteration s handles position t = len-1-s of its own sequence (the sequences of a warp may differ in
+  // length: the shorter one simply runs out of live steps first); operands are fetched PF iterations ahead
+  float beta = 0.f;
+  float xq[PF], aq[PF];
+  int tq[PF];
+#pragma unroll
+  for (int u = 0; u < PF; ++u) {
+    xq[u] = ldx(len - 1 - u);
+    aq[u] = lda(len - 2 - u);
+    tq[u] = ldtag(len - 2 - u);
+  }
+  float a_t = lda(len - 1);     // alpha_t[i] of the current position
+  int tag_t = ldtag(len - 1);   // y_t
+  for (int s0 = 0; s0 < wmax; s0 += PF) {
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int sidx = s0 + u;
+      const int t = len - 1 - sidx;
+      const float x = xq[u], a_prev = aq[u];
+      const int tag_prev = tq[u];
+      xq[u] = ldx(t - PF);
+      aq[u] = lda(t - 1 - PF);
+      tq[u] = ldtag(t - 1 - PF);
+      if (sidx < wmax) {                    // warp-uniform: every lane takes part in the shuffles
+        const bool live = t >= 0;           // uniform over the lanes of one sequence
+        if (io && live) {
+          const float p = __expf(a_t + beta - lz);
+          dp[(size_t)t * K] = gco * ((i == tag_t ? 1.f : 0.f) - p);
+        }
+        const float w = (tag_ok && live) ? x + beta : -INFINITY;
+        float v[K];
+        float m = -INFINITY;
+#pragma unroll
+        for (int jj = 0; jj < K; ++jj) {
+          v[jj] = tr[jj] + __shfl_sync(0xffffffffu, w, g * GS + jj);
+          m = fmaxf(m, v[jj]);
+        }
+        if (live && t >= 1) {
+          const float mm = (fabsf(m) <= 3.0e38f) ? m : 0.f;
+          const float am = a_prev - lz;
+          float sum = 0.f;
+#pragma unroll
+          for (int jj = 0; jj < K; ++jj) {
+            sum += __expf(v[jj] - mm);
+            acc[jj] += __expf(am + v[jj]) - ((i == tag_prev && jj == tag_t) ? 1.f : 0.f);
+          }
+          beta = __logf(sum) + mm;
+          a_t = a_prev;
+          tag_t = tag_prev;
+        }
+      }
+    }
+  }
+  if (io && len > 0) {
+#pragma unroll
+    for (int jj = 0; jj < K; ++jj) atomicAdd(d_trans + i * K + jj, -gco * acc[jj]);
+  }
+}
+
+template <int K>
+int launch_loglik_bwd_lanes(const float* logits, const int32_t* tags, const int32_t* seq_len, const float* trans,
+                            const float* alpha_ws, const float* logz, const float* d_ll, float scale, float* d_logits,
+                            float* d_trans, int B, int L, cudaStream_t st) {
+  constexpr int SPW = Lanes<K>::SPW;
+  crf_loglik_bwd_lanes_kernel<K><<<(B + SPW - 1) / SPW, 32, 0, st>>>(logits, tags, seq_len, trans, alpha_ws, logz, d_ll, scale,
+                                                                 d_logits, d_trans, B, L);
+  return ner_launch_status();
+}
+
 template <int K>
 int launch_viterbi_lanes(const float* logits, const int32_t* seq_len, const float* trans, int32_t* tags_out,
                          float* best_score, int B, int L, cudaStream_t st) {
@@ -232,6 +349,16 @@ int launch_loglik_lanes(const float* logits, const int32_t* tags, const int32_t*
 int ner_crf_viterbi_small(const float* logits, const int32_t* seq_len, const float* trans, int32_t* tags_out,
                           float* best_score, int B, int L, int K, cudaStream_t st) {
 #define CALL(KK) return launch_viterbi_lanes<KK>(logits, seq_len, trans, tags_out, best_score, B, L, st)
+  NER_CRF_DISPATCH_K(K, CALL)
+#undef CALL
+  return NER_ERR_UNSUPPORTED;
+}
+
+int ner_crf_loglik_bwd_small(const float* logits, const int32_t* tags, const int32_t* seq_len, const float* trans,
+                             const float* alpha_ws, const float* logz, const float* d_ll, float scale, float* d_logits,
+                             float* d_trans, int B, int L, int K, cudaStream_t st) {
+#define CALL(KK) \
+  return launch_loglik_bwd_lanes<KK>(logits, tags, seq_len, trans, alpha_ws, logz, d_ll, scale, d_logits, d_trans, B, L, st)
   NER_CRF_DISPATCH_K(K, CALL)
 #undef CALL
   return NER_ERR_UNSUPPORTED;

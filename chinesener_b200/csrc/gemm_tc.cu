@@ -24,6 +24,8 @@
 //                              stages its own 128 A rows and HALF of the B tile, so the L2->smem
 //                              bytes per FLOP drop by 1.5x vs the 128x256 single-CTA tile (the
 //                              single-CTA kernel is L2-feed-bound at ~9-10 TB/s).
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "tc_common.cuh"
@@ -685,6 +687,16 @@ int make_map_out(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, bool
   return r == CUDA_SUCCESS ? NER_OK : NER_ERR_INVALID_ARG;
 }
 
+// NER_GEMM_POLICY=1: "auto" picks the 128x256 tile whenever N allows instead of fitting waves (tuning hook).
+int gemm_auto_policy() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NER_GEMM_POLICY");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 bool epi_is_f32(int mode) { return mode == NER_EPI_F32 || mode == NER_EPI_RES_F32 || mode == NER_EPI_RES_RELU_F32; }
 
 int sm_count() {
@@ -821,7 +833,11 @@ extern "C" int ner_gemm_bf16(const void* A, const void* Wt, const float* bias, c
   if (bn == NER_TILE_SK_256 || bn == NER_TILE_SK_128) {
     sk = true;
     bn = (bn == NER_TILE_SK_256) ? 256 : 128;
-  } else if (bn == 0) {
+  } else if (bn == NER_TILE_AUTO_THROUGHPUT || (bn == 0 && gemm_auto_policy() == 1)) {
+    // throughput policy: several streams keep the SMs busy, so take the tile with the best FLOP rate
+    bn = (N % 256 == 0) ? 256 : (N % 192 == 0) ? 192 : 128;
+  }
+  if (bn == 0) {
     // Cost model in units of one 128x256 k-block per CTA.  Whole-tile scheduling: ceil(tiles/SMs) waves
     // of num_kb k-blocks, the relative tile costs measured on B200 (profiles/): the 128-wide tile is
     // smem-bandwidth-bound.  Stream-K (128x256 tiles): every CTA gets ceil(tiles*num_kb/SMs) k-blocks

@@ -65,6 +65,7 @@ class Estimator:
         streams > 1: consecutive batches run on different CUDA streams (sentences are independent, SURVEY
         8(e)), so the SMs a kernel of one batch leaves idle — the partial last wave of every encoder GEMM
         at the packed M of a 64-sentence batch — are taken by the other batch's kernels."""
+        from . import ops
         ring, inflight = {}, []
         depth = max(depth, streams + 1) if streams > 1 else depth
         side = [torch.cuda.Stream() for _ in range(streams)] if streams > 1 else None
@@ -81,7 +82,13 @@ class Estimator:
             ctx = torch.cuda.stream(side[k % streams]) if side is not None else contextlib.nullcontext()
             with ctx:
                 dev = self.to_device(feats)
-                _, pred_ids = self.forward_device(dev, False)
+                tile0 = ops.DEFAULT_TILE
+                if side is not None:          # other streams fill a GEMM's partial last wave: take the fastest tile
+                    ops.DEFAULT_TILE = ops.TILE_AUTO_THROUGHPUT
+                try:
+                    _, pred_ids = self.forward_device(dev, False)
+                finally:
+                    ops.DEFAULT_TILE = tile0
                 key = (tuple(pred_ids.shape), k % (depth + 1))
                 buf = ring.get(key)
                 if buf is None:

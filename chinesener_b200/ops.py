@@ -12,6 +12,8 @@ EPI_F32, EPI_BF16, EPI_GELU_TANH_BF16, EPI_GELU_ERF_BF16, EPI_RELU_BF16, EPI_RES
 EPI_DIAG_DISCARD = 99
 TILE_2CTA_128, TILE_2CTA_256 = 1128, 1256   # CTA-pair (cta_group::2) tiles of ner_gemm_bf16
 TILE_SK_128, TILE_SK_256 = 2128, 2256       # stream-K scheduling of 128 x {128,256} tiles
+TILE_AUTO_THROUGHPUT = 3000                 # auto, preferring the tile with the best FLOP rate (multi-stream serving)
+DEFAULT_TILE = 0                            # what gemm_bf16(tile_n=None) passes; predict_iter(streams>1) switches it
 
 
 def _i32(t):
@@ -47,8 +49,10 @@ def crf_loglik_fwd(logits, tags, seq_len, trans, want_alpha=False, exact=False):
 
 
 # --------------------------------------------------------------------------- dense (tcgen05)
-def gemm_bf16(a, wt, bias=None, residual=None, epilogue=EPI_BF16, tile_n=0, out=None):
-    """out[M,N] = epilogue(a[M,K] @ wt[N,K]^T + bias).  a, wt bf16; see ner_gemm_bf16."""
+def gemm_bf16(a, wt, bias=None, residual=None, epilogue=EPI_BF16, tile_n=None, out=None):
+    """out[M,N] = epilogue(a[M,K] @ wt[N,K]^T + bias).  a, wt bf16; see ner_gemm_bf16.  tile_n None = DEFAULT_TILE."""
+    if tile_n is None:
+        tile_n = DEFAULT_TILE
     require_cuda(a, wt, bias, residual, out)
     assert a.dtype == torch.bfloat16 and wt.dtype == torch.bfloat16
     M, K = a.shape

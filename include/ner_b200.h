@@ -95,6 +95,10 @@ int ner_crf_loglik_bwd(const float* logits, const int32_t* tags, const int32_t* 
 #define NER_TILE_2CTA_256 1256
 #define NER_TILE_SK_128 2128
 #define NER_TILE_SK_256 2256
+/* tile_n = 0 fits whole waves on the SMs (best latency of ONE GEMM).  NER_TILE_AUTO_THROUGHPUT takes the
+ * tile with the best FLOP rate (128 x 256 when N % 256 == 0): the choice when several streams keep the
+ * SMs busy, so a partial last wave is not idle time. */
+#define NER_TILE_AUTO_THROUGHPUT 3000
 
 /* out[M,N] = epilogue(A[M,K] · Wt[N,K]^T + bias[N]).  A and Wt are bf16,
  * K contiguous (Wt is the TF kernel [K,N] transposed once by
@@ -204,6 +208,7 @@ typedef struct {
   int vocab_size, type_vocab_size, max_position;
   float ln_eps;   /* 1e-12 */
   int gelu_erf;   /* 0: tanh approximation (google-research/bert modeling.gelu), 1: erf */
+  int gemm_tile;  /* tile_n passed to every ner_gemm_bf16 of the composite calls: 0 or NER_TILE_AUTO_THROUGHPUT */
 } ner_bert_config;
 
 typedef struct {

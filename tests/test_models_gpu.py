@@ -194,9 +194,20 @@ def test_two_stream_predict_iter_on_the_bert_plugin(tmp_path):
     est = engine.Estimator("bert_bilstm_crf", params)
     batches = [{k: (v.pin_memory() if torch.is_tensor(v) else v)
                 for k, v in synthetic.msra_batch(16, 64, vocab=SMALL_BERT['vocab_size'], seed=90 + i).items()} for i in range(6)]
+    from chinesener_b200 import ops
     est.predict(batches[0])
     _scale_up(est.store, ["logits/kernel"], 8.0)
-    ref = [est.predict(b)['pred_ids'] for b in batches]
+    # streams > 1 switches the encoder GEMMs to the throughput tile policy; a different tile shape may round a
+    # bf16 dense output differently in the last bit, so the blocking reference is taken under the same policy
+    ops.DEFAULT_TILE = ops.TILE_AUTO_THROUGHPUT
+    try:
+        ref = [est.predict(b)['pred_ids'] for b in batches]
+    finally:
+        ops.DEFAULT_TILE = 0
     outs = list(est.predict_iter(iter(batches), streams=2))
     for o, r in zip(outs, ref):
         assert torch.equal(o['pred_ids'], r)
+    # against the wave-fitting tile policy the tags agree up to isolated last-bit flips
+    ref0 = [est.predict(b)['pred_ids'] for b in batches]
+    diff = sum(int((o['pred_ids'] != r).sum()) for o, r in zip(outs, ref0))
+    assert diff <= 8, diff
