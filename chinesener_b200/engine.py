@@ -119,7 +119,7 @@ class Estimator:
             if 'bert' in self.model_name:
                 train_utils.bert_train_op(loss, p['lr'], p['num_train_steps'], p['warmup_ratio'], p['diff_lr_times'])
             elif 'transformer' in self.model_name:
-                raise NotImplementedError("transformer_train_op (Adam + Noam) is not built yet")
+                train_utils.transformer_train_op(loss, p['lr'], p['num_train_steps'], p['warmup_ratio'])
             else:
                 train_utils.custom_train_op(loss, p['lr'], p['step_per_epoch'], p['decay_rate'])
         return loss

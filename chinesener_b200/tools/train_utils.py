@@ -135,5 +135,28 @@ def bert_train_op(loss, init_lr, num_train_steps, warmup_ratio, diff_lr_times, v
     return lrs
 
 
+def noam_scheme(init_lr, global_step, warmup_steps=4000.):
+    """reference tools/transformer/modules.py:209-217: lr rises linearly to init_lr over warmup_steps, then ~ step^-0.5."""
+    step = float(global_step + 1)
+    return init_lr * warmup_steps ** 0.5 * min(step * warmup_steps ** -1.5, step ** -0.5)
+
+
+def transformer_train_op(loss, init_lr, num_train_steps, warmup_ratio, store=None):
+    """tf.train.AdamOptimizer(noam_scheme(...)).minimize(loss) (reference :353-362) — plain Adam, no clipping."""
+    store = store or variables.default_store()
+    fs = _flat(store)
+    world = allreduce_gradients(fs.grads)
+    lr = noam_scheme(init_lr, store.global_step, int(num_train_steps * warmup_ratio))
+    t = store.global_step + 1
+    b1, b2 = 0.9, 0.999
+    lr_t = lr * (1 - b2 ** t) ** 0.5 / (1 - b1 ** t)
+    ops.adam_step(fs.params, fs.grads, fs.m, fs.v, lr=lr_t, beta1=b1, beta2=b2, eps=1e-8, mode=1, clip=0.0,
+                  grad_scale=1.0 / world)
+    store.global_step += 1
+    store.touch()
+    fs.zero_grads()
+    return lr
+
+
 def _decays(name):
     return not any(tok in name for tok in ("LayerNorm", "layer_norm", "bias"))
