@@ -118,6 +118,24 @@ class ClockSampler:
                 "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run this rank's host threads on the CPUs NVML reports as local to its GPU
+    (kernel launches and pinned-memory copies from the far socket are what made single ranks straggle at N=8)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return {"cpus_before": before, "cpus_after": len(os.sched_getaffinity(0))}
+    except Exception as e:      # no NVML / restricted cpuset: keep the inherited affinity
+        return {"error": str(e)[:80]}
+
+
 def make_estimator():
     from chinesener_b200 import engine, synthetic
     params = dict(synthetic.data_params(SEQ_LEN, LABELS), pretrain_dir="")
@@ -264,6 +282,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the sm_100a kernels have no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None   # N=1 keeps every host CPU for the cpu_baseline leg
     dist = None
     if world > 1:
         import torch.distributed as dist_
@@ -384,12 +403,6 @@ def run_ours(args):
         del est_t
     clocks = sampler.stop() if rank == 0 else None
 
-    if dist is not None:
-        t = torch.tensor([t_res, t_e2e, t_train or 0.0, t_res2], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_res, t_e2e, t_res2 = float(t[0]), float(t[1]), float(t[3])
-        t_train = float(t[2]) if t_train is not None else None
-
     # ---- host enqueue time of one step (GPU parked behind a spin kernel): says whether the step is launch-bound
     torch.cuda.synchronize()
     torch.cuda._sleep(40_000_000)
@@ -398,6 +411,18 @@ def run_ours(args):
         step_resident(i)
     host_ms = (time.perf_counter() - h0) * 1e3 / 5
     torch.cuda.synchronize()
+
+    per_rank = None
+    if dist is not None:
+        mine = torch.tensor([t_res, t_res2, t_e2e, t_train or 0.0, host_ms], device="cuda", dtype=torch.float64)
+        allr = torch.empty((world, mine.numel()), device="cuda", dtype=torch.float64)
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank = {"columns": ["single_stream_s", "multi_stream_s", "e2e_s", "train_s", "host_enqueue_ms_per_step"],
+                    "rows": [[round(float(x), 6) for x in r] for r in allr.cpu()]}
+        t = torch.tensor([t_res, t_e2e, t_train or 0.0, t_res2], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_res, t_e2e, t_res2 = float(t[0]), float(t[1]), float(t[3])
+        t_train = float(t[2]) if t_train is not None else None
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM), instrumented pass on rank 0
     roof = cpu = None
@@ -453,6 +478,7 @@ def run_ours(args):
                     "ms_per_step": 1e3 * t_e2e / args.steps, "api": f"Estimator.predict_iter(depth={NS + 1}, streams={NS})",
                     "blocking_predict_ms_per_step": 1e3 * t_e2e_blocking / args.steps},
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "clocks": clocks, "roofline": roof,
+            "per_rank": per_rank, "cpu_affinity": numa,
         }
         if t_train is not None:
             line["train"] = {"value": sent / t_train, "unit": "sentences/sec", "ms_per_step": 1e3 * t_train / args.steps,

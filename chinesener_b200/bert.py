@@ -138,7 +138,7 @@ def bert_forward(input_ids, input_mask, segment_ids, cfg, store=None, scope="ber
         of = torch.empty((rows, H), dtype=torch.float32, device=dev)
         ob = torch.empty((rows, H), dtype=torch.bfloat16, device=dev)
         need = _lib.lib().ner_bert_encoder_workspace_bytes(ctypes.byref(c), rows)
-        key = (dev.index, torch.cuda.current_stream().cuda_stream)
+        key = (dev.index, _lib.stream())
         ws = _ws_cache.get(key)
         if ws is None or ws.numel() < need:
             ws = torch.empty((need,), dtype=torch.uint8, device=dev)
