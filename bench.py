@@ -295,7 +295,7 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > 126 MB L2
 
     def step_resident(i):
-        return est.forward_device(dev_batches[i % nb])
+        return est.predict_device(dev_batches[i % nb])     # the PREDICT path of Estimator.predict*, inputs resident
 
     def barrier():
         torch.cuda.synchronize()

@@ -82,6 +82,9 @@ SIGNATURES["ner_bert_encoder_train_fwd"] = (_i, [_c.POINTER(BertConfig)] + [_vp]
 SIGNATURES["ner_bert_encoder_train_bwd"] = (_i, [_c.POINTER(BertConfig), _vp, _c.POINTER(BertLayerWeights), _c.POINTER(BertLayerGrads)]
                                             + [_vp] * 5 + [_vp] * 3 + [_i, _i, _c.c_float, _c.c_float, _c.c_uint64, _vp, _vp,
                                                                        _c.c_size_t, _vp, _c.c_size_t, _vp])
+SIGNATURES["ner_bert_bilstm_crf_predict_workspace_bytes"] = (_c.c_size_t, [_c.POINTER(BertConfig), _i, _i, _i, _i, _i])
+SIGNATURES["ner_bert_bilstm_crf_predict"] = (_i, [_c.POINTER(BertConfig)] + [_vp] * 5 + [_c.POINTER(BertLayerWeights)] + [_vp] * 4
+                                             + [_i, _i] + [_vp] * 3 + [_i] + [_vp] * 4 + [_i, _i, _i, _vp, _vp, _c.c_size_t, _vp])
 SIGNATURES["ner_bert_embed_sum"] = (_i, [_vp] * 6 + [_i] * 6 + [_vp])
 SIGNATURES["ner_axpy_f32"] = (_i, [_vp, _vp, _c.c_size_t, _c.c_float, _vp])
 SIGNATURES["ner_bert_encoder_workspace_bytes"] = (_c.c_size_t, [_c.POINTER(BertConfig), _i])

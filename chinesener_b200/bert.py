@@ -15,12 +15,20 @@ from . import ops, variables
 from .config import BERT_BASE_CHINESE
 
 
+_cfg_cache = {}
+
+
 def load_bert_config(pretrain_dir):
-    cfg = dict(BERT_BASE_CHINESE)
-    path = os.path.join(pretrain_dir or "", "bert_config.json")
-    if pretrain_dir and os.path.exists(path):
-        with open(path) as f:
-            cfg.update(json.load(f))
+    """bert_config.json of params['pretrain_dir'] over the Google chinese_L-12_H-768_A-12 defaults (read once per
+    directory: the layer functions ask for it on every call)."""
+    cfg = _cfg_cache.get(pretrain_dir)
+    if cfg is None:
+        cfg = dict(BERT_BASE_CHINESE)
+        path = os.path.join(pretrain_dir or "", "bert_config.json")
+        if pretrain_dir and os.path.exists(path):
+            with open(path) as f:
+                cfg.update(json.load(f))
+        _cfg_cache[pretrain_dir] = cfg
     return cfg
 
 

@@ -46,6 +46,19 @@ class Estimator:
             out['mask'].total_tokens = int(m.sum())
         return out
 
+    def predict_device(self, dev_features):
+        """PREDICT on device-resident features -> pred_ids (device).  One fused C call when the plugin has an
+        executor in fastpath.FUSED_PREDICT (same kernels as build_graph, see fastpath.py), else build_graph."""
+        if self.params.get('fused_predict', True):
+            from . import fastpath
+            fn = fastpath.FUSED_PREDICT.get(self.model_name)
+            if fn is not None:
+                with variables.use_store(self.store):
+                    pred = fn(self, dev_features)
+                if pred is not None:
+                    return pred
+        return self.forward_device(dev_features, False)[1]
+
     def forward_device(self, dev_features, is_training=False):
         with variables.use_store(self.store):
             return self.build_graph(dev_features, None, self.params, is_training)
@@ -53,7 +66,7 @@ class Estimator:
     def predict(self, features):
         """PREDICT mode on one host batch -> dict(pred_ids int32 [B,L] on host, label_ids, tokens)."""
         dev = self.to_device(features)
-        _, pred_ids = self.forward_device(dev, False)
+        pred_ids = self.predict_device(dev)
         return {'pred_ids': pred_ids.cpu(), 'label_ids': features.get('label_ids'), 'tokens': features.get('tokens')}
 
     def predict_iter(self, batches, depth=2, streams=1):
@@ -86,7 +99,7 @@ class Estimator:
                 if side is not None:          # other streams fill a GEMM's partial last wave: take the fastest tile
                     ops.DEFAULT_TILE = ops.TILE_AUTO_THROUGHPUT
                 try:
-                    _, pred_ids = self.forward_device(dev, False)
+                    pred_ids = self.predict_device(dev)
                 finally:
                     ops.DEFAULT_TILE = tile0
                 key = (tuple(pred_ids.shape), k % (depth + 1))

@@ -267,6 +267,25 @@ int ner_bert_embed_sum(const float* word_emb, const float* type_emb, const float
                        const int32_t* ids, const int32_t* seg, float* out, int B, int L, int H,
                        int vocab, int n_type, int max_pos, ner_stream_t stream);
 
+/* The whole PREDICT step of model/bert_bilstm_crf.py:8-34 in one call (what a PREDICT session.run
+ * of that plugin executes: BertModel -> bilstm -> dense(logits) -> crf_decode; the log-likelihood
+ * is not fetched in PREDICT).  Same kernels, same order as the layer-by-layer entry points above.
+ * lstm_wx_bf16 [8*lstm_hidden, H] = ner_pack_weight_bf16 of [kernel_fw[:H] | kernel_bw[:H]],
+ * lstm_bias [8*lstm_hidden] = [bias_fw | bias_bw], lstm_wh_* = kernel[H:, :] f32,
+ * lstm_activation as ner_bilstm_recurrence, logits_w [2*lstm_hidden, num_tags], trans [K,K].
+ * n_packed = number of valid tokens (sum of mask), known on the host; pred_ids [B,L] i32. */
+size_t ner_bert_bilstm_crf_predict_workspace_bytes(const ner_bert_config* cfg, int B, int L, int rows,
+                                                   int lstm_hidden, int num_tags);
+int ner_bert_bilstm_crf_predict(const ner_bert_config* cfg, const float* word_emb, const float* type_emb,
+                                const float* pos_emb, const float* emb_ln_gamma, const float* emb_ln_beta,
+                                const ner_bert_layer_weights* layers, const void* lstm_wx_bf16,
+                                const float* lstm_bias, const float* lstm_wh_fw, const float* lstm_wh_bw,
+                                int lstm_hidden, int lstm_activation, const float* logits_w,
+                                const float* logits_b, const float* trans, int num_tags,
+                                const int32_t* ids, const int32_t* mask, const int32_t* seg,
+                                const int32_t* seq_len, int B, int L, int n_packed, int32_t* pred_ids,
+                                void* workspace, size_t workspace_bytes, ner_stream_t stream);
+
 /* ------------------------------------------------------------------------ *
  * BiLSTM — tools/layer.py:27-41 bilstm() -> bidirectional_dynamic_rnn(LSTMCell)
  * ------------------------------------------------------------------------ */

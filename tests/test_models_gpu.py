@@ -211,3 +211,25 @@ def test_two_stream_predict_iter_on_the_bert_plugin(tmp_path):
     ref0 = [est.predict(b)['pred_ids'] for b in batches]
     diff = sum(int((o['pred_ids'] != r).sum()) for o, r in zip(outs, ref0))
     assert diff <= 8, diff
+
+
+def test_fused_predict_call_equals_build_graph(tmp_path):
+    """fastpath.FUSED_PREDICT['bert_bilstm_crf'] (one C call per step) launches the kernels of build_graph():
+    identical pred_ids, ragged lengths, an empty sentence included."""
+    import json
+    (tmp_path / "bert_config.json").write_text(json.dumps(SMALL_BERT))
+    params = dict(synthetic.data_params(64), pretrain_dir=str(tmp_path))
+    est = engine.Estimator("bert_bilstm_crf", params)
+    batches = [synthetic.msra_batch(16, 64, vocab=SMALL_BERT['vocab_size'], seed=70 + i) for i in range(3)]
+    est.predict(batches[0])                               # creates the variables through build_graph
+    _scale_up(est.store, ["logits/kernel"], 8.0)
+    from chinesener_b200 import fastpath
+    for b in batches:
+        dev = est.to_device(b)
+        fused = fastpath.bert_bilstm_crf_predict(est, dev)
+        assert fused is not None                          # the fused executor applied
+        _, ref = est.forward_device(dev, False)
+        assert torch.equal(fused, ref)
+        assert torch.equal(est.predict(b)['pred_ids'], ref.cpu())
+    est.params['fused_predict'] = False
+    assert torch.equal(est.predict(batches[1])['pred_ids'], est.forward_device(est.to_device(batches[1]), False)[1].cpu())
