@@ -210,6 +210,20 @@ __global__ void __launch_bounds__(256) axpy_kernel(float* __restrict__ dst, cons
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = fmaf(a, src[i], dst[i]);
 }
 
+// d_pre = d_act where act > 0 else 0   (tf.nn.relu gradient, all f32)
+__global__ void __launch_bounds__(256)
+relu_bwd_kernel(const float* __restrict__ act, const float* __restrict__ dact, float* __restrict__ dpre, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dpre[i] = act[i] > 0.f ? dact[i] : 0.f;
+}
+
+extern "C" int ner_relu_bwd_f32(const float* act, const float* dact, float* dpre, size_t n, ner_stream_t stream) {
+  if (!act || !dact || !dpre) return n == 0 ? NER_OK : NER_ERR_INVALID_ARG;
+  if (n == 0) return NER_OK;
+  relu_bwd_kernel<<<flat_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(act, dact, dpre, n);
+  return ner_launch_status();
+}
+
 extern "C" int ner_axpy_f32(float* dst, const float* src, size_t n, float a, ner_stream_t stream) {
   if (!dst || !src) return n == 0 ? NER_OK : NER_ERR_INVALID_ARG;
   if (n == 0) return NER_OK;

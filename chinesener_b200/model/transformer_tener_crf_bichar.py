@@ -2,9 +2,9 @@
 """Plugin mirror of reference model/transformer_tener_crf_bichar.py (build_graph :8-42, params :45-62)."""
 import torch
 
-from .. import ops
+from .. import autodiff, ops
 from ..config import TRAIN_PARAMS as _BASE
-from ..tools.layer import crf_decode, crf_layer, dense, _no_training
+from ..tools.layer import crf_decode, crf_layer, dense, dropout
 from ..tools.transformer.encoder import tener_encoder
 from ..tools.transformer.modules import embedding_project
 from .bilstm_crf import _const_table
@@ -14,7 +14,6 @@ def build_graph(features, labels, params, is_training):
     """
     char + bichar embedding -> projection -> TENER encoder -> CRF
     """
-    _no_training(is_training, "transformer_tener_crf_bichar")
     input_ids = features['token_ids']
     bichar_ids = features['bichar_ids']
     label_ids = features['label_ids']
@@ -28,14 +27,20 @@ def build_graph(features, labels, params, is_training):
     embedding = torch.empty((B * L, Ec + Eb), dtype=torch.float32, device=input_ids.device)
     ops.embedding_lookup(char_table, input_ids, out=embedding)
     ops.embedding_lookup(bichar_table, bichar_ids, out=embedding, col_offset=Ec)
-    embedding = embedding_project(embedding, params['d_model'])
+    embedding = embedding_project(embedding, params['d_model'], is_training=is_training)
+    embedding = dropout(embedding, params['embedding_dropout'], is_training, seed=1234)
 
-    transformer_output = tener_encoder(encoder_input=embedding.view(B, L, -1), seq_len=seq_len,
+    transformer_output = tener_encoder(encoder_input=embedding if is_training else embedding.view(B, L, -1), seq_len=seq_len,
                                        max_seq_len=params['max_seq_len'], encode_layers=params['encode_layers'],
                                        num_head=params['num_head'], dropout_rate=params['dropout_rate'],
                                        ffn_hidden=params['ffn_hidden'], is_training=is_training)
+    transformer_output = dropout(transformer_output, params['fc_dropout'], is_training, seed=1234)
+    if is_training:                      # [B*L, d] -> [B, L, d] as a recorded op (the tape keys on tensor identity)
+        tape, out2d = autodiff.current(), transformer_output
+        transformer_output = out2d.view(B, L, -1)
+        tape.record(transformer_output, lambda g: tape.add_grad(out2d, g.reshape(out2d.shape)) if g is not None else None)
 
-    logits = dense(transformer_output, units=params['label_size'], name='logits')
+    logits = dense(transformer_output, units=params['label_size'], name='logits', is_training=is_training)
 
     trans, log_likelihood = crf_layer(logits, label_ids, seq_len, params['label_size'], is_training)
     pred_ids = crf_decode(logits, trans, seq_len, params['idx2tag'], is_training)

@@ -303,6 +303,32 @@ def attention_f32(q, k, v, seq_len, B, L, num_heads, head_dim, scale=1.0, bias_u
     return of, hi, lo
 
 
+def attention_f32_bwd(q, k, v, seq_len, B, L, num_heads, head_dim, d_out, scale=1.0, bias_u=None, bias_v=None, rel_table=None):
+    """Backward of attention_f32 -> (dQ, dK, dV [B*L, heads*head_dim] f32, d_bias_u, d_bias_v [heads, head_dim] | None)."""
+    require_cuda(seq_len, bias_u, bias_v, rel_table, d_out)
+    for t in (q, k, v, d_out):
+        assert t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.shape[0] == B * L
+    HD = num_heads * head_dim
+    dq = torch.empty((B * L, HD), dtype=torch.float32, device=q.device)
+    dk = torch.zeros((B * L, HD), dtype=torch.float32, device=q.device)
+    dv = torch.zeros((B * L, HD), dtype=torch.float32, device=q.device)
+    du = torch.zeros((num_heads, head_dim), dtype=torch.float32, device=q.device) if bias_u is not None else None
+    dvb = torch.zeros((num_heads, head_dim), dtype=torch.float32, device=q.device) if bias_v is not None else None
+    check(lib().ner_attention_f32_bwd(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                                      ptr(bias_u), ptr(bias_v), ptr(rel_table), ptr(_i32(seq_len)), scale, d_out.data_ptr(),
+                                      d_out.stride(0), ptr(dq), HD, ptr(dk), HD, ptr(dv), HD, ptr(du), ptr(dvb), B, L, num_heads,
+                                      head_dim, stream()))
+    return dq, dk, dv, du, dvb
+
+
+def relu_bwd(act, dact):
+    require_cuda(act, dact)
+    assert act.dtype == torch.float32 and dact.dtype == torch.float32 and act.numel() == dact.numel()
+    out = torch.empty_like(dact)
+    check(lib().ner_relu_bwd_f32(ptr(act), ptr(dact), ptr(out), act.numel(), stream()))
+    return out
+
+
 # --------------------------------------------------------------------------- training-side kernels
 def _require_rows(x2d):
     """CUDA f32 2-D tensor whose rows are contiguous (a column slice of a wider buffer is fine)."""

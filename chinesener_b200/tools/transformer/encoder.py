@@ -5,10 +5,13 @@ from .tener import relative_multi_head_attention
 
 
 def tener_encoder(encoder_input, seq_len, max_seq_len, encode_layers, num_head, dropout_rate, ffn_hidden, is_training):
-    B, L, d = encoder_input.shape
-    x = encoder_input.reshape(B * L, d)
+    if encoder_input.dim() == 2:          # TRAIN passes the [B*L, d] activation itself (the tape keys on tensor identity)
+        x, (B, L), d = encoder_input, (seq_len.shape[0], max_seq_len), encoder_input.shape[-1]
+    else:
+        B, L, d = encoder_input.shape
+        x = encoder_input.reshape(B * L, d)
     for i in range(encode_layers):
         scope = f"encoding/self_attention_layer_{i}"
         x = relative_multi_head_attention(x, seq_len, B, L, num_head, dropout_rate, is_training, scope)
         x = ffn(x, ffn_hidden, dropout_rate, is_training, scope)
-    return x.view(B, L, d)
+    return x if encoder_input.dim() == 2 else x.view(B, L, d)

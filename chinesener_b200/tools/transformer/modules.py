@@ -5,7 +5,7 @@ LayerNorm / attention in fp32."""
 import numpy as np
 import torch
 
-from ... import ops, variables
+from ... import autodiff, ops, variables
 
 FP32_EPS = float(np.finfo(np.float32).eps)
 
@@ -37,10 +37,58 @@ def dense_f32(x2d, units, name, relu=False, residual=None, use_bias=True):
     return ops.gemm_split_f32(a_hi, a_lo, w_hi, w_lo, b, residual=residual, relu=relu)
 
 
-def embedding_project(embedding2d, d_model, name='embedding/dense'):
+def dense_train(x2d, units, name, relu=False):
+    """TRAIN-mode tf.layers.dense: same forward as dense_f32, records dW = x^T·dy, db = colsum(dy), dx = dy·W^T
+    (tensor-core GEMMs on bf16 casts of the f32 gradients, fp32 accumulation)."""
+    store, tape = variables.default_store(), autodiff.current()
+    y = dense_f32(x2d, units, name, relu=relu)
+    need_dx = tape.needs_grad(x2d)
+
+    def bwd(g):
+        if g is None:
+            return
+        g = g.contiguous()
+        if relu:
+            g = ops.relu_bwd(y, g)
+        ops.colsum_add(g, store.grad(f"{name}/bias"))
+        ops.wgrad_gemm(x2d, g, out=store.grad(f"{name}/kernel"))
+        if need_dx:                                                  # W [K,N] in TF layout is the K-major operand of dy·W^T
+            tape.add_grad(x2d, ops.gemm_bf16(ops.cast_bf16(g), ops.cast_bf16(store.vars[f"{name}/kernel"]), None,
+                                             epilogue=ops.EPI_F32))
+    tape.record(y, bwd)
+    return y
+
+
+def add_and_norm_train(x2d, y2d, scope, dropout_rate):
+    """layer_norm(x + dropout(y)) (reference modules.py:23-37 after the sub-layer's tf.layers.dropout), dropout fused
+    into the LayerNorm kernels; gradients: residual branch -> x, masked branch -> y."""
+    store, tape = variables.default_store(), autodiff.current()
+    d = x2d.shape[-1]
+    kn, bn = f"{scope}/layer_normalization/norm_kernel", f"{scope}/layer_normalization/norm_bias"
+    k = store.get_variable(kn, (d,), variables.ones)
+    b = store.get_variable(bn, (d,), variables.zeros)
+    keep = 1.0 - float(dropout_rate)
+    store.dropout_calls += 1
+    seed = (777 * 1000003 + store.global_step) * 1009 + store.dropout_calls
+    out, _ = ops.layernorm(y2d, k, b, residual=x2d, eps=FP32_EPS, want_bf16=False, keep_prob=keep, seed=seed)
+
+    def bwd(g):
+        if g is None:
+            return
+        dz32, dz16 = ops.layernorm_bwd(y2d, k, g.contiguous(), store.grad(kn), store.grad(bn), residual=x2d, eps=FP32_EPS,
+                                       want_bf16=keep < 1.0, keep_prob=keep, seed=seed)
+        tape.add_grad(x2d, dz32)
+        tape.add_grad(y2d, dz32 if keep >= 1.0 else dz16.float())
+    tape.record(out, bwd)
+    return out
+
+
+def embedding_project(embedding2d, d_model, name='embedding/dense', is_training=False):
     """reference modules.py:11-20 — linear map of the raw char(+bichar) embedding to d_model."""
     if embedding2d.shape[-1] == d_model:
         return embedding2d
+    if is_training:
+        return dense_train(embedding2d, d_model, name)
     return dense_f32(embedding2d, d_model, name)
 
 
@@ -56,6 +104,10 @@ def layer_norm(x2d, scope):
 def ffn(x2d, ffn_hidden, dropout_rate, is_training, scope):
     """reference modules.py:68-80 — dense-relu-dense (+dropout when training) + add & norm."""
     d_model = x2d.shape[-1]
+    if is_training:
+        y = dense_train(x2d, ffn_hidden, f"{scope}/ffn/ffn_inner", relu=True)
+        y = dense_train(y, d_model, f"{scope}/ffn/ffn_outer")
+        return add_and_norm_train(x2d, y, f"{scope}/ffn/add_and_norm", dropout_rate)
     y = dense_f32(x2d, ffn_hidden, f"{scope}/ffn/ffn_inner", relu=True)
     y = dense_f32(y, d_model, f"{scope}/ffn/ffn_outer", residual=x2d)          # x + y fused into the epilogue
     return layer_norm(y, f"{scope}/ffn/add_and_norm")

@@ -196,6 +196,16 @@ int ner_bert_attention(const void* qkv_bf16, const int32_t* mask, void* ctx_bf16
                        int num_heads, int head_dim, float scale, float mask_add,
                        const int32_t* cu_seqlens, float keep_prob, uint64_t seed, ner_stream_t stream);
 
+/* Backward of ner_attention_f32 (TRAIN mode of tools/transformer/tener.py:12-119).  d_out f32 [B*L, ld_dout]
+ * = dL/d out.  Writes dQ (all rows; zero for t >= seq_len) and ACCUMULATES into dK, dV (f32, layouts of K / V),
+ * d_bias_u / d_bias_v [num_heads, head_dim] (nullable) — zero them first.  Scores are recomputed. */
+int ner_attention_f32_bwd(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
+                          const float* bias_u, const float* bias_v, const float* rel_table,
+                          const int32_t* seq_len, float scale, const float* d_out, int ld_dout,
+                          float* dQ, int ld_dq, float* dK, int ld_dk, float* dV, int ld_dv,
+                          float* d_bias_u, float* d_bias_v, int B, int L, int num_heads, int head_dim,
+                          ner_stream_t stream);
+
 /* Whole BertModel forward in one call (what tools/layer.py:68-77 gets from
  * modeling.BertModel(...).get_sequence_output()).  `layers` is a HOST array of per-layer
  * device pointers: dense kernels packed by ner_pack_weight_bf16 ([N,K] bf16; wqkv = the
@@ -354,6 +364,8 @@ int ner_dropout(const float* x, float* y, size_t n, float keep_prob, uint64_t se
 /* Same on bf16 tensors (BertModel's hidden dropout on the bf16 dense outputs; y may alias x). */
 int ner_dropout_bf16(const void* x_bf16, void* y_bf16, size_t n, float keep_prob, uint64_t seed,
                      ner_stream_t stream);
+/* tf.nn.relu gradient: dpre = dact where act > 0 else 0 (f32 [n]; dpre may alias dact). */
+int ner_relu_bwd_f32(const float* act, const float* dact, float* dpre, size_t n, ner_stream_t stream);
 /* dst[i] += a * src[i]. */
 int ner_axpy_f32(float* dst, const float* src, size_t n, float a, ner_stream_t stream);
 /* out[0] += sum(g^2)  (tf.clip_by_global_norm, tools/train_utils.py:315). */

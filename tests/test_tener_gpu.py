@@ -100,3 +100,90 @@ def test_tener_plugin_matches_oracle_at_fp32_accuracy():
     agree = (out['pred_ids'].numpy() == ref['pred_ids']).mean()
     assert agree > 0.999, agree
     assert (out['pred_ids'].numpy()[feats['mask'].numpy() == 0] == 0).all()
+
+
+@pytest.mark.parametrize("B,L,NH,DH,rel", [(3, 64, 8, 20, True), (2, 256, 8, 20, True), (2, 96, 4, 40, True), (2, 70, 3, 32, False)])
+def test_attention_f32_backward(B, L, NH, DH, rel):
+    """ner_attention_f32_bwd vs float64 autograd of the reference formulation (tener.py:12-74 via oracle.shift)."""
+    g = torch.Generator().manual_seed(B * L + DH + 1)
+    d = NH * DH
+    q, k, v, do = (torch.randn(B * L, d, generator=g) * 0.5 for _ in range(4))
+    u = torch.randn(NH, DH, generator=g) * 0.3
+    vb = torch.randn(NH, DH, generator=g) * 0.3
+    lens = torch.randint(1, L + 1, (B,), generator=g, dtype=torch.int32)
+    lens[0] = L
+    table = torch.from_numpy(np.asarray(otf.sinusoidal_positional_encoding(DH, np.arange(-L, L)), dtype=np.float32)) if rel else None
+    scale = 1.0 if rel else DH ** -0.5
+    qd, kd, vd, ud, vbd = (t.double().requires_grad_(True) for t in (q, k, v, u, vb))
+    sh = lambda t: t.view(B, L, NH, DH).permute(0, 2, 1, 3)
+    Q, K, V = sh(qd), sh(kd), sh(vd)
+    if rel:
+        s = torch.einsum('bnqd,bnkd->bnqk', Q + ud[:, None, :], K) + otf.shift(torch.einsum('bnqd,ld->bnql', Q + vbd[:, None, :], table.double()))
+    else:
+        s = Q @ K.transpose(-1, -2) * scale
+    mask = (torch.arange(L)[None, :] < lens.long()[:, None])
+    s = s + (~mask)[:, None, None, :].double() * otf.MASK_ADD
+    out = (torch.softmax(s, -1) @ V).permute(0, 2, 1, 3).reshape(B * L, d)
+    rowmask = mask.reshape(B * L, 1).double()                 # padded query rows never reach the loss
+    (out * do.double() * rowmask).sum().backward()
+    dq, dk, dv, du, dvb = ops.attention_f32_bwd(q.cuda(), k.cuda(), v.cuda(), lens.cuda(), B, L, NH, DH, do.cuda(), scale=scale,
+                                                bias_u=u.cuda() if rel else None, bias_v=vb.cuda() if rel else None,
+                                                rel_table=table.cuda() if rel else None)
+    for name, got, ref in (("dq", dq, qd.grad), ("dk", dk, kd.grad), ("dv", dv, vd.grad)):
+        err = (got.cpu().double() - ref).abs().max().item()
+        assert err < 2e-4 * max(1.0, ref.abs().max().item()), (name, err)
+    if rel:
+        for name, got, ref in (("du", du, ud.grad), ("dvb", dvb, vbd.grad)):
+            err = (got.cpu().double() - ref).abs().max().item()
+            assert err < 5e-4 * max(1.0, ref.abs().max().item()), (name, err)
+
+
+def _tener_setup(B=4, L=64, V=2000, VB=3000, drop=0.0):
+    feats = synthetic.msra_batch(B, L, vocab=V, seed=19)
+    g = torch.Generator().manual_seed(3)
+    feats['bichar_ids'] = torch.randint(0, VB, (B, L), generator=g, dtype=torch.int32)
+    emb = torch.nn.functional.normalize(torch.randn(V, 50, generator=g), dim=1).numpy()
+    bemb = torch.nn.functional.normalize(torch.randn(VB, 50, generator=g), dim=1).numpy()
+    params = dict(synthetic.data_params(L), embedding=emb, bichar_embedding=bemb, embedding_dropout=drop, fc_dropout=drop,
+                  dropout_rate=drop)
+    return engine.Estimator("transformer_tener_crf_bichar", params), feats, emb, bemb
+
+
+def test_tener_gradients_match_oracle_autograd():
+    """TRAIN mode of transformer_tener_crf_bichar (BASELINE config 5's model): every variable's gradient against
+    float64 autograd of the oracle (bf16 operands in the gradient GEMMs: 3e-2 of each gradient's scale)."""
+    from chinesener_b200 import autodiff, variables
+    from oracle import crf_torch
+    est, feats, emb, bemb = _tener_setup()
+    est.evaluate(feats)
+    w = est.store.state_dict()
+    wd = {k: v.double().clone().requires_grad_(True) for k, v in w.items()}
+    x = torch.cat([torch.from_numpy(emb).double()[feats['token_ids'].long()], torch.from_numpy(bemb).double()[feats['bichar_ids'].long()]], -1)
+    x = x @ wd["embedding/dense/kernel"] + wd["embedding/dense/bias"]
+    x = otf.tener_encoder(x, feats['seq_len'], wd, est.params['encode_layers'], est.params['num_head'])
+    logits = x @ wd['logits/kernel'] + wd['logits/bias']
+    ll = crf_torch.crf_log_likelihood(logits, feats['label_ids'], feats['seq_len'], wd['crf_layer/transitions'])
+    ref_loss = (-ll).mean()
+    ref_loss.backward()
+    dev = est.to_device(feats)
+    with variables.use_store(est.store), autodiff.recording(est.store) as tape:
+        loss, _ = est.build_graph(dev, None, est.params, True)
+        tape.backward()
+    assert abs(float(loss) - float(ref_loss)) < 2e-3 * max(1.0, abs(float(ref_loss)))
+    gscale = max(v.grad.abs().max().item() for v in wd.values() if v.grad is not None)
+    worst = {}
+    for name, v in wd.items():
+        if v.grad is None:
+            continue
+        g = est.store.grads[name].cpu().double()
+        worst[name] = (g - v.grad).abs().max().item() / max(v.grad.abs().max().item(), 1e-3 * gscale)
+    bad = {k: e for k, e in worst.items() if e > 3e-2}
+    print("tener max relative gradient error:", max(worst.values()), "over", len(worst), "variables")
+    assert not bad, bad
+
+
+def test_tener_training_reduces_the_loss():
+    est, feats, _, _ = _tener_setup(drop=0.2)
+    est.params.update(lr=2e-3, num_train_steps=200, warmup_ratio=0.1)
+    losses = [float(est.train_step(feats)) for _ in range(40)]
+    assert np.isfinite(losses).all() and losses[-1] < 0.7 * losses[0], losses
