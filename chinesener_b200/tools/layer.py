@@ -19,11 +19,6 @@ class TrainingPathNotBuilt(NotImplementedError):
     pass
 
 
-def _no_training(is_training, what):
-    if is_training:
-        raise TrainingPathNotBuilt(f"{what}: is_training=True needs the backward kernels (see DESIGN.md §scope)")
-
-
 def pretrain_bert_embedding(input_ids, input_mask, segment_ids, pretrain_dir, drop_out, is_training):
     """reference tools/layer.py:63-81 — BertModel(...).get_sequence_output() (+ dropout when training).
 
