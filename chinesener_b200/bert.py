@@ -200,6 +200,41 @@ def _tf_casts(store, cfg, scope):
     return store.cached(("bert_tf_casts", scope), build)
 
 
+def bert_forward_f32(input_ids, input_mask, segment_ids, cfg, store=None, scope="bert", gelu="tanh"):
+    """BertModel forward at fp32 accuracy (BASELINE config 2: "bert_crf ... fp32", logits within 1e-3 of the
+    reference): every dense layer is the 3-term split-bf16 product on the tcgen05 kernel (ops.gemm_split_f32,
+    ~2^-16 relative), attention is the fp32 kernel (ner_attention_f32, head_dim 64), LayerNorm / GELU / residual
+    stream in f32.  Padded layout; keys are limited to the mask's prefix length, which equals the additive
+    (1-mask)*-10000 of attention_layer() because exp(-10000 - max) is exactly 0 in fp32.  ~3x the GEMM work of the
+    bf16 path: a parity mode, not the benchmark path."""
+    from .tools.transformer.modules import dense_f32
+    store = store or variables.default_store()
+    create_bert_variables(cfg, store, scope)
+    B, L = input_ids.shape
+    H, NH, I = cfg["hidden_size"], cfg["num_attention_heads"], cfg["intermediate_size"]
+    v = store.vars
+    ids, seg = ops._i32(input_ids), (None if segment_ids is None else ops._i32(segment_ids))
+    lens = ops._i32(input_mask).sum(1).to(torch.int32)
+    we, te, pe = (v[f"{scope}/embeddings/{n}"] for n in ("word_embeddings", "token_type_embeddings", "position_embeddings"))
+    x, _ = ops.bert_embed_ln(we, te, pe, v[f"{scope}/embeddings/LayerNorm/gamma"], v[f"{scope}/embeddings/LayerNorm/beta"], ids, seg,
+                             eps=1e-12)
+    with variables.use_store(store):
+        for li in range(cfg["num_hidden_layers"]):
+            p = f"{scope}/encoder/layer_{li}"
+            q = dense_f32(x, H, f"{p}/attention/self/query")
+            k = dense_f32(x, H, f"{p}/attention/self/key")
+            val = dense_f32(x, H, f"{p}/attention/self/value")
+            ctx, _, _ = ops.attention_f32(q, k, val, lens, B, L, NH, H // NH, scale=(H // NH) ** -0.5)
+            y = dense_f32(ctx, H, f"{p}/attention/output/dense", residual=x)
+            x1, _ = ops.layernorm(y, v[f"{p}/attention/output/LayerNorm/gamma"], v[f"{p}/attention/output/LayerNorm/beta"],
+                                  eps=1e-12, want_bf16=False)
+            h = ops.gelu_f32(dense_f32(x1, I, f"{p}/intermediate/dense"), erf=(gelu == "erf"), inplace=True)
+            y2 = dense_f32(h, H, f"{p}/output/dense", residual=x1)
+            x, _ = ops.layernorm(y2, v[f"{p}/output/LayerNorm/gamma"], v[f"{p}/output/LayerNorm/beta"], eps=1e-12,
+                                 want_bf16=False)
+    return x
+
+
 def _train_composite(input_ids, input_mask, segment_ids, cfg, store, tape, scope, gelu, keep_h, keep_a):
     """TRAIN forward + recorded backward through the two C-ABI composites (bert_train.cu): the host
     enqueues the whole encoder with two calls instead of ~480 (the per-kernel path is launch-bound)."""

@@ -386,6 +386,25 @@ extern "C" int ner_colsum_bf16_add(const void* x_bf16, float* out, int M, int N,
   return ner_launch_status();
 }
 
+// GELU on f32 activations (the fp32-accurate BERT mode keeps the FFN intermediate in f32)
+__global__ void __launch_bounds__(256) gelu_f32_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n, int erf_variant) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = x[i];
+    if (erf_variant)
+      y[i] = 0.5f * v * (1.f + erff(v * 0.7071067811865476f));
+    else
+      y[i] = 0.5f * v * (1.f + tanhf(0.7978845608028654f * (v + 0.044715f * v * v * v)));
+  }
+}
+
+extern "C" int ner_gelu_f32(const float* x, float* y, size_t n, int erf_variant, ner_stream_t stream) {
+  if (!x || !y) return n == 0 ? NER_OK : NER_ERR_INVALID_ARG;
+  if (n == 0) return NER_OK;
+  gelu_f32_kernel<<<flat_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n, erf_variant);
+  return ner_launch_status();
+}
+
 extern "C" int ner_gelu_bf16(const void* pre_bf16, void* act_bf16, size_t n, int erf_variant, ner_stream_t stream) {
   if (!pre_bf16 || !act_bf16 || (n % 4) != 0) return n == 0 ? NER_OK : NER_ERR_INVALID_ARG;
   if (n == 0) return NER_OK;

@@ -60,8 +60,14 @@ class Estimator:
         return self.forward_device(dev_features, False)[1]
 
     def forward_device(self, dev_features, is_training=False):
-        with variables.use_store(self.store):
-            return self.build_graph(dev_features, None, self.params, is_training)
+        from .tools import layer
+        prec0 = layer.BERT_PRECISION
+        layer.BERT_PRECISION = self.params.get('bert_precision', prec0)
+        try:
+            with variables.use_store(self.store):
+                return self.build_graph(dev_features, None, self.params, is_training)
+        finally:
+            layer.BERT_PRECISION = prec0
 
     def predict(self, features):
         """PREDICT mode on one host batch -> dict(pred_ids int32 [B,L] on host, label_ids, tokens)."""

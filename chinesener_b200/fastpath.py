@@ -29,7 +29,7 @@ def bert_bilstm_crf_predict(est, dev):
     store, params = est.store, est.params
     mask = dev['mask']
     total = getattr(mask, "total_tokens", None)
-    if total is None or not _layer.PACK_SEQUENCES or _bert.PER_KERNEL:
+    if total is None or not _layer.PACK_SEQUENCES or _bert.PER_KERNEL or params.get('bert_precision', _layer.BERT_PRECISION) != 'bf16':
         return None
     if params.get('cell_type', 'lstm').lower() != 'lstm' or params.get('cell_size', 1) != 1:
         return None

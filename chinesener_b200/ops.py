@@ -456,6 +456,14 @@ def gelu_bf16(pre, erf=False):
     return out
 
 
+def gelu_f32(x, erf=False, inplace=False):
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    y = x if inplace else torch.empty_like(x)
+    check(lib().ner_gelu_f32(ptr(x), ptr(y), x.numel(), 1 if erf else 0, stream()))
+    return y
+
+
 def gelu_bwd_bf16(pre, dact, erf=False):
     require_cuda(pre, dact)
     out = torch.empty_like(pre)

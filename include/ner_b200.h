@@ -403,6 +403,8 @@ int ner_colsum_bf16_add(const void* x_bf16, float* out, int M, int N, ner_stream
 /* GELU on a saved bf16 pre-activation (training forward) and its backward d_pre = d_act * gelu'(pre).
  * n % 4 == 0.  erf_variant: 0 tanh approximation, 1 erf. */
 int ner_gelu_bf16(const void* pre_bf16, void* act_bf16, size_t n, int erf_variant, ner_stream_t stream);
+/* Same on f32 (exact tanhf / erff): the FFN activation of the fp32-accurate BERT mode (y may alias x). */
+int ner_gelu_f32(const float* x, float* y, size_t n, int erf_variant, ner_stream_t stream);
 int ner_gelu_bwd_bf16(const void* pre_bf16, const void* dact_bf16, void* dpre_bf16, size_t n,
                       int erf_variant, ner_stream_t stream);
 /* Embedding backward: scatter-add dx [B*L,H] f32 into d_word [vocab,H], d_type [n_type,H],

@@ -233,3 +233,38 @@ def test_fused_predict_call_equals_build_graph(tmp_path):
         assert torch.equal(est.predict(b)['pred_ids'], ref.cpu())
     est.params['fused_predict'] = False
     assert torch.equal(est.predict(batches[1])['pred_ids'], est.forward_device(est.to_device(batches[1]), False)[1].cpu())
+
+
+def test_bert_crf_fp32_mode_logits_within_1e3_of_the_oracle(tmp_path):
+    """BASELINE config 2 ("bert_crf ... fp32"): with params['bert_precision'] = 'fp32' the emission logits are
+    within 1e-3 of the float64 oracle (the north-star tolerance for fp32 emission logits), tags bit-exact on them."""
+    import json
+    from chinesener_b200 import ops
+    from chinesener_b200.tools import layer
+    B, L = 6, 48
+    (tmp_path / "bert_config.json").write_text(json.dumps(SMALL_BERT))
+    feats = synthetic.msra_batch(B, L, vocab=SMALL_BERT['vocab_size'], seed=5)
+    params = dict(synthetic.data_params(L), pretrain_dir=str(tmp_path), bert_precision='fp32')
+    est = engine.Estimator("bert_crf", params)
+    est.evaluate(feats)
+    _scale_up(est.store, ["logits/kernel"], 8.0)
+    out = est.evaluate(feats)
+    w = est.store.state_dict()
+    p = dict(est.params, num_hidden_layers=2, num_attention_heads=12)
+    ref = omodels.bert_crf(w, feats, p, dtype=torch.float64, emulate_bf16=False)
+    dev = est.to_device(feats)
+    layer.BERT_PRECISION = 'fp32'
+    try:
+        with variables.use_store(est.store):
+            emb = layer.pretrain_bert_embedding(dev['token_ids'], dev['mask'], dev['segment_ids'], est.params['pretrain_dir'], 0.1, False)
+            logits = layer.dense(emb, 10, 'logits')
+    finally:
+        layer.BERT_PRECISION = 'bf16'
+    valid = (torch.arange(L)[None, :] < feats['seq_len'][:, None])
+    err = (logits.cpu().double() - ref['logits'])[valid].abs().max().item()
+    print(f"bert_crf fp32 mode: max|logit - fp64 oracle| = {err:.2e} (max |logit| {ref['logits'][valid].abs().max().item():.2f})")
+    assert err < 1e-3
+    assert abs(out['loss'] - ref['loss']) < 1e-3 * max(1.0, abs(ref['loss']))
+    ref_pred, _ = crf.crf_decode(logits.cpu().numpy(), w['crf_layer/transitions'].numpy(), feats['seq_len'].numpy(), dtype=np.float32)
+    np.testing.assert_array_equal(out['pred_ids'].numpy(), ref_pred)
+    assert (out['pred_ids'].numpy() == ref['pred_ids']).mean() > 0.999
