@@ -12,6 +12,8 @@ Tolerances (written here as the contract):
     bounded (5e-2 abs); the fp32-accurate configuration (config 2, 1e-3 abs) is the split-bf16
     mode — see DESIGN.md §4.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -268,3 +270,28 @@ def test_bert_crf_fp32_mode_logits_within_1e3_of_the_oracle(tmp_path):
     ref_pred, _ = crf.crf_decode(logits.cpu().numpy(), w['crf_layer/transitions'].numpy(), feats['seq_len'].numpy(), dtype=np.float32)
     np.testing.assert_array_equal(out['pred_ids'].numpy(), ref_pred)
     assert (out['pred_ids'].numpy() == ref['pred_ids']).mean() > 0.999
+
+
+def test_infer_helper_text_to_entities_in_process(tmp_path):
+    """reference inference.py: text -> features -> PREDICT -> entities, on the local engine (random weights, so only the
+    plumbing is asserted: the entity strings are exactly what extract_entity reads off the predicted tags)."""
+    import json
+    from chinesener_b200.data.tokenizer import FullTokenizer
+    from chinesener_b200.inference import InferHelper, TAG2IDX
+    from chinesener_b200.tools.infer_utils import extract_entity
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "warmup_features.json"), encoding="utf8"))
+    vocab = dict(gold["bert_vocab_subset"])
+    vocab.setdefault("[UNK]", 100)
+    cfg = dict(SMALL_BERT, vocab_size=21128)
+    (tmp_path / "bert_config.json").write_text(json.dumps(cfg))
+    params = dict(synthetic.data_params(150), pretrain_dir=str(tmp_path))
+    est = engine.Estimator("bert_bilstm_crf", params)
+    helper = InferHelper(150, TAG2IDX, "bert_bilstm_crf", FullTokenizer(vocab), estimator=est)
+    helper.infer(gold["text"])                                   # first call creates the variables
+    _scale_up(est.store, ["logits/kernel"], 8.0)
+    ent = helper.infer(gold["text"])
+    from chinesener_b200.data.base_preprocess import features_to_batch
+    pred = est.predict(features_to_batch([helper.feature]))['pred_ids'].numpy()[0]
+    assert pred[42:].tolist() == [0] * (150 - 42)                # zero beyond seq_len
+    idx2tag = {v: k for k, v in TAG2IDX.items()}
+    assert dict(ent) == dict(extract_entity(helper.feature['tokens'], [int(i) for i in pred], idx2tag))
