@@ -62,6 +62,11 @@ def example_features(ex):
         for ff, _, vv in fields(kv[2]):
             if ff == 1:       # bytes_list
                 out[name] = [x.decode('utf8') for _, _, x in fields(vv)]
+            elif ff == 2:     # float_list (packed)
+                vals = []
+                for _, wt, c in fields(vv):
+                    vals.extend(struct.unpack('<%df' % (len(c) // 4), c))
+                out[name] = vals
             elif ff == 3:     # int64_list (packed)
                 vals = []
                 for _, wt, c in fields(vv):
@@ -78,7 +83,7 @@ def example_features(ex):
 
 def main():
     golden = {"text": TEXT, "max_seq_len": 150, "models": {}}
-    for model in ("bert_bilstm_crf", "bilstm_crf"):
+    for model in ("bert_bilstm_crf", "bilstm_crf", "bilstm_crf_softlexicon"):
         rec = first_record(os.path.join(REF, "serving_model", model, "1", "assets.extra", "tf_serving_warmup_requests"))
         req = sub(rec, [6, 1])                                   # PredictionLog.predict_log.request
         for f, _, entry in fields(req):
@@ -92,6 +97,14 @@ def main():
     g = golden["models"]["bilstm_crf"]
     golden["giga_vocab_subset"] = {t: i for t, i in zip(g["tokens"], g["token_ids"]) if t != '[PAD]'}
     golden["giga_n_vocab"] = g["token_ids"][-1]                   # '[PAD]' = n_vocab
+    # SoftLexicon record: keep the layout facts and the first rows (6000 ids / float weights per sentence)
+    sl = golden["models"].pop("bilstm_crf_softlexicon")
+    ids, wts = sl["softlexicon_ids"], sl["softlexicon_weights"]
+    golden["softlexicon"] = {"seq_len": sl["seq_len"], "n_ids": len(ids), "ids_first_rows": ids[:120],
+                             "weights_first_rows": wts[:120], "ids_row_40": ids[40 * 40:41 * 40],
+                             "weights_row_40": wts[40 * 40:41 * 40],
+                             "row_weight_sums": [sum(wts[r * 40:(r + 1) * 40]) for r in range(150)],
+                             "none_id": max(ids) - 1, "pad_id": max(ids), "token_ids": sl["token_ids"]}
     with open(os.path.join(os.path.dirname(__file__), "warmup_features.json"), "w", encoding="utf8") as f:
         json.dump(golden, f, ensure_ascii=False, indent=0)
 
