@@ -295,3 +295,35 @@ def test_infer_helper_text_to_entities_in_process(tmp_path):
     assert pred[42:].tolist() == [0] * (150 - 42)                # zero beyond seq_len
     idx2tag = {v: k for k, v in TAG2IDX.items()}
     assert dict(ent) == dict(extract_entity(helper.feature['tokens'], [int(i) for i in pred], idx2tag))
+
+
+def test_softlexicon_host_features_feed_the_plugin():
+    """SoftLexiconProc features (host builder) -> features_to_batch -> bilstm_crf_softlexicon PREDICT: the pooled lexicon
+    embedding the kernel computes equals the weighted sum the builder's ids / weights describe."""
+    from chinesener_b200 import ops
+    from chinesener_b200.data.base_preprocess import features_to_batch
+    from chinesener_b200.data.tokenizer import TokenizerAdapter, TokenizerGiga
+    from chinesener_b200.data.word_enhance import SoftLexiconProc, WordVocab
+    from chinesener_b200.inference import TAG2IDX
+    chars = list("给中央军委员美国太平洋海上将总部司令")
+    words = ["中央", "中央军委", "军委", "委员", "美国", "太平洋", "海军", "上将", "总部", "司令"] + chars
+    vocab = WordVocab(words, {w: 5 + 3 * i for i, w in enumerate(words)})
+    proc = SoftLexiconProc(TokenizerGiga, 32, TAG2IDX, TokenizerAdapter(chars), vocab)
+    sents = ["给中央军委委员", "美国太平洋总部司令海军上将"]
+    feats = [proc.build_seq_feature(s) for s in sents]
+    batch = features_to_batch(feats)
+    batch['softlexicon_ids'] = torch.tensor([f['softlexicon_ids'] for f in feats], dtype=torch.int32)
+    batch['softlexicon_weights'] = torch.tensor([f['softlexicon_weights'] for f in feats], dtype=torch.float32)
+    g = torch.Generator().manual_seed(0)
+    emb = torch.randn(len(chars) + 2, 50, generator=g).numpy()
+    wemb = torch.randn(vocab.n_word + 3, 50, generator=g).numpy()
+    params = dict(synthetic.data_params(32), embedding=emb, word_embedding=wemb, word_enhance_dim=4, max_lexicon_len=10)
+    est = engine.Estimator("bilstm_crf_softlexicon", params)
+    out = est.predict(batch)
+    assert out['pred_ids'].shape == (2, 32) and (out['pred_ids'][0, 7:] == 0).all()
+    ids = batch['softlexicon_ids'].view(2, 32, 40).cuda()
+    wts = batch['softlexicon_weights'].view(2, 32, 40).cuda()
+    table = est.store.vars['word_enhance/softlexicon_embedding']
+    pooled = ops.softlexicon_pool(table, ids, wts, 4, 10)
+    ref = (table[ids.long()] * wts[..., None]).view(2, 32, 4, 10, 50).sum(3).reshape(2, 32, 200)
+    torch.testing.assert_close(pooled, ref, rtol=1e-5, atol=1e-6)
