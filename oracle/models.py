@@ -60,6 +60,22 @@ def bilstm_crf_softlexicon(w, features, params, dtype=torch.float32, emulate_bf1
     return _crf_tail(logits, w, features)
 
 
+def bert_bilstm_crf_softlexicon(w, features, params, dtype=torch.float32, emulate_bf16=False, gelu_variant="tanh"):
+    """model/bert_bilstm_crf_softlexicon.py:14-67 (eval mode): concat([pooled lexicon, BERT sequence output]) -> bilstm."""
+    B = features["token_ids"].shape[0]
+    L = params["max_seq_len"]
+    G, S = params["word_enhance_dim"], params["max_lexicon_len"]
+    seq = nn.bert_encoder(w, features["token_ids"], features["mask"], features["segment_ids"],
+                          num_layers=params.get("num_hidden_layers", 12), num_heads=params.get("num_attention_heads", 12),
+                          dtype=dtype, gelu_variant=gelu_variant, emulate_bf16=emulate_bf16)
+    ids = features["softlexicon_ids"].view(B, L, G * S)
+    wts = features["softlexicon_weights"].view(B, L, G * S)
+    wh = nn.softlexicon_pool(w["word_enhance/softlexicon_embedding"].to(dtype), ids, wts.to(dtype), G, S)
+    lstm = nn.bilstm(torch.cat([wh, seq], dim=-1), w, features["seq_len"], params["rnn_activation"], 1.0, dtype, emulate_bf16)
+    logits = nn.dense(lstm, w["logits/kernel"].to(dtype), w["logits/bias"].to(dtype))
+    return _crf_tail(logits, w, features)
+
+
 def transformer_tener_crf_bichar(w, features, params, dtype=torch.float32):
     """model/transformer_tener_crf_bichar.py:8-42 (eval mode)."""
     from . import transformer as tfm

@@ -327,3 +327,39 @@ def test_softlexicon_host_features_feed_the_plugin():
     pooled = ops.softlexicon_pool(table, ids, wts, 4, 10)
     ref = (table[ids.long()] * wts[..., None]).view(2, 32, 4, 10, 50).sum(3).reshape(2, 32, 200)
     torch.testing.assert_close(pooled, ref, rtol=1e-5, atol=1e-6)
+
+
+def _bert_softlex_setup(tmp_path, B=4, L=32, NW=4000, drop=0.0, keep=1.0):
+    import json
+    cfg = dict(SMALL_BERT, hidden_dropout_prob=drop, attention_probs_dropout_prob=drop)
+    (tmp_path / "bert_config.json").write_text(json.dumps(cfg))
+    feats = synthetic.msra_batch(B, L, vocab=SMALL_BERT['vocab_size'], seed=31)
+    ids, wts = synthetic.softlexicon_features(B, L, NW, seed=31, lens=feats['seq_len'].numpy())
+    feats['softlexicon_ids'], feats['softlexicon_weights'] = ids, wts
+    g = torch.Generator().manual_seed(4)
+    wemb = torch.nn.functional.normalize(torch.randn(NW, 50, generator=g), dim=1).numpy()
+    params = dict(synthetic.data_params(L), pretrain_dir=str(tmp_path), word_embedding=wemb, word_enhance_dim=4, max_lexicon_len=10,
+                  embedding_dropout=drop, keep_prob_list=[keep])
+    return engine.Estimator("bert_bilstm_crf_softlexicon", params), feats
+
+
+def test_bert_bilstm_crf_softlexicon_plugin(tmp_path):
+    """a further plugin on the same kernels (BERT encoder + lexicon pool + BiLSTM(H=200, tanh) + CRF)."""
+    est, feats = _bert_softlex_setup(tmp_path)
+    est.evaluate(feats)
+    _scale_up(est.store, ["logits/kernel"], 6.0)
+    out = est.evaluate(feats)
+    w = est.store.state_dict()
+    p = dict(est.params, num_hidden_layers=2, num_attention_heads=12)
+    ref = omodels.bert_bilstm_crf_softlexicon(w, feats, p, dtype=torch.float64, emulate_bf16=True)
+    assert abs(out['loss'] - ref['loss']) < 5e-3 * max(1.0, abs(ref['loss']))
+    assert (out['pred_ids'].numpy() == ref['pred_ids']).mean() > 0.99
+    assert (out['pred_ids'].numpy()[feats['mask'].numpy() == 0] == 0).all()
+
+
+def test_bert_bilstm_crf_softlexicon_trains(tmp_path):
+    est, feats = _bert_softlex_setup(tmp_path, drop=0.1, keep=0.9)
+    est.params.update(lr=1e-5, num_train_steps=100, warmup_ratio=0.1)
+    losses = [float(est.train_step(feats)) for _ in range(12)]
+    assert np.isfinite(losses).all() and losses[-1] < 0.85 * losses[0], losses
+    assert float(est.store.grads['word_enhance/softlexicon_embedding'].abs().sum()) == 0.0     # zeroed after the step
