@@ -119,3 +119,32 @@ def sinusoidal_positional_encoding(emb_dim, pos_seq):
     enc = np.einsum('i,j->ij', np.asarray(pos_seq, dtype=np.float64), inv_freq)
     out = np.where(np.arange(emb_dim)[None, :] % 2 == 1, np.cos(enc), np.sin(enc))
     return out.astype(np.float32)
+
+
+def multi_head_attention(x2d, seq_len, B, L, num_head, dropout_rate, is_training, scope):
+    """reference modules.py:129-175 with key = value = query = x: projected K/V/Q, scaled dot product over the valid
+    keys (fp32 attention kernel), output projection, dropout, add & norm."""
+    d_model = x2d.shape[-1]
+    dh = d_model // num_head
+    p = f"{scope}/multi_head_attention"
+    dense = dense_train if is_training else dense_f32
+    k = dense(x2d, d_model, f"{p}/pre_key_project")
+    v = dense(x2d, d_model, f"{p}/pre_value_project")
+    q = dense(x2d, d_model, f"{p}/pre_query_project")
+    scale = dh ** -0.5
+    ctx, _, _ = ops.attention_f32(q, k, v, seq_len, B, L, num_head, dh, scale=scale)
+    if not is_training:
+        y = dense_f32(ctx, d_model, f"{p}/post_linear_project", residual=x2d)
+        return layer_norm(y, f"{p}/add_and_norm")
+    tape = autodiff.current()
+
+    def bwd(g):
+        if g is None:
+            return
+        dq, dk, dv, _, _ = ops.attention_f32_bwd(q, k, v, seq_len, B, L, num_head, dh, g.contiguous(), scale=scale)
+        tape.add_grad(q, dq)
+        tape.add_grad(k, dk)
+        tape.add_grad(v, dv)
+    tape.record(ctx, bwd)
+    y = dense_train(ctx, d_model, f"{p}/post_linear_project")
+    return add_and_norm_train(x2d, y, f"{p}/add_and_norm", dropout_rate)

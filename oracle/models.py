@@ -87,3 +87,18 @@ def transformer_tener_crf_bichar(w, features, params, dtype=torch.float32):
     x = tfm.tener_encoder(x, features["seq_len"], w, params["encode_layers"], params["num_head"])
     logits = nn.dense(x, w["logits/kernel"].to(dtype), w["logits/bias"].to(dtype))
     return _crf_tail(logits, w, features)
+
+
+def transformer_crf_bichar(w, features, params, dtype=torch.float32):
+    """model/transformer_crf_bichar.py:8-46 (eval mode): projected char+bichar embedding + sinusoidal positions."""
+    from . import transformer as tfm
+    char = torch.as_tensor(params["embedding"]).to(dtype)[features["token_ids"].long()]
+    bichar = torch.as_tensor(params["bichar_embedding"]).to(dtype)[features["bichar_ids"].long()]
+    x = torch.cat([char, bichar], dim=-1)
+    if x.shape[-1] != params["d_model"]:
+        x = x @ w["embedding/dense/kernel"].to(dtype) + w["embedding/dense/bias"].to(dtype)
+    L = params["max_seq_len"]
+    x = x + tfm.sinusoidal_positional_encoding(params["d_model"], np.arange(L), dtype)[None]
+    x = tfm.transformer_encoder(x, features["seq_len"], w, params["encode_layers"], params["num_head"])
+    logits = nn.dense(x, w["logits/kernel"].to(dtype), w["logits/bias"].to(dtype))
+    return _crf_tail(logits, w, features)

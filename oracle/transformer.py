@@ -62,6 +62,32 @@ def relative_multi_head_attention(x, mask, w, prefix, num_head):
                          g("add_and_norm/layer_normalization/norm_bias"))
 
 
+def multi_head_attention(x, mask, w, prefix, num_head):
+    """tools/transformer/modules.py:129-175 with key = value = query = x (scaled dot product, projected key)."""
+    B, L, d_model = x.shape
+    dh = d_model // num_head
+    g = lambda n: w[f"{prefix}/{n}"].to(x.dtype)
+    proj = lambda n: x @ g(f"{n}/kernel") + g(f"{n}/bias")
+    split = lambda t: t.view(B, L, num_head, dh).permute(0, 2, 1, 3)
+    key, value, query = split(proj("pre_key_project")), split(proj("pre_value_project")), split(proj("pre_query_project"))
+    weight = query @ key.transpose(-1, -2) / (dh ** 0.5) + (1 - mask.to(x.dtype))[:, None, None, :] * MASK_ADD
+    out = (torch.softmax(weight, dim=-1) @ value).permute(0, 2, 1, 3).reshape(B, L, d_model)
+    out = out @ g("post_linear_project/kernel") + g("post_linear_project/bias")
+    return layer_norm_tf(x + out, g("add_and_norm/layer_normalization/norm_kernel"),
+                         g("add_and_norm/layer_normalization/norm_bias"))
+
+
+def transformer_encoder(x, seq_len, w, encode_layers, num_head):
+    """tools/transformer/encoder.py:6-19."""
+    B, L, _ = x.shape
+    mask = (torch.arange(L)[None, :] < seq_len.long()[:, None])
+    for i in range(encode_layers):
+        p = f"encoding/self_attention_layer_{i}"
+        x = multi_head_attention(x, mask, w, f"{p}/multi_head_attention", num_head)
+        x = ffn(x, w, f"{p}/ffn")
+    return x
+
+
 def ffn(x, w, prefix):
     g = lambda n: w[f"{prefix}/{n}"].to(x.dtype)
     y = torch.relu(x @ g("ffn_inner/kernel") + g("ffn_inner/bias"))

@@ -187,3 +187,56 @@ def test_tener_training_reduces_the_loss():
     est.params.update(lr=2e-3, num_train_steps=200, warmup_ratio=0.1)
     losses = [float(est.train_step(feats)) for _ in range(40)]
     assert np.isfinite(losses).all() and losses[-1] < 0.7 * losses[0], losses
+
+
+def _abs_setup(B=4, L=64, V=2000, VB=3000, drop=0.0):
+    feats = synthetic.msra_batch(B, L, vocab=V, seed=23)
+    g = torch.Generator().manual_seed(5)
+    feats['bichar_ids'] = torch.randint(0, VB, (B, L), generator=g, dtype=torch.int32)
+    emb = torch.nn.functional.normalize(torch.randn(V, 50, generator=g), dim=1).numpy()
+    bemb = torch.nn.functional.normalize(torch.randn(VB, 50, generator=g), dim=1).numpy()
+    params = dict(synthetic.data_params(L), embedding=emb, bichar_embedding=bemb, embedding_dropout=drop, dropout_rate=drop)
+    return engine.Estimator("transformer_crf_bichar", params), feats, emb, bemb
+
+
+def test_transformer_crf_bichar_plugin_matches_oracle():
+    """the absolute-position transformer plugin on the same kernels (logits at fp32 accuracy)."""
+    est, feats, emb, bemb = _abs_setup()
+    est.evaluate(feats)
+    est.store.vars["logits/kernel"].mul_(4.0)
+    est.store.touch()
+    out = est.evaluate(feats)
+    w = est.store.state_dict()
+    ref = omodels.transformer_crf_bichar(w, feats, est.params, dtype=torch.float64)
+    assert abs(out['loss'] - ref['loss']) < 1e-3 * max(1.0, abs(ref['loss']))
+    assert (out['pred_ids'].numpy() == ref['pred_ids']).mean() > 0.995
+
+
+def test_transformer_crf_bichar_gradients_and_training():
+    from chinesener_b200 import autodiff, variables
+    from oracle import crf_torch
+    est, feats, emb, bemb = _abs_setup()
+    est.evaluate(feats)
+    w = est.store.state_dict()
+    wd = {k: v.double().clone().requires_grad_(True) for k, v in w.items()}
+    L = feats['token_ids'].shape[1]
+    x = torch.cat([torch.from_numpy(emb).double()[feats['token_ids'].long()], torch.from_numpy(bemb).double()[feats['bichar_ids'].long()]], -1)
+    x = x @ wd["embedding/dense/kernel"] + wd["embedding/dense/bias"]
+    x = x + otf.sinusoidal_positional_encoding(160, np.arange(L), torch.float64)[None]
+    x = otf.transformer_encoder(x, feats['seq_len'], wd, est.params['encode_layers'], est.params['num_head'])
+    logits = x @ wd['logits/kernel'] + wd['logits/bias']
+    ref_loss = (-crf_torch.crf_log_likelihood(logits, feats['label_ids'], feats['seq_len'], wd['crf_layer/transitions'])).mean()
+    ref_loss.backward()
+    dev = est.to_device(feats)
+    with variables.use_store(est.store), autodiff.recording(est.store) as tape:
+        loss, _ = est.build_graph(dev, None, est.params, True)
+        tape.backward()
+    assert abs(float(loss) - float(ref_loss.detach())) < 2e-3 * max(1.0, abs(float(ref_loss.detach())))
+    gscale = max(v.grad.abs().max().item() for v in wd.values() if v.grad is not None)
+    worst = {n: (est.store.grads[n].cpu().double() - v.grad).abs().max().item() / max(v.grad.abs().max().item(), 1e-3 * gscale)
+             for n, v in wd.items() if v.grad is not None}
+    assert max(worst.values()) < 3e-2, {k: e for k, e in worst.items() if e > 3e-2}
+    est2, feats2, _, _ = _abs_setup(drop=0.2)
+    est2.params.update(lr=2e-3, num_train_steps=200, warmup_ratio=0.1)
+    losses = [float(est2.train_step(feats2)) for _ in range(40)]
+    assert np.isfinite(losses).all() and losses[-1] < 0.7 * losses[0], losses
