@@ -38,6 +38,7 @@ SIGNATURES = {
     "ner_dense_small_n_bwd": (_i, [_vp] * 6 + [_i, _i, _i, _vp]),
     "ner_dropout": (_i, [_vp, _vp, _c.c_size_t, _c.c_float, _c.c_uint64, _vp]),
     "ner_relu_bwd_f32": (_i, [_vp, _vp, _vp, _c.c_size_t, _vp]),
+    "ner_relu_f32": (_i, [_vp, _vp, _c.c_size_t, _vp]),
     "ner_attention_f32_bwd": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _c.c_float, _vp, _i, _vp, _i, _vp, _i, _vp, _i,
                                    _vp, _vp, _i, _i, _i, _i, _vp]),
     "ner_dropout_bf16": (_i, [_vp, _vp, _c.c_size_t, _c.c_float, _c.c_uint64, _vp]),

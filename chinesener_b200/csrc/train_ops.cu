@@ -217,6 +217,18 @@ relu_bwd_kernel(const float* __restrict__ act, const float* __restrict__ dact, f
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dpre[i] = act[i] > 0.f ? dact[i] : 0.f;
 }
 
+__global__ void __launch_bounds__(256) relu_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = fmaxf(x[i], 0.f);
+}
+
+extern "C" int ner_relu_f32(const float* x, float* y, size_t n, ner_stream_t stream) {
+  if (!x || !y) return n == 0 ? NER_OK : NER_ERR_INVALID_ARG;
+  if (n == 0) return NER_OK;
+  relu_kernel<<<flat_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n);
+  return ner_launch_status();
+}
+
 extern "C" int ner_relu_bwd_f32(const float* act, const float* dact, float* dpre, size_t n, ner_stream_t stream) {
   if (!act || !dact || !dpre) return n == 0 ? NER_OK : NER_ERR_INVALID_ARG;
   if (n == 0) return NER_OK;

@@ -321,6 +321,14 @@ def attention_f32_bwd(q, k, v, seq_len, B, L, num_heads, head_dim, d_out, scale=
     return dq, dk, dv, du, dvb
 
 
+def relu(x, inplace=False):
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    y = x if inplace else torch.empty_like(x)
+    check(lib().ner_relu_f32(ptr(x), ptr(y), x.numel(), stream()))
+    return y
+
+
 def relu_bwd(act, dact):
     require_cuda(act, dact)
     assert act.dtype == torch.float32 and dact.dtype == torch.float32 and act.numel() == dact.numel()

@@ -175,6 +175,65 @@ def _bilstm_train(embedding, activation, hidden_units_list, keep_prob_list, cell
     return out
 
 
+def cnn_layer(embedding, filter_list, kernel_size_list, activation, drop_out, is_training):
+    """reference tools/layer.py:44-60 — tf.layers.conv1d(padding='SAME') per kernel size (+ dropout), concatenated.
+    A kernel-k convolution over [B, L, C] is the label-projection kernel (ner_dense_small_n, filters <= 32) applied to the
+    k shifted copies of the sequence laid side by side (TF 'SAME': (k-1)//2 zero rows before, k//2 after); the shifts are
+    slices of one zero-padded buffer.  TRAIN: the same kernel's backward tap by tap, the shifted gradient slices are added back."""
+    if activation not in ('relu', None):
+        raise Exception("cnn_layer: only activation='relu' / None is built")
+    B, L, C = embedding.shape
+    store, tape = variables.default_store(), (autodiff.current() if is_training else None)
+    x = embedding.float() if embedding.dtype != torch.float32 else embedding
+    outputs = []
+    for filters, k in zip(filter_list, kernel_size_list):
+        name = f"cnn_kernel{k}"
+        w = store.get_variable(f"{name}/kernel", (k, C, filters), variables.glorot_uniform)       # TF conv1d kernel [k, in, out]
+        b = store.get_variable(f"{name}/bias", (filters,), variables.zeros)
+        pl, pr = (k - 1) // 2, k // 2
+        xp = torch.nn.functional.pad(x, (0, 0, pl, pr))
+        cols = torch.cat([xp[:, j:j + L] for j in range(k)], dim=-1).reshape(B * L, k * C).contiguous()
+        w2d = w.reshape(k * C, filters)
+        pre = ops.dense_small_n(cols, w2d, b)
+        out = ops.relu(pre) if activation == 'relu' else pre
+        if tape is not None:
+            need_dx = tape.needs_grad(embedding)
+
+            def bwd(g, xp=xp, w=w, out=out, name=name, k=k, pl=pl):
+                if g is None:
+                    return
+                g = g.reshape(B * L, -1).contiguous()
+                if activation == 'relu':
+                    g = ops.relu_bwd(out, g)
+                dW, db = store.grad(f"{name}/kernel"), store.grad(f"{name}/bias")
+                dxp = torch.zeros_like(xp) if need_dx else None
+                for j in range(k):            # one tap at a time: [C, filters] weight + its partial fit the kernel's smem
+                    xj = xp[:, j:j + L].reshape(B * L, C)
+                    dxj = ops.dense_small_n_bwd(xj, w[j], g, dW[j], db if j == 0 else None, want_dx=need_dx)
+                    if need_dx:
+                        dxp[:, j:j + L] += dxj.view(B, L, C)
+                if need_dx:
+                    tape.add_grad(embedding, dxp[:, pl:pl + L].contiguous())
+            tape.record(out, bwd)
+        out = dropout(out, drop_out, is_training, seed=1234)
+        out3 = out.view(B, L, filters)
+        if tape is not None:                      # the tape keys on tensor identity: record the reshape
+            tape.record(out3, lambda g, out=out: tape.add_grad(out, g.reshape(out.shape)) if g is not None else None)
+        outputs.append(out3)
+    output = outputs[0] if len(outputs) == 1 else torch.cat(outputs, dim=-1)
+    if tape is not None and len(outputs) > 1:
+        widths = [o.shape[-1] for o in outputs]
+
+        def cat_bwd(g):
+            if g is not None:
+                off = 0
+                for o, wd in zip(outputs, widths):
+                    tape.add_grad(o, g[..., off:off + wd].contiguous())
+                    off += wd
+        tape.record(output, cat_bwd)
+    return output
+
+
 def dense(inputs, units, name='logits', is_training=False):
     """tf.layers.dense(inputs, units, activation=None, use_bias=True, name=name) for units <= 32."""
     F = inputs.shape[-1]

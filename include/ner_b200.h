@@ -364,6 +364,8 @@ int ner_dropout(const float* x, float* y, size_t n, float keep_prob, uint64_t se
 /* Same on bf16 tensors (BertModel's hidden dropout on the bf16 dense outputs; y may alias x). */
 int ner_dropout_bf16(const void* x_bf16, void* y_bf16, size_t n, float keep_prob, uint64_t seed,
                      ner_stream_t stream);
+/* tf.nn.relu on f32 [n] (y may alias x). */
+int ner_relu_f32(const float* x, float* y, size_t n, ner_stream_t stream);
 /* tf.nn.relu gradient: dpre = dact where act > 0 else 0 (f32 [n]; dpre may alias dact). */
 int ner_relu_bwd_f32(const float* act, const float* dact, float* dpre, size_t n, ner_stream_t stream);
 /* dst[i] += a * src[i]. */

@@ -102,3 +102,18 @@ def transformer_crf_bichar(w, features, params, dtype=torch.float32):
     x = tfm.transformer_encoder(x, features["seq_len"], w, params["encode_layers"], params["num_head"])
     logits = nn.dense(x, w["logits/kernel"].to(dtype), w["logits/bias"].to(dtype))
     return _crf_tail(logits, w, features)
+
+
+def bert_cnn_crf(w, features, params, dtype=torch.float32, emulate_bf16=False, gelu_variant="tanh"):
+    """model/bert_cnn_crf.py:8-36 (eval mode): tf.layers.conv1d(padding='SAME', relu) per kernel size over the BERT output."""
+    seq = nn.bert_encoder(w, features["token_ids"], features["mask"], features["segment_ids"],
+                          num_layers=params.get("num_hidden_layers", 12), num_heads=params.get("num_attention_heads", 12),
+                          dtype=dtype, gelu_variant=gelu_variant, emulate_bf16=emulate_bf16)
+    outs = []
+    for filters, k in zip(params["filter_list"], params["kernel_size_list"]):
+        kern = w[f"cnn_kernel{k}/kernel"].to(dtype)                    # [k, C, F]
+        x = torch.nn.functional.pad(seq.transpose(1, 2), ((k - 1) // 2, k // 2))        # TF 'SAME'
+        y = torch.nn.functional.conv1d(x, kern.permute(2, 1, 0), w[f"cnn_kernel{k}/bias"].to(dtype)).transpose(1, 2)
+        outs.append(torch.relu(y))
+    logits = nn.dense(torch.cat(outs, -1), w["logits/kernel"].to(dtype), w["logits/bias"].to(dtype))
+    return _crf_tail(logits, w, features)

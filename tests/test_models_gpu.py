@@ -363,3 +363,32 @@ def test_bert_bilstm_crf_softlexicon_trains(tmp_path):
     losses = [float(est.train_step(feats)) for _ in range(12)]
     assert np.isfinite(losses).all() and losses[-1] < 0.85 * losses[0], losses
     assert float(est.store.grads['word_enhance/softlexicon_embedding'].abs().sum()) == 0.0     # zeroed after the step
+
+
+def _bert_cnn_setup(tmp_path, B=4, L=32, drop=0.0):
+    import json
+    cfg = dict(SMALL_BERT, hidden_dropout_prob=drop, attention_probs_dropout_prob=drop)
+    (tmp_path / "bert_config.json").write_text(json.dumps(cfg))
+    feats = synthetic.msra_batch(B, L, vocab=SMALL_BERT['vocab_size'], seed=41)
+    params = dict(synthetic.data_params(L), pretrain_dir=str(tmp_path), embedding_dropout=drop, cnn_dropout=drop)
+    return engine.Estimator("bert_cnn_crf", params), feats
+
+
+def test_bert_cnn_crf_plugin(tmp_path):
+    """BertModel + conv1d(k=4, SAME, relu) + CRF; the window reads BERT outputs of [PAD] positions."""
+    est, feats = _bert_cnn_setup(tmp_path)
+    est.evaluate(feats)
+    _scale_up(est.store, ["logits/kernel"], 6.0)
+    out = est.evaluate(feats)
+    w = est.store.state_dict()
+    p = dict(est.params, num_hidden_layers=2, num_attention_heads=12)
+    ref = omodels.bert_cnn_crf(w, feats, p, dtype=torch.float64, emulate_bf16=True)
+    assert abs(out['loss'] - ref['loss']) < 5e-3 * max(1.0, abs(ref['loss']))
+    assert (out['pred_ids'].numpy() == ref['pred_ids']).mean() > 0.99
+
+
+def test_bert_cnn_crf_trains(tmp_path):
+    est, feats = _bert_cnn_setup(tmp_path, drop=0.1)
+    est.params.update(lr=2e-5, num_train_steps=100, warmup_ratio=0.1)
+    losses = [float(est.train_step(feats)) for _ in range(12)]
+    assert np.isfinite(losses).all() and losses[-1] < 0.85 * losses[0], losses
