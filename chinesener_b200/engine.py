@@ -57,7 +57,7 @@ class Estimator:
                     pred = fn(self, dev_features)
                 if pred is not None:
                     return pred
-        return self.forward_device(dev_features, False)[1]
+        return self.forward_device(dev_features, False)[1]      # multi-task plugins return (loss, pred_ids, task_ids)
 
     def forward_device(self, dev_features, is_training=False):
         from .tools import layer
@@ -132,7 +132,7 @@ class Estimator:
         dev = features if all(not torch.is_tensor(v) or v.is_cuda for v in features.values()) else self.to_device(features)
         self.store.dropout_calls = 0
         with variables.use_store(self.store), autodiff.recording(self.store) as tape:
-            loss, _ = self.build_graph(dev, None, self.params, True)
+            loss = self.build_graph(dev, None, self.params, True)[0]
             tape.backward()
             p = self.params
             if 'bert' in self.model_name:
@@ -145,5 +145,5 @@ class Estimator:
 
     def evaluate(self, features):
         dev = self.to_device(features)
-        loss, pred_ids = self.forward_device(dev, False)
+        loss, pred_ids = self.forward_device(dev, False)[:2]
         return {'loss': float(loss), 'pred_ids': pred_ids.cpu()}

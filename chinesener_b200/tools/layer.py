@@ -105,7 +105,7 @@ def bilstm(embedding, cell_type, activation, hidden_units_list, keep_prob_list, 
         B, L, D = embedding.shape
     H = hidden_units_list[0]
     store = variables.default_store()
-    scope = "bilstm_layer/bidirectional_rnn"
+    scope = variables.scoped("bilstm_layer/bidirectional_rnn")
     for d in ("fw", "bw"):
         store.get_variable(f"{scope}/{d}/multi_rnn_cell/cell_0/lstm_cell/kernel", (D + H, 4 * H), variables.glorot_uniform)
         store.get_variable(f"{scope}/{d}/multi_rnn_cell/cell_0/lstm_cell/bias", (4 * H,), variables.zeros)
@@ -130,7 +130,7 @@ def _bilstm_train(embedding, activation, hidden_units_list, keep_prob_list, cell
     B, L, D = embedding.shape
     H = hidden_units_list[0]
     store = variables.default_store()
-    scope = "bilstm_layer/bidirectional_rnn"
+    scope = variables.scoped("bilstm_layer/bidirectional_rnn")
     names = {}
     for d in ("fw", "bw"):
         names[d] = (f"{scope}/{d}/multi_rnn_cell/cell_0/lstm_cell/kernel", f"{scope}/{d}/multi_rnn_cell/cell_0/lstm_cell/bias")
@@ -238,6 +238,7 @@ def dense(inputs, units, name='logits', is_training=False):
     """tf.layers.dense(inputs, units, activation=None, use_bias=True, name=name) for units <= 32."""
     F = inputs.shape[-1]
     lead = inputs.shape[:-1]
+    name = variables.scoped(name)
     w = variables.get_variable(f"{name}/kernel", (F, units), variables.glorot_uniform)
     b = variables.get_variable(f"{name}/bias", (units,), variables.zeros)
     tape = autodiff.current()
@@ -270,7 +271,8 @@ def dense(inputs, units, name='logits', is_training=False):
 
 def crf_layer(logits, label_ids, seq_len, label_size, is_training):
     """reference tools/layer.py:112-131 -> (trans, log_likelihood [B])."""
-    trans = variables.get_variable("crf_layer/transitions", (label_size, label_size), variables.xavier)
+    tname = variables.scoped("crf_layer/transitions")
+    trans = variables.get_variable(tname, (label_size, label_size), variables.xavier)
     if label_ids is None:
         return trans, None
     tape = autodiff.current()
@@ -284,12 +286,46 @@ def crf_layer(logits, label_ids, seq_len, label_size, is_training):
             B = lg.shape[0]
             d_ll = g if g is not None else torch.full((B,), -1.0 / B, dtype=torch.float32, device=lg.device)
             d_logits, d_trans = ops.crf_loglik_bwd(lg, label_ids, seq_len, trans, alpha, logz, d_ll.contiguous(), 1.0)
-            store.grad("crf_layer/transitions").add_(d_trans)
+            store.grad(tname).add_(d_trans)
             tape.add_grad(logits, d_logits)
         tape.record(ll, bwd)
         return trans, ll
     # EVAL / PREDICT: built lazily — evaluated when the loss is fetched (EVAL), never in PREDICT
     return trans, variables.Deferred(lambda: ops.crf_loglik_fwd(logits, label_ids, seq_len, trans)[0])
+
+
+def concat(tensors, is_training=False):
+    """tf.concat(tensors, axis=-1) with the tape entry that splits the gradient back."""
+    out = torch.cat(tensors, dim=-1)
+    tape = autodiff.current() if is_training else None
+    if tape is not None:
+        widths = [t.shape[-1] for t in tensors]
+
+        def bwd(g):
+            if g is not None:
+                off = 0
+                for t, wd in zip(tensors, widths):
+                    tape.add_grad(t, g[..., off:off + wd].contiguous())
+                    off += wd
+        tape.record(out, bwd)
+    return out
+
+
+def masked_task_loss(log_likelihoods, masks, weights, batch_size, is_training):
+    """sum_t w_t * sum(-ll_t[mask_t]) / batch — the loss of the multi-task plugins (reference
+    model/bert_bilstm_crf_mtl.py:42,61,64).  TRAIN: seeds d loss / d ll_t = -w_t mask_t / batch on the tape."""
+    coef = [m.to(torch.float32) * (float(w) / batch_size) for m, w in zip(masks, weights)]
+    tape = autodiff.current() if is_training else None
+    if tape is None:
+        return variables.Deferred(lambda: sum((-(ll.value() if isinstance(ll, variables.Deferred) else ll) * c).sum()
+                                              for ll, c in zip(log_likelihoods, coef)))
+    loss = sum((-ll * c).sum() for ll, c in zip(log_likelihoods, coef))
+
+    def bwd(g):
+        for ll, c in zip(log_likelihoods, coef):
+            tape.add_grad(ll, -c)
+    tape.record(loss, bwd)
+    return loss
 
 
 def crf_decode(logits, trans, seq_len, idx2tag, is_training, mask=None):

@@ -141,6 +141,26 @@ def get_variable(name, shape, initializer, trainable=True):
     return default_store().get_variable(name, shape, initializer, trainable)
 
 
+_scope = ""
+
+
+@contextlib.contextmanager
+def variable_scope(name):
+    """tf.variable_scope(name, reuse=tf.AUTO_REUSE) for the layer functions that take part in the multi-task plugins
+    (bilstm / dense / crf_layer resolve their variable names through `scoped`)."""
+    global _scope
+    prev = _scope
+    _scope = f"{prev}{name}/"
+    try:
+        yield
+    finally:
+        _scope = prev
+
+
+def scoped(name):
+    return _scope + name
+
+
 class Deferred:
     """A graph tensor that is evaluated only when fetched.  The reference builds `loss` and `pred_ids` in one
     TF graph and a session run computes only what the mode fetches: PREDICT never runs the log-likelihood

@@ -117,3 +117,29 @@ def bert_cnn_crf(w, features, params, dtype=torch.float32, emulate_bf16=False, g
         outs.append(torch.relu(y))
     logits = nn.dense(torch.cat(outs, -1), w["logits/kernel"].to(dtype), w["logits/bias"].to(dtype))
     return _crf_tail(logits, w, features)
+
+
+def bert_bilstm_crf_mtl(w, features, params, dtype=torch.float32, emulate_bf16=False, gelu_variant="tanh"):
+    """model/bert_bilstm_crf_mtl.py:8-66 (eval mode): shared BERT, one BiLSTM+logits+CRF tower per task scope,
+    loss = sum_t weight_t * sum(-ll_t[task_ids == t]) / batch, pred_ids picked per sentence by task_ids."""
+    seq = nn.bert_encoder(w, features["token_ids"], features["mask"], features["segment_ids"],
+                          num_layers=params.get("num_hidden_layers", 12), num_heads=params.get("num_attention_heads", 12),
+                          dtype=dtype, gelu_variant=gelu_variant, emulate_bf16=emulate_bf16)
+    task_ids = features["task_ids"].numpy()
+    lens = features["seq_len"].numpy()
+    loss, preds, logits_all, prev = 0.0, [], [], None
+    for t, task in enumerate(params["task_list"]):
+        lstm = nn.bilstm(seq, w, features["seq_len"], params["rnn_activation"], 1.0, dtype, emulate_bf16,
+                         prefix=f"{task}/bilstm_layer/bidirectional_rnn")
+        feats = torch.cat([prev, lstm], -1) if (t == 1 and params["asymmetry"]) else lstm
+        prev = lstm
+        logits = nn.dense(feats, w[f"{task}/logits/kernel"].to(dtype), w[f"{task}/logits/bias"].to(dtype))
+        lg = logits.detach().to(torch.float32).numpy()
+        trans = w[f"{task}/crf_layer/transitions"].to(torch.float32).numpy()
+        K = trans.shape[0]
+        ll = crf.crf_log_likelihood(lg, np.minimum(features["label_ids"].numpy(), K - 1), lens, trans, dtype=np.float64)
+        loss += params["task_weight"][t] * float(np.sum(-ll[task_ids == t]))
+        preds.append(crf.crf_decode(lg, trans, lens, dtype=np.float32)[0])
+        logits_all.append(logits)
+    pred = np.where((task_ids == 0)[:, None], preds[0], preds[1])
+    return dict(logits=logits_all, loss=loss / len(task_ids), pred_ids=pred)

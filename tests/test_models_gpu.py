@@ -392,3 +392,50 @@ def test_bert_cnn_crf_trains(tmp_path):
     est.params.update(lr=2e-5, num_train_steps=100, warmup_ratio=0.1)
     losses = [float(est.train_step(feats)) for _ in range(12)]
     assert np.isfinite(losses).all() and losses[-1] < 0.85 * losses[0], losses
+
+
+def _mtl_setup(tmp_path, asymmetry, B=6, L=32, drop=0.0):
+    import json
+    cfg = dict(SMALL_BERT, hidden_dropout_prob=drop, attention_probs_dropout_prob=drop)
+    (tmp_path / "bert_config.json").write_text(json.dumps(cfg))
+    feats = synthetic.msra_batch(B, L, vocab=SMALL_BERT['vocab_size'], seed=43)
+    feats['task_ids'] = torch.tensor([0, 1, 1, 0, 1, 0][:B], dtype=torch.int32)
+    base = synthetic.data_params(L)
+    cws = dict(label_size=5, idx2tag={i: t for i, t in enumerate(['[PAD]', 'B', 'M', 'E', 'S'])})
+    # task-2 sentences carry task-2 label ids (< 5)
+    t2 = feats['task_ids'] == 1
+    feats['label_ids'][t2] = feats['label_ids'][t2] % 5
+    params = dict(base, pretrain_dir=str(tmp_path), embedding_dropout=drop, task_list=['msra', 'cws'],
+                  msra=dict(label_size=base['label_size'], idx2tag=base['idx2tag']), cws=cws,
+                  task_weight=[1.0, 0.5], asymmetry=asymmetry, keep_prob_list=[1.0 - drop])
+    return engine.Estimator("bert_bilstm_crf_mtl", params), feats
+
+
+@pytest.mark.parametrize("asymmetry", [False, True])
+def test_bert_bilstm_crf_mtl_plugin(tmp_path, asymmetry):
+    """two BiLSTM+CRF towers under variable scopes on one shared BERT; masked per-task loss."""
+    est, feats = _mtl_setup(tmp_path, asymmetry)
+    est.evaluate(feats)
+    _scale_up(est.store, ["msra/logits/kernel", "cws/logits/kernel"], 6.0)
+    out = est.evaluate(feats)
+    w = est.store.state_dict()
+    assert "msra/bilstm_layer/bidirectional_rnn/fw/multi_rnn_cell/cell_0/lstm_cell/kernel" in w
+    assert tuple(w["cws/crf_layer/transitions"].shape) == (5, 5)
+    assert w["cws/logits/kernel"].shape[0] == (512 if asymmetry else 256)
+    p = dict(est.params, num_hidden_layers=2, num_attention_heads=12)
+    ref = omodels.bert_bilstm_crf_mtl(w, feats, p, dtype=torch.float64, emulate_bf16=True)
+    assert abs(out['loss'] - ref['loss']) < 5e-3 * max(1.0, abs(ref['loss']))
+    assert (out['pred_ids'].numpy() == ref['pred_ids']).mean() > 0.99
+    # PREDICT through the public call gives the same tags
+    assert torch.equal(est.predict(feats)['pred_ids'], out['pred_ids'])
+
+
+def test_bert_bilstm_crf_mtl_trains(tmp_path):
+    est, feats = _mtl_setup(tmp_path, True, drop=0.1)
+    est.params.update(lr=1e-5, num_train_steps=100, warmup_ratio=0.1)
+    losses = [float(est.train_step(feats)) for _ in range(12)]
+    assert np.isfinite(losses).all() and losses[-1] < 0.85 * losses[0], losses
+    # both towers and the shared encoder moved
+    g = est.store.grads
+    for name in ("msra/crf_layer/transitions", "cws/logits/kernel", "cws/bilstm_layer/bidirectional_rnn/bw/multi_rnn_cell/cell_0/lstm_cell/kernel"):
+        assert name in g
