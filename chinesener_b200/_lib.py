@@ -39,6 +39,9 @@ SIGNATURES = {
     "ner_dropout": (_i, [_vp, _vp, _c.c_size_t, _c.c_float, _c.c_uint64, _vp]),
     "ner_relu_bwd_f32": (_i, [_vp, _vp, _vp, _c.c_size_t, _vp]),
     "ner_relu_f32": (_i, [_vp, _vp, _c.c_size_t, _vp]),
+    "ner_reduce_max_time": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "ner_reduce_max_time_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _c.c_float, _vp]),
+    "ner_softmax_xent": (_i, [_vp, _vp, _vp, _vp, _i, _i, _c.c_float, _vp]),
     "ner_attention_f32_bwd": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _c.c_float, _vp, _i, _vp, _i, _vp, _i, _vp, _i,
                                    _vp, _vp, _i, _i, _i, _i, _vp]),
     "ner_dropout_bf16": (_i, [_vp, _vp, _c.c_size_t, _c.c_float, _c.c_uint64, _vp]),

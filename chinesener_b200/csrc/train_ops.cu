@@ -154,6 +154,57 @@ adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
   }
 }
 
+
+// tf.reduce_max(x[B,L,C], axis=1) -> y[B,C]: one thread per (b, c), a warp reads 32 consecutive c per step
+__global__ void __launch_bounds__(256)
+reduce_max_time_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int L, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  const float* p = x + (size_t)b * L * C + c;
+  float m = p[0];
+  for (int t = 1; t < L; ++t) m = fmaxf(m, p[(size_t)t * C]);
+  y[i] = m;
+}
+
+// its gradient as TF defines it (math_grad._MinOrMaxGrad): every position that equals the max gets dy / #ties.
+// dx[b,t,c] += scale * dy[b,c] / ties   (scale folds the gradient flip of the adversarial plugin)
+__global__ void __launch_bounds__(256)
+reduce_max_time_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
+                           float* __restrict__ dx, int B, int L, int C, float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  const float* p = x + (size_t)b * L * C + c;
+  float* q = dx + (size_t)b * L * C + c;
+  const float m = y[i];
+  int ties = 0;
+  for (int t = 0; t < L; ++t) ties += (p[(size_t)t * C] == m);
+  const float g = scale * dy[i] / (float)ties;
+  for (int t = 0; t < L; ++t)
+    if (p[(size_t)t * C] == m) q[(size_t)t * C] += g;
+}
+
+// tf.nn.sparse_softmax_cross_entropy_with_logits on [B, N<=32] rows: loss[b] = logsumexp(z_b) - z_b[label_b];
+// dz (optional) = scale * (softmax(z_b) - onehot(label_b))
+__global__ void __launch_bounds__(128)
+softmax_xent_kernel(const float* __restrict__ z, const int* __restrict__ labels, float* __restrict__ loss,
+                    float* __restrict__ dz, int B, int N, float scale) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* r = z + (size_t)b * N;
+  float m = r[0];
+  for (int n = 1; n < N; ++n) m = fmaxf(m, r[n]);
+  float s = 0.f;
+  for (int n = 0; n < N; ++n) s += expf(r[n] - m);
+  const int lab = labels[b];
+  loss[b] = (m + logf(s)) - r[lab];
+  if (dz != nullptr) {
+    const float inv = 1.f / s;
+    for (int n = 0; n < N; ++n) dz[(size_t)b * N + n] = scale * (expf(r[n] - m) * inv - (n == lab ? 1.f : 0.f));
+  }
+}
+
 int flat_grid(size_t n) {
   size_t g = (n + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
@@ -277,5 +328,32 @@ extern "C" int ner_adam_step(float* p, const float* g, float* m, float* v, size_
   adam_step_kernel<<<flat_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps,
                                                                                weight_decay, mode, clip, gnorm_sq,
                                                                                grad_scale);
+  return ner_launch_status();
+}
+
+extern "C" int ner_reduce_max_time(const float* x, float* y, int B, int L, int C, ner_stream_t stream) {
+  if (B < 0 || L < 1 || C < 1) return NER_ERR_INVALID_ARG;
+  if (B == 0) return NER_OK;
+  if (!x || !y) return NER_ERR_INVALID_ARG;
+  reduce_max_time_kernel<<<(B * C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, B, L, C);
+  return ner_launch_status();
+}
+
+extern "C" int ner_reduce_max_time_bwd(const float* x, const float* y, const float* dy, float* dx, int B, int L, int C,
+                                       float scale, ner_stream_t stream) {
+  if (B < 0 || L < 1 || C < 1) return NER_ERR_INVALID_ARG;
+  if (B == 0) return NER_OK;
+  if (!x || !y || !dy || !dx) return NER_ERR_INVALID_ARG;
+  reduce_max_time_bwd_kernel<<<(B * C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, dy, dx, B, L, C, scale);
+  return ner_launch_status();
+}
+
+extern "C" int ner_softmax_xent(const float* logits, const int32_t* labels, float* loss, float* dlogits, int B, int N,
+                                float scale, ner_stream_t stream) {
+  if (B < 0 || N < 1) return NER_ERR_INVALID_ARG;
+  if (N > 32) return NER_ERR_UNSUPPORTED;
+  if (B == 0) return NER_OK;
+  if (!logits || !labels || !loss) return NER_ERR_INVALID_ARG;
+  softmax_xent_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(logits, labels, loss, dlogits, B, N, scale);
   return ner_launch_status();
 }

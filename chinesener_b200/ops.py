@@ -337,6 +337,36 @@ def relu_bwd(act, dact):
     return out
 
 
+def reduce_max_time(x):
+    """tf.reduce_max(x[B,L,C], axis=1) -> [B,C] f32."""
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 3
+    B, L, C = x.shape
+    y = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    check(lib().ner_reduce_max_time(ptr(x), ptr(y), B, L, C, stream()))
+    return y
+
+
+def reduce_max_time_bwd(x, y, dy, dx, scale=1.0):
+    """dx[b,t,c] += scale * dy[b,c] / ties where x == max (TF's reduce_max gradient)."""
+    require_cuda(x, y, dy, dx)
+    B, L, C = x.shape
+    assert dy.dtype == torch.float32 and tuple(dy.shape) == (B, C) and dx.shape == x.shape
+    check(lib().ner_reduce_max_time_bwd(ptr(x), ptr(y), ptr(dy), ptr(dx), B, L, C, float(scale), stream()))
+    return dx
+
+
+def softmax_xent(logits, labels, scale=1.0, want_grad=False):
+    """sparse softmax cross entropy per row [B, N<=32] -> loss [B] (and scale * (softmax - onehot))."""
+    require_cuda(logits, labels)
+    assert logits.dtype == torch.float32 and labels.dtype == torch.int32 and logits.dim() == 2
+    B, N = logits.shape
+    loss = torch.empty((B,), dtype=torch.float32, device=logits.device)
+    dz = torch.empty_like(logits) if want_grad else None
+    check(lib().ner_softmax_xent(ptr(logits), ptr(labels), ptr(loss), ptr(dz), B, N, float(scale), stream()))
+    return (loss, dz) if want_grad else loss
+
+
 # --------------------------------------------------------------------------- training-side kernels
 def _require_rows(x2d):
     """CUDA f32 2-D tensor whose rows are contiguous (a column slice of a wider buffer is fine)."""

@@ -311,6 +311,34 @@ def concat(tensors, is_training=False):
     return out
 
 
+def reduce_max_flip(x, shrink, is_training):
+    """flip_gradient(tf.reduce_max(x, axis=1), shrink) (reference model/bert_bilstm_crf_adv.py:35-37,
+    tools/train_utils.py:47-63): max over time forward; backward sends -shrink * g to every position that attains it."""
+    x = x.contiguous()
+    y = ops.reduce_max_time(x)
+    tape = autodiff.current() if is_training else None
+    if tape is not None and tape.needs_grad(x):
+        def bwd(g):
+            if g is not None:
+                tape.add_grad(x, ops.reduce_max_time_bwd(x, y, g.contiguous(), torch.zeros_like(x), scale=-float(shrink)))
+        tape.record(y, bwd)
+    return y
+
+
+def softmax_cross_entropy_mean(logits, labels, weight, is_training):
+    """weight * tf.reduce_mean(tf.nn.sparse_softmax_cross_entropy_with_logits(labels, logits)); a loss root: TRAIN seeds
+    d/d logits = weight / B * (softmax - onehot) on the tape."""
+    B = logits.shape[0]
+    tape = autodiff.current() if is_training else None
+    lg = logits.contiguous()
+    if tape is None:
+        return ops.softmax_xent(lg, labels).mean() * weight
+    xent, dz = ops.softmax_xent(lg, labels, scale=float(weight) / B, want_grad=True)
+    loss = xent.mean() * weight
+    tape.record(loss, lambda g: tape.add_grad(logits, dz))
+    return loss
+
+
 def masked_task_loss(log_likelihoods, masks, weights, batch_size, is_training):
     """sum_t w_t * sum(-ll_t[mask_t]) / batch — the loss of the multi-task plugins (reference
     model/bert_bilstm_crf_mtl.py:42,61,64).  TRAIN: seeds d loss / d ll_t = -w_t mask_t / batch on the tape."""

@@ -368,6 +368,16 @@ int ner_dropout_bf16(const void* x_bf16, void* y_bf16, size_t n, float keep_prob
 int ner_relu_f32(const float* x, float* y, size_t n, ner_stream_t stream);
 /* tf.nn.relu gradient: dpre = dact where act > 0 else 0 (f32 [n]; dpre may alias dact). */
 int ner_relu_bwd_f32(const float* act, const float* dact, float* dpre, size_t n, ner_stream_t stream);
+/* tf.reduce_max(x[B,L,C], axis=1) -> y[B,C] (reference model/bert_bilstm_crf_adv.py:35, the task discriminator's pool). */
+int ner_reduce_max_time(const float* x, float* y, int B, int L, int C, ner_stream_t stream);
+/* Its TF gradient, accumulated: dx[b,t,c] += scale * dy[b,c] / ties wherever x[b,t,c] == y[b,c]
+ * (scale = -shrink_gradient_reverse folds FlipGradientBuilder, tools/train_utils.py:47-63). */
+int ner_reduce_max_time_bwd(const float* x, const float* y, const float* dy, float* dx, int B, int L, int C,
+                            float scale, ner_stream_t stream);
+/* tf.nn.sparse_softmax_cross_entropy_with_logits (model/bert_bilstm_crf_adv.py:46) on [B, N <= 32]:
+ * loss[b]; dlogits (nullable) = scale * (softmax - onehot). */
+int ner_softmax_xent(const float* logits, const int32_t* labels, float* loss, float* dlogits, int B, int N,
+                     float scale, ner_stream_t stream);
 /* dst[i] += a * src[i]. */
 int ner_axpy_f32(float* dst, const float* src, size_t n, float a, ner_stream_t stream);
 /* out[0] += sum(g^2)  (tf.clip_by_global_norm, tools/train_utils.py:315). */

@@ -143,3 +143,31 @@ def bert_bilstm_crf_mtl(w, features, params, dtype=torch.float32, emulate_bf16=F
         logits_all.append(logits)
     pred = np.where((task_ids == 0)[:, None], preds[0], preds[1])
     return dict(logits=logits_all, loss=loss / len(task_ids), pred_ids=pred)
+
+
+def bert_bilstm_crf_adv(w, features, params, dtype=torch.float32, emulate_bf16=False, gelu_variant="tanh"):
+    """model/bert_bilstm_crf_adv.py:9-87 (eval mode; seq_len passed to the task-2 bilstm, see the plugin mirror):
+    loss = sum_t weight_t * sum(-ll_t[task_ids == t]) / batch + lambda * mean(xent(discriminator(max_t shared), task_ids))."""
+    seq = nn.bert_encoder(w, features["token_ids"], features["mask"], features["segment_ids"],
+                          num_layers=params.get("num_hidden_layers", 12), num_heads=params.get("num_attention_heads", 12),
+                          dtype=dtype, gelu_variant=gelu_variant, emulate_bf16=emulate_bf16)
+    task_ids = features["task_ids"].numpy()
+    lens = features["seq_len"].numpy()
+    act = params["rnn_activation"]
+    share = nn.bilstm(seq, w, features["seq_len"], act, 1.0, dtype, emulate_bf16,
+                      prefix="task_discriminator/bilstm_layer/bidirectional_rnn")
+    pool = share.max(dim=1).values
+    dlogits = nn.dense(pool, w["task_discriminator/logits/kernel"].to(dtype), w["task_discriminator/logits/bias"].to(dtype))
+    xent = torch.nn.functional.cross_entropy(dlogits, features["task_ids"].long(), reduction="mean")
+    loss, preds = 0.0, []
+    for t, task in enumerate(params["task_list"]):
+        scope = f"task{t + 1}_{task}"
+        lstm = nn.bilstm(seq, w, features["seq_len"], act, 1.0, dtype, emulate_bf16, prefix=f"{scope}/bilstm_layer/bidirectional_rnn")
+        logits = nn.dense(torch.cat([share, lstm], -1), w[f"{scope}/logits/kernel"].to(dtype), w[f"{scope}/logits/bias"].to(dtype))
+        lg = logits.detach().to(torch.float32).numpy()
+        trans = w[f"{scope}/crf_layer/transitions"].to(torch.float32).numpy()
+        ll = crf.crf_log_likelihood(lg, np.minimum(features["label_ids"].numpy(), trans.shape[0] - 1), lens, trans, dtype=np.float64)
+        loss += params["task_weight"][t] * float(np.sum(-ll[task_ids == t]))
+        preds.append(crf.crf_decode(lg, trans, lens, dtype=np.float32)[0])
+    pred = np.where((task_ids == 0)[:, None], preds[0], preds[1])
+    return dict(loss=loss / len(task_ids) + params["lambda"] * float(xent), adv_loss=float(xent), pred_ids=pred, disc_logits=dlogits)

@@ -439,3 +439,64 @@ def test_bert_bilstm_crf_mtl_trains(tmp_path):
     g = est.store.grads
     for name in ("msra/crf_layer/transitions", "cws/logits/kernel", "cws/bilstm_layer/bidirectional_rnn/bw/multi_rnn_cell/cell_0/lstm_cell/kernel"):
         assert name in g
+
+
+def test_reduce_max_flip_and_xent_kernels():
+    """ner_reduce_max_time(_bwd) / ner_softmax_xent against PyTorch fp32 autograd (tolerance 1e-6; ties split as TF does)."""
+    from chinesener_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, L, C = 5, 17, 200
+    x = torch.randn(B, L, C, generator=g).relu()          # relu -> exact ties at 0, like the padded LSTM output
+    x[1, :, 7] = 0.0
+    x[2, 3, 9] = x[2, 11, 9] = 4.5
+    dy = torch.randn(B, C, generator=g)
+    xd, dyd = x.cuda(), dy.cuda()
+    y = ops.reduce_max_time(xd)
+    assert torch.equal(y.cpu(), x.max(dim=1).values)
+    dx = ops.reduce_max_time_bwd(xd, y, dyd, torch.zeros_like(xd), scale=-0.25).cpu()
+    eq = (x == x.max(dim=1, keepdim=True).values).float()
+    ref = -0.25 * eq / eq.sum(1, keepdim=True) * dy[:, None, :]
+    assert torch.allclose(dx, ref, atol=1e-6)
+    z = torch.randn(9, 2, generator=g) * 3
+    lab = torch.randint(0, 2, (9,), generator=g, dtype=torch.int32)
+    zr = z.clone().requires_grad_(True)
+    lr_ = torch.nn.functional.cross_entropy(zr, lab.long(), reduction='none')
+    (lr_.sum() * 0.3).backward()
+    loss, dz = ops.softmax_xent(z.cuda(), lab.cuda(), scale=0.3, want_grad=True)
+    assert torch.allclose(loss.cpu(), lr_.detach(), atol=1e-6) and torch.allclose(dz.cpu(), zr.grad, atol=1e-6)
+
+
+def _adv_setup(tmp_path, drop=0.0):
+    est, feats = _mtl_setup(tmp_path, True, drop=drop)
+    params = dict(est.params, hidden_units_list=[100], share_dropout=drop, shrink_gradient_reverse=0.01)
+    params['lambda'] = 0.5
+    return engine.Estimator("bert_bilstm_crf_adv", params), feats
+
+
+def test_bert_bilstm_crf_adv_plugin(tmp_path):
+    """shared BiLSTM + task discriminator (max-pool, gradient flip) + two private towers."""
+    est, feats = _adv_setup(tmp_path)
+    est.evaluate(feats)
+    _scale_up(est.store, ["task1_msra/logits/kernel", "task2_cws/logits/kernel", "task_discriminator/logits/kernel"], 6.0)
+    out = est.evaluate(feats)
+    w = est.store.state_dict()
+    assert tuple(w["task_discriminator/logits/kernel"].shape) == (200, 2)
+    assert tuple(w["task2_cws/logits/kernel"].shape) == (400, 5)
+    p = dict(est.params, num_hidden_layers=2, num_attention_heads=12)
+    ref = omodels.bert_bilstm_crf_adv(w, feats, p, dtype=torch.float64, emulate_bf16=True)
+    assert ref['adv_loss'] > 0.05                       # the discriminator term is a visible share of the loss
+    assert abs(out['loss'] - ref['loss']) < 5e-3 * max(1.0, abs(ref['loss']))
+    assert (out['pred_ids'].numpy() == ref['pred_ids']).mean() > 0.99
+
+
+def test_bert_bilstm_crf_adv_trains(tmp_path):
+    est, feats = _adv_setup(tmp_path, drop=0.1)
+    est.params.update(lr=1e-5, num_train_steps=100, warmup_ratio=0.1)
+    names = ("task_discriminator/logits/kernel", "task_discriminator/bilstm_layer/bidirectional_rnn/fw/multi_rnn_cell/cell_0/lstm_cell/kernel",
+             "task1_msra/crf_layer/transitions", "task2_cws/logits/bias", "task_discriminator/logits/bias")
+    losses = [float(est.train_step(feats))]
+    before = {n: est.store.vars[n].clone() for n in names}
+    losses += [float(est.train_step(feats)) for _ in range(11)]
+    assert np.isfinite(losses).all() and losses[-1] < 0.85 * losses[0], losses
+    for n in names:                                   # every branch receives gradient (the optimizer clears store.grads)
+        assert float((est.store.vars[n] - before[n]).abs().max()) > 0, n
