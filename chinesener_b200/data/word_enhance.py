@@ -50,6 +50,35 @@ def build_soft_lexicon(sentence, vocab):
     return [OrderedDict((k, [vocab.vocab2idx[w] for w in v]) for k, v in lex.items()) for lex in soft_lexicon]
 
 
+def combine_soft_lexicon(idx_list):
+    """Union, set by set, of the lexicons of the characters one word piece swallowed (reference data/word_enhance.py:
+    150-160).  The reference walks the keys of Soft2Idx, which include 'None' — a key build_soft_lexicon never creates, so
+    its loop raises KeyError — and would emit the sets in S/M/B/E order where unmerged rows are B/M/E/S; this restatement
+    keeps the B/M/E/S row layout the pooling kernel is fed everywhere else."""
+    merged = OrderedDict((k, []) for k in SoftKeys)
+    for lexicon in idx_list:
+        for key in SoftKeys:
+            for i in lexicon[key]:
+                if i not in merged[key]:
+                    merged[key].append(i)
+    return merged
+
+
+def align_with_token(idx_list, tokens, combine_func=combine_soft_lexicon):
+    """Reference data/word_enhance.py:89-119 — the BERT tokenizer can put several characters into one word piece
+    ('1994' -> '19', '##94'); per-character features are merged so there is one row per token.  combine_func: the reference
+    picks it by word-enhance method (soft lexicon: union; softword: max; bichar: min)."""
+    token_len = [len(t.replace('##', '')) if t != '[UNK]' else 1 for t in tokens if t not in ('[CLS]', '[SEP]', '[PAD]')]
+    if len(idx_list) == len(token_len):
+        return idx_list                       # no mismatch between the word pieces and the characters
+    pos, output_list = 0, []
+    for tl in token_len:
+        output_list.append(idx_list[pos] if tl == 1 else combine_func(idx_list[pos:pos + tl]))
+        pos += tl
+    assert len(output_list) == len(token_len)
+    return output_list
+
+
 def postproc_soft_lexicon(output_list, vocab, vocabfreq=None):
     """-> (ids, weights), each seq_len x (4 * MaxLexiconLen)."""
     vocabfreq = vocab.vocab_freq if vocabfreq is None else vocabfreq
@@ -77,7 +106,7 @@ def postproc_soft_lexicon(output_list, vocab, vocabfreq=None):
 
 
 class SoftLexiconProc(BasicProc):
-    """BasicProc + softlexicon_ids / softlexicon_weights (non-bert tokenizers: one lexicon row per character)."""
+    """BasicProc + softlexicon_ids / softlexicon_weights (one lexicon row per token; word pieces merge their characters)."""
 
     def __init__(self, tokenizer_type, max_seq_len, tag2idx, tokenizer, vocab, vocabfreq=None):
         super(SoftLexiconProc, self).__init__(tokenizer_type, max_seq_len, tag2idx, tokenizer)
@@ -94,9 +123,10 @@ class SoftLexiconProc(BasicProc):
 
     def build_seq_feature(self, sentence):
         f_seq = super(SoftLexiconProc, self).build_seq_feature(sentence)
+        soft_lexicon = build_soft_lexicon(sentence, self.vocab)
         if self.tokenizer_type == TokenizerBert:
-            raise NotImplementedError("word-piece alignment of the lexicon (align_with_token) is not built")
-        ids, weights = postproc_soft_lexicon(build_soft_lexicon(sentence, self.vocab), self.vocab, self.vocabfreq)
+            soft_lexicon = align_with_token(soft_lexicon, f_seq['tokens'])
+        ids, weights = postproc_soft_lexicon(soft_lexicon, self.vocab, self.vocabfreq)
         f_seq['softlexicon_ids'] = self.format_soft_seq(ids)
         f_seq['softlexicon_weights'] = self.format_soft_seq(weights, type='weight')
         return f_seq
