@@ -482,7 +482,7 @@ def run_ours(args):
         }
         if t_train is not None:
             line["train"] = {"value": sent / t_train, "unit": "sentences/sec", "ms_per_step": 1e3 * t_train / args.steps,
-                             "what": "TRAIN step of the same plugin: forward (padded layout, dropout on) + backward + "
+                             "what": "TRAIN step of the same plugin: forward (sequence-packed encoder, dropout on) + backward + "
                                      + ("one NCCL all-reduce of the flat fp32 gradient buffer + " if world > 1 else "")
                                      + "global-norm clip + AdamW (bert_train_op); device-resident batches"}
         if cpu is not None:

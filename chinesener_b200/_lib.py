@@ -55,6 +55,9 @@ SIGNATURES = {
     "ner_gelu_bwd_bf16": (_i, [_vp, _vp, _vp, _c.c_size_t, _i, _vp]),
     "ner_bert_embed_bwd": (_i, [_vp] * 6 + [_i] * 5 + [_vp]),
     "ner_bert_attention_bwd": (_i, [_vp] * 5 + [_i] * 4 + [_c.c_float, _c.c_float, _c.c_float, _c.c_uint64, _vp]),
+    "ner_bert_attention_bwd_packed": (_i, [_vp] * 5 + [_i] * 4 + [_c.c_float, _c.c_float, _c.c_uint64, _vp]),
+    "ner_gather_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "ner_scatter_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "ner_adam_step": (_i, [_vp] * 4 + [_c.c_size_t] + [_c.c_float] * 5 + [_i, _c.c_float, _vp, _c.c_float, _vp]),
     "ner_softlexicon_pool_fwd": (_i, [_vp] * 4 + [_i] * 6 + [_vp]),
     "ner_embedding_lookup": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -90,6 +93,15 @@ SIGNATURES["ner_bert_encoder_train_fwd"] = (_i, [_c.POINTER(BertConfig)] + [_vp]
 SIGNATURES["ner_bert_encoder_train_bwd"] = (_i, [_c.POINTER(BertConfig), _vp, _c.POINTER(BertLayerWeights), _c.POINTER(BertLayerGrads)]
                                             + [_vp] * 5 + [_vp] * 3 + [_i, _i, _c.c_float, _c.c_float, _c.c_uint64, _vp, _vp,
                                                                        _c.c_size_t, _vp, _c.c_size_t, _vp])
+SIGNATURES["ner_bert_train_packed_saved_bytes"] = (_c.c_size_t, [_c.POINTER(BertConfig), _i])
+SIGNATURES["ner_bert_train_packed_scratch_bytes"] = (_c.c_size_t, [_c.POINTER(BertConfig), _i, _i])
+SIGNATURES["ner_bert_encoder_train_fwd_packed"] = (_i, [_c.POINTER(BertConfig)] + [_vp] * 5 + [_c.POINTER(BertLayerWeights)] + [_vp] * 2
+                                                   + [_i, _i, _vp, _vp, _i, _c.c_float, _c.c_float, _c.c_uint64, _vp, _vp, _vp,
+                                                      _c.c_size_t, _vp])
+SIGNATURES["ner_bert_encoder_train_bwd_packed"] = (_i, [_c.POINTER(BertConfig), _vp, _c.POINTER(BertLayerWeights),
+                                                        _c.POINTER(BertLayerGrads)] + [_vp] * 5 + [_vp] * 2
+                                                   + [_i, _i, _vp, _vp, _i, _c.c_float, _c.c_float, _c.c_uint64, _vp, _vp,
+                                                      _c.c_size_t, _vp, _c.c_size_t, _vp])
 SIGNATURES["ner_bert_bilstm_crf_predict_workspace_bytes"] = (_c.c_size_t, [_c.POINTER(BertConfig), _i, _i, _i, _i, _i])
 SIGNATURES["ner_bert_bilstm_crf_predict"] = (_i, [_c.POINTER(BertConfig)] + [_vp] * 5 + [_c.POINTER(BertLayerWeights)] + [_vp] * 4
                                              + [_i, _i] + [_vp] * 3 + [_i] + [_vp] * 4 + [_i, _i, _i, _vp, _vp, _c.c_size_t, _vp])

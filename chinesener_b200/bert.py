@@ -235,9 +235,11 @@ def bert_forward_f32(input_ids, input_mask, segment_ids, cfg, store=None, scope=
     return x
 
 
-def _train_composite(input_ids, input_mask, segment_ids, cfg, store, tape, scope, gelu, keep_h, keep_a):
+def _train_composite(input_ids, input_mask, segment_ids, cfg, store, tape, scope, gelu, keep_h, keep_a, pack=None):
     """TRAIN forward + recorded backward through the two C-ABI composites (bert_train.cu): the host
-    enqueues the whole encoder with two calls instead of ~480 (the per-kernel path is launch-bound)."""
+    enqueues the whole encoder with two calls instead of ~480 (the per-kernel path is launch-bound).
+    pack (PackInfo): the sequence-packed composites — every per-token kernel runs on the real tokens only; the output
+    keeps the padded [B,L,H] shape with zero rows at [PAD]."""
     import ctypes
     from . import _lib
     B, L = input_ids.shape
@@ -247,6 +249,8 @@ def _train_composite(input_ids, input_mask, segment_ids, cfg, store, tape, scope
     c, arr, layers = _c_tables(store, cfg, scope, gelu)
     dev = input_ids.device
     ids, seg, mask = ops._i32(input_ids), (None if segment_ids is None else ops._i32(segment_ids)), ops._i32(input_mask)
+    if pack is not None:
+        return _train_composite_packed(ids, seg, cfg, store, tape, scope, keep_h, keep_a, pack, c, arr, layers)
     saved_b = _lib.lib().ner_bert_train_saved_bytes(ctypes.byref(c), rows)
     saved = torch.empty(saved_b, dtype=torch.uint8, device=dev)
     out32 = torch.empty((rows, H), dtype=torch.float32, device=dev)
@@ -295,7 +299,68 @@ def _train_composite(input_ids, input_mask, segment_ids, cfg, store, tape, scope
     return out
 
 
-def bert_forward_train(input_ids, input_mask, segment_ids, cfg, store, tape, scope="bert", gelu="tanh"):
+def _layer_grad_table(store, cfg, scope, layers):
+    from . import _lib
+    casts = _tf_casts(store, cfg, scope)
+    gr = store.grad
+    garr = (_lib.BertLayerGrads * len(layers))()
+    for li in range(len(layers)):
+        p = f"{scope}/encoder/layer_{li}"
+        cs = casts[li]
+        ptrs = [cs["wqkv"], cs["wo"], cs["wi"], cs["wd"]]
+        ptrs += [gr(f"{p}/attention/self/{n}/kernel") for n in ("query", "key", "value")]
+        ptrs += [gr(f"{p}/attention/self/{n}/bias") for n in ("query", "key", "value")]
+        ptrs += [gr(f"{p}/attention/output/dense/kernel"), gr(f"{p}/attention/output/dense/bias"),
+                 gr(f"{p}/attention/output/LayerNorm/gamma"), gr(f"{p}/attention/output/LayerNorm/beta"),
+                 gr(f"{p}/intermediate/dense/kernel"), gr(f"{p}/intermediate/dense/bias"),
+                 gr(f"{p}/output/dense/kernel"), gr(f"{p}/output/dense/bias"),
+                 gr(f"{p}/output/LayerNorm/gamma"), gr(f"{p}/output/LayerNorm/beta")]
+        garr[li] = _lib.BertLayerGrads(*[t.data_ptr() for t in ptrs])
+    return garr
+
+
+def _train_composite_packed(ids, seg, cfg, store, tape, scope, keep_h, keep_a, pack, c, arr, layers):
+    import ctypes
+    from . import _lib
+    B, L = ids.shape
+    H = cfg["hidden_size"]
+    n = pack.total
+    v = store.vars
+    dev = ids.device
+    saved_b = _lib.lib().ner_bert_train_packed_saved_bytes(ctypes.byref(c), n)
+    saved = torch.empty(saved_b, dtype=torch.uint8, device=dev)
+    out32 = torch.empty((B * L, H), dtype=torch.float32, device=dev)
+    out16 = torch.empty((B * L, H), dtype=torch.bfloat16, device=dev)
+    store.dropout_calls += 1
+    seed = ((4321 * 1000003 + store.global_step) * 1009 + 64 * store.dropout_calls) & 0xFFFFFFFFFFFFFFFF
+    names = ("word_embeddings", "token_type_embeddings", "position_embeddings", "LayerNorm/gamma", "LayerNorm/beta")
+    emb = [v[f"{scope}/embeddings/{k}"] for k in names]
+    ops.check(_lib.lib().ner_bert_encoder_train_fwd_packed(
+        ctypes.byref(c), *[ops.ptr(t) for t in emb], arr, ops.ptr(ids), ops.ptr(seg), B, L, ops.ptr(pack.cu_seqlens),
+        ops.ptr(pack.tok_src), n, float(keep_h), float(keep_a), seed, ops.ptr(out32), ops.ptr(out16), ops.ptr(saved), saved_b,
+        ops.stream()))
+    _lib.LAUNCHES += 9 + 11 * len(layers)
+    out = out32.view(B, L, H)
+    out.bf16 = out16.view(B, L, H)
+
+    def bwd(g):
+        if g is None:
+            return
+        garr = _layer_grad_table(store, cfg, scope, layers)
+        scratch_b = _lib.lib().ner_bert_train_packed_scratch_bytes(ctypes.byref(c), n, B * L)
+        scratch = torch.empty(scratch_b, dtype=torch.uint8, device=dev)
+        d = g.reshape(B * L, H).contiguous()
+        demb = [store.grad(f"{scope}/embeddings/{k}") for k in names]
+        ops.check(_lib.lib().ner_bert_encoder_train_bwd_packed(
+            ctypes.byref(c), ops.ptr(emb[3]), arr, garr, *[ops.ptr(t) for t in demb], ops.ptr(ids), ops.ptr(seg), B, L,
+            ops.ptr(pack.cu_seqlens), ops.ptr(pack.tok_src), n, float(keep_h), float(keep_a), seed, ops.ptr(d), ops.ptr(saved),
+            saved_b, ops.ptr(scratch), scratch_b, ops.stream()))
+        _lib.LAUNCHES += 6 + 33 * len(layers)
+    tape.record(out, bwd)
+    return out
+
+
+def bert_forward_train(input_ids, input_mask, segment_ids, cfg, store, tape, scope="bert", gelu="tanh", pack=None):
     """Training-mode BertModel forward on the padded layout: same kernels, every intermediate the
     backward pass needs is kept, and the backward closure is recorded on `tape`.
     BertModel(is_training=True) dropout (bert modeling.py: hidden_dropout_prob after the embedding
@@ -306,7 +371,7 @@ def bert_forward_train(input_ids, input_mask, segment_ids, cfg, store, tape, sco
     keep_h = 1.0 - float(cfg.get("hidden_dropout_prob", 0.1))
     keep_a = 1.0 - float(cfg.get("attention_probs_dropout_prob", 0.1))
     if not PER_KERNEL:
-        return _train_composite(input_ids, input_mask, segment_ids, cfg, store, tape, scope, gelu, keep_h, keep_a)
+        return _train_composite(input_ids, input_mask, segment_ids, cfg, store, tape, scope, gelu, keep_h, keep_a, pack=pack)
 
     def next_seed():
         store.dropout_calls += 1

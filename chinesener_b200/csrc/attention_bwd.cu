@@ -87,10 +87,16 @@ template <bool DROP>
 __global__ void __launch_bounds__(NW * 32)
 bert_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ mask,
                           const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ dctx,
-                          __nv_bfloat16* __restrict__ dqkv, int L, int NH, int Lp, float scale, float mask_add,
-                          float keep, uint32_t seed_lo, uint32_t seed_hi) {
+                          __nv_bfloat16* __restrict__ dqkv, int Lpad, int NH, int Lp_max, float scale, float mask_add,
+                          const int32_t* __restrict__ cu_seqlens, float keep, uint32_t seed_lo, uint32_t seed_hi) {
   const uint32_t dsa = seed_lo ^ ((uint32_t)(blockIdx.y * NH + blockIdx.x) * 0x9E3779B1u), dthr = keep_threshold(keep);
   const float dik = 1.f / keep;
+  // padded mode: rows [b*L, (b+1)*L), keys masked by `mask`; packed mode: rows [cu[b], cu[b+1]), all keys valid and the
+  // tile loops stop at the sequence's own length (same convention as the forward kernel, attention.cu)
+  const size_t row_base = cu_seqlens ? (size_t)cu_seqlens[blockIdx.y] : (size_t)blockIdx.y * Lpad;
+  const int L = cu_seqlens ? (cu_seqlens[blockIdx.y + 1] - cu_seqlens[blockIdx.y]) : Lpad;
+  const int Lp = cu_seqlens ? (L + 63) / 64 * 64 : Lp_max;
+  if (L == 0) return;
   extern __shared__ __align__(16) uint8_t smraw[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smraw);
   __nv_bfloat16* Ks = Qs + (size_t)Lp * PITCH;
@@ -105,9 +111,9 @@ bert_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HD = NH * D;
   const size_t rs = (size_t)3 * HD;
-  const __nv_bfloat16* base = qkv + (size_t)b * L * rs + h * D;
-  const __nv_bfloat16* obase = ctx + (size_t)b * L * HD + h * D;
-  const __nv_bfloat16* dobase = dctx + (size_t)b * L * HD + h * D;
+  const __nv_bfloat16* base = qkv + row_base * rs + h * D;
+  const __nv_bfloat16* obase = ctx + row_base * HD + h * D;
+  const __nv_bfloat16* dobase = dctx + row_base * HD + h * D;
 
   for (int idx = tid; idx < Lp * 8; idx += NW * 32) {
     const int row = idx >> 3, ch = idx & 7;
@@ -126,7 +132,7 @@ bert_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* 
   }
   cp_async_commit();
   for (int k = tid; k < Lp; k += NW * 32) {
-    s_madd[k] = (k < L) ? (1.f - (float)mask[(size_t)b * L + k]) * mask_add : -1e30f;
+    s_madd[k] = (k < L) ? (cu_seqlens ? 0.f : (1.f - (float)mask[(size_t)b * Lpad + k]) * mask_add) : -1e30f;
     s_m[k] = 0.f;
     s_li[k] = 0.f;
     s_D[k] = 0.f;
@@ -235,7 +241,7 @@ bert_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* 
       }
       mma_p_b(dq, s, Ks, kb, lane);
     }
-    __nv_bfloat16* dqb = dqkv + (size_t)b * L * rs + h * D;
+    __nv_bfloat16* dqb = dqkv + row_base * rs + h * D;
 #pragma unroll
     for (int dt = 0; dt < 8; ++dt) {
       if (r0 < L) *reinterpret_cast<uint32_t*>(dqb + (size_t)r0 * rs + dt * 8 + cq) = pack2(dq[dt][0] * scale, dq[dt][1] * scale);
@@ -288,8 +294,8 @@ bert_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* 
       mma_p_b(dv, st, Os, qb, lane);   // dV += P^T dO
       mma_p_b(dk, dpt, Qs, qb, lane);  // dK += dS^T Q
     }
-    __nv_bfloat16* dkb = dqkv + (size_t)b * L * rs + HD + h * D;
-    __nv_bfloat16* dvb = dqkv + (size_t)b * L * rs + 2 * HD + h * D;
+    __nv_bfloat16* dkb = dqkv + row_base * rs + HD + h * D;
+    __nv_bfloat16* dvb = dqkv + row_base * rs + 2 * HD + h * D;
 #pragma unroll
     for (int dt = 0; dt < 8; ++dt) {
       if (k0 < L) {
@@ -306,13 +312,12 @@ bert_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* 
 
 }  // namespace
 
-extern "C" int ner_bert_attention_bwd(const void* qkv_bf16, const int32_t* mask, const void* ctx_bf16,
-                                      const void* dctx_bf16, void* dqkv_bf16, int B, int L, int num_heads,
-                                      int head_dim, float scale, float mask_add, float keep_prob, uint64_t seed,
-                                      ner_stream_t stream) {
+static int attention_bwd_launch(const void* qkv_bf16, const int32_t* mask, const void* ctx_bf16, const void* dctx_bf16,
+                                void* dqkv_bf16, int B, int L, int num_heads, int head_dim, float scale, float mask_add,
+                                const int32_t* cu_seqlens, float keep_prob, uint64_t seed, ner_stream_t stream) {
   if (B < 0 || L < 1 || num_heads < 1 || !(keep_prob > 0.f)) return NER_ERR_INVALID_ARG;
   if (B == 0) return NER_OK;
-  if (!qkv_bf16 || !mask || !ctx_bf16 || !dctx_bf16 || !dqkv_bf16) return NER_ERR_INVALID_ARG;
+  if (!qkv_bf16 || (!mask && !cu_seqlens) || !ctx_bf16 || !dctx_bf16 || !dqkv_bf16) return NER_ERR_INVALID_ARG;
   if (head_dim != D) return NER_ERR_UNSUPPORTED;
   const int Lp = (L + 63) / 64 * 64;
   const size_t smem = (size_t)4 * Lp * PITCH * 2 + (size_t)4 * Lp * 4;
@@ -324,6 +329,24 @@ extern "C" int ner_bert_attention_bwd(const void* qkv_bf16, const int32_t* mask,
   kern<<<grid, NW * 32, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv_bf16), mask, static_cast<const __nv_bfloat16*>(ctx_bf16),
       static_cast<const __nv_bfloat16*>(dctx_bf16), static_cast<__nv_bfloat16*>(dqkv_bf16), L, num_heads, Lp, scale,
-      mask_add, keep_prob, (uint32_t)seed, (uint32_t)(seed >> 32));
+      mask_add, cu_seqlens, keep_prob, (uint32_t)seed, (uint32_t)(seed >> 32));
   return ner_launch_status();
+}
+
+extern "C" int ner_bert_attention_bwd(const void* qkv_bf16, const int32_t* mask, const void* ctx_bf16,
+                                      const void* dctx_bf16, void* dqkv_bf16, int B, int L, int num_heads,
+                                      int head_dim, float scale, float mask_add, float keep_prob, uint64_t seed,
+                                      ner_stream_t stream) {
+  if (!mask) return B == 0 ? NER_OK : NER_ERR_INVALID_ARG;
+  return attention_bwd_launch(qkv_bf16, mask, ctx_bf16, dctx_bf16, dqkv_bf16, B, L, num_heads, head_dim, scale, mask_add,
+                              nullptr, keep_prob, seed, stream);
+}
+
+extern "C" int ner_bert_attention_bwd_packed(const void* qkv_bf16, const int32_t* cu_seqlens, const void* ctx_bf16,
+                                             const void* dctx_bf16, void* dqkv_bf16, int B, int L, int num_heads,
+                                             int head_dim, float scale, float keep_prob, uint64_t seed,
+                                             ner_stream_t stream) {
+  if (!cu_seqlens) return B == 0 ? NER_OK : NER_ERR_INVALID_ARG;
+  return attention_bwd_launch(qkv_bf16, nullptr, ctx_bf16, dctx_bf16, dqkv_bf16, B, L, num_heads, head_dim, scale, 0.f,
+                              cu_seqlens, keep_prob, seed, stream);
 }

@@ -76,6 +76,17 @@ extern "C" size_t ner_bert_train_saved_bytes(const ner_bert_config* cfg, int row
   return (size_t)cfg->num_layers * layer_saved_bytes(R, H, I) + al(R * H * 4) /* embedding sum */;
 }
 
+extern "C" size_t ner_bert_train_packed_saved_bytes(const ner_bert_config* cfg, int n_packed) {
+  if (!cfg || n_packed < 0) return 0;
+  const size_t R = (size_t)n_packed, H = (size_t)cfg->hidden_size;
+  return ner_bert_train_saved_bytes(cfg, n_packed) + al(R * H * 4) + al(R * H * 2) /* packed encoder output */;
+}
+
+extern "C" size_t ner_bert_train_packed_scratch_bytes(const ner_bert_config* cfg, int n_packed, int padded_rows) {
+  if (!cfg || n_packed < 0 || padded_rows < n_packed) return 0;
+  return ner_bert_train_scratch_bytes(cfg, n_packed) + al((size_t)padded_rows * cfg->hidden_size * 4) /* padded d_embedding */;
+}
+
 extern "C" size_t ner_bert_train_scratch_bytes(const ner_bert_config* cfg, int rows) {
   if (!cfg || rows < 0) return 0;
   const size_t R = (size_t)rows, Rp = (R + 7) / 8 * 8, H = (size_t)cfg->hidden_size, I = (size_t)cfg->intermediate_size;
@@ -90,27 +101,48 @@ extern "C" size_t ner_bert_train_scratch_bytes(const ner_bert_config* cfg, int r
          + al(3 * H * 4);       // fused QKV bias gradient
 }
 
-extern "C" int ner_bert_encoder_train_fwd(const ner_bert_config* cfg, const float* word_emb, const float* type_emb,
-                                          const float* pos_emb, const float* emb_ln_gamma, const float* emb_ln_beta,
-                                          const ner_bert_layer_weights* layers, const int32_t* ids, const int32_t* mask,
-                                          const int32_t* seg, int B, int L, float hidden_keep, float attn_keep,
-                                          uint64_t seed, float* out_f32, void* out_bf16, void* saved, size_t saved_bytes,
-                                          ner_stream_t stream) {
-  if (!cfg || !layers || !out_f32 || !out_bf16 || !ids || !mask || !saved) return NER_ERR_INVALID_ARG;
+// Packed mode (cu_seqlens / tok_src / n_packed from ner_seq_pack_plan): every per-token kernel runs on the n_packed real
+// tokens only and the attention kernels take cu_seqlens; the padded <-> packed row moves happen once at each end
+// (embedding sum in, encoder output out; d_out in, embedding gradient out).  [PAD] rows of the output are zero.
+static int train_fwd_impl(const ner_bert_config* cfg, const float* word_emb, const float* type_emb,
+                          const float* pos_emb, const float* emb_ln_gamma, const float* emb_ln_beta,
+                          const ner_bert_layer_weights* layers, const int32_t* ids, const int32_t* mask,
+                          const int32_t* seg, int B, int L, const int32_t* cu_seqlens, const int32_t* tok_src, int n_packed,
+                          float hidden_keep, float attn_keep,
+                          uint64_t seed, float* out_f32, void* out_bf16, void* saved, size_t saved_bytes,
+                          ner_stream_t stream) {
+  const bool packed = cu_seqlens != nullptr;
+  if (!cfg || !layers || !out_f32 || !out_bf16 || !ids || (!mask && !packed) || !saved) return NER_ERR_INVALID_ARG;
   if (B < 0 || L < 1 || !(hidden_keep > 0.f) || hidden_keep > 1.f || !(attn_keep > 0.f) || attn_keep > 1.f)
     return NER_ERR_INVALID_ARG;
+  if (packed && (!tok_src || n_packed < 0 || n_packed > B * L)) return NER_ERR_INVALID_ARG;
   if (B == 0) return NER_OK;
-  const int rows = B * L, H = cfg->hidden_size, NH = cfg->num_heads, I = cfg->intermediate_size;
+  const int rows = packed ? n_packed : B * L, H = cfg->hidden_size, NH = cfg->num_heads, I = cfg->intermediate_size;
   if (H % NH != 0) return NER_ERR_INVALID_ARG;
-  if (saved_bytes < ner_bert_train_saved_bytes(cfg, rows)) return NER_ERR_WORKSPACE;
+  if (saved_bytes < (packed ? ner_bert_train_packed_saved_bytes(cfg, rows) : ner_bert_train_saved_bytes(cfg, rows)))
+    return NER_ERR_WORKSPACE;
+  cudaStream_t cst = static_cast<cudaStream_t>(stream);
+  if (packed) {
+    if (cudaMemsetAsync(out_f32, 0, (size_t)B * L * H * 4, cst) != cudaSuccess) return NER_ERR_CUDA_BASE - (int)cudaGetLastError();
+    if (cudaMemsetAsync(out_bf16, 0, (size_t)B * L * H * 2, cst) != cudaSuccess) return NER_ERR_CUDA_BASE - (int)cudaGetLastError();
+    if (rows == 0) return NER_OK;
+  }
   const size_t R = (size_t)rows, lb = layer_saved_bytes(R, H, I);
   uint8_t* base = static_cast<uint8_t*>(saved);
   float* emb_sum = reinterpret_cast<float*>(base + (size_t)cfg->num_layers * lb);
+  float* last32 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(emb_sum) + al(R * H * 4));   // packed mode only
+  void* last16 = reinterpret_cast<uint8_t*>(last32) + al(R * H * 4);
   const int gelu_erf = cfg->gelu_erf ? 1 : 0;
   const float scale = 1.0f / sqrtf((float)(H / NH));
 
   // embeddings: sum -> LayerNorm -> dropout   (layer_norm_and_dropout of embedding_postprocessor)
   LayerSaved s0 = carve(base, R, H, I);
+  if (packed) {   // padded sum staged in the caller's (still unused) output buffer, real rows gathered out of it
+    NER_TRY(ner_bert_embed_sum(word_emb, type_emb, pos_emb, ids, seg, out_f32, B, L, H, cfg->vocab_size, cfg->type_vocab_size,
+                               cfg->max_position, stream));
+    NER_TRY(ner_gather_rows(out_f32, tok_src, emb_sum, rows, H * 4, stream));
+    if (cudaMemsetAsync(out_f32, 0, (size_t)B * L * H * 4, cst) != cudaSuccess) return NER_ERR_CUDA_BASE - (int)cudaGetLastError();
+  } else
   NER_TRY(ner_bert_embed_sum(word_emb, type_emb, pos_emb, ids, seg, emb_sum, B, L, H, cfg->vocab_size, cfg->type_vocab_size,
                              cfg->max_position, stream));
   NER_TRY(ner_layernorm(emb_sum, 0, nullptr, emb_ln_gamma, emb_ln_beta, s0.x32, s0.x16, rows, H, cfg->ln_eps, stream));
@@ -123,11 +155,11 @@ extern "C" int ner_bert_encoder_train_fwd(const ner_bert_config* cfg, const floa
     LayerSaved s = carve(base + (size_t)l * lb, R, H, I);
     const bool last = l + 1 == cfg->num_layers;
     LayerSaved nx = last ? s : carve(base + (size_t)(l + 1) * lb, R, H, I);
-    float* o32 = last ? out_f32 : nx.x32;
-    void* o16 = last ? out_bf16 : nx.x16;
+    float* o32 = last ? (packed ? last32 : out_f32) : nx.x32;
+    void* o16 = last ? (packed ? last16 : out_bf16) : nx.x16;
     const uint64_t sa = seed + 1 + 3 * (uint64_t)l, s1 = sa + 1, s2 = sa + 2;
     NER_TRY(ner_gemm_bf16(s.x16, w.wqkv, w.bqkv, nullptr, s.qkv, rows, 3 * H, H, NER_EPI_BF16, 0, stream));
-    NER_TRY(ner_bert_attention(s.qkv, mask, s.ctx, B, L, NH, H / NH, scale, -10000.0f, nullptr, attn_keep, sa, stream));
+    NER_TRY(ner_bert_attention(s.qkv, mask, s.ctx, B, L, NH, H / NH, scale, -10000.0f, cu_seqlens, attn_keep, sa, stream));
     NER_TRY(ner_gemm_bf16(s.ctx, w.wo, w.bo, nullptr, s.y1, rows, H, H, NER_EPI_BF16, 0, stream));
     NER_TRY(ner_layernorm_dropout(s.y1, 1, s.x32, w.ln1_gamma, w.ln1_beta, s.x1_32, s.x1_16, rows, H, cfg->ln_eps, hidden_keep, s1,
                                   stream));
@@ -137,21 +169,55 @@ extern "C" int ner_bert_encoder_train_fwd(const ner_bert_config* cfg, const floa
     NER_TRY(ner_layernorm_dropout(s.y2, 1, s.x1_32, w.ln2_gamma, w.ln2_beta, o32, o16, rows, H, cfg->ln_eps, hidden_keep, s2,
                                   stream));
   }
+  if (packed) {
+    NER_TRY(ner_scatter_rows(last32, tok_src, out_f32, rows, H * 4, stream));
+    NER_TRY(ner_scatter_rows(last16, tok_src, out_bf16, rows, H * 2, stream));
+  }
   return NER_OK;
 }
 
-extern "C" int ner_bert_encoder_train_bwd(const ner_bert_config* cfg, const float* emb_ln_gamma,
-                                          const ner_bert_layer_weights* layers, const ner_bert_layer_grads* grads,
-                                          float* d_word_emb, float* d_type_emb, float* d_pos_emb, float* d_emb_ln_gamma,
-                                          float* d_emb_ln_beta, const int32_t* ids, const int32_t* mask,
+extern "C" int ner_bert_encoder_train_fwd(const ner_bert_config* cfg, const float* word_emb, const float* type_emb,
+                                          const float* pos_emb, const float* emb_ln_gamma, const float* emb_ln_beta,
+                                          const ner_bert_layer_weights* layers, const int32_t* ids, const int32_t* mask,
                                           const int32_t* seg, int B, int L, float hidden_keep, float attn_keep,
-                                          uint64_t seed, const float* d_out, const void* saved, size_t saved_bytes,
-                                          void* scratch, size_t scratch_bytes, ner_stream_t stream) {
-  if (!cfg || !layers || !grads || !d_out || !saved || !scratch || !ids || !mask || !emb_ln_gamma) return NER_ERR_INVALID_ARG;
+                                          uint64_t seed, float* out_f32, void* out_bf16, void* saved, size_t saved_bytes,
+                                          ner_stream_t stream) {
+  if (!mask) return NER_ERR_INVALID_ARG;
+  return train_fwd_impl(cfg, word_emb, type_emb, pos_emb, emb_ln_gamma, emb_ln_beta, layers, ids, mask, seg, B, L, nullptr, nullptr,
+                        0, hidden_keep, attn_keep, seed, out_f32, out_bf16, saved, saved_bytes, stream);
+}
+
+extern "C" int ner_bert_encoder_train_fwd_packed(const ner_bert_config* cfg, const float* word_emb, const float* type_emb,
+                                                 const float* pos_emb, const float* emb_ln_gamma, const float* emb_ln_beta,
+                                                 const ner_bert_layer_weights* layers, const int32_t* ids, const int32_t* seg,
+                                                 int B, int L, const int32_t* cu_seqlens, const int32_t* tok_src, int n_packed,
+                                                 float hidden_keep, float attn_keep, uint64_t seed, float* out_f32,
+                                                 void* out_bf16, void* saved, size_t saved_bytes, ner_stream_t stream) {
+  if (!cu_seqlens) return NER_ERR_INVALID_ARG;
+  return train_fwd_impl(cfg, word_emb, type_emb, pos_emb, emb_ln_gamma, emb_ln_beta, layers, ids, nullptr, seg, B, L, cu_seqlens,
+                        tok_src, n_packed, hidden_keep, attn_keep, seed, out_f32, out_bf16, saved, saved_bytes, stream);
+}
+
+static int train_bwd_impl(const ner_bert_config* cfg, const float* emb_ln_gamma,
+                          const ner_bert_layer_weights* layers, const ner_bert_layer_grads* grads,
+                          float* d_word_emb, float* d_type_emb, float* d_pos_emb, float* d_emb_ln_gamma,
+                          float* d_emb_ln_beta, const int32_t* ids, const int32_t* mask,
+                          const int32_t* seg, int B, int L, const int32_t* cu_seqlens, const int32_t* tok_src, int n_packed,
+                          float hidden_keep, float attn_keep,
+                          uint64_t seed, const float* d_out, const void* saved, size_t saved_bytes,
+                          void* scratch, size_t scratch_bytes, ner_stream_t stream) {
+  const bool packed = cu_seqlens != nullptr;
+  if (!cfg || !layers || !grads || !d_out || !saved || !scratch || !ids || (!mask && !packed) || !emb_ln_gamma) return NER_ERR_INVALID_ARG;
   if (!d_word_emb || !d_type_emb || !d_pos_emb || !d_emb_ln_gamma || !d_emb_ln_beta) return NER_ERR_INVALID_ARG;
   if (B < 0 || L < 1) return NER_ERR_INVALID_ARG;
-  if (B == 0) return NER_OK;
-  const int rows = B * L, H = cfg->hidden_size, NH = cfg->num_heads, I = cfg->intermediate_size;
+  if (packed && (!tok_src || n_packed < 0 || n_packed > B * L)) return NER_ERR_INVALID_ARG;
+  if (B == 0 || (packed && n_packed == 0)) return NER_OK;
+  const int rows = packed ? n_packed : B * L, H = cfg->hidden_size, NH = cfg->num_heads, I = cfg->intermediate_size;
+  if (packed) {
+    if (saved_bytes < ner_bert_train_packed_saved_bytes(cfg, rows) ||
+        scratch_bytes < ner_bert_train_packed_scratch_bytes(cfg, rows, B * L))
+      return NER_ERR_WORKSPACE;
+  } else
   if (saved_bytes < ner_bert_train_saved_bytes(cfg, rows) || scratch_bytes < ner_bert_train_scratch_bytes(cfg, rows))
     return NER_ERR_WORKSPACE;
   const size_t R = (size_t)rows, lb = layer_saved_bytes(R, H, I);
@@ -172,11 +238,16 @@ extern "C" int ner_bert_encoder_train_bwd(const ner_bert_config* cfg, const floa
   void* dqkv = p;                              p += al(R * 3 * H * 2);
   void* xt = p;                                p += al(W * Rp * 2);
   void* dyt = p;                               p += al(W * Rp * 2);
-  float* dbqkv = reinterpret_cast<float*>(p);
+  float* dbqkv = reinterpret_cast<float*>(p);  p += al((size_t)3 * H * 4);
+  float* dpad = reinterpret_cast<float*>(p);   // packed mode: padded [B*L, H] embedding gradient
   const int gelu_erf = cfg->gelu_erf ? 1 : 0;
   const float scale = 1.0f / sqrtf((float)(H / NH));
 
   const float* d = d_out;   // gradient w.r.t. the current layer's output (f32 [rows, H])
+  if (packed) {             // the caller's d_out is padded: keep the real tokens' rows
+    NER_TRY(ner_gather_rows(d_out, tok_src, dA, rows, H * 4, stream));
+    d = dA;
+  }
   for (int l = cfg->num_layers - 1; l >= 0; --l) {
     const ner_bert_layer_weights& w = layers[l];
     const ner_bert_layer_grads& g = grads[l];
@@ -200,7 +271,10 @@ extern "C" int ner_bert_encoder_train_bwd(const ner_bert_config* cfg, const floa
     NER_TRY(wgrad(s.ctx, H, nullptr, dz16, H, g.d_wo, rows, Rp, xt, dyt, st));
     NER_TRY(ner_gemm_bf16(dz16, g.wo_kn, nullptr, nullptr, dctx, rows, H, H, NER_EPI_BF16, 0, stream));
     // ---- attention core + fused QKV projection
-    NER_TRY(ner_bert_attention_bwd(s.qkv, mask, s.ctx, dctx, dqkv, B, L, NH, H / NH, scale, -10000.0f, attn_keep, sa, stream));
+    if (packed)
+      NER_TRY(ner_bert_attention_bwd_packed(s.qkv, cu_seqlens, s.ctx, dctx, dqkv, B, L, NH, H / NH, scale, attn_keep, sa, stream));
+    else
+      NER_TRY(ner_bert_attention_bwd(s.qkv, mask, s.ctx, dctx, dqkv, B, L, NH, H / NH, scale, -10000.0f, attn_keep, sa, stream));
     if (cudaMemsetAsync(dbqkv, 0, (size_t)3 * H * 4, st) != cudaSuccess) return NER_ERR_CUDA_BASE - (int)cudaGetLastError();
     NER_TRY(ner_colsum_bf16_add(dqkv, dbqkv, rows, 3 * H, stream));
     NER_TRY(ner_axpy_f32(g.d_bq, dbqkv, H, 1.f, stream));
@@ -225,6 +299,39 @@ extern "C" int ner_bert_encoder_train_bwd(const ner_bert_config* cfg, const floa
   }
   NER_TRY(ner_layernorm_bwd(emb_sum, 0, nullptr, emb_ln_gamma, d, dz32, nullptr, d_emb_ln_gamma, d_emb_ln_beta, rows, H,
                             cfg->ln_eps, stream));
-  return ner_bert_embed_bwd(dz32, ids, seg, d_word_emb, d_type_emb, d_pos_emb, B, L, H, cfg->vocab_size, cfg->type_vocab_size,
+  const float* demb = dz32;
+  if (packed) {
+    if (cudaMemsetAsync(dpad, 0, (size_t)B * L * H * 4, st) != cudaSuccess) return NER_ERR_CUDA_BASE - (int)cudaGetLastError();
+    NER_TRY(ner_scatter_rows(dz32, tok_src, dpad, rows, H * 4, stream));
+    demb = dpad;
+  }
+  return ner_bert_embed_bwd(demb, ids, seg, d_word_emb, d_type_emb, d_pos_emb, B, L, H, cfg->vocab_size, cfg->type_vocab_size,
                             stream);
+}
+
+extern "C" int ner_bert_encoder_train_bwd(const ner_bert_config* cfg, const float* emb_ln_gamma,
+                                          const ner_bert_layer_weights* layers, const ner_bert_layer_grads* grads,
+                                          float* d_word_emb, float* d_type_emb, float* d_pos_emb, float* d_emb_ln_gamma,
+                                          float* d_emb_ln_beta, const int32_t* ids, const int32_t* mask,
+                                          const int32_t* seg, int B, int L, float hidden_keep, float attn_keep,
+                                          uint64_t seed, const float* d_out, const void* saved, size_t saved_bytes,
+                                          void* scratch, size_t scratch_bytes, ner_stream_t stream) {
+  if (!mask) return NER_ERR_INVALID_ARG;
+  return train_bwd_impl(cfg, emb_ln_gamma, layers, grads, d_word_emb, d_type_emb, d_pos_emb, d_emb_ln_gamma, d_emb_ln_beta, ids,
+                        mask, seg, B, L, nullptr, nullptr, 0, hidden_keep, attn_keep, seed, d_out, saved, saved_bytes, scratch,
+                        scratch_bytes, stream);
+}
+
+extern "C" int ner_bert_encoder_train_bwd_packed(const ner_bert_config* cfg, const float* emb_ln_gamma,
+                                                 const ner_bert_layer_weights* layers, const ner_bert_layer_grads* grads,
+                                                 float* d_word_emb, float* d_type_emb, float* d_pos_emb,
+                                                 float* d_emb_ln_gamma, float* d_emb_ln_beta, const int32_t* ids,
+                                                 const int32_t* seg, int B, int L, const int32_t* cu_seqlens,
+                                                 const int32_t* tok_src, int n_packed, float hidden_keep, float attn_keep,
+                                                 uint64_t seed, const float* d_out, const void* saved, size_t saved_bytes,
+                                                 void* scratch, size_t scratch_bytes, ner_stream_t stream) {
+  if (!cu_seqlens) return NER_ERR_INVALID_ARG;
+  return train_bwd_impl(cfg, emb_ln_gamma, layers, grads, d_word_emb, d_type_emb, d_pos_emb, d_emb_ln_gamma, d_emb_ln_beta, ids,
+                        nullptr, seg, B, L, cu_seqlens, tok_src, n_packed, hidden_keep, attn_keep, seed, d_out, saved,
+                        saved_bytes, scratch, scratch_bytes, stream);
 }

@@ -205,6 +205,20 @@ softmax_xent_kernel(const float* __restrict__ z, const int* __restrict__ labels,
   }
 }
 
+// Row moves between the padded [B*L, .] and the packed [n, .] layouts (rows are multiples of 16 bytes):
+// gather: dst row r = src row idx[r];  scatter: dst row idx[r] = src row r.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256)
+move_rows_kernel(const uint4* __restrict__ src, const int32_t* __restrict__ idx, uint4* __restrict__ dst, int n, int vpr) {
+  const size_t total = (size_t)n * vpr, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / vpr, c = i - r * vpr;
+    const size_t j = (size_t)idx[r] * vpr + c;
+    if (SCATTER) dst[j] = src[i];
+    else dst[i] = src[j];
+  }
+}
+
 int flat_grid(size_t n) {
   size_t g = (n + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
@@ -355,5 +369,25 @@ extern "C" int ner_softmax_xent(const float* logits, const int32_t* labels, floa
   if (B == 0) return NER_OK;
   if (!logits || !labels || !loss) return NER_ERR_INVALID_ARG;
   softmax_xent_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(logits, labels, loss, dlogits, B, N, scale);
+  return ner_launch_status();
+}
+
+extern "C" int ner_gather_rows(const void* src, const int32_t* idx, void* dst, int n, int row_bytes, ner_stream_t stream) {
+  if (n < 0 || row_bytes < 16 || row_bytes % 16 != 0) return NER_ERR_INVALID_ARG;
+  if (n == 0) return NER_OK;
+  if (!src || !idx || !dst) return NER_ERR_INVALID_ARG;
+  const int vpr = row_bytes / 16;
+  move_rows_kernel<false><<<flat_grid((size_t)n * vpr), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(src), idx, static_cast<uint4*>(dst), n, vpr);
+  return ner_launch_status();
+}
+
+extern "C" int ner_scatter_rows(const void* src, const int32_t* idx, void* dst, int n, int row_bytes, ner_stream_t stream) {
+  if (n < 0 || row_bytes < 16 || row_bytes % 16 != 0) return NER_ERR_INVALID_ARG;
+  if (n == 0) return NER_OK;
+  if (!src || !idx || !dst) return NER_ERR_INVALID_ARG;
+  const int vpr = row_bytes / 16;
+  move_rows_kernel<true><<<flat_grid((size_t)n * vpr), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(src), idx, static_cast<uint4*>(dst), n, vpr);
   return ner_launch_status();
 }

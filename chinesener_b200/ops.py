@@ -517,12 +517,35 @@ def bert_embed_bwd(dx, ids, seg, d_word, d_type, d_pos):
                                    ptr(d_pos), B, L, H, d_word.shape[0], d_type.shape[0], stream()))
 
 
-def bert_attention_bwd(qkv, mask, ctx, dctx, B, L, num_heads, head_dim=64, scale=None, mask_add=-10000.0, keep_prob=1.0, seed=0):
-    require_cuda(qkv, mask, ctx, dctx)
+def gather_rows(src2d, idx, n):
+    """dst row r = src row idx[r] for r < n (padded -> packed layout)."""
+    require_cuda(src2d, idx)
+    assert idx.dtype == torch.int32 and src2d.dim() == 2
+    dst = torch.empty((n, src2d.shape[1]), dtype=src2d.dtype, device=src2d.device)
+    check(lib().ner_gather_rows(ptr(src2d), ptr(idx), ptr(dst), n, src2d.shape[1] * src2d.element_size(), stream()))
+    return dst
+
+
+def scatter_rows(src2d, idx, rows):
+    """dst [rows, C] zeros with dst row idx[r] = src row r (packed -> padded layout)."""
+    require_cuda(src2d, idx)
+    assert idx.dtype == torch.int32 and src2d.dim() == 2
+    dst = torch.zeros((rows, src2d.shape[1]), dtype=src2d.dtype, device=src2d.device)
+    check(lib().ner_scatter_rows(ptr(src2d), ptr(idx), ptr(dst), src2d.shape[0], src2d.shape[1] * src2d.element_size(), stream()))
+    return dst
+
+
+def bert_attention_bwd(qkv, mask, ctx, dctx, B, L, num_heads, head_dim=64, scale=None, mask_add=-10000.0, keep_prob=1.0, seed=0,
+                       cu_seqlens=None):
+    require_cuda(qkv, mask, ctx, dctx, cu_seqlens)
     assert qkv.dtype == torch.bfloat16 and ctx.dtype == torch.bfloat16 and dctx.dtype == torch.bfloat16
     dqkv = torch.empty_like(qkv)
     if scale is None:
         scale = 1.0 / (head_dim ** 0.5)
+    if cu_seqlens is not None:
+        check(lib().ner_bert_attention_bwd_packed(ptr(qkv), ptr(cu_seqlens), ptr(ctx), ptr(dctx), ptr(dqkv), B, L, num_heads, head_dim,
+                                                  scale, float(keep_prob), int(seed) & 0xFFFFFFFFFFFFFFFF, stream()))
+        return dqkv
     check(lib().ner_bert_attention_bwd(ptr(qkv), ptr(_i32(mask)), ptr(ctx), ptr(dctx), ptr(dqkv), B, L, num_heads, head_dim,
                                        scale, mask_add, float(keep_prob), int(seed) & 0xFFFFFFFFFFFFFFFF, stream()))
     return dqkv

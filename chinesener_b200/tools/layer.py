@@ -13,6 +13,8 @@ from .. import ops, variables
 # Remove padding rows from the token-major activations of the BERT plugins (exact for loss and
 # pred_ids: the CRF never reads t >= seq_len).  NER_B200_PACK=0 keeps the padded layout.
 PACK_SEQUENCES = os.environ.get("NER_B200_PACK", "1") != "0"
+# TRAIN mode of BertModel on the packed layout too (ner_bert_encoder_train_fwd_packed / _bwd_packed)
+TRAIN_PACK = os.environ.get("NER_B200_TRAIN_PACK", "1") != "0"
 # 'bf16': bf16 tcgen05 operands (BASELINE config 3, the benchmark path); 'fp32': fp32-accurate encoder (config 2's
 # "fp32": split-bf16 dense + fp32 attention, emission logits within 1e-3 of the reference).  Estimator sets it from
 # params['bert_precision'] around build_graph.
@@ -35,7 +37,10 @@ def pretrain_bert_embedding(input_ids, input_mask, segment_ids, pretrain_dir, dr
         tape = autodiff.current()
         if tape is None:
             raise TrainingPathNotBuilt("pretrain_bert_embedding(is_training=True) needs an autodiff tape (engine.train_step)")
-        emb = _bert.bert_forward_train(input_ids, input_mask, segment_ids, cfg, variables.default_store(), tape)
+        # TRAIN_PACK: the encoder runs on the real tokens only; its output keeps the [B,L,H] shape, zero at [PAD] (positions
+        # no layer after it reads when PACK_SEQUENCES holds — plugins whose next layer does read them switch it off)
+        pack = _bert.make_pack(input_mask) if (PACK_SEQUENCES and TRAIN_PACK and not _bert.PER_KERNEL) else None
+        emb = _bert.bert_forward_train(input_ids, input_mask, segment_ids, cfg, variables.default_store(), tape, pack=pack)
         return dropout(emb, rate=drop_out, is_training=True, seed=1234)
     if BERT_PRECISION == 'fp32':
         return _bert.bert_forward_f32(input_ids, input_mask, segment_ids, cfg).view(B, L, -1)

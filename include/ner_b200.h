@@ -271,6 +271,31 @@ int ner_bert_encoder_train_bwd(const ner_bert_config* cfg, const float* emb_ln_g
                                float hidden_keep, float attn_keep, uint64_t seed, const float* d_out,
                                const void* saved, size_t saved_bytes, void* scratch,
                                size_t scratch_bytes, ner_stream_t stream);
+/* Sequence-packed TRAIN composites (cu_seqlens / tok_src / n_packed from ner_seq_pack_plan): the per-token kernels run on
+ * the n_packed real tokens only — BertModel's work on [PAD] positions feeds nothing that bert_bilstm_crf / bert_crf read
+ * (tools/layer.py:35 and :122,140 stop at seq_len) — and attention takes cu_seqlens.  ids / seg / out_f32 / out_bf16 /
+ * d_out keep the padded [B*L, .] layout of the non-packed calls; [PAD] rows of the outputs are zero.  Same dropout seed
+ * scheme (masks are indexed by packed element).  Workspaces: the two *_packed_* size functions below. */
+size_t ner_bert_train_packed_saved_bytes(const ner_bert_config* cfg, int n_packed);
+size_t ner_bert_train_packed_scratch_bytes(const ner_bert_config* cfg, int n_packed, int padded_rows);
+int ner_bert_encoder_train_fwd_packed(const ner_bert_config* cfg, const float* word_emb, const float* type_emb,
+                                      const float* pos_emb, const float* emb_ln_gamma, const float* emb_ln_beta,
+                                      const ner_bert_layer_weights* layers, const int32_t* ids, const int32_t* seg,
+                                      int B, int L, const int32_t* cu_seqlens, const int32_t* tok_src, int n_packed,
+                                      float hidden_keep, float attn_keep, uint64_t seed, float* out_f32,
+                                      void* out_bf16, void* saved, size_t saved_bytes, ner_stream_t stream);
+int ner_bert_encoder_train_bwd_packed(const ner_bert_config* cfg, const float* emb_ln_gamma,
+                                      const ner_bert_layer_weights* layers, const ner_bert_layer_grads* grads,
+                                      float* d_word_emb, float* d_type_emb, float* d_pos_emb,
+                                      float* d_emb_ln_gamma, float* d_emb_ln_beta, const int32_t* ids,
+                                      const int32_t* seg, int B, int L, const int32_t* cu_seqlens,
+                                      const int32_t* tok_src, int n_packed, float hidden_keep, float attn_keep,
+                                      uint64_t seed, const float* d_out, const void* saved, size_t saved_bytes,
+                                      void* scratch, size_t scratch_bytes, ner_stream_t stream);
+/* Row moves between the padded and the packed layouts (row_bytes a multiple of 16):
+ * gather: dst row r = src row idx[r];  scatter: dst row idx[r] = src row r (rows not named keep their content). */
+int ner_gather_rows(const void* src, const int32_t* idx, void* dst, int n, int row_bytes, ner_stream_t stream);
+int ner_scatter_rows(const void* src, const int32_t* idx, void* dst, int n, int row_bytes, ner_stream_t stream);
 /* word[ids] + type[seg] + pos[0:L] without the LayerNorm -> f32 [B*L,H] (operand of the embedding
  * LayerNorm backward). */
 int ner_bert_embed_sum(const float* word_emb, const float* type_emb, const float* pos_emb,
@@ -431,6 +456,11 @@ int ner_bert_attention_bwd(const void* qkv_bf16, const int32_t* mask, const void
                            const void* dctx_bf16, void* dqkv_bf16, int B, int L, int num_heads,
                            int head_dim, float scale, float mask_add, float keep_prob, uint64_t seed,
                            ner_stream_t stream);
+/* Packed layout: sequence b occupies rows [cu_seqlens[b], cu_seqlens[b+1]) of qkv / ctx / dctx / dqkv, every key valid. */
+int ner_bert_attention_bwd_packed(const void* qkv_bf16, const int32_t* cu_seqlens, const void* ctx_bf16,
+                                  const void* dctx_bf16, void* dqkv_bf16, int B, int L, int num_heads,
+                                  int head_dim, float scale, float keep_prob, uint64_t seed,
+                                  ner_stream_t stream);
 
 #ifdef __cplusplus
 }
