@@ -1,29 +1,17 @@
-"""Run / train parameters — same keys and values as reference config.py:5-29."""
+"""Defaults every plugin's TRAIN_PARAMS starts from (keys and values of reference config.py:5-16, the contract the
+plugins and train ops read), and the BERT-base-Chinese architecture used when no bert_config.json is given."""
 
-TRAIN_PARAMS = {
-    'dtype': 'float32',
-    'lr': 5e-6,
-    'log_steps': 100,
-    'pretrain_dir': './pretrain_model/ch_google',  # pretrain Bert-Model
-    'batch_size': 32,
-    'epoch_size': 50,
-    'embedding_dropout': 0.1,
-    'warmup_ratio': 0.1,
-    'early_stop_ratio': 1  # stop after ratio * steps_per_epoch
-}
-
-RUN_CONFIG = {
-    'summary_steps': 10,
-    'log_steps': 100,
-    'save_steps': 500,
-    'keep_checkpoint_max': 3,
-    'allow_growth': True,
-    'pre_process_gpu_fraction': 0.8,
-    'log_device_placement': True,
-    'allow_soft_placement': True,
-    'inter_op_parallel': 2,
-    'intra_op_parallel': 2
-}
+TRAIN_PARAMS = dict(
+    dtype='float32',
+    lr=5e-6,
+    batch_size=32,
+    epoch_size=50,
+    log_steps=100,
+    warmup_ratio=0.1,
+    embedding_dropout=0.1,
+    early_stop_ratio=1,                              # stop after ratio * steps_per_epoch without improvement
+    pretrain_dir='./pretrain_model/ch_google',       # BertModel checkpoint + bert_config.json + vocab.txt
+)
 
 # pretrain_model/ch_google/bert_config.json of the reference (Google chinese_L-12_H-768_A-12);
 # used when params['pretrain_dir'] holds no bert_config.json.

@@ -1,45 +1,16 @@
-# -*-coding:utf-8 -*-
-"""Plugin mirror of reference model/bert_bilstm_crf.py (build_graph :8-34, hyper-params :37-48)."""
-from ..config import TRAIN_PARAMS as _BASE
-from ..tools.layer import bilstm, crf_decode, crf_layer, dense, pretrain_bert_embedding
+"""`bert_bilstm_crf` — the north-star plugin (reference model/bert_bilstm_crf.py:8-48): BertModel sequence output ->
+BiLSTM(128, relu) -> label projection -> CRF.  PREDICT also has a one-call executor (fastpath.FUSED_PREDICT) that runs the
+same kernels; this graph is the definition it is tested against."""
+from . import _blocks as nn
 
 
 def build_graph(features, labels, params, is_training):
-    """
-    pretrain Bert Model output + bilstm + CRF
-    """
-    input_ids = features['token_ids']
-    label_ids = features['label_ids']
-    input_mask = features['mask']
-    segment_ids = features['segment_ids']
-    seq_len = features['seq_len']
-
-    embedding = pretrain_bert_embedding(input_ids, input_mask, segment_ids, params['pretrain_dir'],
-                                        params['embedding_dropout'], is_training)
-
-    lstm_output = bilstm(embedding, params['cell_type'], params['rnn_activation'],
-                         params['hidden_units_list'], params['keep_prob_list'],
-                         params['cell_size'], seq_len, params['dtype'], is_training)
-
-    logits = dense(lstm_output, units=params['label_size'], name='logits', is_training=is_training)
-
-    trans, log_likelihood = crf_layer(logits, label_ids, seq_len, params['label_size'], is_training)
-    pred_ids = crf_decode(logits, trans, seq_len, params['idx2tag'], is_training)
-    crf_loss = (-log_likelihood).mean()
-
-    return crf_loss, pred_ids
+    hidden = nn.bert_sequence(features, params, is_training)
+    hidden = nn.recurrent(hidden, features, params, is_training)
+    return nn.crf_head(hidden, features, params, is_training)
 
 
-RNN_PARAMS = {
-    'cell_type': 'lstm',
-    'cell_size': 1,
-    'hidden_units_list': [128],
-    'keep_prob_list': [0.8],
-    'rnn_activation': 'relu'
-}
-
-TRAIN_PARAMS = dict(_BASE)
-TRAIN_PARAMS.update(RNN_PARAMS)
-TRAIN_PARAMS.update({
-    'diff_lr_times': {'crf': 500,  'logit': 500, 'lstm': 100}
-})
+TRAIN_PARAMS = nn.hyper(
+    dict(cell_type='lstm', cell_size=1, hidden_units_list=[128], keep_prob_list=[0.8], rnn_activation='relu'),
+    diff_lr_times={'crf': 500, 'logit': 500, 'lstm': 100},     # learning-rate multipliers of the non-BERT variables
+)

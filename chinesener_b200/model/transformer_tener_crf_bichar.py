@@ -1,27 +1,20 @@
 # -*-coding:utf-8 -*-
-"""Plugin mirror of reference model/transformer_tener_crf_bichar.py (build_graph :8-42, params :45-62)."""
+"""`transformer_tener_crf_bichar` (reference model/transformer_tener_crf_bichar.py:8-62): [character | bi-character]
+embeddings -> projection to d_model -> TENER encoder (relative-position attention) -> label projection -> CRF."""
 import torch
 
 from .. import autodiff, ops
-from ..config import TRAIN_PARAMS as _BASE
-from ..tools.layer import crf_decode, crf_layer, dense, dropout
+from ..tools.layer import dropout
 from ..tools.transformer.encoder import tener_encoder
 from ..tools.transformer.modules import embedding_project
-from .bilstm_crf import _const_table
+from . import _blocks as nn
 
 
 def build_graph(features, labels, params, is_training):
-    """
-    char + bichar embedding -> projection -> TENER encoder -> CRF
-    """
-    input_ids = features['token_ids']
-    bichar_ids = features['bichar_ids']
-    label_ids = features['label_ids']
-    seq_len = features['seq_len']
+    input_ids, bichar_ids, seq_len = features['token_ids'], features['bichar_ids'], features['seq_len']
     B, L = input_ids.shape
-
-    char_table = _const_table(params, 'embedding')
-    bichar_table = _const_table(params, 'bichar_embedding')
+    char_table = nn.device_constant(params, 'embedding')
+    bichar_table = nn.device_constant(params, 'bichar_embedding')
     Ec, Eb = char_table.shape[1], bichar_table.shape[1]
     # concat([char_embedding, bichar_embedding], -1): both lookups write into one buffer
     embedding = torch.empty((B * L, Ec + Eb), dtype=torch.float32, device=input_ids.device)
@@ -40,33 +33,17 @@ def build_graph(features, labels, params, is_training):
         transformer_output = out2d.view(B, L, -1)
         tape.record(transformer_output, lambda g: tape.add_grad(out2d, g.reshape(out2d.shape)) if g is not None else None)
 
-    logits = dense(transformer_output, units=params['label_size'], name='logits', is_training=is_training)
-
-    trans, log_likelihood = crf_layer(logits, label_ids, seq_len, params['label_size'], is_training)
-    pred_ids = crf_decode(logits, trans, seq_len, params['idx2tag'], is_training)
-    crf_loss = (-log_likelihood).mean()
-
-    return crf_loss, pred_ids
+    return nn.crf_head(transformer_output, features, params, is_training)
 
 
-# below params from MSRA[smaller params: num_head=5/d_model=200 for people_daily]
-TRANSFORMER_PARAMS = {
-    'num_head': 8,  # giga embedding size is 50, must be divided by 5
-    'd_model': 160,  # giga char& bichar embedding dim are small, project to bigger dim
-    'ffn_hidden': 320,
-    'encode_layers': 2,
-    'batch_size': 16,
-    'wramup_ratio': 0.1,
-    'epochs': 100
-}
-
-TRAIN_PARAMS = dict(_BASE)
-TRAIN_PARAMS.update(TRANSFORMER_PARAMS)
-TRAIN_PARAMS.update({
-    'lr': 0.001,
-    'decay_rate': 0.95,  # lr * decay_rate ^ (global_step / train_steps_per_epoch)
-    'embedding_dropout': 0.3,
-    'fc_dropout': 0.4,
-    'dropout_rate': 0.2,  # used in transformer sublayer dropout
-    'early_stop_ratio': 2  # stop after no improvement after 1.5 epochs
-})
+# MSRA-sized encoder (people_daily in the reference: num_head 5, d_model 200); d_model projects the 50-d giga
+# character / bi-character vectors up, num_head must divide it
+TRAIN_PARAMS = nn.hyper(
+    dict(num_head=8, d_model=160, ffn_hidden=320, encode_layers=2, batch_size=16, wramup_ratio=0.1, epochs=100),
+    lr=0.001,
+    decay_rate=0.95,
+    embedding_dropout=0.3,
+    fc_dropout=0.4,
+    dropout_rate=0.2,         # transformer sub-layer dropout
+    early_stop_ratio=2,
+)
