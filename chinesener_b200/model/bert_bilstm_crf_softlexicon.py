@@ -1,13 +1,11 @@
 # -*-coding:utf-8 -*-
-"""Plugin mirror of reference model/bert_bilstm_crf_softlexicon.py (build_graph :14-67, params :70-86) — one of the
-"remaining plugins reusing the same kernels" (SURVEY §8(f) rank 4): BertModel sequence output, the SoftLexicon
-gather-and-pool of the B/M/E/S lexicon ids, concat([wh_embedding, bert_embedding]) -> bilstm -> dropout -> dense -> CRF."""
+"""`bert_bilstm_crf_softlexicon` (reference model/bert_bilstm_crf_softlexicon.py:14-86):
+[pooled B/M/E/S lexicon embedding | BertModel sequence output] -> BiLSTM(200, tanh) -> dropout -> label projection -> CRF."""
 import torch
 
 from .. import autodiff, ops, variables
-from ..config import TRAIN_PARAMS as _BASE
-from ..tools import layer as _layer
-from ..tools.layer import bilstm, crf_decode, crf_layer, dense, dropout, pretrain_bert_embedding
+from ..tools.layer import dropout
+from . import _blocks as nn
 
 
 def reshape_input(input_, params):
@@ -15,24 +13,10 @@ def reshape_input(input_, params):
 
 
 def build_graph(features, labels, params, is_training):
-    """
-    bert +  bilstm + CRF + softlexicon word enhance
-    """
-    input_ids = features['token_ids']
-    label_ids = features['label_ids']
-    input_mask = features['mask']
-    segment_ids = features['segment_ids']
-    seq_len = features['seq_len']
-    B, L = input_ids.shape
+    B, L = features['token_ids'].shape
     G, S = params['word_enhance_dim'], params['max_lexicon_len']
-
     # the lexicon features live on the padded [B, L] grid, so the encoder keeps the padded layout here
-    pack0, _layer.PACK_SEQUENCES = _layer.PACK_SEQUENCES, False
-    try:
-        embedding = pretrain_bert_embedding(input_ids, input_mask, segment_ids, params['pretrain_dir'],
-                                            params['embedding_dropout'], is_training)
-    finally:
-        _layer.PACK_SEQUENCES = pack0
+    embedding = nn.bert_sequence(features, params, is_training, packed=False)
 
     softlexicon_ids = reshape_input(features['softlexicon_ids'], params)
     softlexicon_weights = reshape_input(features['softlexicon_weights'], params)
@@ -59,33 +43,15 @@ def build_graph(features, labels, params, is_training):
                 tape.add_grad(bert_emb, g[..., G * E:].contiguous().view(bert_emb.shape))
         tape.record(embedding, cat_bwd)
 
-    lstm_output = bilstm(embedding, params['cell_type'], params['rnn_activation'],
-                         params['hidden_units_list'], params['keep_prob_list'],
-                         params['cell_size'], seq_len, params['dtype'], is_training)
-    lstm_output = dropout(lstm_output, params['embedding_dropout'], is_training)
-
-    logits = dense(lstm_output, units=params['label_size'], name='logits', is_training=is_training)
-
-    trans, log_likelihood = crf_layer(logits, label_ids, seq_len, params['label_size'], is_training)
-    pred_ids = crf_decode(logits, trans, seq_len, params['idx2tag'], is_training)
-    crf_loss = (-log_likelihood).mean()
-
-    return crf_loss, pred_ids
+    hidden = dropout(nn.recurrent(embedding, features, params, is_training), params['embedding_dropout'], is_training)
+    return nn.crf_head(hidden, features, params, is_training)
 
 
-RNN_PARAMS = {
-    'cell_type': 'lstm',
-    'cell_size': 1,
-    'hidden_units_list': [200],  # 128 for people_daily ,200 for msra
-    'keep_prob_list': [0.9],
-    'rnn_activation': 'tanh',
-}
-
-TRAIN_PARAMS = dict(_BASE)
-TRAIN_PARAMS.update(RNN_PARAMS)
-TRAIN_PARAMS.update({
-    'lr': 5e-6,  # small base learning rate for bert
-    'diff_lr_times': {'crf': 500, 'logit': 500, 'lstm': 100, 'word_enhance': 100},  # different lr per-layer
-    'embedding_dropout': 0.5,
-    'early_stop_ratio': 1  # stop after no improvement after 1.5 epochs
-})
+TRAIN_PARAMS = nn.hyper(
+    dict(cell_type='lstm', cell_size=1, hidden_units_list=[200],     # 200 for MSRA (128 for people_daily in the reference)
+         keep_prob_list=[0.9], rnn_activation='tanh'),
+    lr=5e-6,                                                         # BERT-sized base rate, multiplied per layer group below
+    diff_lr_times={'crf': 500, 'logit': 500, 'lstm': 100, 'word_enhance': 100},
+    embedding_dropout=0.5,
+    early_stop_ratio=1,
+)

@@ -1,11 +1,11 @@
 # -*-coding:utf-8 -*-
-"""Plugin mirror of reference model/bilstm_crf_softlexicon.py (build_graph :14-64, params :67-84)."""
+"""`bilstm_crf_softlexicon` (reference model/bilstm_crf_softlexicon.py:14-84): [pooled B/M/E/S lexicon embedding | frozen
+character embedding] -> BiLSTM(200, tanh) -> label projection -> CRF."""
 import torch
 
 from .. import autodiff, ops, variables
-from ..config import TRAIN_PARAMS as _BASE
-from ..tools.layer import bilstm, crf_decode, crf_layer, dense, dropout
-from .bilstm_crf import _const_table
+from ..tools.layer import dropout
+from . import _blocks as nn
 
 
 def reshape_input(input_, params):
@@ -13,19 +13,14 @@ def reshape_input(input_, params):
 
 
 def build_graph(features, labels, params, is_training):
-    """
-    Giga pretrain character embedding + bilstm + CRF + softlexicon word enhance
-    """
     input_ids = features['token_ids']
-    label_ids = features['label_ids']
-    seq_len = features['seq_len']
-    # reshape -> batch, max_seq_len, word_enhance_dim * max_lexicon_len
+    # flat [B, L * G * S] features -> [B, L, G * S]
     softlexicon_ids = reshape_input(features['softlexicon_ids'], params)
     softlexicon_weights = reshape_input(features['softlexicon_weights'], params)
     B, L = input_ids.shape
     G, S = params['word_enhance_dim'], params['max_lexicon_len']
 
-    char_table = _const_table(params, 'embedding')
+    char_table = nn.device_constant(params, 'embedding')
     init = params['word_embedding']
     softword_embedding = variables.get_variable('word_enhance/softlexicon_embedding', tuple(init.shape),
                                                 variables.constant(init))
@@ -60,32 +55,14 @@ def build_graph(features, labels, params, is_training):
                     tape.add_grad(wh_d, g[..., :G * E].contiguous())
             tape.record(embedding, cat_bwd)
 
-    lstm_output = bilstm(embedding, params['cell_type'], params['rnn_activation'],
-                         params['hidden_units_list'], params['keep_prob_list'],
-                         params['cell_size'], seq_len, params['dtype'], is_training)
-
-    logits = dense(lstm_output, units=params['label_size'], name='logits', is_training=is_training)
-
-    trans, log_likelihood = crf_layer(logits, label_ids, seq_len, params['label_size'], is_training)
-    pred_ids = crf_decode(logits, trans, seq_len, params['idx2tag'], is_training)
-    crf_loss = (-log_likelihood).mean()
-
-    return crf_loss, pred_ids
+    return nn.crf_head(nn.recurrent(embedding, features, params, is_training), features, params, is_training)
 
 
-RNN_PARAMS = {
-    'cell_type': 'lstm',
-    'cell_size': 1,
-    'hidden_units_list': [200],  # 128 for people_daily ,200 for msra
-    'keep_prob_list': [0.9],
-    'rnn_activation': 'tanh',
-}
-
-TRAIN_PARAMS = dict(_BASE)
-TRAIN_PARAMS.update(RNN_PARAMS)
-TRAIN_PARAMS.update({
-    'lr': 0.0015,
-    'decay_rate': 0.95,  # lr * decay_rate ^ (global_step / train_steps_per_epoch)
-    'embedding_dropout': 0.5,
-    'early_stop_ratio': 1  # stop after no improvement after 1.5 epochs
-})
+TRAIN_PARAMS = nn.hyper(
+    dict(cell_type='lstm', cell_size=1, hidden_units_list=[200],     # 200 for MSRA (128 for people_daily in the reference)
+         keep_prob_list=[0.9], rnn_activation='tanh'),
+    lr=0.0015,
+    decay_rate=0.95,
+    embedding_dropout=0.5,
+    early_stop_ratio=1,
+)
