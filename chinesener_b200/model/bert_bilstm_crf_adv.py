@@ -8,7 +8,7 @@ file cannot build its graph as written; this mirror passes seq_len there as the 
 import torch
 
 from .. import variables
-from ..config import TRAIN_PARAMS as _BASE
+from . import _blocks as nn
 from ..tools.layer import (bilstm, concat, crf_decode, crf_layer, dense, dropout, masked_task_loss,
                            pretrain_bert_embedding, reduce_max_flip, softmax_cross_entropy_mean)
 
@@ -62,21 +62,12 @@ def build_graph(features, labels, params, is_training):
     return loss, pred_ids, task_ids
 
 
-RNN_PARAMS = {
-    'cell_type': 'lstm',
-    'cell_size': 1,
-    'hidden_units_list': [100],
-    'keep_prob_list': [0.8],
-    'rnn_activation': 'relu'
-}
-
-TRAIN_PARAMS = dict(_BASE)
-TRAIN_PARAMS.update(RNN_PARAMS)
-TRAIN_PARAMS.update({
-    'diff_lr_times': {'crf': 500, 'logit': 100, 'lstm': 100},
-    'lambda': 0.5,  # weight of task discriminator, can be tuned
-    'task_weight': [1, 1],  # weight for 2 task
-    'shrink_gradient_reverse': 0.001,  # CWS+NER task 0.01, NER+NER task 0.001, can be tuned.
-    'share_dropout': 0.2,
-    'batch_size': 32
-})
+TRAIN_PARAMS = nn.hyper(
+    dict(cell_type='lstm', cell_size=1, hidden_units_list=[100], keep_prob_list=[0.8], rnn_activation='relu'),
+    diff_lr_times={'crf': 500, 'logit': 100, 'lstm': 100},
+    task_weight=[1, 1],
+    share_dropout=0.2,
+    shrink_gradient_reverse=0.001,     # the reference suggests 0.01 for CWS+NER, 0.001 for NER+NER
+    batch_size=32,
+    **{'lambda': 0.5},                 # weight of the task-discriminator loss
+)

@@ -4,7 +4,7 @@ one shared BertModel, one BiLSTM + logits + CRF tower per task; `task_ids` picks
 import torch
 
 from .. import variables
-from ..config import TRAIN_PARAMS as _BASE
+from . import _blocks as nn
 from ..tools.layer import bilstm, concat, crf_decode, crf_layer, dense, masked_task_loss, pretrain_bert_embedding
 
 
@@ -53,19 +53,9 @@ def build_graph(features, labels, params, is_training):
     return loss, pred_ids, task_ids
 
 
-RNN_PARAMS = {
-    'cell_type': 'lstm',
-    'cell_size': 1,
-    'hidden_units_list': [128],
-    'keep_prob_list': [0.8],
-    'rnn_activation': 'relu',
-    'batch_size': 32
-}
-
-TRAIN_PARAMS = dict(_BASE)
-TRAIN_PARAMS.update(RNN_PARAMS)
-TRAIN_PARAMS.update({
-    'diff_lr_times': {'crf': 500, 'logit': 500, 'lstm': 100},
-    'task_weight': [1, 1],  # equal weight for CWS+NER / NER+NER
-    'asymmetry': True  # task2 is the main task and also reads task1's hidden states
-})
+TRAIN_PARAMS = nn.hyper(
+    dict(cell_type='lstm', cell_size=1, hidden_units_list=[128], keep_prob_list=[0.8], rnn_activation='relu', batch_size=32),
+    diff_lr_times={'crf': 500, 'logit': 500, 'lstm': 100},
+    task_weight=[1, 1],       # equal weight for CWS+NER / NER+NER
+    asymmetry=True,           # task 2 is the main task and also reads task 1's hidden states
+)

@@ -1,14 +1,14 @@
 # -*-coding:utf-8 -*-
-"""Plugin mirror of reference model/transformer_crf_bichar.py (build_graph :8-46, params :50-68) — SURVEY §8(f) rank 4:
-char + bichar embedding -> projection + sinusoidal absolute positions -> transformer encoder -> CRF."""
+"""`transformer_crf_bichar` (reference model/transformer_crf_bichar.py:8-68):
+character + bi-character embedding -> projection + sinusoidal absolute positions -> transformer encoder -> CRF."""
 import numpy as np
 import torch
 
 from .. import autodiff, ops
-from ..config import TRAIN_PARAMS as _BASE
 from ..tools.layer import crf_decode, crf_layer, dense, dropout
 from ..tools.transformer.encoder import transformer_encoder
 from ..tools.transformer.modules import embedding_project, sinusoidal_positional_encoding
+from . import _blocks as nn
 from .bilstm_crf import _const_table
 
 _pos_cache = {}
@@ -67,23 +67,12 @@ def build_graph(features, labels, params, is_training):
     return crf_loss, pred_ids
 
 
-# below params from MSRA. here num_head and d_model are set small to compare with FLAT[too big can cause OOM]
-TRANSFORMER_PARAMS = {
-    'num_head': 8,
-    'd_model': 160,
-    'ffn_hidden': 320,
-    'encode_layers': 2,
-    'batch_size': 16,
-    'wramup_ratio': 0.1,
-    'epochs': 100
-}
-
-TRAIN_PARAMS = dict(_BASE)
-TRAIN_PARAMS.update(TRANSFORMER_PARAMS)
-TRAIN_PARAMS.update({
-    'lr': 0.001,
-    'decay_rate': 0.95,  # lr * decay_rate ^ (global_step / train_steps_per_epoch)
-    'embedding_dropout': 0.3,
-    'dropout_rate': 0.2,  # used in transformer sublayer dropout
-    'early_stop_ratio': 2  # stop after no improvement after 1.5 epochs
-})
+# MSRA-sized encoder, kept small as in the reference (its comparison point is FLAT)
+TRAIN_PARAMS = nn.hyper(
+    dict(num_head=8, d_model=160, ffn_hidden=320, encode_layers=2, batch_size=16, wramup_ratio=0.1, epochs=100),
+    lr=0.001,
+    decay_rate=0.95,
+    embedding_dropout=0.3,
+    dropout_rate=0.2,         # transformer sub-layer dropout
+    early_stop_ratio=2,
+)
