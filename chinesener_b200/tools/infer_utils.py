@@ -1,41 +1,51 @@
-# -*-coding:utf-8 -*-
-"""Entity extraction for the inference path (reference tools/infer_utils.py:76-118)."""
+"""Entity extraction for the in-process inference path — behaviour of reference tools/infer_utils.py:76-118
+(`extract_entity`, `fix_tokens`), which `inference.InferHelper.infer` applies to the PREDICT output."""
 from collections import defaultdict
+
+_SPECIAL_TOKENS = frozenset(('[PAD]', '[CLS]', '[SEP]'))
 
 
 def extract_entity(tokens, pred_ids, idx2tag):
-    """Collect the entity strings of every type from a BIO tag sequence (reference :76-101)."""
-    assert len(tokens) == len(pred_ids), '{}!={} tokens and pred_ids must have same length'.format(len(tokens), len(pred_ids))
-    ngram = ''
-    entity = defaultdict(set)
-    prev_tag = idx2tag[pred_ids[0]]
-    for t, i in zip(tokens, pred_ids):
-        tag = idx2tag[i]
-        if tag.split('-')[0] == 'I':
-            if prev_tag[0].split('-')[0] in ['B', 'I']:
-                ngram += t
+    """{entity type: set of surface strings} read off a BIO tag sequence.
+
+    Rules kept from the reference (:76-101): an `I-*` tag extends the open span only when the previous tag starts with
+    B or I; any other tag closes the span, whose type is the type of the tag just before; `B-*` opens a new one."""
+    if len(tokens) != len(pred_ids):
+        raise AssertionError('{}!={} tokens and pred_ids must have same length'.format(len(tokens), len(pred_ids)))
+    found = defaultdict(set)
+    pieces, last = [], idx2tag[pred_ids[0]]
+
+    def close():
+        text = ''.join(pieces)
+        if text != '':
+            found[last.split('-')[1]].add(text)
+
+    for tok, idx in zip(tokens, pred_ids):
+        tag = idx2tag[idx]
+        kind = tag.split('-')[0]
+        if kind == 'I':
+            if last[:1] in ('B', 'I'):
+                pieces.append(tok)
         else:
-            if ngram != '':
-                entity[prev_tag.split('-')[1]].add(ngram)
-            ngram = t if tag.split('-')[0] == 'B' else ''
-        prev_tag = tag
-    if ngram != '':
-        entity[prev_tag.split('-')[1]].add(ngram)
-    return entity
+            close()
+            pieces = [tok] if kind == 'B' else []
+        last = tag
+    close()
+    return found
 
 
 def fix_tokens(sentence, tokens):
-    """Put the original characters back where WordPiece produced [UNK] or a ## continuation (reference :104-118)."""
-    j = 0
-    for i in range(len(tokens)):
-        if tokens[i] == '[UNK]':
-            tokens[i] = sentence[j]
-            j += 1
-        elif tokens[i][:2] == '##':
-            tokens[i] = tokens[i].replace('##', '')
-            j += len(tokens[i])
-        elif tokens[i] in ['[PAD]', '[CLS]', '[SEP]']:
+    """Restore the raw characters WordPiece replaced: `[UNK]` becomes the character under the cursor, `##xx` loses its
+    continuation mark (reference :104-118).  Edits `tokens` in place and returns it."""
+    cursor = 0
+    for k, tok in enumerate(tokens):
+        if tok in _SPECIAL_TOKENS:
             continue
-        else:
-            j += len(tokens[i])
+        if tok == '[UNK]':
+            tokens[k] = sentence[cursor]
+            cursor += 1
+            continue
+        if tok.startswith('##'):
+            tok = tokens[k] = tok.replace('##', '')
+        cursor += len(tok)
     return tokens

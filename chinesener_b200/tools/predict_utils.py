@@ -9,25 +9,28 @@ def decode_prediction(tokens, tags):
     B-x starts an entity, I-x of the same type extends it, an I-y of another type appends
     '[ERROR]', anything else closes it; '##' word-piece markers are stripped.
     """
-    assert len(tokens) == len(tags), \
-        'NER Decode {}!={}: token and pred_ids must have same len'.format(len(tokens), tags)
-    result = defaultdict(set)
-    entity, type1 = '', ''
+    if len(tokens) != len(tags):
+        raise AssertionError('NER Decode {}!={}: token and pred_ids must have same len'.format(len(tokens), tags))
+    spans = defaultdict(set)
+    state = {'text': '', 'type': ''}          # the open entity
+
+    def flush(new_text='', new_type=None):
+        if state['text']:
+            spans[state['type']].add(state['text'])
+        state['text'] = new_text
+        if new_type is not None:
+            state['type'] = new_type
+
     for token, tag in zip(tokens, tags):
-        text = (token.decode() if isinstance(token, bytes) else token).replace('##', '')
+        piece = (token.decode() if isinstance(token, bytes) else token).replace('##', '')
         if 'B' in tag:
-            if entity:
-                result[type1].add(entity)
-            entity, type1 = text, tag.split('-')[1]
+            flush(piece, tag.split('-')[1])
         elif 'I' in tag:
-            entity += text if tag.split('-')[1] == type1 else '[ERROR]'
+            state['text'] += piece if tag.split('-')[1] == state['type'] else '[ERROR]'
         else:
-            if entity:
-                result[type1].add(entity)
-            entity = ''
-    if entity:
-        result[type1].add(entity)
-    return result
+            flush()
+    flush()
+    return spans
 
 
 def process_prediction(pred_dict, idx2tag):
