@@ -99,10 +99,14 @@ class ClockSampler:
         if self.h is not None:
             self.stop_flag = True
             self.t.join(timeout=1)
-            sm = [r[0] for r in self.rows]
+            # host-only stretches between the GPU-timed regions (building tables / estimators) would dilute the median
+            # with idle-clock samples: take it over the samples NVML reports as busy (utilisation window >= 10 %)
+            busy = [r for r in self.rows if r[2] >= 10]
+            rows = busy if len(busy) >= 20 else self.rows
+            sm = [r[0] for r in rows]
             reasons = sorted({n for r in self.rows for n in r[1]})
             return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
-                    "samples": len(sm), "source": "nvml, 2 ms poll over the device-resident and e2e timed regions"}
+                    "samples": len(self.rows), "samples_under_load": len(busy), "source": "nvml, 2 ms poll from the first device-resident timed step to the last kernel-roofline launch"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -201,28 +205,63 @@ def pick_cpu_threads():
     return best
 
 
-def time_cpu_reference(n_sent, reps, seed=99):
-    """The reference's CPU path (PyTorch-CPU fp32 restatement; TF 1.14 is not installable) on all host cores."""
-    from chinesener_b200 import synthetic
+def time_cpu_reference(weights, params, host_batches_, reps=2):
+    """The reference's CPU path (PyTorch-CPU fp32 restatement; TF 1.14 is not installable) on the host cores, over the
+    SAME 64-sentence host batches and the SAME weights the GPU arm was timed on.  -> (sentences/s, rep seconds, outputs of
+    the first timed batch): the outputs are the checker of `parity_checked`."""
     from oracle import models as omodels
     torch.set_num_threads(pick_cpu_threads())
-    w, params = oracle_weights_and_params()
-    ts = []
-    for r in range(reps + 1):
-        feats = synthetic.msra_batch(n_sent, SEQ_LEN, seed=seed + r)
+    small = {k: (v[:8] if torch.is_tensor(v) else v) for k, v in host_batches_[0].items()}
+    with torch.no_grad():
+        omodels.bert_bilstm_crf(weights, small, params, dtype=torch.float32)        # warms the thread pool / allocator
+    ts, first = [], None
+    for r in range(reps):
+        feats = host_batches_[r % len(host_batches_)]
         t0 = time.perf_counter()
         with torch.no_grad():
-            omodels.bert_bilstm_crf(w, feats, params, dtype=torch.float32)
+            out = omodels.bert_bilstm_crf(weights, feats, params, dtype=torch.float32)
         ts.append(time.perf_counter() - t0)
-    ts = ts[1:] if len(ts) > 1 else ts  # first rep warms the thread pool / allocator
-    return n_sent / float(np.median(ts)), ts
+        if first is None:
+            first = out
+    n_sent = host_batches_[0]['token_ids'].shape[0]
+    return n_sent / float(np.median(ts)), ts, first
+
+
+def check_parity(est, feats, oracle_out):
+    """pred_ids of one TIMED batch against the oracle, outside every timed region.
+    (1) Viterbi tags from Estimator.predict must equal, bit for bit, the oracle's Viterbi run on the CUDA path's own fp32
+        emission logits (integer output);  (2) tag agreement with the end-to-end fp32 CPU oracle (its own logits) and the
+        max |logit| distance to it are reported as numbers (bf16 operands vs fp32: not expected to be bit-equal)."""
+    from chinesener_b200 import variables
+    from chinesener_b200.tools import layer
+    from oracle import crf as ocrf
+    dev = est.to_device(feats)
+    pred = est.predict(feats)['pred_ids'].numpy()
+    with variables.use_store(est.store):
+        emb = layer.pretrain_bert_embedding(dev['token_ids'], dev['mask'], dev['segment_ids'], est.params['pretrain_dir'], 0.1, False)
+        x = layer.bilstm(emb, 'lstm', est.params['rnn_activation'], est.params['hidden_units_list'], [1.0], 1, dev['seq_len'], 'float32', False)
+        logits = layer.dense(x, LABELS, 'logits')
+    torch.cuda.synchronize()
+    lg = logits.cpu().numpy()
+    trans = est.store.vars['crf_layer/transitions'].cpu().numpy()
+    lens = feats['seq_len'].numpy()
+    ref_pred, _ = ocrf.crf_decode(lg, trans, lens, dtype=np.float32)
+    valid = np.arange(SEQ_LEN)[None, :] < lens[:, None]
+    bit_exact = bool(np.array_equal(pred, ref_pred))
+    agree = float((pred == oracle_out['pred_ids'])[valid].mean())
+    err = float(np.abs(lg - oracle_out['logits'].numpy())[valid].max())
+    return {"parity_checked": bool(bit_exact and agree >= 0.99), "viterbi_bit_exact_on_cuda_logits": bit_exact,
+            "tag_agreement_with_cpu_oracle": agree, "max_abs_logit_diff_vs_fp32_cpu_oracle": err,
+            "max_abs_logit": float(np.abs(oracle_out['logits'].numpy())[valid].max()),
+            "what": "batch 0 of the timed batches; Estimator.predict tags == oracle Viterbi on the CUDA logits (bit-exact), "
+                    "and vs the PyTorch-CPU fp32 oracle end to end (rate); checked outside the timed regions"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sent = 32
+    n_sent = B_PER_GPU           # the same 64-sentence batch our arm steps over
     per_step = []
     from chinesener_b200 import synthetic
     from oracle import models as omodels
@@ -243,7 +282,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(per_step), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": n_sent, "seq_len": SEQ_LEN,
-                   "note": "bounded sample: each step = 32 sentences of the same workload on the host cores"},
+                   "note": "each step = one 64-sentence batch of the same workload on the host cores"},
         "cpu_baseline": {"value": value, "unit": "sentences/sec", "cores": pick_cpu_threads(), "host_cpus": os.cpu_count(), "kind": "port",
                          "sample": f"{len(per_step)} steps x {n_sent} sentences, PyTorch-CPU fp32 restatement "
                                    f"(oracle/models.py) of model/bert_bilstm_crf.py; TF 1.14 not installable"},
@@ -251,6 +290,129 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def _time_launches(fn, warm=3, iters=10, flush=None):
+    """Average CUDA-event duration (ms) of `fn`'s launches on the current stream: >= 3 warm-ups, a synchronize on both
+    sides, optional untimed L2 flush before every timed launch.  -> (mean_ms, min_ms)."""
+    for _ in range(max(warm, 3)):
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    ts = [s.elapsed_time(e) for s, e in evs]
+    return float(np.mean(ts)), float(min(ts))
+
+
+def crf_rooflines(hbm_peak, peak_src, B=262144, L=128, K=LABELS):
+    """SURVEY 8(d) "CRF kernel roofline run": B = 262 144 sequences, L = 128, K = 10, full lengths (1.34 GB of emission
+    logits >> 126 MB L2, so every launch is L2-cold by construction).  Algorithmic bytes per sentence:
+    forward-alpha L*(4K+4)+8, Viterbi read L*4K+4 + write L*4+4 (backpointers stay on chip and are not counted)."""
+    from chinesener_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.randn(B, L, K, device="cuda", generator=g)
+    tr = torch.randn(K, K, device="cuda", generator=g) * 0.5
+    lens = torch.full((B,), L, dtype=torch.int32, device="cuda")
+    tags = torch.randint(0, K, (B, L), device="cuda", dtype=torch.int32, generator=g)
+    out = {}
+    for key, fn, byts in (
+            ("roofline_crf_fwd", lambda: ops.crf_loglik_fwd(x, tags, lens, tr), B * L * (4 * K + 4) + 8 * B + 4 * K * K),
+            ("roofline_crf_viterbi", lambda: ops.crf_viterbi(x, lens, tr), B * L * 4 * K + 4 * B + 4 * K * K + B * L * 4 + 4 * B)):
+        ms, best = _time_launches(fn, warm=3, iters=10)
+        gbs = byts / (ms * 1e-3) / 1e9
+        out[key] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+                    "ms_per_launch": ms, "best_ms": best, "algorithmic_bytes_per_launch": byts, "launches_timed": 10,
+                    "workload": f"B={B} L={L} K={K} full lengths, fp32 logits (working set 1.5 GB >> L2)", "peak_source": peak_src}
+    del x, tags
+    torch.cuda.empty_cache()
+    return out
+
+
+def softlexicon_roofline(hbm_peak, peak_src, flush, V=704370, E=50, L=128):
+    """SoftLexicon gather-and-pool: config 4's [704 370, 50] fp32 table (140.9 MB > L2), 40 slots per
+    token.  `dense`: every slot a random word (the 8(d) upper bound, 9 120 B/token); `realistic`: the slot statistics of
+    the reference's warm-up record (a few words per token, empty sets hold <None>, the rest <PAD> with weight 0 — rows the
+    kernel never fetches).  Algorithmic bytes = 40*(4+4) ids/weights + nnz*4E gathered rows + 4*4E output, nnz counted
+    from the generated weights.  L2 flushed (untimed) before every timed launch."""
+    from chinesener_b200 import ops, synthetic
+    g = torch.Generator(device="cuda").manual_seed(7)
+    table = torch.nn.functional.normalize(torch.randn(V, E, device="cuda", generator=g), dim=1).contiguous()
+    res = {}
+    for B in (B_PER_GPU, 2048):
+        for realistic in (False, True):
+            ids, w = synthetic.softlexicon_features_device(B * L, V, realistic=realistic, seed=11)
+            out = torch.empty((B * L, 4 * E), dtype=torch.float32, device="cuda")
+            nnz = int((w != 0).sum())
+            byts = B * L * (40 * 8 + 4 * E * 4) + nnz * E * 4
+            ms, best = _time_launches(lambda: ops.softlexicon_pool(table, ids, w, 4, 10, out=out), warm=3, iters=10, flush=flush)
+            gbs = byts / (ms * 1e-3) / 1e9
+            res[f"{'realistic' if realistic else 'dense'}_B{B}"] = {
+                "achieved": gbs, "frac": gbs / hbm_peak, "ms_per_launch": ms, "best_ms": best, "algorithmic_bytes_per_launch": byts,
+                "nonzero_slots_per_token": nnz / (B * L)}
+    head = res["dense_B2048"]
+    return {"bound": "hbm", "achieved": head["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": head["frac"], "traffic": None,
+            "headline": "dense_B2048 (262 144 tokens per launch; B=64 launches last a few us and are launch-latency bound)",
+            "table": [V, E], "variants": res, "peak_source": peak_src}
+
+
+def other_configs(steps, flush):
+    """PREDICT sentences/s of BASELINE configs 2, 4, 5 (device-resident batches, L2 flushed between timed steps, CUDA
+    events per step) — config 3 is the line's `value`."""
+    from chinesener_b200 import engine, synthetic
+    out = {}
+    g = torch.Generator().manual_seed(5)
+    char = torch.nn.functional.normalize(torch.randn(11329, 50, generator=g), dim=1).numpy()
+
+    def run(name, est, feats, B):
+        dev = est.to_device({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in feats.items()})
+        fn = lambda: est.predict_device(dev)
+        ms, best = _time_launches(fn, warm=3, iters=steps, flush=flush)
+        out[name]["value"], out[name]["unit"], out[name]["ms_per_step"] = B / (ms * 1e-3), "sentences/sec", ms
+        out[name]["best_ms"] = best
+
+    # config 2: bert_crf msra seq_len=128 bs=32 fp32 (split-bf16 dense + fp32 attention/LayerNorm: the 1e-3 mode)
+    B, L = 32, 128
+    out["config2_bert_crf_fp32"] = {"workload": "bert_crf msra seq_len=128 bs=32, bert_precision='fp32' (3 bf16 tcgen05 GEMMs per dense "
+                                                "layer, fp32 attention), MSRA-shaped lengths, PREDICT", "dtype": "f32 (split bf16)"}
+    est = engine.Estimator("bert_crf", dict(synthetic.data_params(L, LABELS), pretrain_dir="", bert_precision="fp32"))
+    run("config2_bert_crf_fp32", est, synthetic.msra_batch(B, L, seed=21), B)
+    del est
+    # config 4: bilstm_crf_softlexicon seq_len=128 bs=64, [704 370, 50] lexicon table
+    B, L, NW = 64, 128, 704370
+    out["config4_bilstm_crf_softlexicon"] = {"workload": "bilstm_crf_softlexicon seq_len=128 bs=64: B/M/E/S gather-and-pool over the "
+                                                         "[704370,50] table (realistic slot statistics) + BiLSTM(200, tanh) + CRF, PREDICT",
+                                             "dtype": "f32 (bf16 LSTM input projection)"}
+    feats = synthetic.msra_batch(B, L, vocab=11329, seed=22)
+    ids, w = synthetic.softlexicon_features_device(B * L, NW, realistic=True, seed=23)
+    valid = (torch.arange(L)[None, :] < feats['seq_len'][:, None]).reshape(B * L, 1)
+    feats['softlexicon_ids'] = torch.where(valid, ids.cpu(), torch.zeros_like(ids.cpu())).view(B, L * 40)
+    feats['softlexicon_weights'] = (w.cpu() * valid).view(B, L * 40)
+    wemb = torch.nn.functional.normalize(torch.randn(NW, 50, generator=g), dim=1).numpy()
+    est = engine.Estimator("bilstm_crf_softlexicon", dict(synthetic.data_params(L, LABELS), embedding=char, word_embedding=wemb,
+                                                          word_enhance_dim=4, max_lexicon_len=10))
+    run("config4_bilstm_crf_softlexicon", est, feats, B)
+    del est, wemb
+    # config 5: transformer_tener_crf_bichar seq_len=256 bs=32
+    B, L, NB = 32, 256, 300000
+    out["config5_transformer_tener_crf_bichar"] = {"workload": "transformer_tener_crf_bichar msra seq_len=256 bs=32: char|bichar embedding -> "
+                                                               "2 TENER layers (relative-position attention, d=160, 8 heads) + CRF, PREDICT",
+                                                   "dtype": "f32 (split bf16 dense)"}
+    feats = synthetic.msra_batch(B, L, vocab=11329, seed=24)
+    feats['bichar_ids'] = torch.randint(0, NB, (B, L), generator=g, dtype=torch.int32)
+    bemb = torch.nn.functional.normalize(torch.randn(NB, 50, generator=g), dim=1).numpy()
+    est = engine.Estimator("transformer_tener_crf_bichar", dict(synthetic.data_params(L, LABELS), embedding=char, bichar_embedding=bemb))
+    run("config5_transformer_tener_crf_bichar", est, feats, B)
+    del est
+    torch.cuda.empty_cache()
+    return out
 
 
 class GemmTimer:
@@ -401,7 +563,6 @@ def run_ours(args):
         barrier()
         t_train = sum(s.elapsed_time(e) for s, e in evs) / 1e3
         del est_t
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- host enqueue time of one step (GPU parked behind a spin kernel): says whether the step is launch-bound
     torch.cuda.synchronize()
@@ -444,18 +605,30 @@ def run_ours(args):
         achieved = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (tcgen05.mma kind::f16, all dense layers)",
                 "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                # DRAM bytes of one in-step launch of the dominant kernel from `ncu --set full` (trip 27,
-                # profiles/r01_ncu_gemm_in_step_trip27_details.txt: gemm_bf16_tc_kernel<256>, QKV projection of a packed
-                # batch, dram read 9.42 MB, write 0): below the 22.8 MB of algorithmic operand bytes because the A operand
-                # and the output stay in the 126 MB L2 between kernels; only the weights stream from HBM.
-                "traffic": 9418752, "traffic_unit": "bytes per launch (ncu, one launch)",
+                # DRAM bytes per launch are not measurable inside an un-profiled run; the `ncu --set full` capture of an
+                # in-step launch lives in profiles/ (README there) and is quoted in DESIGN.md, not here
+                "traffic": None,
                 "peak_source": f"{how} bf16_tflops_sustained", "launches_timed": n,
                 "gemm_share_of_step": (ms / min(args.steps, 5)) / (1e3 * t_res / args.steps) if t_res > 0 else None}
+        extra = {}
+        if not args.no_kernel_rooflines and world == 1:     # single-GPU kernel figures: reported on the N=1 line
+            extra.update(crf_rooflines(hbm_peak, f"{how} hbm_gbs"))
+            extra["roofline_softlexicon"] = softlexicon_roofline(hbm_peak, f"{how} hbm_gbs", flush)
+            extra["configs"] = other_configs(min(args.steps, 20), flush)
+        clocks = sampler.stop()        # the NVML record covers every GPU-timed region above; the CPU leg below is host-only
         if world == 1 and not args.no_cpu_baseline:
-            v, ts = time_cpu_reference(16, 2)
+            from chinesener_b200 import synthetic as _syn
+            oparams = dict(_syn.data_params(SEQ_LEN, LABELS), rnn_activation=est.params['rnn_activation'])
+            hb = [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in b.items()} for b in batches[:2]]
+            v, ts, first = time_cpu_reference(est.store.state_dict(), oparams, hb, reps=2)
             cpu = {"value": v, "unit": "sentences/sec", "cores": pick_cpu_threads(), "host_cpus": os.cpu_count(), "kind": "port",
-                   "sample": f"2 timed reps x 16 sentences (L=128) of the same workload; PyTorch-CPU fp32 restatement "
-                             f"of model/bert_bilstm_crf.py (TF 1.14 not installable); rep seconds {['%.2f' % x for x in ts]}"}
+                   "sample": f"2 timed reps x one 64-sentence batch (L=128) of the timed workload, same weights as the GPU arm; "
+                             f"PyTorch-CPU fp32 restatement of model/bert_bilstm_crf.py (TF 1.14 not installable); rep seconds "
+                             f"{['%.2f' % x for x in ts]}"}
+            extra["parity"] = check_parity(est, batches[0], first)
+            extra["parity_checked"] = extra["parity"]["parity_checked"]
+        else:
+            extra["parity_checked"] = False
 
     if rank == 0:
         sent = B_PER_GPU * world * args.steps
@@ -487,6 +660,7 @@ def run_ours(args):
                                      + "global-norm clip + AdamW (bert_train_op); device-resident batches"}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        line.update(extra)
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -499,6 +673,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-kernel-rooflines", dest="no_kernel_rooflines", action="store_true",
+                    help="skip the stand-alone CRF / SoftLexicon roofline runs and the config 2/4/5 PREDICT timings")
     ap.add_argument("--no-train", dest="no_train", action="store_true", help="skip the TRAIN-step figure")
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams per GPU that consecutive PREDICT batches alternate over")
     args = ap.parse_args()

@@ -20,16 +20,49 @@ _cfg_cache = {}
 
 def load_bert_config(pretrain_dir):
     """bert_config.json of params['pretrain_dir'] over the Google chinese_L-12_H-768_A-12 defaults (read once per
-    directory: the layer functions ask for it on every call)."""
+    directory: the layer functions ask for it on every call).  An empty pretrain_dir is the explicit synthetic mode
+    (BERT-base-Chinese architecture, random initialisation: bench.py, tests); a non-empty one must hold
+    bert_config.json — the reference's modeling.BertConfig.from_json_file fails loudly there, and so does this."""
     cfg = _cfg_cache.get(pretrain_dir)
     if cfg is None:
         cfg = dict(BERT_BASE_CHINESE)
-        path = os.path.join(pretrain_dir or "", "bert_config.json")
-        if pretrain_dir and os.path.exists(path):
+        if pretrain_dir:
+            path = os.path.join(pretrain_dir, "bert_config.json")
+            if not os.path.exists(path):
+                raise FileNotFoundError(f"{path} not found: params['pretrain_dir'] must hold bert_config.json (+ bert_model.ckpt); "
+                                        "pass pretrain_dir='' for a randomly initialised BERT-base-Chinese")
             with open(path) as f:
                 cfg.update(json.load(f))
+        cfg["_pretrain_dir"] = pretrain_dir
         _cfg_cache[pretrain_dir] = cfg
     return cfg
+
+
+def load_bert_checkpoint(pretrain_dir, store=None, scope="bert"):
+    """reference tools/train_utils.py:91-102 — initialise the BertModel variables from `<pretrain_dir>/bert_model.ckpt`
+    (a TensorFlow tensor bundle, read by tf_checkpoint.py) or `<pretrain_dir>/bert_model.npz` (name -> array).  As
+    get_assignment_map_from_checkpoint does, every store variable whose name the checkpoint holds is assigned; shapes
+    must agree.  -> number of variables loaded (0 and a warning when the directory holds no checkpoint)."""
+    import warnings
+
+    import numpy as np
+
+    from . import tf_checkpoint
+    store = store or variables.default_store()
+    prefix = tf_checkpoint.find_checkpoint(pretrain_dir)
+    npz = os.path.join(pretrain_dir or "", "bert_model.npz")
+    if prefix is not None:
+        names = [n for n in store.vars if n.startswith(scope + "/")]
+        tensors = tf_checkpoint.load_tf_checkpoint(prefix, names=set(names))
+    elif pretrain_dir and os.path.exists(npz):
+        with np.load(npz) as z:
+            tensors = {k: z[k] for k in z.files if k in store.vars}
+    else:
+        warnings.warn(f"no bert_model.ckpt / bert_model.npz under {pretrain_dir!r}: the BertModel variables keep their random "
+                      "initialisation (the reference would load pretrained weights here)")
+        return 0
+    store.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in tensors.items()}, strict=True)
+    return len(tensors)
 
 
 def create_bert_variables(cfg, store, scope="bert"):
@@ -37,6 +70,7 @@ def create_bert_variables(cfg, store, scope="bert"):
     H, I = cfg["hidden_size"], cfg["intermediate_size"]
     tn = variables.truncated_normal(cfg.get("initializer_range", 0.02))
     gv = store.get_variable
+    fresh = f"{scope}/embeddings/word_embeddings" not in store.vars
     gv(f"{scope}/embeddings/word_embeddings", (cfg["vocab_size"], H), tn)
     gv(f"{scope}/embeddings/token_type_embeddings", (cfg["type_vocab_size"], H), tn)
     gv(f"{scope}/embeddings/position_embeddings", (cfg["max_position_embeddings"], H), tn)
@@ -61,6 +95,10 @@ def create_bert_variables(cfg, store, scope="bert"):
     # gradients are None there, so apply_gradients never touches it -> not trainable here
     gv(f"{scope}/pooler/dense/kernel", (H, H), tn, trainable=False)
     gv(f"{scope}/pooler/dense/bias", (H,), variables.zeros, trainable=False)
+    if fresh and cfg.get("_pretrain_dir"):
+        # every bert plugin of the reference calls load_bert_checkpoint(params['pretrain_dir']) right after building
+        # BertModel (model/bert_bilstm_crf.py:21): do it when the variables come into existence
+        load_bert_checkpoint(cfg["_pretrain_dir"], store, scope)
 
 
 def _packed(store, cfg, scope):

@@ -2,9 +2,38 @@
 """Feature-dict builder with the reference's surface (reference data/base_preprocess.py:137-227, BasicProc) minus the
 TFRecord writer: one sentence -> {'tokens','token_ids','segment_ids','mask','seq_len'[, 'labels','label_ids']} padded to
 max_seq_len, and `features_to_batch` -> the int32 tensor dict the plugins' build_graph consumes (dataset.py:21-37)."""
+import re
+
 import torch
 
 from .tokenizer import TokenizerBert, TokenizerGiga
+
+SoftWord, ExSoftWord, SoftLexicon, BiChar = 'softword', 'ex_softword', 'softlexicon', 'bichar'
+WordEnhanceMethod = [SoftWord, ExSoftWord, SoftLexicon, BiChar]
+
+
+def extract_prefix_surfix(model_name):
+    """-> (word_enhance, tokenizer_type) from the model name (reference :25-36): a name containing 'bert' uses the BERT
+    tokenizer, else giga; the word-enhance method is the first of softword / softlexicon / ex_softword / bichar the
+    alternation finds (leftmost match, alternatives tried in that order — 'ex_softword' names match 'softword' only
+    when no earlier position matches, exactly as the reference's regex does)."""
+    m = re.search('({})|({})|({})|({})'.format(SoftWord, SoftLexicon, ExSoftWord, BiChar), model_name)
+    word_enhance = m.group() if m else None
+    tokenizer_type = TokenizerBert if re.search('({})'.format(TokenizerBert), model_name) else TokenizerGiga
+    return word_enhance, tokenizer_type
+
+
+def get_instance(tokenizer_type, max_seq_len, tag2idx, tokenizer, word_enhance=None, **kwargs):
+    """reference :75-93 — the processor class for a word-enhance method.  Only the methods whose plugins are in scope
+    are built (None -> BasicProc, softlexicon -> SoftLexiconProc); the tokenizer object is passed in instead of being
+    looked up by name because vocabularies / vectors live wherever the caller keeps them."""
+    assert word_enhance in [None] + WordEnhanceMethod, 'word_enhance must in {}'.format(','.join(WordEnhanceMethod))
+    if word_enhance is None:
+        return BasicProc(tokenizer_type, max_seq_len, tag2idx, tokenizer)
+    if word_enhance == SoftLexicon:
+        from .word_enhance import SoftLexiconProc
+        return SoftLexiconProc(tokenizer_type, max_seq_len, tag2idx, tokenizer, **kwargs)
+    raise NotImplementedError('word_enhance={} plugins are out of scope (SURVEY 8)'.format(word_enhance))
 
 
 class BasicProc(object):
@@ -55,6 +84,15 @@ def features_to_batch(features, pin_memory=False):
     out = {k: torch.tensor([f[k] for f in features], dtype=torch.int32) for k in ('token_ids', 'mask', 'segment_ids')}
     out['seq_len'] = torch.tensor([f['seq_len'] for f in features], dtype=torch.int32)
     out['label_ids'] = torch.tensor([f.get('label_ids', [0] * L) for f in features], dtype=torch.int32)
+    # optional per-plugin features (dataset.py:29-36, MultiDataset.add_discriminator :88-90)
+    for k in ('softlexicon_ids', 'bichar_ids', 'softword_ids'):
+        if k in features[0]:
+            out[k] = torch.tensor([f[k] for f in features], dtype=torch.int32)
+    for k in ('softlexicon_weights', 'ex_softword_ids'):
+        if k in features[0]:
+            out[k] = torch.tensor([f[k] for f in features], dtype=torch.float32)
+    if 'task_ids' in features[0]:      # one task id per sentence (serving receiver: FixedLenFeature([], int64), infer_utils.py:60-63)
+        out['task_ids'] = torch.tensor([int(f['task_ids']) for f in features], dtype=torch.int32)
     if pin_memory:
         out = {k: v.pin_memory() for k, v in out.items()}
     out['tokens'] = [f['tokens'] for f in features]

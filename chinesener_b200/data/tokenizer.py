@@ -132,6 +132,32 @@ def get_bert_tokenizer(model_dir='./pretrain_model/ch_google/'):
     return FullTokenizer(os.path.join(model_dir, 'vocab.txt'), do_lower_case=True)
 
 
+class TextVectors(object):
+    """The three attributes of gensim's KeyedVectors the reference reads (`index2word`, `vectors`, `vector_size`),
+    loaded from a GloVe-style text file — one `word v_1 ... v_d` line per entry, no header — which is what
+    pretrain_model/glove_2_wv.py:11-23 converts and loads (pretrain_model/giga/__init__.py).  A repeated word keeps its
+    first vector, as load_word2vec_format does."""
+
+    def __init__(self, path):
+        import numpy as np
+        words, rows, seen = [], [], set()
+        with open(path, encoding='utf-8') as f:
+            for line in f:
+                parts = line.rstrip().split(' ')
+                if len(parts) < 3 or parts[0] in seen:
+                    continue
+                seen.add(parts[0])
+                words.append(parts[0])
+                rows.append(np.asarray(parts[1:], dtype=np.float32))
+        self.index2word, self.vectors = words, np.stack(rows)
+        self.vector_size = self.vectors.shape[1]
+
+
+def get_giga_tokenizer(vec_file='./pretrain_model/giga/gigaword_chn.all.a2b.uni.ite50.vec'):
+    """reference data/tokenizer.py:24-33 — the character tokenizer of every non-BERT model."""
+    return TokenizerAdapter(TextVectors(vec_file))
+
+
 class TokenizerAdapter(object):
     """reference data/tokenizer.py:47-100 — character tokenizer over a word2vec-style model (`index2word`, optional
     `vectors`); here `model` may also be a plain list of vocabulary entries."""
@@ -146,6 +172,17 @@ class TokenizerAdapter(object):
         n_vocab = len(vocab2idx)
         vocab2idx.update({'[PAD]': n_vocab, '[UNK]': n_vocab + 1})
         return vocab2idx
+
+    def embedding(self, seed=None):
+        """reference :68-74 (a property there): pretrained vectors + two N(0,1) rows for [PAD] / [UNK], every row scaled
+        to unit L2 norm (tools/utils.py:10-14).  The reference draws the add-on rows from numpy's unseeded global
+        stream; `seed` makes the draw repeatable."""
+        import numpy as np
+        rng = np.random.default_rng(seed) if seed is not None else np.random
+        emb = np.vstack((np.asarray(self.model.vectors), rng.normal(0, 1, size=(2, self.model.vector_size)))).astype(np.float32)
+        norm = np.linalg.norm(emb, axis=1, keepdims=True)
+        norm[norm == 0] = np.finfo(np.float32).eps
+        return emb / norm
 
     @staticmethod
     def full2half(text):

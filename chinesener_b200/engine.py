@@ -125,6 +125,18 @@ class Estimator:
             for st in side:
                 torch.cuda.current_stream().wait_stream(st)
 
+    def predict_sentences(self, batches, depth=2, streams=1):
+        """tf.estimator.Estimator.predict(input_fn) as the reference consumes it (main.py:52-55, evaluation.py:16-24):
+        one dict PER SENTENCE — {'pred_ids': int32 [L], 'label_ids': int32 [L], 'tokens': [L]} as numpy arrays / lists —
+        the element type of `<model>_predict.pkl` and the input of evaluation.SingleEval.  (predict / predict_iter yield
+        one dict per batch.)"""
+        for out in self.predict_iter(batches, depth=depth, streams=streams):
+            pred = out['pred_ids'].numpy()
+            lab = out['label_ids'].numpy() if torch.is_tensor(out['label_ids']) else out['label_ids']
+            tok = out['tokens']
+            for b in range(pred.shape[0]):
+                yield {'pred_ids': pred[b], 'label_ids': None if lab is None else lab[b], 'tokens': None if tok is None else tok[b]}
+
     def train_step(self, features):
         """TRAIN mode of model_fn (reference tools/train_utils.py:151-168): forward with the tape,
         backward, then the train op the reference picks by model name (:156-164).  -> loss (float)."""

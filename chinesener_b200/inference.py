@@ -5,8 +5,8 @@ import re
 
 import numpy as np
 
-from .data.base_preprocess import BasicProc, features_to_batch
-from .data.tokenizer import TokenizerBert, TokenizerGiga
+from .data.base_preprocess import extract_prefix_surfix, features_to_batch, get_instance
+from .data.tokenizer import TokenizerBert
 from .tools.infer_utils import extract_entity, fix_tokens
 
 MAX_SEQ_LEN = 150
@@ -14,11 +14,15 @@ TAG2IDX = {'[PAD]': 0, 'O': 1, 'B-ORG': 2, 'I-ORG': 3, 'B-PER': 4, 'I-PER': 5, '
 
 
 class InferHelper(object):
-    def __init__(self, max_seq_len, tag2idx, model_name, tokenizer, estimator=None):
+    """`tokenizer` (and, for the word-enhance models, the keyword arguments their processor needs — the SoftLexicon word
+    vocabulary) are passed in where the reference looks them up by module name; the processor class is picked from the
+    model name exactly as the reference does (extract_prefix_surfix + get_instance, inference.py:36-39)."""
+
+    def __init__(self, max_seq_len, tag2idx, model_name, tokenizer, estimator=None, **proc_kwargs):
         self.model_name = model_name
-        self.tokenizer_type = TokenizerBert if re.search('bert', model_name) else TokenizerGiga
-        self.mtl = 1 if re.search('(mtl)|(adv)', model_name) else 0
-        self.proc = BasicProc(self.tokenizer_type, max_seq_len, tag2idx, tokenizer)
+        self.word_enhance, self.tokenizer_type = extract_prefix_surfix(model_name)
+        self.mtl = 1 if re.search('(mtl)|(adv)', model_name) else 0            # whether is multitask
+        self.proc = get_instance(self.tokenizer_type, max_seq_len, tag2idx, tokenizer, word_enhance=self.word_enhance, **proc_kwargs)
         self.max_seq_len, self.tag2idx = max_seq_len, tag2idx
         self.idx2tag = dict((v, k) for k, v in tag2idx.items())
         self.estimator = estimator

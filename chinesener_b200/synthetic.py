@@ -82,6 +82,32 @@ def softlexicon_features(B, L, n_word, seed=1234, realistic=True, G=4, S=10, len
     return torch.from_numpy(ids.reshape(B, L * G * S)), torch.from_numpy(w.reshape(B, L * G * S))
 
 
+def softlexicon_features_device(n_tok, n_word, realistic=True, seed=1234, G=4, S=10, device="cuda"):
+    """Vectorised variant for large token counts: ids int32 / weights f32 [n_tok, G*S] on `device`.
+    Layout as the reference's postproc_soft_lexicon (data/word_enhance.py:163-205): per group the matched words first, then
+    <PAD> (= n_word-1, frequency 0 -> weight 0); an empty group holds <None> (= n_word-2, frequency 1) in slot 0; weights
+    = frequency / sum of the token's 40 frequencies.  realistic: 0-3 words per group (p = .35/.4/.17/.08, the slot
+    statistics of the serving warm-up record); dense: all 10 slots of every group are words."""
+    g = torch.Generator(device=device).manual_seed(seed + 7)
+    pad_id, none_id = n_word - 1, n_word - 2
+    if realistic:
+        p = torch.tensor([0.35, 0.4, 0.17, 0.08], device=device)
+        cnt = torch.multinomial(p, n_tok * G, replacement=True, generator=g).view(n_tok, G)
+    else:
+        cnt = torch.full((n_tok, G), S, device=device, dtype=torch.long)
+    slot = torch.arange(S, device=device).view(1, 1, S)
+    is_word = slot < cnt.unsqueeze(-1)
+    is_none = (cnt.unsqueeze(-1) == 0) & (slot == 0)
+    words = torch.randint(0, n_word - 2, (n_tok, G, S), device=device, generator=g, dtype=torch.int32)
+    freq = torch.randint(1, 1000, (n_tok, G, S), device=device, generator=g).to(torch.float32)
+    ids = torch.where(is_word, words, torch.full_like(words, pad_id))
+    ids = torch.where(is_none, torch.full_like(words, none_id), ids)
+    w = torch.where(is_word, freq, torch.zeros_like(freq))
+    w = torch.where(is_none, torch.ones_like(freq), w)
+    w = w / w.sum(dim=(1, 2), keepdim=True)
+    return ids.view(n_tok, G * S).contiguous(), w.view(n_tok, G * S).contiguous()
+
+
 def data_params(L, label_size=10, n_sample=45000, batch_size=32, epoch_size=50):
     step_per_epoch = n_sample // batch_size
     return {'label_size': label_size, 'max_seq_len': L, 'idx2tag': dict(MSRA_IDX2TAG), 'n_sample': n_sample,

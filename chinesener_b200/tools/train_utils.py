@@ -50,6 +50,24 @@ class FlatState:
             self.group_ranges[g] = (min(s, off), off + pad(k))
             off += pad(k)
         store.touch()
+        # optimizer slots restored from a checkpoint before this buffer existed, or carried over from the buffer this one
+        # replaces (the trainable set changed): Adam moments survive by variable name
+        slots = getattr(store, "_slot_init", None)
+        if slots:
+            self.load_slots(slots)
+            store._slot_init = None
+
+    def slot_dict(self):
+        """name -> (m, v) views, for checkpoints (TF checkpoints carry `<var>/adam_m`, `<var>/adam_v`)."""
+        return {n: (self.m[s:e].view(self.store.vars[n].shape), self.v[s:e].view(self.store.vars[n].shape))
+                for n, (s, e) in self.slices.items()}
+
+    def load_slots(self, slots):
+        for n, (m, v) in slots.items():
+            if n in self.slices:
+                s, e = self.slices[n]
+                self.m[s:e].copy_(torch.as_tensor(m, dtype=torch.float32).reshape(-1))
+                self.v[s:e].copy_(torch.as_tensor(v, dtype=torch.float32).reshape(-1))
 
     def zero_grads(self):
         self.grads.zero_()
@@ -58,6 +76,8 @@ class FlatState:
 def _flat(store, group_of=None):
     fs = getattr(store, "_flat_state", None)
     if fs is None or set(fs.names) != set(store.trainable_names()):
+        if fs is not None:
+            store._slot_init = {n: (m.clone(), v.clone()) for n, (m, v) in fs.slot_dict().items()}
         fs = FlatState(store, group_of)
         store._flat_state = fs
     return fs
@@ -138,6 +158,8 @@ def bert_train_op(loss, init_lr, num_train_steps, warmup_ratio, diff_lr_times, v
 def noam_scheme(init_lr, global_step, warmup_steps=4000.):
     """reference tools/transformer/modules.py:209-217: lr rises linearly to init_lr over warmup_steps, then ~ step^-0.5."""
     step = float(global_step + 1)
+    if warmup_steps <= 0:      # runs shorter than 1/warmup_ratio steps: the factor warmup_steps ** 0.5 is 0 (the reference's
+        return 0.0             # Python-side 0 ** -1.5 raises while building the graph; lr = 0 is the limit it stands for)
     return init_lr * warmup_steps ** 0.5 * min(step * warmup_steps ** -1.5, step ** -0.5)
 
 
@@ -160,3 +182,9 @@ def transformer_train_op(loss, init_lr, num_train_steps, warmup_ratio, store=Non
 
 def _decays(name):
     return not any(tok in name for tok in ("LayerNorm", "layer_norm", "bias"))
+
+
+def load_bert_checkpoint(pretrain_dir, store=None):
+    """reference tools/train_utils.py:91-102 (kept at the reference's location; the reader lives in bert.py)."""
+    from ..bert import load_bert_checkpoint as _load
+    return _load(pretrain_dir, store)
