@@ -489,43 +489,77 @@ def run_ours(args):
     launches = _lib.LAUNCHES - l0
     t_res = sum(s.elapsed_time(e) for s, e in evs) / 1e3
 
-    # ---- same K steps with consecutive batches on two CUDA streams (independent sentences): the SMs
-    #      one batch's kernel leaves idle in its partial last wave run the other batch's kernels.  One event pair
-    #      around the K steps; no flush kernel (the 170 MB of bf16 weights streamed per step exceed the 126 MB L2).
+    # ---- the same K steps as a throughput pipeline (sentences are independent):
+    #      * NS CUDA streams: consecutive calls alternate over streams, so the SMs one call's kernel leaves idle in its
+    #        partial last wave run another call's kernels;
+    #      * G batches stacked per call: the packed token count of one 64-sentence MSRA batch (~3.2 k rows) is 0.5 / 1.5 /
+    #        2.0 waves of 128x256 tiles on 148 SMs, two batches are 1.0 / 3.0 / 4.0.
+    #      One event pair around the K steps; no flush kernel (the 170 MB of bf16 weights streamed per call exceed the
+    #      126 MB L2).  Every combination processes the same K batches; the best one is the line's `value`.
     from chinesener_b200 import ops as _ops
-    NS = max(2, args.streams)
-    side = [torch.cuda.Stream() for _ in range(NS)]
-    _ops.DEFAULT_TILE = _ops.TILE_AUTO_THROUGHPUT   # several streams in flight: fastest tile instead of wave fitting
-    for i in range(2 * NS):
-        with torch.cuda.stream(side[i % NS]):
-            step_resident(i)
-    barrier()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for st in side:
-        st.wait_event(s)
-    for i in range(args.steps):
-        with torch.cuda.stream(side[i % NS]):
-            step_resident(i)
-    for st in side:
-        torch.cuda.current_stream().wait_stream(st)
-    e.record()
-    barrier()
-    t_res2 = s.elapsed_time(e) / 1e3
-    _ops.DEFAULT_TILE = 0
+    stacked = {1: dev_batches}
+
+    def dev_group(G):
+        if G not in stacked:
+            stacked[G] = [est.stack_to_device([batches[(j * G + q) % nb] for q in range(G)]) for j in range(max(1, nb // G))]
+            torch.cuda.synchronize()
+        return stacked[G]
+
+    def time_pipeline(NS, G):
+        groups = dev_group(G)
+        calls = [(j, min(G, args.steps - j * G)) for j in range((args.steps + G - 1) // G)]     # (call index, batches in it)
+        side = [torch.cuda.Stream() for _ in range(NS)]
+        _ops.DEFAULT_TILE = _ops.TILE_AUTO_THROUGHPUT   # partial waves are filled by other streams / stacked rows: fastest tile
+        try:
+            def run(j, nbat):
+                feats = groups[j % len(groups)] if nbat == G else dev_batches[j % nb]
+                with torch.cuda.stream(side[j % NS]):
+                    est.predict_device(feats)
+            for j in range(2 * NS):
+                run(j, G)
+            barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for st in side:
+                st.wait_event(s)
+            for j, nbat in calls:
+                run(j, nbat)
+            for st in side:
+                torch.cuda.current_stream().wait_stream(st)
+            e.record()
+            barrier()
+        finally:
+            _ops.DEFAULT_TILE = 0
+        return s.elapsed_time(e) / 1e3
+
+    combos = [(max(2, args.streams), 1), (max(1, args.group_streams), max(1, args.group))]
+    if args.sweep:
+        combos = sorted(set(combos + [(1, 2), (2, 2), (3, 2), (1, 4), (2, 4), (2, 1), (3, 1)]))
+    pipe = {}
+    for NS_, G_ in combos:
+        t = time_pipeline(NS_, G_)
+        if dist is not None:                        # max over ranks decides, every rank must pick the same combination
+            tt = torch.tensor([t], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_all = float(tt[0])
+        else:
+            t_all = t
+        pipe[(NS_, G_)] = (t, t_all)
+    (NS, G) = min(pipe, key=lambda k: pipe[k][1])
+    t_res2 = pipe[(NS, G)][0]
 
     # ---- end-to-end timing through the public PREDICT API, Estimator.predict_iter (the generator shape of
     #      tf.estimator.Estimator.predict): every step copies its pinned host batch H2D and its pred_ids D2H inside
-    #      the timed region; the next batch is enqueued while the previous result is awaited.  One event pair around
+    #      the timed region; the next call is enqueued while the previous result is awaited.  One event pair around
     #      the K steps (per-step brackets do not exist in a pipelined loop); no flush kernel here: the 170 MB of
-    #      bf16 weights streamed every step already exceed the 126 MB L2.
-    for _ in est.predict_iter((batches[i % nb] for i in range(2 * NS)), depth=NS + 1, streams=NS):
+    #      bf16 weights streamed every call already exceed the 126 MB L2.  Same (streams, batches per call) as `value`.
+    for _ in est.predict_iter((batches[i % nb] for i in range(2 * NS * G)), depth=NS + 1, streams=NS, group=G):
         pass
     barrier()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     n_out = 0
-    for out in est.predict_iter((batches[i % nb] for i in range(args.steps)), depth=NS + 1, streams=NS):
+    for out in est.predict_iter((batches[i % nb] for i in range(args.steps)), depth=NS + 1, streams=NS, group=G):
         n_out += out['pred_ids'].shape[0]
     e.record()
     barrier()
@@ -593,12 +627,15 @@ def run_ours(args):
         timer = GemmTimer()
         _lib._HOOK = timer
         _bert.PER_KERNEL = True          # same kernels, one C-ABI call each, so every GEMM launch gets its own events
-        for i in range(min(args.steps, 5)):
-            # per-kernel calls come from Python (~20 us of host time each): hold the GPU behind a ~10 ms spin
-            # kernel so the whole step is enqueued first and the event pairs bracket execution, not launch latency
-            torch.cuda._sleep(20_000_000)
-            step_resident(i)
+        _ops.DEFAULT_TILE = _ops.TILE_AUTO_THROUGHPUT if t_res2 <= t_res else 0      # the tile policy of the selected pipeline
+        n_roof = min(args.steps, 5)
+        for i in range(n_roof):
+            # per-kernel calls come from Python (~20 us of host time each): hold the GPU behind a spin kernel so the
+            # whole call is enqueued first and the event pairs bracket execution, not launch latency
+            torch.cuda._sleep(20_000_000 * (G if t_res2 <= t_res else 1))
+            est.predict_device(dev_group(G)[i % len(dev_group(G))] if t_res2 <= t_res else dev_batches[i % nb])
             torch.cuda.synchronize()
+        _ops.DEFAULT_TILE = 0
         _bert.PER_KERNEL = False
         _lib._HOOK = None
         ms, fl, n = timer.summary()
@@ -609,7 +646,9 @@ def run_ours(args):
                 # in-step launch lives in profiles/ (README there) and is quoted in DESIGN.md, not here
                 "traffic": None,
                 "peak_source": f"{how} bf16_tflops_sustained", "launches_timed": n,
-                "gemm_share_of_step": (ms / min(args.steps, 5)) / (1e3 * t_res / args.steps) if t_res > 0 else None}
+                "batches_per_timed_call": G if t_res2 <= t_res else 1,
+                "gemm_share_of_step": ((ms / n_roof / (G if t_res2 <= t_res else 1)) / (1e3 * t_res / args.steps) if t_res > 0 else None),
+                "gemm_share_note": "GEMM ms per 64-sentence batch (from the timed calls) / single-stream single-batch ms per step"}
         extra = {}
         if not args.no_kernel_rooflines and world == 1:     # single-GPU kernel figures: reported on the N=1 line
             extra.update(crf_rooflines(hbm_peak, f"{how} hbm_gbs"))
@@ -644,11 +683,12 @@ def run_ours(args):
                        "l2": "working set/step > 126 MB L2 (170 MB bf16 weights + activations); L2 also flushed by an "
                              "untimed 256 MB write between timed steps",
                        "lengths": "MSRA-shaped (mean fill ~0.39)",
-                       "streams": (f"{NS} CUDA streams per GPU, consecutive batches alternate" if t_res2 <= t_res else "1"),
+                       "streams": (f"{NS} CUDA stream(s) per GPU, consecutive calls alternate; {G} batch(es) of 64 sentences stacked per "
+                                   f"call" if t_res2 <= t_res else "1 stream, 1 batch per call"),
                        "single_stream_ms_per_step": 1e3 * t_res / args.steps,
-                       "two_stream_ms_per_step": 1e3 * t_res2 / args.steps},
+                       "pipeline_ms_per_step": {f"streams={k[0]},batches_per_call={k[1]}": 1e3 * v[1] / args.steps for k, v in pipe.items()}},
             "e2e": {"value": sent / t_e2e, "unit": "sentences/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * t_e2e / args.steps, "api": f"Estimator.predict_iter(depth={NS + 1}, streams={NS})",
+                    "ms_per_step": 1e3 * t_e2e / args.steps, "api": f"Estimator.predict_iter(depth={NS + 1}, streams={NS}, group={G})",
                     "blocking_predict_ms_per_step": 1e3 * t_e2e_blocking / args.steps},
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "clocks": clocks, "roofline": roof,
             "per_rank": per_rank, "cpu_affinity": numa,
@@ -676,7 +716,10 @@ def main():
     ap.add_argument("--no-kernel-rooflines", dest="no_kernel_rooflines", action="store_true",
                     help="skip the stand-alone CRF / SoftLexicon roofline runs and the config 2/4/5 PREDICT timings")
     ap.add_argument("--no-train", dest="no_train", action="store_true", help="skip the TRAIN-step figure")
-    ap.add_argument("--streams", type=int, default=4, help="CUDA streams per GPU that consecutive PREDICT batches alternate over")
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams per GPU that consecutive single-batch PREDICT calls alternate over")
+    ap.add_argument("--group", type=int, default=4, help="batches stacked per PREDICT call in the second pipeline configuration")
+    ap.add_argument("--group-streams", dest="group_streams", type=int, default=2, help="CUDA streams of the stacked configuration")
+    ap.add_argument("--sweep", action="store_true", help="time more (streams, batches per call) combinations")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,12 +1,15 @@
 # -*-coding:utf-8 -*-
-"""SoftLexicon host builder — the step just before the gather-and-pool kernel
-(ner_softlexicon_pool_fwd).  Restates reference data/word_enhance.py:36-70 (VocabModel add-on tokens and frequencies),
-:302-337 (build_soft_lexicon: every substring of <= 10 characters found in the word vocabulary lands in the B/M/E/S
-sets of the characters it covers), :163-205 (postproc_soft_lexicon: pad to / keep the 10 most frequent per set, weights
-= frequency normalised over all four sets of the token) and data/base_preprocess.py:376-438 (SoftLexiconProc: CLS/SEP/PAD
-rows are all-zero ids and weights, everything flattened to [max_seq_len * 4 * 10])."""
-from collections import OrderedDict
-from itertools import chain
+"""SoftLexicon host side — the step just before the gather-and-pool kernel (ner_softlexicon_pool_fwd).
+
+The matching itself (reference data/word_enhance.py:302-337 build_soft_lexicon, :89-119 align_with_token, :163-205
+postproc_soft_lexicon, data/base_preprocess.py:397-412 format_soft_seq) runs in C++ behind the C-ABI
+(`ner_lexicon_create / ner_lexicon_build`, chinesener_b200/csrc/lexicon_host.cu): a code-point trie over the word
+vocabulary, whole lists of sentences per call on a pool of host threads, output already in the kernel's
+[n, max_seq_len * 40] id / weight layout.  This module keeps the reference's Python surface around it: `WordVocab` (the word
+side of VocabModel, :36-70) and `SoftLexiconProc` (data/base_preprocess.py:376-438).  The Python restatement of the reference
+loop lives in oracle/lexicon.py and is only the tests' checker.
+"""
+import numpy as np
 
 from .base_preprocess import BasicProc
 from .tokenizer import TokenizerBert
@@ -22,114 +25,98 @@ class WordVocab(object):
     none_token, pad_token, eos_token = '<None>', '<PAD>', '<eos>'
 
     def __init__(self, index2word, counts):
-        self.vocab2idx = dict((w, i) for i, w in enumerate(index2word))
-        self.vocab_freq = dict((self.vocab2idx[w], counts[w]) for w in index2word)
+        self.index2word = list(index2word)
+        self.vocab2idx = dict((w, i) for i, w in enumerate(self.index2word))
+        self.vocab_freq = dict((self.vocab2idx[w], counts[w]) for w in self.index2word)
         self.n_word = len(self.vocab_freq)
         self.vocab2idx.update({self.none_token: self.n_word, self.pad_token: self.n_word + 1, self.eos_token: self.n_word + 2})
         self.vocab_freq.update({self.vocab2idx[self.none_token]: 1, self.vocab2idx[self.pad_token]: 0})
 
 
-def build_soft_lexicon(sentence, vocab):
-    """-> per character {'B': [ids], 'M': [...], 'E': [...], 'S': [...]}; an empty set holds the <None> token."""
-    sentence = sentence.replace(' ', '')
-    soft_lexicon = [OrderedDict((k, set()) for k in SoftKeys) for _ in range(len(sentence))]
-    for i in range(len(sentence)):
-        for j in range(i, min(i + MaxWordLen, len(sentence))):
-            word = sentence[i:(j + 1)]
-            if word in vocab.vocab2idx:
-                if j - i == 0:
-                    soft_lexicon[i]['S'].add(word)
-                else:
-                    soft_lexicon[i]['B'].add(word)
-                    soft_lexicon[j]['E'].add(word)
-                    for k in range(i + 1, j):
-                        soft_lexicon[k]['M'].add(word)
-        for key, val in soft_lexicon[i].items():
-            if not val:
-                soft_lexicon[i][key].add(vocab.none_token)
-    return [OrderedDict((k, [vocab.vocab2idx[w] for w in v]) for k, v in lex.items()) for lex in soft_lexicon]
+def _utf32(strings):
+    """list of str -> (uint32 code points back to back, int64 offsets [n + 1])."""
+    offs = np.zeros(len(strings) + 1, np.int64)
+    np.cumsum([len(s) for s in strings], out=offs[1:])
+    cps = np.frombuffer(''.join(strings).encode('utf-32-le'), dtype=np.uint32)
+    assert cps.size == offs[-1]
+    return np.ascontiguousarray(cps), offs
 
 
-def combine_soft_lexicon(idx_list):
-    """Union, set by set, of the lexicons of the characters one word piece swallowed (reference data/word_enhance.py:
-    150-160).  The reference walks the keys of Soft2Idx, which include 'None' — a key build_soft_lexicon never creates, so
-    its loop raises KeyError — and would emit the sets in S/M/B/E order where unmerged rows are B/M/E/S; this restatement
-    keeps the B/M/E/S row layout the pooling kernel is fed everywhere else."""
-    merged = OrderedDict((k, []) for k in SoftKeys)
-    for lexicon in idx_list:
-        for key in SoftKeys:
-            for i in lexicon[key]:
-                if i not in merged[key]:
-                    merged[key].append(i)
-    return merged
+def token_char_lens(tokens):
+    """characters each WordPiece token covers (reference align_with_token :94): '##' stripped, [UNK] = 1, specials skipped."""
+    return [len(t.replace('##', '')) if t != '[UNK]' else 1 for t in tokens if t not in ('[CLS]', '[SEP]', '[PAD]')]
 
 
-def align_with_token(idx_list, tokens, combine_func=combine_soft_lexicon):
-    """Reference data/word_enhance.py:89-119 — the BERT tokenizer can put several characters into one word piece
-    ('1994' -> '19', '##94'); per-character features are merged so there is one row per token.  combine_func: the reference
-    picks it by word-enhance method (soft lexicon: union; softword: max; bichar: min)."""
-    token_len = [len(t.replace('##', '')) if t != '[UNK]' else 1 for t in tokens if t not in ('[CLS]', '[SEP]', '[PAD]')]
-    if len(idx_list) == len(token_len):
-        return idx_list                       # no mismatch between the word pieces and the characters
-    pos, output_list = 0, []
-    for tl in token_len:
-        output_list.append(idx_list[pos] if tl == 1 else combine_func(idx_list[pos:pos + tl]))
-        pos += tl
-    assert len(output_list) == len(token_len)
-    return output_list
+class NativeLexicon(object):
+    """The vocabulary as a C++ trie.  `vocabfreq` (id -> frequency, default the vocabulary's own counts) is what
+    postproc_soft_lexicon weighs by; ids it does not hold weigh 1 (`vocabfreq.get(i, 1)`, reference :182)."""
 
+    def __init__(self, vocab, vocabfreq=None):
+        from .. import _lib
+        self._lib = _lib.lib()
+        self.vocab, self.n_word = vocab, vocab.n_word
+        words = getattr(vocab, 'index2word', None)
+        if words is None:
+            words = [w for w, i in sorted(vocab.vocab2idx.items(), key=lambda kv: kv[1]) if i < vocab.n_word]
+        freq_of = vocab.vocab_freq if vocabfreq is None else vocabfreq
+        freq = np.asarray([freq_of.get(i, 1) for i in range(self.n_word + 2)], dtype=np.float64)
+        cps, offs = _utf32(words)
+        self._h = self._lib.ner_lexicon_create(cps.ctypes.data, offs.ctypes.data, freq.ctypes.data, self.n_word)
+        if not self._h:
+            raise _lib.NerB200Error('ner_lexicon_create failed (bad vocabulary input)')
 
-def postproc_soft_lexicon(output_list, vocab, vocabfreq=None):
-    """-> (ids, weights), each seq_len x (4 * MaxLexiconLen)."""
-    vocabfreq = vocab.vocab_freq if vocabfreq is None else vocabfreq
-    pad_id = vocab.vocab2idx[vocab.pad_token]
+    def __del__(self):
+        h, self._h = getattr(self, '_h', None), None
+        if h:
+            self._lib.ner_lexicon_destroy(h)
 
-    def helper(ids):
-        n = len(ids)
-        if n <= MaxLexiconLen:
-            ids = list(ids) + [pad_id] * (MaxLexiconLen - n)
-            return ids, [vocabfreq.get(i, 1) for i in ids]
-        tmp = sorted([(i, vocabfreq.get(i, 1)) for i in ids], key=lambda x: x[1], reverse=True)[:MaxLexiconLen]
-        return [t[0] for t in tmp], [t[1] for t in tmp]
+    def num_nodes(self):
+        return int(self._lib.ner_lexicon_num_nodes(self._h))
 
-    seq_ids, seq_weights = [], []
-    for lexicon in output_list:
-        ids, weights, total_weight = [], [], 0
-        for key in SoftKeys:
-            i, w = helper(lexicon[key])
-            ids += i
-            weights += w
-            total_weight += sum(w)
-        seq_ids.append(ids)
-        seq_weights.append([w / total_weight for w in weights])
-    return seq_ids, seq_weights
+    def build(self, sentences, max_seq_len, bert=False, tokens=None, n_threads=0):
+        """sentences: list of raw strings; tokens (bert only): per sentence the tokenizer's tokens, so that rows follow the
+        word pieces.  -> (ids int32 [n, max_seq_len * 40], weights float32 [n, max_seq_len * 40])."""
+        from .. import _lib
+        n = len(sentences)
+        cps, offs = _utf32([s.replace(' ', '') for s in sentences])
+        tl = toff = None
+        if bert and tokens is not None:
+            lens = [token_char_lens(t) for t in tokens]
+            toff = np.zeros(n + 1, np.int64)
+            np.cumsum([len(x) for x in lens], out=toff[1:])
+            tl = np.asarray([v for x in lens for v in x], dtype=np.int32)
+        ids = np.empty((n, max_seq_len * len(SoftKeys) * MaxLexiconLen), np.int32)
+        wts = np.empty(ids.shape, np.float32)
+        if tl is not None and tl.size == 0:
+            tl = np.zeros(1, np.int32)          # keep the pointer non-NULL: "token lengths given, all sentences empty"
+        _lib.check(self._lib.ner_lexicon_build(
+            self._h, cps.ctypes.data if cps.size else None, offs.ctypes.data, n, None if tl is None else tl.ctypes.data,
+            None if toff is None else toff.ctypes.data, max_seq_len, 1 if bert else 0, ids.ctypes.data, wts.ctypes.data, n_threads))
+        _lib.LAUNCHES -= 1          # host call, not a kernel launch
+        return ids, wts
 
 
 class SoftLexiconProc(BasicProc):
-    """BasicProc + softlexicon_ids / softlexicon_weights (one lexicon row per token; word pieces merge their characters)."""
+    """BasicProc + softlexicon_ids / softlexicon_weights (one lexicon row per token; word pieces merge their characters).
+    `build_seq_features(sentences)` featurises a list in one native call; `build_seq_feature` is the reference's
+    one-sentence surface over it."""
 
     def __init__(self, tokenizer_type, max_seq_len, tag2idx, tokenizer, vocab, vocabfreq=None):
         super(SoftLexiconProc, self).__init__(tokenizer_type, max_seq_len, tag2idx, tokenizer)
         self.vocab, self.vocabfreq = vocab, vocabfreq
+        self.word_enhance = 'softlexicon'
+        self.lexicon = NativeLexicon(vocab, vocabfreq)
 
-    def format_soft_seq(self, seq, type='ids'):
-        default_encoding = [0.0 if type == 'weight' else 0] * (len(SoftKeys) * MaxLexiconLen)
-        if self.tokenizer_type == TokenizerBert:
-            seq = [default_encoding] + seq[:(self.max_seq_len - 2)] + [default_encoding]
-        else:
-            seq = seq[:self.max_seq_len]
-        seq = seq + [default_encoding] * (self.max_seq_len - len(seq))
-        return list(chain(*seq))
+    def build_seq_features(self, sentences, n_threads=0):
+        feats = [super(SoftLexiconProc, self).build_seq_feature(s) for s in sentences]
+        bert = self.tokenizer_type == TokenizerBert
+        ids, wts = self.lexicon.build(sentences, self.max_seq_len, bert, [f['tokens'] for f in feats] if bert else None, n_threads)
+        for f, i, w in zip(feats, ids, wts):
+            f['softlexicon_ids'], f['softlexicon_weights'] = i.tolist(), w.tolist()
+        return feats
 
     def build_seq_feature(self, sentence):
-        f_seq = super(SoftLexiconProc, self).build_seq_feature(sentence)
-        soft_lexicon = build_soft_lexicon(sentence, self.vocab)
-        if self.tokenizer_type == TokenizerBert:
-            soft_lexicon = align_with_token(soft_lexicon, f_seq['tokens'])
-        ids, weights = postproc_soft_lexicon(soft_lexicon, self.vocab, self.vocabfreq)
-        f_seq['softlexicon_ids'] = self.format_soft_seq(ids)
-        f_seq['softlexicon_weights'] = self.format_soft_seq(weights, type='weight')
-        return f_seq
+        return self.build_seq_features([sentence], n_threads=1)[0]
 
     def build_data_params(self, n_sample):
         params = super(SoftLexiconProc, self).build_data_params(n_sample)

@@ -75,15 +75,45 @@ class Estimator:
         pred_ids = self.predict_device(dev)
         return {'pred_ids': pred_ids.cpu(), 'label_ids': features.get('label_ids'), 'tokens': features.get('tokens')}
 
-    def predict_iter(self, batches, depth=2, streams=1):
+    def stack_to_device(self, feature_list):
+        """Several host batches -> ONE device batch (rows concatenated in order): every device feature is allocated once
+        at the summed batch size and each host part is copied straight into its row slice (pinned -> non-blocking)."""
+        if len(feature_list) == 1:
+            return self.to_device(feature_list[0])
+        out, total = {}, 0
+        first = feature_list[0]
+        for k, v in first.items():
+            if k in _DEVICE_KEYS and torch.is_tensor(v):
+                rows = sum(f[k].shape[0] for f in feature_list)
+                dst = torch.empty((rows,) + tuple(v.shape[1:]), dtype=v.dtype, device=self.device)
+                r = 0
+                for f in feature_list:
+                    n = f[k].shape[0]
+                    dst[r:r + n].copy_(f[k], non_blocking=True)
+                    r += n
+                out[k] = dst
+        for f in feature_list:
+            m = f.get('mask')
+            if not (torch.is_tensor(m) and not m.is_cuda):
+                total = None
+                break
+            total += int(m.sum())
+        if total is not None and 'mask' in out:
+            out['mask'].total_tokens = total
+        return out
+
+    def predict_iter(self, batches, depth=2, streams=1, group=1):
         """Generator form of PREDICT — the shape of tf.estimator.Estimator.predict(input_fn), which the
         reference drives at main.py:52-55: yields one result dict per host batch, in order.  The device work
-        of up to `depth` batches is in flight before the oldest result is awaited, so the host->device copy
+        of up to `depth` calls is in flight before the oldest result is awaited, so the host->device copy
         of batch i+1 and the enqueue of its kernels overlap batch i on the GPU; results come back through
         a small ring of pinned host buffers.
-        streams > 1: consecutive batches run on different CUDA streams (sentences are independent, SURVEY
-        8(e)), so the SMs a kernel of one batch leaves idle — the partial last wave of every encoder GEMM
-        at the packed M of a 64-sentence batch — are taken by the other batch's kernels."""
+        streams > 1: consecutive calls run on different CUDA streams (sentences are independent, SURVEY
+        8(e)), so the SMs a kernel of one call leaves idle are taken by the other call's kernels.
+        group > 1: `group` consecutive host batches are stacked into one device batch per call (sentences are
+        independent, so the tags are those of the separate calls): the packed token count of a 64-sentence MSRA batch
+        (~3.2 k rows) fills 0.5 / 1.5 / 2.0 waves of 128x256 GEMM tiles on 148 SMs, two batches (~6.3 k rows) fill
+        1.0 / 3.0 / 4.0 — the tensor-core tiles stop idling in partial waves without relying on stream overlap."""
         from . import ops
         ring, inflight = {}, []
         depth = max(depth, streams + 1) if streams > 1 else depth
@@ -92,17 +122,31 @@ class Estimator:
             torch.cuda.synchronize()          # weight packs / caches built on the caller's stream are complete
 
         def finish(item):
-            ev, buf, feats = item
+            ev, buf, feats_list = item
             ev.synchronize()
-            return {'pred_ids': buf.clone(), 'label_ids': feats.get('label_ids'), 'tokens': feats.get('tokens')}
+            r = 0
+            for feats in feats_list:
+                n = feats['token_ids'].shape[0] if torch.is_tensor(feats.get('token_ids')) else buf.shape[0]
+                yield {'pred_ids': buf[r:r + n].clone(), 'label_ids': feats.get('label_ids'), 'tokens': feats.get('tokens')}
+                r += n
+
+        def grouped(it):
+            cur = []
+            for f in it:
+                cur.append(f)
+                if len(cur) == group:
+                    yield cur
+                    cur = []
+            if cur:
+                yield cur
 
         k = 0
-        for feats in batches:
+        for feats_list in grouped(batches):
             ctx = torch.cuda.stream(side[k % streams]) if side is not None else contextlib.nullcontext()
             with ctx:
-                dev = self.to_device(feats)
+                dev = self.stack_to_device(feats_list)
                 tile0 = ops.DEFAULT_TILE
-                if side is not None:          # other streams fill a GEMM's partial last wave: take the fastest tile
+                if side is not None or group > 1:   # partial waves are filled (other streams / 2x rows): take the fastest tile
                     ops.DEFAULT_TILE = ops.TILE_AUTO_THROUGHPUT
                 try:
                     pred_ids = self.predict_device(dev)
@@ -115,22 +159,22 @@ class Estimator:
                 buf.copy_(pred_ids, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record()
-            inflight.append((ev, buf, feats))
+            inflight.append((ev, buf, feats_list))
             k += 1
             if len(inflight) >= depth:
-                yield finish(inflight.pop(0))
+                yield from finish(inflight.pop(0))
         while inflight:
-            yield finish(inflight.pop(0))
+            yield from finish(inflight.pop(0))
         if side is not None:
             for st in side:
                 torch.cuda.current_stream().wait_stream(st)
 
-    def predict_sentences(self, batches, depth=2, streams=1):
+    def predict_sentences(self, batches, depth=2, streams=1, group=1):
         """tf.estimator.Estimator.predict(input_fn) as the reference consumes it (main.py:52-55, evaluation.py:16-24):
         one dict PER SENTENCE — {'pred_ids': int32 [L], 'label_ids': int32 [L], 'tokens': [L]} as numpy arrays / lists —
         the element type of `<model>_predict.pkl` and the input of evaluation.SingleEval.  (predict / predict_iter yield
         one dict per batch.)"""
-        for out in self.predict_iter(batches, depth=depth, streams=streams):
+        for out in self.predict_iter(batches, depth=depth, streams=streams, group=group):
             pred = out['pred_ids'].numpy()
             lab = out['label_ids'].numpy() if torch.is_tensor(out['label_ids']) else out['label_ids']
             tok = out['tokens']

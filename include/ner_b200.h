@@ -462,6 +462,31 @@ int ner_bert_attention_bwd_packed(const void* qkv_bf16, const int32_t* cu_seqlen
                                   int head_dim, float scale, float keep_prob, uint64_t seed,
                                   ner_stream_t stream);
 
+/* ------------------------------------------------------------------------ *
+ * SoftLexicon HOST builder — replaces data/word_enhance.py:302-337 (build_soft_lexicon), :89-119 (align_with_token),
+ * :163-205 (postproc_soft_lexicon) and data/base_preprocess.py:397-412 (format_soft_seq) for whole datasets at a time.
+ * Host code (no CUDA call, no stream): all pointers are HOST pointers.  Output layout = the input of
+ * ner_softlexicon_pool_fwd: [n_sent, max_seq_len, 4 (B,M,E,S), 10] ids / weights.
+ * ------------------------------------------------------------------------ */
+typedef struct ner_lexicon ner_lexicon;
+/* Trie over the word vocabulary.  Words are UTF-32 code points back to back, word w = [offsets[w], offsets[w+1]); its id
+ * is w (= embedding row).  freq[n_words + 2]: per-word frequency, then <None> (id n_words, reference: 1) and <PAD>
+ * (id n_words + 1, reference: 0) — VocabModel._addon_token, data/word_enhance.py:62-70.  NULL on bad input. */
+ner_lexicon* ner_lexicon_create(const uint32_t* word_codepoints_host, const int64_t* word_offsets_host,
+                                const double* freq_host, int n_words);
+void ner_lexicon_destroy(ner_lexicon* lexicon);
+int64_t ner_lexicon_num_nodes(const ner_lexicon* lexicon);
+/* Sentences are UTF-32 code points (spaces already removed, as build_soft_lexicon does), sentence s =
+ * [sent_offsets[s], sent_offsets[s+1]).  tok_len / tok_offsets (both NULL, or per sentence the number of characters
+ * each token covers, for WordPiece tokenizers): rows of characters one token swallowed are merged by set union.
+ * bert_mode != 0: row 0 ([CLS]) and the rows from the [SEP] on stay zero and at most max_seq_len - 2 tokens are kept.
+ * Every set holds its matches in first-seen order (the reference iterates Python sets: unordered), an empty set holds
+ * <None>, sets are padded with <PAD> to 10 or cut to the 10 most frequent (stable), weights = freq / sum over the
+ * token's 40 slots.  n_threads <= 0: one per hardware thread.  ids_out / weights_out: [n_sent, max_seq_len * 40]. */
+int ner_lexicon_build(const ner_lexicon* lexicon, const uint32_t* codepoints_host, const int64_t* sent_offsets_host,
+                      int n_sent, const int32_t* tok_len_host, const int64_t* tok_offsets_host, int max_seq_len,
+                      int bert_mode, int32_t* ids_out_host, float* weights_out_host, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,14 +85,20 @@ def test_checkpoint_round_trips_npz_and_tf_bundle(tmp_path):
     for f in feats[:3]:
         a.train_step(f)
     path = checkpoint.save_checkpoint(a.store, str(tmp_path / "ckpt"))
+    torch.save(a.store.state_dict(), str(tmp_path / "vars.pt"))
     assert path.endswith("model.ckpt-3.npz")
     b = engine.Estimator("bilstm_crf", dict(params))
     b.evaluate(feats[0])                                  # creates (differently initialised) variables
     assert checkpoint.restore_checkpoint(b.store, checkpoint.latest_checkpoint(str(tmp_path / "ckpt"))) == 3
     la, lb = a.train_step(feats[3]), b.train_step(feats[3])
-    assert float(la) == float(lb) and b.store.global_step == 4
-    for k in a.store.vars:                                # identical 4th update: the moments and the step came along
-        assert torch.equal(a.store.vars[k], b.store.vars[k]), k
+    assert abs(float(la) - float(lb)) < 1e-5 * max(1.0, abs(float(la))) and b.store.global_step == 4
+    for k in a.store.vars:        # the same 4th update (atomic float accumulation orders differ between two runs: not bit-equal):
+        assert torch.allclose(a.store.vars[k], b.store.vars[k], rtol=1e-4, atol=1e-6), k      # the moments and the step came along
+    c0 = engine.Estimator("bilstm_crf", dict(params))      # control: variables only, zero moments, step 0 -> a different update
+    c0.evaluate(feats[0])
+    c0.store.load_state_dict({k: v for k, v in torch.load(str(tmp_path / "vars.pt")).items()}, strict=True)
+    c0.train_step(feats[3])
+    assert not torch.allclose(a.store.vars["logits/kernel"], c0.store.vars["logits/kernel"], rtol=1e-4, atol=1e-6)
     prefix = str(tmp_path / "export" / "model.ckpt")
     os.makedirs(os.path.dirname(prefix))
     tensors = {k: v.numpy() for k, v in a.store.state_dict().items()}
