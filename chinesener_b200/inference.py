@@ -47,3 +47,12 @@ class InferHelper(object):
         feature = self.make_feature(text)
         out = self.estimator.predict(features_to_batch([feature]))
         return self.decode_prediction(out['pred_ids'].numpy())
+
+    def infer_batch(self, texts):
+        """Many sentences per call: one PREDICT batch, the tag scan of extract_entity on the GPU (ner_extract_spans) —
+        the tag tensor stays on the device, only the spans come back.  -> one entity dict per text, as infer() gives."""
+        from .tools.infer_utils import extract_entity_device
+        feats = [dict(self.make_feature(t)) for t in texts]
+        dev = self.estimator.to_device(features_to_batch(feats, pin_memory=True))
+        pred = self.estimator.predict_device(dev)
+        return extract_entity_device([f['tokens'] for f in feats], pred, self.idx2tag)

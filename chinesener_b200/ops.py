@@ -549,3 +549,33 @@ def bert_attention_bwd(qkv, mask, ctx, dctx, B, L, num_heads, head_dim=64, scale
     check(lib().ner_bert_attention_bwd(ptr(qkv), ptr(_i32(mask)), ptr(ctx), ptr(dctx), ptr(dqkv), B, L, num_heads, head_dim,
                                        scale, mask_add, float(keep_prob), int(seed) & 0xFFFFFFFFFFFFFFFF, stream()))
     return dqkv
+
+
+# --------------------------------------------------------------------------- entity spans (serving tail)
+def tag_classes(idx2tag):
+    """idx2tag -> (uint8 class table [K] for ner_extract_spans, list of entity types)."""
+    K = max(idx2tag) + 1
+    types, table = [], [0] * K
+    for i, tag in idx2tag.items():
+        head = tag.split('-')[0]
+        kind = 1 if head == 'B' else 2 if head == 'I' else 0
+        t = 0
+        if kind and '-' in tag:
+            name = tag.split('-')[1]
+            if name not in types:
+                types.append(name)
+            t = types.index(name)
+        table[i] = kind | (4 if tag[:1] in ('B', 'I') else 0) | (t << 3)
+    assert len(types) <= 32
+    return torch.tensor(table, dtype=torch.uint8), types
+
+
+def extract_spans(pred_ids, tag_class, cap=None):
+    """pred_ids [B,L] int32 (device), tag_class uint8 [K] (device) -> (spans int32 [B,cap], counts int32 [B])."""
+    require_cuda(pred_ids, tag_class)
+    B, L = pred_ids.shape
+    cap = cap or L            # 'B B B ...': every position can be a span of its own
+    spans = torch.empty((B, cap), dtype=torch.int32, device=pred_ids.device)
+    counts = torch.empty((B,), dtype=torch.int32, device=pred_ids.device)
+    check(lib().ner_extract_spans(ptr(_i32(pred_ids)), ptr(tag_class), ptr(spans), ptr(counts), B, L, tag_class.numel(), cap, stream()))
+    return spans, counts

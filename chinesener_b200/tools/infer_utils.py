@@ -49,3 +49,31 @@ def fix_tokens(sentence, tokens):
             tok = tokens[k] = tok.replace('##', '')
         cursor += len(tok)
     return tokens
+
+
+def extract_entity_device(tokens_batch, pred_ids, idx2tag, _cache={}):
+    """Batched extract_entity with the tag scan on the GPU (ner_extract_spans): pred_ids [B, L] int32 on the device,
+    tokens_batch B lists of L token strings -> list of {type: set of surface strings}, equal to
+    [extract_entity(tokens, pred_ids[b], idx2tag) for b ...].  Only the spans (4 bytes each) cross to the host."""
+    from .. import ops
+    key = tuple(sorted(idx2tag.items()))
+    ent = _cache.get(key)
+    if ent is None:
+        table, types = ops.tag_classes(idx2tag)
+        ent = _cache[key] = (table.to(pred_ids.device), types)
+    table, types = ent
+    if table.device != pred_ids.device:
+        table = table.to(pred_ids.device)
+    spans, counts = ops.extract_spans(pred_ids, table)
+    counts = counts.cpu().numpy()
+    spans = spans[:, :max(int(counts.max()), 1)].cpu().numpy() if len(counts) else spans.cpu().numpy()
+    out = []
+    for b, toks in enumerate(tokens_batch):
+        found = defaultdict(set)
+        for w in spans[b, :counts[b]]:
+            s, e, t = int(w) & 0xFFF, (int(w) >> 12) & 0xFFF, int(w) >> 24
+            text = ''.join(toks[s:e])
+            if text != '':
+                found[types[t]].add(text)
+        out.append(found)
+    return out

@@ -462,6 +462,16 @@ int ner_bert_attention_bwd_packed(const void* qkv_bf16, const int32_t* cu_seqlen
                                   int head_dim, float scale, float keep_prob, uint64_t seed,
                                   ner_stream_t stream);
 
+/* tools/infer_utils.py:76-99  extract_entity — the tag-sequence half of it, on the device: pred_ids [B,L] i32 ->
+ * per sentence the entity spans in order.  tag_class [K] u8 describes idx2tag: bits 0-1 kind (0 other, 1 'B', 2 'I' by
+ * tag.split('-')[0]), bit 2 = the tag's first character is 'B' or 'I' (the reference's test on the previous tag),
+ * bits 3-7 entity type id (index of tag.split('-')[1] in the caller's type list).  spans [B,cap] i32, each
+ * start | end << 12 | type << 24 with end exclusive; counts [B] i32 = spans found (may exceed cap: the rest is dropped).
+ * Reproduces the reference scan exactly, including its treatment of ill-formed sequences (an I after an I opens a span,
+ * a span is typed by its LAST tag).  L <= 4095. */
+int ner_extract_spans(const int32_t* pred_ids, const uint8_t* tag_class, int32_t* spans, int32_t* counts, int B, int L,
+                      int K, int cap, ner_stream_t stream);
+
 /* ------------------------------------------------------------------------ *
  * SoftLexicon HOST builder — replaces data/word_enhance.py:302-337 (build_soft_lexicon), :89-119 (align_with_token),
  * :163-205 (postproc_soft_lexicon) and data/base_preprocess.py:397-412 (format_soft_seq) for whole datasets at a time.

@@ -176,3 +176,37 @@ def test_infer_helper_on_mtl_and_softlexicon_plugins(tmp_path):
     assert len(helper.feature['softlexicon_ids']) == L * 40
     pred = est.predict(features_to_batch([helper.feature]))['pred_ids'].numpy()[0]
     assert dict(ent) == dict(extract_entity(helper.feature['tokens'], [int(i) for i in pred], idx2tag))
+
+
+def test_gpu_span_extractor_equals_extract_entity():
+    """ner_extract_spans + host string join == reference-shaped extract_entity (tools/infer_utils.py:76-99) on random —
+    mostly ill-formed — tag sequences: I after O / [PAD], type switches inside a span, B runs, spans touching both ends."""
+    from chinesener_b200.inference import TAG2IDX
+    from chinesener_b200.tools.infer_utils import extract_entity, extract_entity_device
+    idx2tag = {v: k for k, v in TAG2IDX.items()}
+    rng = np.random.default_rng(0)
+    for B, L, p_o in ((64, 150, 0.5), (7, 33, 0.1), (3, 1, 0.3), (130, 64, 0.8), (5, 400, 0.0)):
+        probs = np.array([0.05, p_o, .1, .15, .1, .15, .1, .15, .02, .02])
+        pred = rng.choice(10, size=(B, L), p=probs / probs.sum()).astype(np.int32)
+        pred[0, :] = 3                                          # all I-ORG: one span over the whole sentence
+        if B > 1:
+            pred[1, :] = 2                                      # all B-ORG: L single-token spans
+        tokens = [[chr(0x4E00 + int(rng.integers(0, 3000))) for _ in range(L)] for _ in range(B)]
+        got = extract_entity_device(tokens, torch.from_numpy(pred).cuda(), idx2tag)
+        for b in range(B):
+            want = extract_entity(tokens[b], [int(i) for i in pred[b]], idx2tag)
+            assert dict(got[b]) == dict(want), (B, L, b)
+
+
+def test_infer_batch_uses_the_device_span_path(tmp_path):
+    from chinesener_b200.data.tokenizer import TokenizerAdapter
+    from chinesener_b200.inference import InferHelper, TAG2IDX
+    chars = list("中共中央致中国致公党十一大的贺词各位代表同志们")
+    params = dict(synthetic.data_params(32), embedding=_char_table(len(chars) + 2))
+    est = engine.Estimator("bilstm_crf", params)
+    helper = InferHelper(32, TAG2IDX, "bilstm_crf", TokenizerAdapter(chars), estimator=est)
+    texts = ["中共中央致中国致公党十一大的贺词", "各位代表、各位同志", "中"]
+    helper.infer(texts[0])
+    est.store.vars["logits/kernel"].mul_(30.0)
+    est.store.touch()
+    assert [dict(e) for e in helper.infer_batch(texts)] == [dict(helper.infer(t)) for t in texts]
