@@ -30,7 +30,7 @@ SIGNATURES = {
     "ner_bert_embed_ln": (_i, [_vp] * 9 + [_i] * 6 + [_c.c_float, _vp, _i, _vp]),
     "ner_layernorm": (_i, [_vp, _i] + [_vp] * 5 + [_i, _i, _c.c_float, _vp]),
     "ner_layernorm_dropout": (_i, [_vp, _i] + [_vp] * 5 + [_i, _i, _c.c_float, _c.c_float, _c.c_uint64, _vp]),
-    "ner_bert_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _c.c_float, _c.c_float, _vp, _c.c_float, _c.c_uint64, _vp]),
+    "ner_bert_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _c.c_float, _c.c_float, _vp, _i, _c.c_float, _c.c_uint64, _vp]),
     "ner_bilstm_recurrence": (_i, [_vp] * 5 + [_i, _i, _i, _i, _c.c_float, _vp, _vp, _vp, _vp, _c.c_float, _c.c_uint64, _vp]),
     "ner_bilstm_recurrence_bwd": (_i, [_vp] * 7 + [_i, _i, _i, _i, _c.c_float, _c.c_uint64, _vp]),
     "ner_transpose_cast_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

@@ -7,6 +7,8 @@
 // shared memory with cp.async (row pitch 144 B -> conflict-free fragment loads / ldmatrix),
 // scores and probabilities never leave registers.  (Attention is 2.7 % of the encoder FLOPs;
 // the dense layers run on tcgen05 — see gemm_tc.cu.)
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -199,13 +201,32 @@ bert_attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __re
 
 }  // namespace
 
+int ner_bert_attention_tc(const void* qkv_bf16, const int32_t* mask, void* ctx_bf16, int B, int L, int num_heads, int head_dim,
+                          float scale, float mask_add, const int32_t* cu_seqlens, int n_rows, cudaStream_t st);
+
+static int attn_variant() {
+  const char* e = getenv("NER_ATTN_VARIANT");   // tuning / test hook, read per call: 1 = mma.sync kernel everywhere
+  return e ? atoi(e) : 0;
+}
+
 extern "C" int ner_bert_attention(const void* qkv_bf16, const int32_t* mask, void* ctx_bf16, int B, int L,
                                   int num_heads, int head_dim, float scale, float mask_add,
-                                  const int32_t* cu_seqlens, float keep_prob, uint64_t seed, ner_stream_t stream) {
+                                  const int32_t* cu_seqlens, int n_rows, float keep_prob, uint64_t seed,
+                                  ner_stream_t stream) {
   if (B < 0 || L < 1 || num_heads < 1 || !(keep_prob > 0.f)) return NER_ERR_INVALID_ARG;
   if (B == 0) return NER_OK;
   if (!qkv_bf16 || (!mask && !cu_seqlens) || !ctx_bf16) return NER_ERR_INVALID_ARG;
+  if (n_rows < 0 || (!cu_seqlens && n_rows != 0 && n_rows != B * L)) return NER_ERR_INVALID_ARG;
   if (head_dim != D) return NER_ERR_UNSUPPORTED;
+  if (keep_prob >= 1.f && attn_variant() != 1) {
+    // inference: tcgen05 kernel (S and O in tensor memory, operands by TMA); packed mode needs the row count of qkv
+    const int rows = cu_seqlens ? n_rows : B * L;
+    if (rows > 0) {
+      const int rc = ner_bert_attention_tc(qkv_bf16, mask, ctx_bf16, B, L, num_heads, head_dim, scale, mask_add, cu_seqlens,
+                                           rows, static_cast<cudaStream_t>(stream));
+      if (rc != NER_ERR_UNSUPPORTED) return rc;
+    }
+  }
   const int Lp = (L + KB - 1) / KB * KB;
   const size_t smem = (size_t)2 * Lp * PITCH * 2 + (size_t)Lp * 4;
   if (smem > 227 * 1024) return NER_ERR_UNSUPPORTED;  // L <= ~780

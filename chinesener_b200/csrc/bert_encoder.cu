@@ -59,7 +59,7 @@ extern "C" int ner_bert_encoder_fwd(const ner_bert_config* cfg, const float* wor
     const ner_bert_layer_weights& w = layers[l];
     rc = ner_gemm_bf16(out_bf16, w.wqkv, w.bqkv, nullptr, qkv, rows, 3 * H, H, NER_EPI_BF16, cfg->gemm_tile, stream);
     if (rc != NER_OK) return rc;
-    rc = ner_bert_attention(qkv, mask, ctx, B, L, NH, H / NH, scale, -10000.0f, cu_seqlens, 1.0f, 0, stream);
+    rc = ner_bert_attention(qkv, mask, ctx, B, L, NH, H / NH, scale, -10000.0f, cu_seqlens, rows, 1.0f, 0, stream);
     if (rc != NER_OK) return rc;
     rc = ner_gemm_bf16(ctx, w.wo, w.bo, nullptr, y, rows, H, H, NER_EPI_BF16, cfg->gemm_tile, stream);
     if (rc != NER_OK) return rc;

@@ -176,7 +176,7 @@ static int train_fwd_impl(const ner_bert_config* cfg, const float* word_emb, con
     void* o16 = last ? (packed ? last16 : out_bf16) : nx.x16;
     const uint64_t sa = seed + 1 + 3 * (uint64_t)l, s1 = sa + 1, s2 = sa + 2;
     NER_TRY(ner_gemm_bf16(s.x16, w.wqkv, w.bqkv, nullptr, s.qkv, rows, 3 * H, H, NER_EPI_BF16, 0, stream));
-    NER_TRY(ner_bert_attention(s.qkv, mask, s.ctx, B, L, NH, H / NH, scale, -10000.0f, cu_seqlens, attn_keep, sa, stream));
+    NER_TRY(ner_bert_attention(s.qkv, mask, s.ctx, B, L, NH, H / NH, scale, -10000.0f, cu_seqlens, rows, attn_keep, sa, stream));
     NER_TRY(ner_gemm_bf16(s.ctx, w.wo, w.bo, nullptr, s.y1, rows, H, H, NER_EPI_BF16, 0, stream));
     NER_TRY(ner_layernorm_dropout(s.y1, 1, s.x32, w.ln1_gamma, w.ln1_beta, s.x1_32, s.x1_16, rows, H, cfg->ln_eps, hidden_keep, s1,
                                   stream));

@@ -2,7 +2,7 @@
 #include "common.cuh"
 #include <stdio.h>
 
-extern "C" int ner_abi_version(void) { return 1; }
+extern "C" int ner_abi_version(void) { return 2; }   // 2: ner_bert_attention takes n_rows
 
 extern "C" const char* ner_strerror(int status) {
   static thread_local char buf[160];

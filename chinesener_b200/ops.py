@@ -162,7 +162,7 @@ def bert_attention(qkv, mask, B, L, num_heads, head_dim=64, scale=None, mask_add
     if scale is None:
         scale = 1.0 / (head_dim ** 0.5)
     check(lib().ner_bert_attention(ptr(qkv), ptr(mask), ptr(ctx), B, L, num_heads, head_dim, scale, mask_add,
-                                   ptr(cu_seqlens), float(keep_prob), int(seed) & 0xFFFFFFFFFFFFFFFF, stream()))
+                                   ptr(cu_seqlens), int(qkv.shape[0]), float(keep_prob), int(seed) & 0xFFFFFFFFFFFFFFFF, stream()))
     return ctx
 
 

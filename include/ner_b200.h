@@ -191,10 +191,14 @@ int ner_layernorm_dropout(const void* y, int y_is_bf16, const float* residual, c
  * BERT: scale = 1/sqrt(64), mask_add = -10000.  Packed mode: cu_seqlens [B+1] non-NULL — sequence b
  * occupies rows [cu[b], cu[b+1]) of qkv/ctx, every key is valid, mask is ignored.
  * keep_prob < 1: attention_probs dropout of BertModel in training (probabilities scaled by
- * keep(seed; b, head, q, k) / keep_prob after the softmax); keep_prob = 1: inference. */
+ * keep(seed; b, head, q, k) / keep_prob after the softmax); keep_prob = 1: inference.
+ * n_rows: rows of qkv / ctx — the packed token count in packed mode (0 = unknown), B*L or 0 in padded mode.
+ * keep_prob = 1 with known n_rows and L <= 256 runs on tcgen05 (S = Q K^T and O = P V accumulate in tensor memory, Q/K/V
+ * tiles arrive by TMA, V is consumed as an MN-major operand); otherwise a warp-level mma.sync kernel (ABI version 2). */
 int ner_bert_attention(const void* qkv_bf16, const int32_t* mask, void* ctx_bf16, int B, int L,
                        int num_heads, int head_dim, float scale, float mask_add,
-                       const int32_t* cu_seqlens, float keep_prob, uint64_t seed, ner_stream_t stream);
+                       const int32_t* cu_seqlens, int n_rows, float keep_prob, uint64_t seed,
+                       ner_stream_t stream);
 
 /* Backward of ner_attention_f32 (TRAIN mode of tools/transformer/tener.py:12-119).  d_out f32 [B*L, ld_dout]
  * = dL/d out.  Writes dQ (all rows; zero for t >= seq_len) and ACCUMULATES into dK, dV (f32, layouts of K / V),

@@ -82,3 +82,29 @@ if __name__ == "__main__":
     if "gemm_packed" in which:          # short run for an ncu launch list (true per-kernel durations)
         res["gemm"] = bench_gemm(packed_only=True, iters=3)
     print(json.dumps(res, indent=1))
+
+
+def bench_attention():
+    """tcgen05 attention vs the mma.sync kernel at the bench shapes: one MSRA-shaped 64-sentence batch and four stacked."""
+    import os
+    from chinesener_b200 import synthetic
+    import numpy as np
+    out = {}
+    NH, D = 12, 64
+    for B in (64, 256):
+        lens = synthetic.msra_lengths(B, 128, np.random.default_rng(1234))
+        T = int(lens.sum())
+        qkv = torch.randn(T, 3 * NH * D, device="cuda").to(torch.bfloat16)
+        cu = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32, device="cuda")
+        for name, var in (("tcgen05", None), ("mma_sync", "1")):
+            if var:
+                os.environ["NER_ATTN_VARIANT"] = var
+            med, best = timeit(lambda: ops.bert_attention(qkv, None, B, 128, NH, D, cu_seqlens=cu), iters=30)
+            os.environ.pop("NER_ATTN_VARIANT", None)
+            flops = 4.0 * float((lens.astype(np.float64) ** 2).sum()) * NH * D
+            out[f"{name}_B{B}"] = dict(us=round(med * 1e3, 2), best_us=round(best * 1e3, 2), tokens=T, TFLOPs=round(flops / med / 1e9, 1))
+    return out
+
+
+if __name__ == "__main__" and "attn" in sys.argv[1:]:
+    print(json.dumps({"attention": bench_attention()}, indent=1))
