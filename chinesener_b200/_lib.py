@@ -19,6 +19,7 @@ _vp, _i = _c.c_void_p, _c.c_int
 SIGNATURES = {
     "ner_strerror": (_c.c_char_p, [_i]),
     "ner_abi_version": (_i, []),
+    "ner_build_info": (_c.c_char_p, []),
     "ner_crf_viterbi": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ner_crf_loglik_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ner_crf_loglik_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _c.c_float, _vp, _vp, _i, _i, _i, _vp]),
@@ -45,7 +46,8 @@ SIGNATURES = {
     "ner_attention_f32_bwd": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _c.c_float, _vp, _i, _vp, _i, _vp, _i, _vp, _i,
                                    _vp, _vp, _i, _i, _i, _i, _vp]),
     "ner_dropout_bf16": (_i, [_vp, _vp, _c.c_size_t, _c.c_float, _c.c_uint64, _vp]),
-    "ner_sumsq_add": (_i, [_vp, _c.c_size_t, _vp, _vp]),
+    "ner_sumsq_add": (_i, [_vp, _c.c_size_t, _vp, _vp, _vp]),
+    "ner_sumsq_scratch_floats": (_c.c_size_t, []),
     "ner_layernorm_bwd": (_i, [_vp, _i] + [_vp] * 7 + [_i, _i, _c.c_float, _vp]),
     "ner_layernorm_dropout_bwd": (_i, [_vp, _i] + [_vp] * 7 + [_i, _i, _c.c_float, _c.c_float, _c.c_uint64, _vp]),
     "ner_transpose_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
@@ -111,6 +113,7 @@ SIGNATURES["ner_bert_encoder_workspace_bytes"] = (_c.c_size_t, [_c.POINTER(BertC
 SIGNATURES["ner_bert_encoder_fwd"] = (_i, [_c.POINTER(BertConfig)] + [_vp] * 5 + [_c.POINTER(BertLayerWeights)] + [_vp] * 3
                                       + [_i, _i, _vp, _vp, _i, _vp, _vp, _vp, _c.c_size_t, _vp])
 
+SIGNATURES["ner_bert_train_bwd_set_layer_events"] = (_i, [_vp, _i])
 SIGNATURES["ner_extract_spans"] = (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp])
 SIGNATURES["ner_lexicon_create"] = (_vp, [_vp, _vp, _vp, _i])
 SIGNATURES["ner_lexicon_destroy"] = (None, [_vp])

@@ -328,10 +328,15 @@ def _train_composite(input_ids, input_mask, segment_ids, cfg, store, tape, scope
         d = g.reshape(rows, H).contiguous()
         demb = [gr(f"{scope}/embeddings/{n}") for n in ("word_embeddings", "token_type_embeddings", "position_embeddings",
                                                         "LayerNorm/gamma", "LayerNorm/beta")]
+        ex = getattr(store, '_grad_exchange', None)
+        if ex is not None:
+            ex.before_bert_backward()
         ops.check(_lib.lib().ner_bert_encoder_train_bwd(
             ctypes.byref(c), ops.ptr(emb[3]), arr, garr, *[ops.ptr(t) for t in demb], ops.ptr(ids), ops.ptr(mask), ops.ptr(seg),
             B, L, float(keep_h), float(keep_a), seed & 0xFFFFFFFFFFFFFFFF, ops.ptr(d), ops.ptr(saved), saved_b, ops.ptr(scratch),
             scratch_b, ops.stream()))
+        if ex is not None:
+            ex.after_bert_backward()
         _lib.LAUNCHES += 3 + 33 * len(layers)
     tape.record(out, bwd)
     return out
@@ -389,10 +394,15 @@ def _train_composite_packed(ids, seg, cfg, store, tape, scope, keep_h, keep_a, p
         scratch = torch.empty(scratch_b, dtype=torch.uint8, device=dev)
         d = g.reshape(B * L, H).contiguous()
         demb = [store.grad(f"{scope}/embeddings/{k}") for k in names]
+        ex = getattr(store, '_grad_exchange', None)
+        if ex is not None:
+            ex.before_bert_backward()
         ops.check(_lib.lib().ner_bert_encoder_train_bwd_packed(
             ctypes.byref(c), ops.ptr(emb[3]), arr, garr, *[ops.ptr(t) for t in demb], ops.ptr(ids), ops.ptr(seg), B, L,
             ops.ptr(pack.cu_seqlens), ops.ptr(pack.tok_src), n, float(keep_h), float(keep_a), seed, ops.ptr(d), ops.ptr(saved),
             saved_b, ops.ptr(scratch), scratch_b, ops.stream()))
+        if ex is not None:
+            ex.after_bert_backward()
         _lib.LAUNCHES += 6 + 33 * len(layers)
     tape.record(out, bwd)
     return out

@@ -38,12 +38,35 @@ def _newest_header():
     return max(os.path.getmtime(h) for h in hs)
 
 
+def source_hash():
+    """sha256 over every source the library is built from (csrc/*.cu, csrc/*.cuh, include/*.h, in name order): compiled
+    into capi.cu and echoed by `ner_build_info()`, so a loaded .so can be matched against the tree it claims to come from."""
+    import hashlib
+    h = hashlib.sha256()
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    files += [os.path.join(INCLUDE, f) for f in sorted(os.listdir(INCLUDE)) if f.endswith(".h")]
+    for p in files:
+        h.update(os.path.basename(p).encode() + b"\0")
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def _compile(src, verbose):
     obj = os.path.join(OBJDIR, src[:-3] + ".o")
     srcp = os.path.join(CSRC, src)
-    if os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(srcp), _newest_header()):
+    extra = []
+    if src == "capi.cu":            # carries the source hash: recompiled whenever any source changed
+        digest = source_hash()
+        stamp = os.path.join(OBJDIR, "capi.hash")
+        extra = ['-DNER_SOURCE_HASH="%s"' % digest]
+        if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == digest:
+            return obj, False
+        with open(stamp, "w") as f:
+            f.write(digest)
+    elif os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(srcp), _newest_header()):
         return obj, False
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-c", srcp, "-o", obj]
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-I", INCLUDE, "-c", srcp, "-o", obj]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)

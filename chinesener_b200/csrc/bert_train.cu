@@ -10,6 +10,8 @@
 //   pre bf16 | inter bf16 | y2 bf16   (y1 / y2 are kept UNdropped: the LayerNorm kernels apply the hidden dropout);    the encoder output is the caller's out_f32 / out_bf16.
 // Dropout seeds: every site draws seed = base + index (embedding 0; layer l: 1+3l attention probs,
 // 2+3l attention-output dense, 3+3l FFN-output dense); the backward call regenerates the masks.
+#include <vector>
+
 #include "common.cuh"
 
 namespace {
@@ -215,6 +217,16 @@ extern "C" int ner_bert_encoder_train_fwd_packed(const ner_bert_config* cfg, con
                         tok_src, n_packed, hidden_keep, attn_keep, seed, out_f32, out_bf16, saved, saved_bytes, stream);
 }
 
+// Optional per-layer completion events of the backward composites (data-parallel gradient exchange overlapped with the
+// backward pass): events[l] is recorded on the composite's stream once every gradient of encoder layer l has been enqueued.
+static thread_local std::vector<cudaEvent_t> tl_layer_events;
+
+extern "C" int ner_bert_train_bwd_set_layer_events(void* const* events_host, int n_events) {
+  if (n_events < 0 || (n_events > 0 && !events_host)) return NER_ERR_INVALID_ARG;
+  tl_layer_events.assign(reinterpret_cast<cudaEvent_t const*>(events_host), reinterpret_cast<cudaEvent_t const*>(events_host) + n_events);
+  return NER_OK;
+}
+
 static int train_bwd_impl(const ner_bert_config* cfg, const float* emb_ln_gamma,
                           const ner_bert_layer_weights* layers, const ner_bert_layer_grads* grads,
                           float* d_word_emb, float* d_type_emb, float* d_pos_emb, float* d_emb_ln_gamma,
@@ -309,6 +321,9 @@ static int train_bwd_impl(const ner_bert_config* cfg, const float* emb_ln_gamma,
     float* dprev = (dx1 == dA) ? dB : dA;
     NER_TRY(ner_gemm_bf16(dqkv, g.wqkv_kn, nullptr, dz32, dprev, rows, H, 3 * H, NER_EPI_RES_F32, 0, stream));
     d = dprev;
+    if (l < (int)tl_layer_events.size() && tl_layer_events[l] != nullptr &&
+        cudaEventRecord(tl_layer_events[l], st) != cudaSuccess)
+      return NER_ERR_CUDA_BASE - (int)cudaGetLastError();
   }
   // ---- embeddings: dropout, LayerNorm of (word + type + position), scatter-add
   float* de = (d == dA) ? dB : dA;

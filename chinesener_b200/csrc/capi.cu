@@ -4,6 +4,17 @@
 
 extern "C" int ner_abi_version(void) { return 2; }   // 2: ner_bert_attention takes n_rows
 
+#ifndef NER_SOURCE_HASH
+#define NER_SOURCE_HASH "unknown"
+#endif
+// "src=<sha256[:16] of csrc/*.cu, csrc/*.cuh, include/*.h> nvcc=<major.minor> arch=sm_100a": what chinesener_b200/build.py
+// computed over the tree this object was compiled from (build provenance: the .so files are shipped prebuilt).
+extern "C" const char* ner_build_info(void) {
+  static char info[128];
+  snprintf(info, sizeof(info), "src=%s nvcc=%d.%d arch=sm_100a", NER_SOURCE_HASH, __CUDACC_VER_MAJOR__, __CUDACC_VER_MINOR__);
+  return info;
+}
+
 extern "C" const char* ner_strerror(int status) {
   static thread_local char buf[160];
   switch (status) {

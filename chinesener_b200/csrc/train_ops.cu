@@ -110,9 +110,12 @@ dropout_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
   }
 }
 
-// sum of squares of a flat buffer -> out[0] (atomic), for clip_by_global_norm
+// sum of squares of a flat buffer, for clip_by_global_norm.  Deterministic: every CTA writes its partial sum (fixed
+// element -> thread map, fixed shuffle order) to partials[blockIdx.x]; the second kernel adds them in index order.  (An atomicAdd
+// per CTA made the norm — and through the clip factor every weight — depend on CTA arrival order: data-parallel replicas that
+// start identical drifted apart by an ulp per step.)
 __global__ void __launch_bounds__(256)
-sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
+sumsq_partial_kernel(const float* __restrict__ g, size_t n, float* __restrict__ partials) {
   float acc = 0.f;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc = fmaf(g[i], g[i], acc);
@@ -123,8 +126,21 @@ sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int i = 0; i < 8; ++i) s += part[i];
-    atomicAdd(out, s);
+    partials[blockIdx.x] = s;
   }
+}
+__global__ void __launch_bounds__(256)
+sumsq_final_kernel(const float* __restrict__ partials, int n, float* __restrict__ out) {
+  __shared__ double part[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += (double)partials[i];
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] += (float)part[0];
 }
 
 // mode 0: AdamWeightDecayOptimizer (bert optimization.py): m,v update, upd = m/(sqrt(v)+eps) (+ wd*p), p -= lr*upd.
@@ -326,10 +342,14 @@ extern "C" int ner_dropout(const float* x, float* y, size_t n, float keep_prob, 
   return ner_launch_status();
 }
 
-extern "C" int ner_sumsq_add(const float* g, size_t n, float* out, ner_stream_t stream) {
-  if (!g || !out) return n == 0 ? NER_OK : NER_ERR_INVALID_ARG;
+extern "C" size_t ner_sumsq_scratch_floats(void) { return (size_t)148 * 16; }
+
+extern "C" int ner_sumsq_add(const float* g, size_t n, float* out, float* scratch, ner_stream_t stream) {
+  if (!g || !out || !scratch) return n == 0 ? NER_OK : NER_ERR_INVALID_ARG;
   if (n == 0) return NER_OK;
-  sumsq_kernel<<<flat_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, n, out);
+  const int grid = flat_grid(n);
+  sumsq_partial_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, n, scratch);
+  sumsq_final_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(scratch, grid, out);
   return ner_launch_status();
 }
 

@@ -32,6 +32,9 @@ class Estimator:
         self.params.update(params)
         self.device = torch.device(device)
         self.store = store or variables.VariableStore(self.device)
+        # data-parallel gradient exchange (N > 1): 'overlap' = bucketed all-reduces behind the backward pass, 'overlap_bf16' =
+        # the same with bf16 buckets, 'single' = one all-reduce of the flat buffer after the backward pass
+        self.store.grad_exchange = self.params.get('grad_exchange', 'overlap')
 
     def to_device(self, features):
         out = {}

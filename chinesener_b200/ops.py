@@ -431,9 +431,16 @@ def dropout(x, keep_prob, seed, inplace=False):
     return y
 
 
+_sumsq_scratch = {}
+
+
 def sumsq_add(g, out):
     require_cuda(g, out)
-    check(lib().ner_sumsq_add(ptr(g), g.numel(), ptr(out), stream()))
+    key = (g.device.index, stream())
+    scratch = _sumsq_scratch.get(key)
+    if scratch is None:
+        scratch = _sumsq_scratch[key] = torch.empty(int(lib().ner_sumsq_scratch_floats()), dtype=torch.float32, device=g.device)
+    check(lib().ner_sumsq_add(ptr(g), g.numel(), ptr(out), ptr(scratch), stream()))
     return out
 
 

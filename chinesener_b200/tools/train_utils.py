@@ -10,6 +10,9 @@ kernels over ONE flat fp32 buffer per state (params / grads / m / v):
 Data parallel: gradients live in one contiguous buffer, so a step issues exactly ONE NCCL
 all-reduce; the 1/world scaling is folded into the optimizer kernel.
 """
+import ctypes
+import re
+
 import torch
 
 from .. import ops, variables
@@ -22,7 +25,10 @@ class FlatState:
         self.store = store
         names = store.trainable_names()
         group_of = group_of or (lambda n: 0)
-        names.sort(key=lambda n: (group_of(n), ))           # stable: groups become contiguous ranges
+        # stable: groups become contiguous ranges; inside a group the BertModel variables follow the order in which the
+        # backward pass completes them (encoder layer 11 first ... layer 0, embeddings last), so that the gradients of a
+        # few consecutive layers are ONE contiguous slice — a bucket of the overlapped data-parallel exchange
+        names.sort(key=lambda n: (group_of(n), _backward_order(n)))
         self.names = names
         self.group_ranges = {}                                # group -> [start, end)
         ALIGN = 64   # floats: every variable starts 256-byte aligned (TMA / 16-byte vector accesses on grads)
@@ -73,6 +79,106 @@ class FlatState:
         self.grads.zero_()
 
 
+_LAYER_RE = re.compile(r'encoder/layer_(\d+)/')
+
+
+def _backward_order(name):
+    m = _LAYER_RE.search(name)
+    if m:
+        return (0, -int(m.group(1)))
+    return (1, 0) if '/embeddings/' in name else (0, -10 ** 6)
+
+
+class GradExchange(object):
+    """The data-parallel gradient exchange of one TRAIN step, overlapped with the backward pass.
+
+    The reference is single device; the B200 engine shards sentences over ranks and sums gradients.  Instead of one
+    all-reduce after the whole backward, the flat gradient buffer (laid out in backward-completion order, FlatState) is
+    cut into contiguous buckets — the dense kernels of encoder layers [11-9] [8-6] [5-3] [2-0], then the rest (embeddings,
+    LayerNorm / bias ranges, the layers above BertModel) — and a layer bucket is all-reduced on a side stream as soon as the event recorded behind its last
+    gradient kernel has fired (ner_bert_train_bwd_set_layer_events), while the layers below are still being differentiated.
+    dtype 'bf16': a bucket travels as bf16 (half the NVLink bytes: cast, all-reduce, cast back on the side stream); the
+    global-norm clip and Adam read the fp32 buffer either way."""
+
+    LAYERS_PER_BUCKET = 3
+
+    def __init__(self, fs, dtype='fp32'):
+        self.fs, self.dtype = fs, dtype
+        self.comm = torch.cuda.Stream()
+        self.tail_event = torch.cuda.Event()
+        layers = sorted({int(m.group(1)) for n in fs.names for m in [_LAYER_RE.search(n)] if m})
+        self.num_layers = (max(layers) + 1) if layers else 0
+        self.layer_events = [torch.cuda.Event() for _ in range(self.num_layers)]
+        for ev in [self.tail_event] + self.layer_events:
+            ev.record()                                  # materialise the handles
+        self._handles = (ctypes.c_void_p * max(self.num_layers, 1))(*[ev.cuda_event for ev in self.layer_events])
+        self.armed = False
+        # buckets: maximal runs of consecutive variables with the same readiness key, in flat-buffer order.  A key is
+        # ('layer', g) for the dense kernels of encoder layers [NL-1-3g .. NL-3-3g] — ready when the lowest of them is
+        # differentiated — and ('tail',) for everything else (embeddings, LayerNorm / bias ranges, the variables of the
+        # layers above BertModel): reduced once the whole backward pass is enqueued.
+        runs = []
+        for n in fs.names:
+            m = _LAYER_RE.search(n)
+            if m and n.startswith('bert/') and _decays(n):
+                key = ('layer', (self.num_layers - 1 - int(m.group(1))) // self.LAYERS_PER_BUCKET)
+            else:
+                key = ('tail',)
+            s, e = fs.slices[n]
+            if runs and runs[-1][0] == key:
+                runs[-1][2] = e
+            else:
+                runs.append([key, s, e])
+        total = fs.grads.numel()
+        self.buckets = []
+        for i, (key, s, e) in enumerate(runs):
+            end = runs[i + 1][1] if i + 1 < len(runs) else total           # cover the alignment padding up to the next run
+            if key[0] == 'layer':
+                lowest = max(self.num_layers - (key[1] + 1) * self.LAYERS_PER_BUCKET, 0)     # last layer of the group to finish
+                ev = self.layer_events[lowest]
+            else:
+                ev = self.tail_event
+            self.buckets.append((key, s, end, ev))
+        self.buckets.sort(key=lambda b: (b[0][0] != 'layer', b[0][1] if b[0][0] == 'layer' else 0, b[1]))   # readiness order
+        self._stage = torch.empty(max(e - s for _, s, e, _ in self.buckets), dtype=torch.bfloat16,
+                                  device=fs.grads.device) if dtype == 'bf16' else None
+
+    # -- called from the BertModel backward closure (bert.py) around the C composite
+    def before_bert_backward(self):
+        from .. import _lib
+        _lib.lib().ner_bert_train_bwd_set_layer_events(self._handles, self.num_layers)
+        self.armed = True
+
+    def after_bert_backward(self):
+        from .. import _lib
+        _lib.lib().ner_bert_train_bwd_set_layer_events(None, 0)
+
+    def finish(self):
+        """Enqueue the bucket all-reduces (each behind its readiness event) and make the caller's stream wait for them.
+        -> world size."""
+        import torch.distributed as dist
+        world = dist.get_world_size()
+        main = torch.cuda.current_stream()
+        self.tail_event.record(main)
+        if not self.armed:                       # no BertModel backward ran in this step: nothing was recorded
+            for ev in self.layer_events:
+                ev.record(main)
+        with torch.cuda.stream(self.comm):
+            for key, s, e, ev in self.buckets:
+                self.comm.wait_event(ev)
+                piece = self.fs.grads[s:e]
+                if self._stage is not None:
+                    half = self._stage[:e - s]
+                    half.copy_(piece)
+                    dist.all_reduce(half, op=dist.ReduceOp.SUM)
+                    piece.copy_(half)
+                else:
+                    dist.all_reduce(piece, op=dist.ReduceOp.SUM)
+        main.wait_stream(self.comm)
+        self.armed = False
+        return world
+
+
 def _flat(store, group_of=None):
     fs = getattr(store, "_flat_state", None)
     if fs is None or set(fs.names) != set(store.trainable_names()):
@@ -90,6 +196,24 @@ def allreduce_gradients(flat_grads):
         dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
         return dist.get_world_size()
     return 1
+
+
+def exchange_gradients(store, fs):
+    """Bucketed, backward-overlapped exchange when the step armed one (GradExchange), else the single all-reduce.  The
+    exchange object is created here on the first multi-rank step — FlatState exists only after the first backward — and
+    the BertModel backward closure of the following steps finds it at `store._grad_exchange`."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return 1
+    mode = getattr(store, 'grad_exchange', 'overlap')          # 'overlap' | 'overlap_bf16' | 'single'
+    if mode == 'skip':                                          # timing diagnostic only: the step without its exchange
+        return dist.get_world_size()
+    if mode == 'single' or not fs.grads.is_cuda:
+        return allreduce_gradients(fs.grads)
+    ex = getattr(store, '_grad_exchange', None)
+    if ex is None or ex.fs is not fs:
+        ex = store._grad_exchange = GradExchange(fs, 'bf16' if mode == 'overlap_bf16' else 'fp32')
+    return ex.finish()
 
 
 def lr_decay(init_lr, global_step, step_per_epoch, decay_rate):
@@ -137,7 +261,7 @@ def bert_train_op(loss, init_lr, num_train_steps, warmup_ratio, diff_lr_times, v
         return (len(keys), 0 if _decays(name) else 1)
 
     fs = _flat(store, group_of)
-    world = allreduce_gradients(fs.grads)
+    world = exchange_gradients(store, fs)
     gsq = torch.zeros(1, dtype=torch.float32, device=fs.grads.device)
     ops.sumsq_add(fs.grads, gsq)
     num_warmup = int(num_train_steps * warmup_ratio)

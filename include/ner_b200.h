@@ -35,6 +35,9 @@ typedef void* ner_stream_t; /* cudaStream_t */
 const char* ner_strerror(int status);
 /* Library/ABI version; bumps when a signature changes. */
 int ner_abi_version(void);
+/* Build provenance: "src=<hash of the sources this library was compiled from> nvcc=<version> arch=sm_100a"; the hash is
+ * chinesener_b200.build.source_hash() of the tree at compile time. */
+const char* ner_build_info(void);
 
 /* ------------------------------------------------------------------------ *
  * CRF  — replaces tf.contrib.crf as called from tools/layer.py
@@ -409,8 +412,11 @@ int ner_softmax_xent(const float* logits, const int32_t* labels, float* loss, fl
                      float scale, ner_stream_t stream);
 /* dst[i] += a * src[i]. */
 int ner_axpy_f32(float* dst, const float* src, size_t n, float a, ner_stream_t stream);
-/* out[0] += sum(g^2)  (tf.clip_by_global_norm, tools/train_utils.py:315). */
-int ner_sumsq_add(const float* g, size_t n, float* out, ner_stream_t stream);
+/* out[0] += sum(g^2)  (tf.clip_by_global_norm, tools/train_utils.py:315).  Deterministic (no float atomics): per-CTA partial
+ * sums go to `scratch` (>= ner_sumsq_scratch_floats() floats) and are added in index order, so identical gradients give a
+ * bit-identical norm on every data-parallel rank and in every run. */
+size_t ner_sumsq_scratch_floats(void);
+int ner_sumsq_add(const float* g, size_t n, float* out, float* scratch, ner_stream_t stream);
 /* One optimizer step over a flat parameter buffer.
  * mode 0 = AdamWeightDecayOptimizer (bert optimization.py; tools/train_utils.py:276-282):
  *   g *= grad_scale * clip / max(sqrt(*gnorm_sq) * grad_scale, clip)  (gnorm_sq NULL / clip 0: no clip);
@@ -465,6 +471,13 @@ int ner_bert_attention_bwd_packed(const void* qkv_bf16, const int32_t* cu_seqlen
                                   const void* dctx_bf16, void* dqkv_bf16, int B, int L, int num_heads,
                                   int head_dim, float scale, float keep_prob, uint64_t seed,
                                   ner_stream_t stream);
+
+/* Data-parallel overlap hook (no reference counterpart — the reference is single device): events_host[l]
+ * (cudaEvent_t, HOST array of n_events handles, NULL entries skipped) is recorded on the stream of the NEXT
+ * ner_bert_encoder_train_bwd / _bwd_packed calls of this host thread as soon as every gradient of encoder layer l is
+ * enqueued, so the caller can all-reduce that layer's slice of the flat gradient buffer while the backward pass of the
+ * layers below still runs.  n_events = 0 clears the hook. */
+int ner_bert_train_bwd_set_layer_events(void* const* events_host, int n_events);
 
 /* tools/infer_utils.py:76-99  extract_entity — the tag-sequence half of it, on the device: pred_ids [B,L] i32 ->
  * per sentence the entity spans in order.  tag_class [K] u8 describes idx2tag: bits 0-1 kind (0 other, 1 'B', 2 'I' by
