@@ -50,6 +50,7 @@ SIGNATURES = {
     "ner_sumsq_scratch_floats": (_c.c_size_t, []),
     "ner_layernorm_bwd": (_i, [_vp, _i] + [_vp] * 7 + [_i, _i, _c.c_float, _vp]),
     "ner_layernorm_dropout_bwd": (_i, [_vp, _i] + [_vp] * 7 + [_i, _i, _c.c_float, _c.c_float, _c.c_uint64, _vp]),
+    "ner_layernorm_dropout_bwd_bias": (_i, [_vp, _i] + [_vp] * 8 + [_i, _i, _c.c_float, _c.c_float, _c.c_uint64, _vp]),
     "ner_transpose_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "ner_colsum_bf16_add": (_i, [_vp, _vp, _i, _i, _vp]),
     "ner_gelu_bf16": (_i, [_vp, _vp, _c.c_size_t, _i, _vp]),
@@ -113,6 +114,19 @@ SIGNATURES["ner_bert_encoder_workspace_bytes"] = (_c.c_size_t, [_c.POINTER(BertC
 SIGNATURES["ner_bert_encoder_fwd"] = (_i, [_c.POINTER(BertConfig)] + [_vp] * 5 + [_c.POINTER(BertLayerWeights)] + [_vp] * 3
                                       + [_i, _i, _vp, _vp, _i, _vp, _vp, _vp, _c.c_size_t, _vp])
 
+class PackEntry(_c.Structure):
+    _fields_ = [("src", _vp), ("K", _i), ("N", _i), ("dst_nk_bf16", _vp), ("ld_nk", _i), ("dst_kn_bf16", _vp), ("ld_kn", _i)]
+
+
+SIGNATURES["ner_pack_weights_group_bf16"] = (_i, [_vp, _vp, _i, _i, _vp])
+
+
+class WgradProblem(_c.Structure):
+    _fields_ = [("x_bf16", _vp), ("ld_x", _i), ("dy_bf16", _vp), ("ld_dy", _i), ("dy_col0", _i), ("dw", _vp), ("k_in", _i),
+                ("n_out", _i)]
+
+
+SIGNATURES["ner_wgrad_group_bf16"] = (_i, [_c.POINTER(WgradProblem), _i, _i, _vp])
 SIGNATURES["ner_bert_train_bwd_set_layer_events"] = (_i, [_vp, _i])
 SIGNATURES["ner_extract_spans"] = (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp])
 SIGNATURES["ner_lexicon_create"] = (_vp, [_vp, _vp, _vp, _i])

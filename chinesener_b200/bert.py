@@ -16,6 +16,7 @@ from .config import BERT_BASE_CHINESE
 
 
 _cfg_cache = {}
+FUSED_PACKS = os.environ.get("NER_B200_FUSED_PACKS", "1") != "0"   # TRAIN: one launch re-packs every encoder kernel
 
 
 def load_bert_config(pretrain_dir):
@@ -101,9 +102,52 @@ def create_bert_variables(cfg, store, scope="bert"):
         load_bert_checkpoint(cfg["_pretrain_dir"], store, scope)
 
 
+def _fused_packs(store, cfg, scope):
+    """TRAIN: both bf16 layouts of every encoder dense kernel — the [N, K] packs of the forward GEMMs (Q | K | V stacked into
+    one [3H, H] operand) and the TF-layout casts of the data-gradient GEMMs (Q | K | V side by side in one [H, 3H]) — refreshed
+    by ONE launch (ops.PackGroup) whenever the store version moved.  The destination buffers and the device table are built
+    once: after the first optimizer step the variables are views of the flat parameter buffer and never move."""
+    v = store.vars
+    NL, H, I = cfg["num_hidden_layers"], cfg["hidden_size"], cfg["intermediate_size"]
+    names = []
+    for l in range(NL):
+        p = f"{scope}/encoder/layer_{l}"
+        names += [f"{p}/attention/self/query/kernel", f"{p}/attention/self/key/kernel", f"{p}/attention/self/value/kernel",
+                  f"{p}/attention/output/dense/kernel", f"{p}/intermediate/dense/kernel", f"{p}/output/dense/kernel"]
+    sig = tuple(v[n].data_ptr() for n in names)
+    ent = store.caches.get(("bert_fused_packs", scope))
+    if ent is None or ent["sig"] != sig:
+        dev = v[names[0]].device
+        bf = lambda *shape: torch.empty(shape, dtype=torch.bfloat16, device=dev)
+        nk = [dict(wqkv=bf(3 * H, H), wo=bf(H, H), wi=bf(I, H), wd=bf(H, I)) for _ in range(NL)]
+        kn = [dict(wqkv=bf(H, 3 * H), wo=bf(H, H), wi=bf(H, I), wd=bf(I, H)) for _ in range(NL)]
+        triples = []
+        for l in range(NL):
+            q, k, vv, o, wi, wd = (v[n] for n in names[6 * l:6 * l + 6])
+            for j, src in enumerate((q, k, vv)):
+                triples.append((src, nk[l]["wqkv"][j * H:(j + 1) * H], kn[l]["wqkv"][:, j * H:(j + 1) * H]))
+            triples += [(o, nk[l]["wo"], kn[l]["wo"]), (wi, nk[l]["wi"], kn[l]["wi"]), (wd, nk[l]["wd"], kn[l]["wd"])]
+        ent = store.caches[("bert_fused_packs", scope)] = dict(sig=sig, nk=nk, kn=kn, group=ops.PackGroup(triples), version=-1)
+    if ent["version"] != store.version:
+        ent["group"].run()
+        ent["version"] = store.version
+    return ent
+
+
 def _packed(store, cfg, scope):
     """bf16 [N,K] packs of every dense kernel (+ fused QKV), rebuilt when the store changes."""
     def build():
+        if getattr(store, "_flat_state", None) is not None and FUSED_PACKS:
+            ent, v, out = _fused_packs(store, cfg, scope), store.vars, []
+            ball = torch.cat([v[f"{scope}/encoder/layer_{l}/attention/self/{n}/bias"] for l in range(cfg["num_hidden_layers"])
+                              for n in ("query", "key", "value")]).view(cfg["num_hidden_layers"], -1)
+            for l in range(cfg["num_hidden_layers"]):
+                p, w = f"{scope}/encoder/layer_{l}", ent["nk"][l]
+                out.append(dict(wqkv=w["wqkv"], bqkv=ball[l], wo=w["wo"], bo=v[f"{p}/attention/output/dense/bias"],
+                                g1=v[f"{p}/attention/output/LayerNorm/gamma"], b1=v[f"{p}/attention/output/LayerNorm/beta"],
+                                wi=w["wi"], bi=v[f"{p}/intermediate/dense/bias"], wd=w["wd"], bd=v[f"{p}/output/dense/bias"],
+                                g2=v[f"{p}/output/LayerNorm/gamma"], b2=v[f"{p}/output/LayerNorm/beta"]))
+            return out
         v = store.vars
         out = []
         for l in range(cfg["num_hidden_layers"]):
@@ -227,6 +271,8 @@ def _tf_casts(store, cfg, scope):
     """bf16 casts of the dense kernels in their TF layout [in, out]: the K-major B operand of the
     data-gradient GEMMs (dX = dY · W^T)."""
     def build():
+        if getattr(store, "_flat_state", None) is not None and FUSED_PACKS:
+            return _fused_packs(store, cfg, scope)["kn"]
         v = store.vars
         out = []
         for l in range(cfg["num_hidden_layers"]):

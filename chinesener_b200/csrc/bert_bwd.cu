@@ -34,21 +34,23 @@ template <bool YBF16, bool DROP>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const void* __restrict__ yv, const float* __restrict__ residual, const float* __restrict__ gamma,
                      const float* __restrict__ dout, float* __restrict__ dz_f32, __nv_bfloat16* __restrict__ dz_bf16,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int H, float eps, float keep,
-                     uint32_t seed_lo, uint32_t seed_hi) {
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int M, int H, float eps,
+                     float keep, uint32_t seed_lo, uint32_t seed_hi) {
   const uint32_t thr = keep_threshold(keep);
   const float inv_keep = 1.f / keep;
-  extern __shared__ float s_acc[];  // [2][H] CTA partials of dgamma / dbeta
-  for (int e = threadIdx.x; e < 2 * H; e += blockDim.x) s_acc[e] = 0.f;
+  extern __shared__ float s_acc[];  // [3][H] CTA partials of dgamma / dbeta / dbias
+  for (int e = threadIdx.x; e < 3 * H; e += blockDim.x) s_acc[e] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int nv4 = (H / 4 + 31) / 32;
   // a lane owns the same columns in every row: d_gamma / d_beta partials stay in registers across the
   // warp's rows and reach shared memory once per warp (per-element shared atomics per row made this
   // kernel 4x slower than its HBM time)
-  float4 ag[LN_MAXV], ab[LN_MAXV];
+  // dbias != NULL: also the column sums of the (masked) dense-branch gradient = the bias gradient of the dense layer that
+  // feeds this LayerNorm (saves the separate column-sum pass over dz_bf16)
+  float4 ag[LN_MAXV], ab[LN_MAXV], ad[LN_MAXV];
 #pragma unroll
-  for (int k = 0; k < LN_MAXV; ++k) ag[k] = ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < LN_MAXV; ++k) ag[k] = ab[k] = ad[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += gridDim.x * (blockDim.x >> 5)) {
     float4 z[LN_MAXV], g[LN_MAXV];
     float4 mk[DROP ? LN_MAXV : 1];
@@ -126,6 +128,7 @@ layernorm_bwd_kernel(const void* __restrict__ yv, const float* __restrict__ resi
           d.x *= mk[k].x; d.y *= mk[k].y; d.z *= mk[k].z; d.w *= mk[k].w;
         }
         if (dz_bf16 != nullptr) st_bf16x4(dz_bf16 + (size_t)row * H + e, d);
+        ad[k].x += d.x; ad[k].y += d.y; ad[k].z += d.z; ad[k].w += d.w;
       }
     }
   }
@@ -141,12 +144,19 @@ layernorm_bwd_kernel(const void* __restrict__ yv, const float* __restrict__ resi
       atomicAdd(&s_acc[H + e + 1], ab[k].y);
       atomicAdd(&s_acc[H + e + 2], ab[k].z);
       atomicAdd(&s_acc[H + e + 3], ab[k].w);
+      if (dbias != nullptr) {
+        atomicAdd(&s_acc[2 * H + e + 0], ad[k].x);
+        atomicAdd(&s_acc[2 * H + e + 1], ad[k].y);
+        atomicAdd(&s_acc[2 * H + e + 2], ad[k].z);
+        atomicAdd(&s_acc[2 * H + e + 3], ad[k].w);
+      }
     }
   }
   __syncthreads();
   for (int e = threadIdx.x; e < H; e += blockDim.x) {
     atomicAdd(dgamma + e, s_acc[e]);
     atomicAdd(dbeta + e, s_acc[H + e]);
+    if (dbias != nullptr) atomicAdd(dbias + e, s_acc[2 * H + e]);
   }
 }
 
@@ -330,15 +340,28 @@ int flat_grid(size_t n) {
 
 }  // namespace
 
+extern "C" int ner_layernorm_dropout_bwd_bias(const void* y, int y_is_bf16, const float* residual, const float* gamma,
+                                              const float* d_out, float* dz_f32, void* dz_bf16, float* d_gamma, float* d_beta,
+                                              float* d_bias, int M, int H, float eps, float keep_prob, uint64_t seed,
+                                              ner_stream_t stream);
+
 extern "C" int ner_layernorm_dropout_bwd(const void* y, int y_is_bf16, const float* residual, const float* gamma,
                                          const float* d_out, float* dz_f32, void* dz_bf16, float* d_gamma, float* d_beta,
                                          int M, int H, float eps, float keep_prob, uint64_t seed, ner_stream_t stream) {
+  return ner_layernorm_dropout_bwd_bias(y, y_is_bf16, residual, gamma, d_out, dz_f32, dz_bf16, d_gamma, d_beta, nullptr, M, H, eps,
+                                        keep_prob, seed, stream);
+}
+
+extern "C" int ner_layernorm_dropout_bwd_bias(const void* y, int y_is_bf16, const float* residual, const float* gamma,
+                                              const float* d_out, float* dz_f32, void* dz_bf16, float* d_gamma, float* d_beta,
+                                              float* d_bias, int M, int H, float eps, float keep_prob, uint64_t seed,
+                                              ner_stream_t stream) {
   if (M < 0 || H < 4) return NER_ERR_INVALID_ARG;
   if (M == 0) return NER_OK;
   if (!y || !gamma || !d_out || !d_gamma || !d_beta || (!dz_f32 && !dz_bf16)) return NER_ERR_INVALID_ARG;
   if (!(keep_prob > 0.f) || keep_prob > 1.f) return NER_ERR_INVALID_ARG;
   if (H % 4 != 0 || H > 128 * LN_MAXV) return NER_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)2 * H * 4;
+  const size_t smem = (size_t)3 * H * 4;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // one CTA per SM (the 160-register row state allows no more): rows per CTA sized so that the grid covers the 148 SMs
   // — 64 rows per CTA left 2/3 of them idle at the packed M of a TRAIN step (50 us per launch for 7 us of HBM time)
@@ -348,8 +371,8 @@ extern "C" int ner_layernorm_dropout_bwd(const void* y, int y_is_bf16, const flo
   const bool drop = keep_prob < 1.f;
   auto kern = y_is_bf16 ? (drop ? layernorm_bwd_kernel<true, true> : layernorm_bwd_kernel<true, false>)
                         : (drop ? layernorm_bwd_kernel<false, true> : layernorm_bwd_kernel<false, false>);
-  kern<<<grid, 256, smem, st>>>(y, residual, gamma, d_out, dz_f32, static_cast<__nv_bfloat16*>(dz_bf16), d_gamma, d_beta, M, H,
-                                eps, keep_prob, (uint32_t)seed, (uint32_t)(seed >> 32));
+  kern<<<grid, 256, smem, st>>>(y, residual, gamma, d_out, dz_f32, static_cast<__nv_bfloat16*>(dz_bf16), d_gamma, d_beta, d_bias, M,
+                                H, eps, keep_prob, (uint32_t)seed, (uint32_t)(seed >> 32));
   return ner_launch_status();
 }
 

@@ -180,6 +180,81 @@ pack_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ ds
   }
 }
 
+// Every bf16 copy of a group of dense kernels in ONE launch (TRAIN re-packs all weights after each optimizer step): per
+// 64 x 64 tile of a TF-layout fp32 kernel [K, N] write (a) the bf16 cast in the same layout into dst_kn (+ column offset through
+// ld_kn: the fused [H, 3H] Q|K|V operand of the data-gradient GEMM) and (b) the transposed bf16 [N, K] pack into dst_nk (K
+// contiguous: the B operand of the forward GEMMs; stacking the Q, K, V packs gives the fused [3H, H] operand).  One read of
+// the fp32 weights, both writes coalesced (the transpose goes through shared memory).
+__global__ void __launch_bounds__(256)
+pack_group_kernel(const ner_pack_entry* __restrict__ entries, const int32_t* __restrict__ tile_start, int count) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  int e = 0;
+  {
+    int lo = 0, hi = count;                 // last entry whose first tile is <= blockIdx.x
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (tile_start[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
+    }
+    e = lo;
+  }
+  const ner_pack_entry en = entries[e];
+  const int t = blockIdx.x - tile_start[e], tn = (en.N + 63) / 64;
+  const int k0 = (t / tn) * 64, n0 = (t % tn) * 64;
+  const int c4 = (threadIdx.x & 15) * 4, r = threadIdx.x >> 4;
+  __nv_bfloat16* kn = static_cast<__nv_bfloat16*>(en.dst_kn_bf16);
+  __nv_bfloat16* nk = static_cast<__nv_bfloat16*>(en.dst_nk_bf16);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + r + 16 * i, n = n0 + c4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < en.K) {
+      if (n + 3 < en.N && (en.N & 3) == 0) v = *reinterpret_cast<const float4*>(en.src + (size_t)k * en.N + n);
+      else {
+        if (n < en.N) v.x = en.src[(size_t)k * en.N + n];
+        if (n + 1 < en.N) v.y = en.src[(size_t)k * en.N + n + 1];
+        if (n + 2 < en.N) v.z = en.src[(size_t)k * en.N + n + 2];
+        if (n + 3 < en.N) v.w = en.src[(size_t)k * en.N + n + 3];
+      }
+    }
+    const __nv_bfloat16 b0 = __float2bfloat16_rn(v.x), b1 = __float2bfloat16_rn(v.y), b2 = __float2bfloat16_rn(v.z),
+                        b3 = __float2bfloat16_rn(v.w);
+    tile[r + 16 * i][c4] = b0; tile[r + 16 * i][c4 + 1] = b1; tile[r + 16 * i][c4 + 2] = b2; tile[r + 16 * i][c4 + 3] = b3;
+    if (kn != nullptr && k < en.K) {
+      __nv_bfloat16* d = kn + (size_t)k * en.ld_kn + n;
+      if (n + 3 < en.N && (en.ld_kn & 3) == 0 && (reinterpret_cast<uintptr_t>(kn) & 7) == 0) {
+        __nv_bfloat162 lo = __halves2bfloat162(b0, b1), hi = __halves2bfloat162(b2, b3);
+        *reinterpret_cast<uint2*>(d) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      } else {
+        if (n < en.N) d[0] = b0;
+        if (n + 1 < en.N) d[1] = b1;
+        if (n + 2 < en.N) d[2] = b2;
+        if (n + 3 < en.N) d[3] = b3;
+      }
+    }
+  }
+  __syncthreads();
+  if (nk != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + r + 16 * i, k = k0 + c4;
+      if (n < en.N) {
+        __nv_bfloat16* d = nk + (size_t)n * en.ld_nk + k;
+        const __nv_bfloat16 b0 = tile[c4][r + 16 * i], b1 = tile[c4 + 1][r + 16 * i], b2 = tile[c4 + 2][r + 16 * i],
+                            b3 = tile[c4 + 3][r + 16 * i];
+        if (k + 3 < en.K && (en.ld_nk & 3) == 0 && (reinterpret_cast<uintptr_t>(nk) & 7) == 0) {
+          __nv_bfloat162 lo = __halves2bfloat162(b0, b1), hi = __halves2bfloat162(b2, b3);
+          *reinterpret_cast<uint2*>(d) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        } else {
+          if (k < en.K) d[0] = b0;
+          if (k + 1 < en.K) d[1] = b1;
+          if (k + 2 < en.K) d[2] = b2;
+          if (k + 3 < en.K) d[3] = b3;
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -359,6 +434,15 @@ extern "C" int ner_pack_weight_bf16(const float* w_kn, void* wt_nk_bf16, int K, 
   if (K < 1 || N < 1 || !w_kn || !wt_nk_bf16) return NER_ERR_INVALID_ARG;
   dim3 grid((N + 31) / 32, (K + 31) / 32);
   pack_weight_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w_kn, static_cast<__nv_bfloat16*>(wt_nk_bf16), K, N);
+  return ner_launch_status();
+}
+
+extern "C" int ner_pack_weights_group_bf16(const ner_pack_entry* entries_device, const int32_t* tile_start_device, int count,
+                                           int total_tiles, ner_stream_t stream) {
+  if (count < 0 || total_tiles < 0) return NER_ERR_INVALID_ARG;
+  if (count == 0 || total_tiles == 0) return NER_OK;
+  if (!entries_device || !tile_start_device) return NER_ERR_INVALID_ARG;
+  pack_group_kernel<<<total_tiles, 256, 0, static_cast<cudaStream_t>(stream)>>>(entries_device, tile_start_device, count);
   return ner_launch_status();
 }
 

@@ -111,7 +111,7 @@ extern "C" size_t ner_bert_train_scratch_bytes(const ner_bert_config* cfg, int r
   const size_t W = I > 3 * H ? I : 3 * H;
   return 2 * al(R * H * 4)      // d ping-pong (f32)
          + al(R * H * 4)        // dz f32 (residual-path gradient)
-         + al(R * H * 2)        // dz bf16
+         + 2 * al(R * H * 2)    // dz bf16 of the two LayerNorm backward passes (both live until the layer's grouped wgrad launch)
          + 2 * al(R * I * 2)    // dinter, dpre
          + al(R * H * 2)        // dctx
          + al(R * 3 * H * 2)    // dqkv
@@ -261,6 +261,7 @@ static int train_bwd_impl(const ner_bert_config* cfg, const float* emb_ln_gamma,
   float* dB = reinterpret_cast<float*>(p);     p += al(R * H * 4);
   float* dz32 = reinterpret_cast<float*>(p);   p += al(R * H * 4);
   void* dz16 = p;                              p += al(R * H * 2);
+  void* dz16b = p;                             p += al(R * H * 2);
   void* dinter = p;                            p += al(R * I * 2);
   void* dpre = p;                              p += al(R * I * 2);
   void* dctx = p;                              p += al(R * H * 2);
@@ -283,23 +284,25 @@ static int train_bwd_impl(const ner_bert_config* cfg, const float* emb_ln_gamma,
     const ner_bert_layer_grads& g = grads[l];
     LayerSaved s = carve(base + (size_t)l * lb, R, H, I);
     const uint64_t sa = seed + 1 + 3 * (uint64_t)l, s1 = sa + 1, s2 = sa + 2;
+    // The layer's six weight gradients go out as ONE grouped launch at the end of the layer (ner_wgrad_group_bf16: token-major
+    // operands read in place, 216 tiles instead of 18..72 per GEMM); shapes the grouped kernel does not take fall back to
+    // transposes + one GEMM per gradient.
+    const bool grouped = (H % 128 == 0) && (I % 256 == 0) && (H % 256 == 0) && (I % 128 == 0);
     // ---- output LayerNorm + FFN
-    NER_TRY(ner_layernorm_dropout_bwd(s.y2, 1, s.x1_32, w.ln2_gamma, d, dz32, dz16, g.d_ln2_gamma, g.d_ln2_beta, rows, H,
-                                      cfg->ln_eps, hidden_keep, s2, stream));   // mask applies to the dense branch (dz16) only
-    NER_TRY(ner_colsum_bf16_add(dz16, g.d_bd, rows, H, stream));
-    NER_TRY(wgrad(s.inter, I, nullptr, dz16, H, g.d_wd, rows, Rp, xt, dyt, st));
+    NER_TRY(ner_layernorm_dropout_bwd_bias(s.y2, 1, s.x1_32, w.ln2_gamma, d, dz32, dz16, g.d_ln2_gamma, g.d_ln2_beta, g.d_bd, rows,
+                                           H, cfg->ln_eps, hidden_keep, s2, stream));   // mask: dense branch (dz16, d_bd) only
+    if (!grouped) NER_TRY(wgrad(s.inter, I, nullptr, dz16, H, g.d_wd, rows, Rp, xt, dyt, st));
     NER_TRY(ner_gemm_bf16(dz16, g.wd_kn, nullptr, nullptr, dinter, rows, I, H, NER_EPI_BF16, 0, stream));
     NER_TRY(ner_gelu_bwd_bf16(s.pre, dinter, dpre, R * I, gelu_erf, stream));
     NER_TRY(ner_colsum_bf16_add(dpre, g.d_bi, rows, I, stream));
-    NER_TRY(wgrad(s.x1_16, H, nullptr, dpre, I, g.d_wi, rows, Rp, xt, dyt, st));
+    if (!grouped) NER_TRY(wgrad(s.x1_16, H, nullptr, dpre, I, g.d_wi, rows, Rp, xt, dyt, st));
     float* dx1 = (d == dA) ? dB : dA;
     NER_TRY(ner_gemm_bf16(dpre, g.wi_kn, nullptr, dz32, dx1, rows, H, I, NER_EPI_RES_F32, 0, stream));
     // ---- attention LayerNorm + output projection
-    NER_TRY(ner_layernorm_dropout_bwd(s.y1, 1, s.x32, w.ln1_gamma, dx1, dz32, dz16, g.d_ln1_gamma, g.d_ln1_beta, rows, H,
-                                      cfg->ln_eps, hidden_keep, s1, stream));
-    NER_TRY(ner_colsum_bf16_add(dz16, g.d_bo, rows, H, stream));
-    NER_TRY(wgrad(s.ctx, H, nullptr, dz16, H, g.d_wo, rows, Rp, xt, dyt, st));
-    NER_TRY(ner_gemm_bf16(dz16, g.wo_kn, nullptr, nullptr, dctx, rows, H, H, NER_EPI_BF16, 0, stream));
+    NER_TRY(ner_layernorm_dropout_bwd_bias(s.y1, 1, s.x32, w.ln1_gamma, dx1, dz32, dz16b, g.d_ln1_gamma, g.d_ln1_beta, g.d_bo, rows,
+                                           H, cfg->ln_eps, hidden_keep, s1, stream));
+    if (!grouped) NER_TRY(wgrad(s.ctx, H, nullptr, dz16b, H, g.d_wo, rows, Rp, xt, dyt, st));
+    NER_TRY(ner_gemm_bf16(dz16b, g.wo_kn, nullptr, nullptr, dctx, rows, H, H, NER_EPI_BF16, 0, stream));
     // ---- attention core + fused QKV projection
     if (packed)
       NER_TRY(ner_bert_attention_bwd_packed(s.qkv, cu_seqlens, s.ctx, dctx, dqkv, B, L, NH, H / NH, scale, attn_keep, sa, stream));
@@ -310,14 +313,20 @@ static int train_bwd_impl(const ner_bert_config* cfg, const float* emb_ln_gamma,
     NER_TRY(ner_axpy_f32(g.d_bq, dbqkv, H, 1.f, stream));
     NER_TRY(ner_axpy_f32(g.d_bk, dbqkv + H, H, 1.f, stream));
     NER_TRY(ner_axpy_f32(g.d_bv, dbqkv + 2 * H, H, 1.f, stream));
-    // dW_q | dW_k | dW_v: the transposed d_qkv [3H, Rp] is three contiguous [H, Rp] operands
-    NER_TRY(ner_transpose_bf16(s.x16, xt, rows, H, Rp, stream));
-    NER_TRY(ner_transpose_bf16(dqkv, dyt, rows, 3 * H, Rp, stream));
-    // one [H, 3H] GEMM (108 tiles of 128 x 128) instead of three [H, H] ones (36 tiles each, a quarter of the SMs busy
-    // for the same per-CTA K loop), then the three column blocks are added into the TF variables' gradients
-    NER_TRY(ner_gemm_bf16(xt, dyt, nullptr, nullptr, dwqkv, H, 3 * H, Rp, NER_EPI_F32, 0, stream));
-    add_split3_kernel<<<148 * 4, 256, 0, st>>>(dwqkv, g.d_wq, g.d_wk, g.d_wv, H);
-    NER_TRY(ner_launch_status());
+    if (grouped) {
+      const ner_wgrad_problem probs[6] = {
+          {s.x16, H, dqkv, 3 * H, 0, g.d_wq, H, H},     {s.x16, H, dqkv, 3 * H, H, g.d_wk, H, H},
+          {s.x16, H, dqkv, 3 * H, 2 * H, g.d_wv, H, H}, {s.ctx, H, dz16b, H, 0, g.d_wo, H, H},
+          {s.x1_16, H, dpre, I, 0, g.d_wi, H, I},       {s.inter, I, dz16, H, 0, g.d_wd, I, H}};
+      NER_TRY(ner_wgrad_group_bf16(probs, 6, rows, stream));
+    } else {
+      // dW_q | dW_k | dW_v: the transposed d_qkv [3H, Rp] is three contiguous [H, Rp] operands
+      NER_TRY(ner_transpose_bf16(s.x16, xt, rows, H, Rp, stream));
+      NER_TRY(ner_transpose_bf16(dqkv, dyt, rows, 3 * H, Rp, stream));
+      NER_TRY(ner_gemm_bf16(xt, dyt, nullptr, nullptr, dwqkv, H, 3 * H, Rp, NER_EPI_F32, 0, stream));
+      add_split3_kernel<<<148 * 4, 256, 0, st>>>(dwqkv, g.d_wq, g.d_wk, g.d_wv, H);
+      NER_TRY(ner_launch_status());
+    }
     float* dprev = (dx1 == dA) ? dB : dA;
     NER_TRY(ner_gemm_bf16(dqkv, g.wqkv_kn, nullptr, dz32, dprev, rows, H, 3 * H, NER_EPI_RES_F32, 0, stream));
     d = dprev;

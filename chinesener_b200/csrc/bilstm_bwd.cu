@@ -14,6 +14,7 @@
 // dW_h = sum_t h_{t-1}^T dz_t is NOT accumulated here: it is one tensor-core GEMM over
 // (h_prev [B*L, H], d_xproj [B*L, 4H]) done by the caller.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -34,8 +35,12 @@ __device__ __forceinline__ float actf(float x) {
 
 // gates: [B, L, 2, 4H] post-activation (sigmoid(i), act(j), sigmoid(f + forget_bias), sigmoid(o));
 // cstate: [B, L, 2, H] cell state after the step; both indexed by the ORIGINAL position of the step.
-template <int R, int ACT>
-__global__ void __launch_bounds__(512, 1)
+// WR > 0 (H = 128): the recurrent matrix slice lives in REGISTERS — thread (k, part) = (tid / 4, tid % 4) keeps
+// kernel[D + rank*HU + k, part*WR .. part*WR + WR) and forms dh_prev[r][k] for all R rows from float4 reads of the gathered
+// gate gradients (one address per `part` in a warp -> broadcasts; the per-part padding of 4 floats keeps the four parts on
+// different banks).  The shared-memory walk it replaces issued two LDS per FMA (6.9 us per step at H = 128).
+template <int R, int ACT, int WR>
+__global__ void __launch_bounds__(WR > 0 ? 256 : 512, 1)
 bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gates, const float* __restrict__ cstate,
                   const float* __restrict__ wh_fw, const float* __restrict__ wh_bw, const int32_t* __restrict__ seq_len,
                   float* __restrict__ d_xproj, int B, int L, int H, int C, float keep_prob, uint32_t seed_lo,
@@ -50,18 +55,32 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
   const int tid = threadIdx.x;
 
   extern __shared__ __align__(16) float smem[];
-  float* Wt = smem;                          // [4H][HU+1]: Wt[col][k] = kernel[D + rank*HU + k, col]
+  float* Wt = smem;                          // [4H][HU+1]: Wt[col][k] = kernel[D + rank*HU + k, col]   (WR == 0 only)
   const int WP = HU + 1;
-  float* dzbuf = Wt + (size_t)G4 * WP;       // [2][R][4H]   all-gathered gate gradients (global column order)
-  float* dhbuf = dzbuf + 2 * R * G4;         // [R][HU]      recurrent dh for the owned units
+  const int G4P = WR > 0 ? G4 + 4 * (G4 / (WR > 0 ? WR : 1)) : G4;     // padded row of the gathered dz (WR path)
+  float* dzbuf = Wt + (WR > 0 ? (size_t)0 : (size_t)G4 * WP);           // [2][R][G4P] all-gathered gate gradients
+  float* dhbuf = dzbuf + 2 * R * G4P;        // [R][HU]      recurrent dh for the owned units
+  auto dzi_of = [&](int col) -> int { return WR > 0 ? col + 4 * (col / (WR > 0 ? WR : 1)) : col; };
   int* s_len = reinterpret_cast<int*>(dhbuf + R * HU);
 
   const float* wh = dir == 0 ? wh_fw : wh_bw;  // [H][4H]
-  for (int idx = tid; idx < HU * G4; idx += blockDim.x) {
-    const int k = idx / G4, col = idx - k * G4;
-    Wt[col * WP + k] = wh[(size_t)(rank * HU + k) * G4 + col];
+  float wreg[WR > 0 ? WR : 1];
+  if (WR > 0) {
+    const int k = tid >> 2, part = tid & 3;
+    if (k < HU) {
+#pragma unroll
+      for (int c = 0; c < (WR > 0 ? WR : 1); c += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(wh + (size_t)(rank * HU + k) * G4 + part * WR + c);
+        wreg[c] = v.x; wreg[c + 1] = v.y; wreg[c + 2] = v.z; wreg[c + 3] = v.w;
+      }
+    }
+  } else {
+    for (int idx = tid; idx < HU * G4; idx += blockDim.x) {
+      const int k = idx / G4, col = idx - k * G4;
+      Wt[col * WP + k] = wh[(size_t)(rank * HU + k) * G4 + col];
+    }
   }
-  for (int idx = tid; idx < 2 * R * G4; idx += blockDim.x) dzbuf[idx] = 0.f;
+  for (int idx = tid; idx < 2 * R * G4P; idx += blockDim.x) dzbuf[idx] = 0.f;
   for (int idx = tid; idx < R * HU; idx += blockDim.x) dhbuf[idx] = 0.f;
   if (tid < R) s_len[tid] = (b0 + tid < B) ? min(max(seq_len[b0 + tid], 0), L) : 0;
   __syncthreads();
@@ -111,7 +130,7 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
   fetch(maxlen - 1);
 
   for (int s = maxlen - 1; s >= 0; --s) {
-    float* dzcur = dzbuf + (s & 1) * R * G4;
+    float* dzcur = dzbuf + (s & 1) * R * G4P;
     float dzi = 0.f, dzj = 0.f, dzf = 0.f, dzo = 0.f;
     const bool live = cell_ok && s < my_len;
     const float i_s = n_i, j_a = n_j, f_s = n_f, o_s = n_o, c_t = n_c, c_prev = n_cp;
@@ -142,10 +161,10 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
       // broadcast this unit's four gate gradients to every CTA (global column order g*H + ug)
       for (int dst = 0; dst < C; ++dst) {
         float* remote = cluster.map_shared_rank(dzcur, dst);
-        remote[cr * G4 + 0 * H + ug] = dzi;
-        remote[cr * G4 + 1 * H + ug] = dzj;
-        remote[cr * G4 + 2 * H + ug] = dzf;
-        remote[cr * G4 + 3 * H + ug] = dzo;
+        remote[cr * G4P + dzi_of(0 * H + ug)] = dzi;
+        remote[cr * G4P + dzi_of(1 * H + ug)] = dzj;
+        remote[cr * G4P + dzi_of(2 * H + ug)] = dzf;
+        remote[cr * G4P + dzi_of(3 * H + ug)] = dzo;
       }
     }
     // arrive before this step's global stores: the barrier's release fence then does not wait for them
@@ -157,8 +176,39 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
       d_xproj[gi + 3 * H + ug] = dzo;
     }
     cluster.barrier_wait();
-    // dh_prev[r][k] for owned k: split the 4H columns over the threads of a (r,k) team
-    {
+    // dh_prev[r][k] for owned k
+    if (WR > 0) {
+      const int k = tid >> 2, part = tid & 3;
+      float acc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = 0.f;
+      if (k < HU) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float4* dz4 = reinterpret_cast<const float4*>(dzcur + r * G4P + part * ((WR > 0 ? WR : 1) + 4));
+#pragma unroll
+          for (int c4 = 0; c4 < (WR > 0 ? WR : 4) / 4; ++c4) {
+            const float4 v = dz4[c4];
+            acc[r] = fmaf(v.x, wreg[4 * c4], acc[r]);
+            acc[r] = fmaf(v.y, wreg[4 * c4 + 1], acc[r]);
+            acc[r] = fmaf(v.z, wreg[4 * c4 + 2], acc[r]);
+            acc[r] = fmaf(v.w, wreg[4 * c4 + 3], acc[r]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 1);
+        acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 2);
+      }
+      __syncthreads();  // everyone done reading dhbuf of this step
+      if (k < HU && part == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (s < s_len[r]) dhbuf[r * HU + k] = acc[r];   // inactive rows carry the recurrent gradient through unchanged
+      }
+    } else {
+      // split the 4H columns over the threads of a (r,k) team
       const int teams = R * HU;
       const int tpt = blockDim.x / teams > 0 ? blockDim.x / teams : 1;  // threads per team
       const int team = tid / tpt, part = tid - team * tpt;
@@ -191,19 +241,21 @@ int pick_cluster_bwd(int H) {
   return 0;
 }
 
-template <int R, int ACT>
+template <int R, int ACT, int WR>
 int launch_bwd(const float* d_out, const float* gates, const float* cstate, const float* wh_fw, const float* wh_bw,
                const int32_t* seq_len, float* d_xproj, int B, int L, int H, int C, float keep_prob, uint64_t seed,
                cudaStream_t st) {
   const int HU = H / C;
-  const size_t smem = ((size_t)4 * H * (HU + 1) + 2 * R * 4 * H + (size_t)R * HU + 32) * 4;
-  auto kern = bilstm_bwd_kernel<R, ACT>;
+  const size_t smem = WR > 0 ? ((size_t)2 * R * (4 * H + 16) + (size_t)R * HU + 32) * 4
+                            : ((size_t)4 * H * (HU + 1) + 2 * R * 4 * H + (size_t)R * HU + 32) * 4;
+  auto kern = bilstm_bwd_kernel<R, ACT, WR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   // threads: R*HU teams x tpt threads, tpt = largest power of two with R*HU*tpt <= 512 (and <= 32)
   int tpt = 1;
   while (tpt < 32 && R * HU * tpt * 2 <= 512) tpt *= 2;
-  const int threads = ((R * HU * tpt + 31) / 32) * 32;
+  int threads = ((R * HU * tpt + 31) / 32) * 32;
+  if (WR > 0) threads = ((max(HU * 4, R * HU) + 31) / 32) * 32;      // (k, part) GEMV threads; the first R*HU also run the cells
   const int ngroups = (B + R - 1) / R;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * ngroups * C));
@@ -239,10 +291,15 @@ extern "C" int ner_bilstm_recurrence_bwd(const float* d_out, const float* gates,
   int R = 1;
   if ((long)2 * B * C > 148) R = 2;
   if (2 * (H / C) > 512) R = 1;
-#define GO(RR)                                                                                                \
-  return activation == 1 ? launch_bwd<RR, 1>(d_out, gates, cstate, wh_fw, wh_bw, seq_len, d_xproj, B, L, H, C, keep_prob, seed, st) \
-                         : launch_bwd<RR, 0>(d_out, gates, cstate, wh_fw, wh_bw, seq_len, d_xproj, B, L, H, C, keep_prob, seed, st)
-  if (R == 2) GO(2);
-  GO(1);
+#define GO(RR, WRR)                                                                                                \
+  return activation == 1 ? launch_bwd<RR, 1, WRR>(d_out, gates, cstate, wh_fw, wh_bw, seq_len, d_xproj, B, L, H, C, keep_prob, seed, st) \
+                         : launch_bwd<RR, 0, WRR>(d_out, gates, cstate, wh_fw, wh_bw, seq_len, d_xproj, B, L, H, C, keep_prob, seed, st)
+  const char* ev = getenv("NER_BPTT_VARIANT");              // tuning / test hook: 1 = shared-memory walk everywhere
+  if (H == 128 && C == 2 && !(ev && atoi(ev) == 1)) {       // register-resident recurrent matrix: 4H / 4 = 128 columns per thread
+    if (R == 2) GO(2, 128);
+    GO(1, 128);
+  }
+  if (R == 2) GO(2, 0);
+  GO(1, 0);
 #undef GO
 }

@@ -486,6 +486,177 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   }
 }
 
+// ===================================================================== grouped weight gradients
+// dW_p[k_in, n_out] += X_p^T[k_in, R] . dY_p[R, n_out]   for a group of problems p (the weight gradients of one encoder layer),
+// ONE persistent launch: the tiles of all problems form one list (128 x 256 output tiles), so the 18..72 tiles of the single
+// GEMMs (K = tokens: 50 k-blocks, a quarter to a half of the SMs idle per launch) become 216 per layer.
+// Both operands are read AS THEY LIE in memory — X [R, k_in] and dY [R, n_out] are token-major, i.e. M / N contiguous and
+// K (tokens) strided: "MN-major" operands of tcgen05.mma (instruction-descriptor bits 15/16).  A k-block is 64 tokens; the A
+// tile arrives as two and the B tile as four {64 columns x 64 tokens} TMA boxes (SWIZZLE_128B), which is the canonical MN-major
+// layout: 64-element blocks along M/N 8 KB apart (leading byte offset), 8-token groups 1 KB apart (stride byte offset); one
+// MMA (K = 16) spans two token groups, consecutive MMAs advance the start address by 2 KB.  No bf16 transposes, no padded
+// copies: TMA zero-fills the token rows past R.  Epilogue = the GEMM's fp32 accumulate-into-gradient path (RES_F32).
+constexpr int WG_MAXP = 6;
+constexpr int WG_BN = 256;
+
+struct WgradGroup {
+  CUtensorMap a[WG_MAXP], b[WG_MAXP], c[WG_MAXP];
+  float* dw[WG_MAXP];
+  int m[WG_MAXP], n[WG_MAXP], b_col0[WG_MAXP];
+  int tile_start[WG_MAXP + 1];
+  int count, rows;
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // next 64-element block along M / N
+  d |= (uint64_t)(1024 >> 4) << 32;                   // next group of 8 tokens along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) {
+  return make_idesc_bf16(M, N) | (1u << 15) | (1u << 16);   // a_major = b_major = MN
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_wgrad_group_kernel(const __grid_constant__ WgradGroup grp) {
+  constexpr int BN = WG_BN;
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int BOX = 64 * 64 * 2;   // one {64 columns x 64 tokens} box
+  nerdev::pdl_launch_dependents();
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * C::A_BYTES;
+  uint8_t* epi_stage = smem + STAGES * (C::A_BYTES + C::B_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + NUM_EPI_WARPS * 4096);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = grp.tile_start[grp.count];
+  const int num_kb = (grp.rows + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_ptr);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  nerdev::pdl_wait();
+
+  auto locate = [&](int tile, int& p, int& m_blk, int& n_blk) {
+    p = 0;
+    while (p + 1 < grp.count && tile >= grp.tile_start[p + 1]) ++p;
+    const int t = tile - grp.tile_start[p], num_n = grp.n[p] / BN;
+    m_blk = t / num_n;
+    n_blk = t - m_blk * num_n;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int p, m_blk, n_blk;
+        locate(tile, p, m_blk, n_blk);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], C::A_BYTES + C::B_BYTES);
+#pragma unroll
+          for (int i = 0; i < BM / 64; ++i)
+            tma_load_2d(smem_a + stage * C::A_BYTES + i * BOX, &grp.a[p], &full_bar[stage], m_blk * BM + i * 64, kb * BK);
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i)
+            tma_load_2d(smem_b + stage * C::B_BYTES + i * BOX, &grp.b[p], &full_bar[stage], grp.b_col0[p] + n_blk * BN + i * 64,
+                        kb * BK);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_mn(BM, BN);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * C::A_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + stage * C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_f16(d_tmem, make_smem_desc_sw128_mn(a_addr + k * 2048, BOX), make_smem_desc_sw128_mn(b_addr + k * 2048, BOX), idesc,
+                     (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int p, m_blk, n_blk;
+      locate(tile, p, m_blk, n_blk);
+      EpiArgs ep{nullptr, grp.dw[p], grp.dw[p], NER_EPI_RES_F32};
+      epilogue_stage_bias<BN>(sbias + acc * BN, ep, n_blk * BN, grp.n[p]);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      epilogue_tile<BN, true>(tmem_base + (uint32_t)(acc * BN), warp, lane, ep, &grp.c[p], epi_stage + (warp - 2) * 4096,
+                              sbias + acc * BN, m_blk * BM, n_blk * BN, grp.m[p], grp.n[p]);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  if (warp >= 2 && lane == 0) tma_store_wait_read<0>();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
 // ===================================================================== cta_group::2 (CTA pair)
 // Protocol (s = smem stage, a = accumulator stage):
 //   full[s]        lives in CTA 0, count 1: CTA 0's producer arrive.expect_tx's the bytes of BOTH CTAs;
@@ -814,6 +985,66 @@ int launch_gemm2(const void* A, const void* Wt, EpiArgs ep, int M, int N, int K,
 }
 
 }  // namespace
+
+// bf16 row-major [rows, cols] with a {64 columns, 64 rows} box, 128-byte swizzle (MN-major operand tiles).
+static int make_map_bf16_box64(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return NER_ERR_NO_DRIVER;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? NER_OK : NER_ERR_INVALID_ARG;
+}
+
+extern "C" int ner_wgrad_group_bf16(const ner_wgrad_problem* problems_host, int count, int rows, ner_stream_t stream) {
+  if (count < 0 || rows < 0 || (count > 0 && !problems_host)) return NER_ERR_INVALID_ARG;
+  if (count == 0 || rows == 0) return NER_OK;
+  if (count > WG_MAXP) return NER_ERR_UNSUPPORTED;
+  WgradGroup g;
+  g.count = count;
+  g.rows = rows;
+  g.tile_start[0] = 0;
+  for (int p = 0; p < count; ++p) {
+    const ner_wgrad_problem& q = problems_host[p];
+    if (!q.x_bf16 || !q.dy_bf16 || !q.dw || q.k_in < 1 || q.n_out < 1 || q.ld_x < q.k_in || q.dy_col0 < 0 ||
+        q.ld_dy < q.dy_col0 + q.n_out)
+      return NER_ERR_INVALID_ARG;
+    if (q.k_in % BM != 0 || q.n_out % WG_BN != 0 || q.ld_x % 8 != 0 || q.ld_dy % 8 != 0 || q.dy_col0 % 64 != 0)
+      return NER_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(q.x_bf16) & 15) || (reinterpret_cast<uintptr_t>(q.dy_bf16) & 15) ||
+        (reinterpret_cast<uintptr_t>(q.dw) & 15))
+      return NER_ERR_INVALID_ARG;
+    int rc = make_map_bf16_box64(&g.a[p], q.x_bf16, (uint64_t)rows, (uint64_t)q.ld_x);
+    if (rc != NER_OK) return rc;
+    rc = make_map_bf16_box64(&g.b[p], q.dy_bf16, (uint64_t)rows, (uint64_t)q.ld_dy);
+    if (rc != NER_OK) return rc;
+    rc = make_map_out(&g.c[p], q.dw, (uint64_t)q.k_in, (uint64_t)q.n_out, true);
+    if (rc != NER_OK) return rc;
+    g.dw[p] = q.dw;
+    g.m[p] = q.k_in;
+    g.n[p] = q.n_out;
+    g.b_col0[p] = q.dy_col0;
+    g.tile_start[p + 1] = g.tile_start[p] + (q.k_in / BM) * (q.n_out / WG_BN);
+  }
+  for (int p = count; p < WG_MAXP; ++p) {
+    g.a[p] = g.a[0]; g.b[p] = g.b[0]; g.c[p] = g.c[0];
+    g.dw[p] = nullptr; g.m[p] = g.n[p] = g.b_col0[p] = 0;
+    g.tile_start[p + 1] = g.tile_start[count];
+  }
+  const size_t smem = Cfg<WG_BN>::SMEM;
+  auto kern = gemm_wgrad_group_kernel;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
+  const int tiles = g.tile_start[count];
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  e = ner_launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), smem, static_cast<cudaStream_t>(stream), g);
+  if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
+  return ner_launch_status();
+}
 
 extern "C" int ner_gemm_bf16(const void* A, const void* Wt, const float* bias, const float* residual, void* out,
                              int M, int N, int K, int epilogue, int tile_n, ner_stream_t stream) {

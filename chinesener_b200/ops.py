@@ -586,3 +586,45 @@ def extract_spans(pred_ids, tag_class, cap=None):
     counts = torch.empty((B,), dtype=torch.int32, device=pred_ids.device)
     check(lib().ner_extract_spans(ptr(_i32(pred_ids)), ptr(tag_class), ptr(spans), ptr(counts), B, L, tag_class.numel(), cap, stream()))
     return spans, counts
+
+
+def wgrad_group(problems, rows):
+    """problems: list of (x bf16 [rows, ld_x], dy bf16 [rows, ld_dy], dy_col0, dw f32 [k_in, n_out]) -> dw += x[:, :k_in]^T dy[:, col0:col0+n_out],
+    all in one launch (ner_wgrad_group_bf16)."""
+    from ._lib import WgradProblem
+    arr = (WgradProblem * len(problems))()
+    for q, (x, dy, col0, dw) in zip(arr, problems):
+        require_cuda(x, dy, dw)
+        assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and dw.dtype == torch.float32
+        q.x_bf16, q.ld_x, q.dy_bf16, q.ld_dy, q.dy_col0 = ptr(x), x.shape[1], ptr(dy), dy.shape[1], int(col0)
+        q.dw, q.k_in, q.n_out = ptr(dw), dw.shape[0], dw.shape[1]
+    check(lib().ner_wgrad_group_bf16(arr, len(problems), int(rows), stream()))
+
+
+class PackGroup(object):
+    """A fixed set of (f32 kernel [K,N], bf16 [N,K] pack view, bf16 [K,N] cast view) triples re-packed by ONE launch
+    (ner_pack_weights_group_bf16).  The table lives on the device; `run()` after every optimizer step."""
+
+    def __init__(self, triples):
+        import ctypes
+        from ._lib import PackEntry
+        arr = (PackEntry * len(triples))()
+        starts = [0]
+        self.keep = triples
+        for q, (src, nk, kn) in zip(arr, triples):
+            require_cuda(src, nk, kn)
+            K, N = src.shape
+            assert src.dtype == torch.float32 and src.is_contiguous()
+            q.src, q.K, q.N = ptr(src), K, N
+            q.dst_nk_bf16, q.ld_nk = (ptr(nk), nk.stride(0)) if nk is not None else (0, 0)
+            q.dst_kn_bf16, q.ld_kn = (ptr(kn), kn.stride(0)) if kn is not None else (0, 0)
+            starts.append(starts[-1] + ((K + 63) // 64) * ((N + 63) // 64))
+        dev = triples[0][0].device
+        raw = bytes(memoryview(arr))
+        self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        self.starts = torch.tensor(starts, dtype=torch.int32, device=dev)
+        self.count, self.tiles = len(triples), starts[-1]
+        self.signature = tuple(ptr(t[0]) for t in triples)
+
+    def run(self):
+        check(lib().ner_pack_weights_group_bf16(ptr(self.table), ptr(self.starts), self.count, self.tiles, stream()))

@@ -114,6 +114,22 @@ int ner_gemm_bf16(const void* A, const void* Wt, const float* bias, const float*
 /* TF dense kernel [K,N] f32 -> bf16 [N,K] (K contiguous), the B-operand layout of
  * ner_gemm_bf16.  Done once per weight (or per optimizer step). */
 int ner_pack_weight_bf16(const float* w_kn, void* wt_nk_bf16, int K, int N, ner_stream_t stream);
+/* The same for a whole group of kernels in one launch, writing BOTH bf16 layouts a TRAIN step needs from one read of the fp32
+ * weights: entry e = TF-layout f32 kernel src [K, N]; dst_kn_bf16 (nullable) receives the cast in place layout with row stride
+ * ld_kn (the K-major operand of the data-gradient GEMMs; a column block of a fused matrix via the pointer offset), dst_nk_bf16
+ * (nullable) the transposed [N, K] pack with row stride ld_nk (the operand of the forward GEMMs).  entries_device [count] and
+ * tile_start_device [count + 1] (prefix sums of ceil(K/64) * ceil(N/64)) are DEVICE arrays; total_tiles = tile_start[count]. */
+typedef struct {
+  const float* src;
+  int K;
+  int N;
+  void* dst_nk_bf16;
+  int ld_nk;
+  void* dst_kn_bf16;
+  int ld_kn;
+} ner_pack_entry;
+int ner_pack_weights_group_bf16(const ner_pack_entry* entries_device, const int32_t* tile_start_device, int count,
+                                int total_tiles, ner_stream_t stream);
 /* Elementwise f32 -> bf16 (round to nearest even). */
 int ner_cast_bf16(const float* src, void* dst_bf16, size_t n, ner_stream_t stream);
 
@@ -442,6 +458,13 @@ int ner_layernorm_dropout_bwd(const void* y, int y_is_bf16, const float* residua
                               const float* d_out, float* dz_f32, void* dz_bf16, float* d_gamma,
                               float* d_beta, int M, int H, float eps, float keep_prob, uint64_t seed,
                               ner_stream_t stream);
+/* Same, and additionally d_bias[H] += column sums of the (masked) dense-branch gradient — the bias gradient of the dense
+ * layer whose output this LayerNorm normalises — so the separate column-sum pass over dz_bf16 is not needed.  d_bias NULL =
+ * ner_layernorm_dropout_bwd. */
+int ner_layernorm_dropout_bwd_bias(const void* y, int y_is_bf16, const float* residual, const float* gamma,
+                                   const float* d_out, float* dz_f32, void* dz_bf16, float* d_gamma, float* d_beta,
+                                   float* d_bias, int M, int H, float eps, float keep_prob, uint64_t seed,
+                                   ner_stream_t stream);
 /* bf16 [M,N] -> bf16 [N,Mp] zero padded (K-major operands of weight-gradient GEMMs). */
 int ner_transpose_bf16(const void* src_bf16, void* dst_bf16, int M, int N, int Mp,
                        ner_stream_t stream);
@@ -471,6 +494,23 @@ int ner_bert_attention_bwd_packed(const void* qkv_bf16, const int32_t* cu_seqlen
                                   const void* dctx_bf16, void* dqkv_bf16, int B, int L, int num_heads,
                                   int head_dim, float scale, float keep_prob, uint64_t seed,
                                   ner_stream_t stream);
+
+/* Weight gradients of several dense layers in ONE launch (tools/train_utils.py:314 `tf.gradients` w.r.t. the dense kernels):
+ *   dw_p[k_in, n_out] (f32, accumulated into) += x_p^T . dy_p[:, dy_col0 : dy_col0 + n_out]
+ * x_p bf16 [rows, ld_x] (the layer's input activations, first k_in columns used), dy_p bf16 [rows, ld_dy] (gradient w.r.t. the
+ * layer's output).  Both are consumed as they lie (token-major = MN-major tcgen05 operands, 64 x 64 TMA boxes): no transposed
+ * copies.  k_in % 128 == 0, n_out % 256 == 0, dy_col0 % 64 == 0, ld % 8 == 0; at most 6 problems per call. */
+typedef struct {
+  const void* x_bf16;
+  int ld_x;
+  const void* dy_bf16;
+  int ld_dy;
+  int dy_col0;
+  float* dw;
+  int k_in;
+  int n_out;
+} ner_wgrad_problem;
+int ner_wgrad_group_bf16(const ner_wgrad_problem* problems_host, int count, int rows, ner_stream_t stream);
 
 /* Data-parallel overlap hook (no reference counterpart — the reference is single device): events_host[l]
  * (cudaEvent_t, HOST array of n_events handles, NULL entries skipped) is recorded on the stream of the NEXT

@@ -108,3 +108,33 @@ def bench_attention():
 
 if __name__ == "__main__" and "attn" in sys.argv[1:]:
     print(json.dumps({"attention": bench_attention()}, indent=1))
+
+
+def bench_wgrad(rows=3150):
+    """One encoder layer's weight gradients: grouped MN-major launch vs the transposes + four GEMMs it replaces."""
+    H, I = 768, 3072
+    x16, ctx = (torch.randn(rows, H, device="cuda").to(torch.bfloat16) for _ in range(2))
+    inter = torch.randn(rows, I, device="cuda").to(torch.bfloat16)
+    dqkv = torch.randn(rows, 3 * H, device="cuda").to(torch.bfloat16)
+    dz = torch.randn(rows, H, device="cuda").to(torch.bfloat16)
+    dpre = torch.randn(rows, I, device="cuda").to(torch.bfloat16)
+    dws = [torch.zeros(a, b, device="cuda") for a, b in ((H, H), (H, H), (H, H), (H, H), (H, I), (I, H))]
+    probs = [(x16, dqkv, 0, dws[0]), (x16, dqkv, H, dws[1]), (x16, dqkv, 2 * H, dws[2]), (ctx, dz, 0, dws[3]),
+             (x16, dpre, 0, dws[4]), (inter, dz, 0, dws[5])]
+    flops = 2.0 * rows * (3 * H * H + H * H + 2 * H * I)
+    med, best = timeit(lambda: ops.wgrad_group(probs, rows), iters=20)
+    out = {"grouped_mn_major": dict(us=round(med * 1e3, 1), TFLOPs=round(flops / med / 1e9, 1))}
+    dw_qkv = torch.zeros(H, 3 * H, device="cuda")
+
+    def old():
+        ops.wgrad_gemm_bf16(x16, dqkv, dw_qkv)
+        ops.wgrad_gemm_bf16(ctx, dz, dws[3])
+        ops.wgrad_gemm_bf16(x16, dpre, dws[4])
+        ops.wgrad_gemm_bf16(inter, dz, dws[5])
+    med, best = timeit(old, iters=20)
+    out["transposes_plus_4_gemms"] = dict(us=round(med * 1e3, 1), TFLOPs=round(flops / med / 1e9, 1))
+    return out
+
+
+if __name__ == "__main__" and "wgrad" in sys.argv[1:]:
+    print(json.dumps({"wgrad": bench_wgrad()}, indent=1))

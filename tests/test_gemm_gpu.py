@@ -101,3 +101,28 @@ def test_gemm_stream_k_on_a_second_stream():
     torch.cuda.synchronize()
     torch.testing.assert_close(o1, ref, rtol=1e-4, atol=1e-3)
     torch.testing.assert_close(o2, ref, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("rows", [3150, 64, 1, 200, 4097])
+def test_grouped_mn_major_weight_gradients(rows):
+    """ner_wgrad_group_bf16: dW += X^T dY for a group of problems in one launch, operands consumed token-major (MN-major
+    tcgen05 descriptors, no transposed copies) — vs fp32 matmuls of the same bf16 operands; accumulation into dW, column
+    slices of a fused dY (the Q/K/V gradients), rows that are not a multiple of the 64-token k-block."""
+    g = torch.Generator().manual_seed(rows)
+    H, I = 768, 3072
+    x16 = torch.randn(rows, H, generator=g).to(torch.bfloat16).cuda()
+    ctx = torch.randn(rows, H, generator=g).to(torch.bfloat16).cuda()
+    inter = torch.randn(rows, I, generator=g).to(torch.bfloat16).cuda()
+    dqkv = (torch.randn(rows, 3 * H, generator=g) * 0.1).to(torch.bfloat16).cuda()
+    dz = (torch.randn(rows, H, generator=g) * 0.1).to(torch.bfloat16).cuda()
+    dpre = (torch.randn(rows, I, generator=g) * 0.1).to(torch.bfloat16).cuda()
+    dws = [torch.randn(a, b, generator=g).cuda() for a, b in ((H, H), (H, H), (H, H), (H, H), (H, I), (I, H))]
+    want = [w.clone() for w in dws]
+    probs = [(x16, dqkv, 0, dws[0]), (x16, dqkv, H, dws[1]), (x16, dqkv, 2 * H, dws[2]), (ctx, dz, 0, dws[3]),
+             (x16, dpre, 0, dws[4]), (inter, dz, 0, dws[5])]
+    ops.wgrad_group(probs, rows)
+    for (x, dy, c0, _), w0, got in zip(probs, want, dws):
+        ref = w0 + x.float().t() @ dy[:, c0:c0 + w0.shape[1]].float()
+        scale = ref.abs().max().item()
+        err = (got - ref).abs().max().item()
+        assert err < 2e-4 * max(1.0, scale), (rows, tuple(w0.shape), c0, err, scale)
