@@ -6,7 +6,7 @@ pointers + the current CUDA stream to libner_b200.so.  Nothing here computes on 
 import torch
 
 from . import _lib
-from ._lib import check, lib, ptr, require_cuda, stream
+from ._lib import NerB200Error, check, lib, ptr, require_cuda, stream
 
 EPI_F32, EPI_BF16, EPI_GELU_TANH_BF16, EPI_GELU_ERF_BF16, EPI_RELU_BF16, EPI_RES_F32, EPI_RES_RELU_F32 = range(7)
 EPI_DIAG_DISCARD = 99
@@ -456,14 +456,16 @@ def adam_step(p, g, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0
 
 # --------------------------------------------------------------------------- encoder backward
 def layernorm_bwd(y, gamma, d_out, d_gamma, d_beta, residual=None, eps=1e-12, want_f32=True, want_bf16=True, keep_prob=1.0,
-                  seed=0):
-    require_cuda(y, gamma, d_out, d_gamma, d_beta, residual)
+                  seed=0, d_bias=None):
+    """d_bias (optional, [H] f32, accumulated into): column sums of the masked dense-branch gradient = the bias gradient of
+    the dense layer whose output this LayerNorm normalises."""
+    require_cuda(y, gamma, d_out, d_gamma, d_beta, residual, d_bias)
     M, H = y.shape
     dz32 = torch.empty((M, H), dtype=torch.float32, device=y.device) if want_f32 else None
     dz16 = torch.empty((M, H), dtype=torch.bfloat16, device=y.device) if want_bf16 else None
-    check(lib().ner_layernorm_dropout_bwd(ptr(y), 1 if y.dtype == torch.bfloat16 else 0, ptr(residual), ptr(gamma), ptr(d_out),
-                                          ptr(dz32), ptr(dz16), ptr(d_gamma), ptr(d_beta), M, H, eps, float(keep_prob),
-                                          int(seed) & 0xFFFFFFFFFFFFFFFF, stream()))
+    check(lib().ner_layernorm_dropout_bwd_bias(ptr(y), 1 if y.dtype == torch.bfloat16 else 0, ptr(residual), ptr(gamma),
+                                               ptr(d_out), ptr(dz32), ptr(dz16), ptr(d_gamma), ptr(d_beta), ptr(d_bias), M, H, eps,
+                                               float(keep_prob), int(seed) & 0xFFFFFFFFFFFFFFFF, stream()))
     return dz32, dz16
 
 
@@ -612,7 +614,10 @@ class PackGroup(object):
         starts = [0]
         self.keep = triples
         for q, (src, nk, kn) in zip(arr, triples):
-            require_cuda(src, nk, kn)
+            require_cuda(src)
+            for t in (nk, kn):          # destinations may be row / column blocks of a fused operand: unit stride along the row only
+                if t is not None and not (t.is_cuda and t.dtype == torch.bfloat16 and t.stride(1) == 1):
+                    raise NerB200Error("PackGroup destinations must be CUDA bf16 matrices with contiguous rows")
             K, N = src.shape
             assert src.dtype == torch.float32 and src.is_contiguous()
             q.src, q.K, q.N = ptr(src), K, N

@@ -158,23 +158,39 @@ def _bilstm_train(embedding, activation, hidden_units_list, keep_prob_list, cell
                 return
             dxp = ops.bilstm_recurrence_bwd(g.contiguous(), gates, cst, pk["wh_fw"], pk["wh_bw"], seq_len, B, L, H,
                                             activation=activation, keep_prob=keep, seed=seed)
-            dwx = ops.wgrad_gemm(x2d, dxp)                                   # [D, 8H] = x^T d_xproj
+            dxp16 = ops.cast_bf16(dxp)
+            gks = [store.grad(names[d][0]) for d in ("fw", "bw")]
             for di, d in enumerate(("fw", "bw")):
-                gk, gb = store.grad(names[d][0]), store.grad(names[d][1])
-                dz = dxp[:, di * 4 * H:(di + 1) * 4 * H]
-                gk[:D] += dwx[:, di * 4 * H:(di + 1) * 4 * H]
-                ops.colsum_add(dz, gb, 1.0)
-                hprev = torch.zeros((B, L, H), dtype=torch.float32, device=out.device)
-                if di == 0:                       # carried (state-dropped) h of the previous forward step
-                    hprev[:, 1:] = hst[:, :-1, :H]
-                else:
-                    hprev[:, :-1] = hst[:, 1:, H:]
-                gk[D:] += ops.wgrad_gemm(hprev.view(B * L, H), dz)            # dW_h = h_prev^T dz
+                ops.colsum_add(dxp[:, di * 4 * H:(di + 1) * 4 * H], store.grad(names[d][1]), 1.0)
+            grouped = pk["Dp"] == D and D % 128 == 0 and H % 128 == 0 and (4 * H) % 256 == 0 and all(k.is_contiguous() for k in gks)
+            if grouped:
+                # dW_x (both directions) and dW_h (both directions) as ONE grouped launch: token-major operands read in place
+                # (ner_wgrad_group_bf16) instead of fp32 transposes + three stream-K GEMMs
+                hprev16 = torch.zeros((2, B, L, H), dtype=torch.bfloat16, device=out.device)
+                hprev16[0, :, 1:] = hst[:, :-1, :H]          # carried (state-dropped) h of the previous forward step
+                hprev16[1, :, :-1] = hst[:, 1:, H:]
+                probs = []
+                for di in range(2):
+                    probs.append((x16, dxp16, di * 4 * H, gks[di][:D]))
+                    probs.append((hprev16[di].view(B * L, H), dxp16, di * 4 * H, gks[di][D:]))
+                ops.wgrad_group(probs, B * L)
+            else:
+                dwx = ops.wgrad_gemm(x2d, dxp)                                   # [D, 8H] = x^T d_xproj
+                for di, d in enumerate(("fw", "bw")):
+                    gk = gks[di]
+                    dz = dxp[:, di * 4 * H:(di + 1) * 4 * H]
+                    gk[:D] += dwx[:, di * 4 * H:(di + 1) * 4 * H]
+                    hprev = torch.zeros((B, L, H), dtype=torch.float32, device=out.device)
+                    if di == 0:                       # carried (state-dropped) h of the previous forward step
+                        hprev[:, 1:] = hst[:, :-1, :H]
+                    else:
+                        hprev[:, :-1] = hst[:, 1:, H:]
+                    gk[D:] += ops.wgrad_gemm(hprev.view(B * L, H), dz)            # dW_h = h_prev^T dz
             if need_dx:
                 wx = torch.cat([store.vars[names[d][0]][:D] for d in ("fw", "bw")], dim=1)   # [D, 8H]: K-major for dx
                 Dn = (D + 31) // 32 * 32
                 wxp = torch.nn.functional.pad(wx, (0, 0, 0, Dn - D)).to(torch.bfloat16).contiguous()
-                dx = ops.gemm_bf16(ops.cast_bf16(dxp), wxp, None, epilogue=ops.EPI_F32)[:, :D]
+                dx = ops.gemm_bf16(dxp16, wxp, None, epilogue=ops.EPI_F32)[:, :D]
                 tape.add_grad(embedding, dx.reshape(B, L, D).contiguous())
         tape.record(out, bwd)
     return out

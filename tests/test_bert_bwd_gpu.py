@@ -178,3 +178,50 @@ def test_layernorm_with_fused_hidden_dropout_forward_and_backward():
     torch.testing.assert_close(dz16.float().cpu().double(), yd.grad, rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(dgam.cpu().double(), gd.grad, rtol=1e-3, atol=1e-3)
     torch.testing.assert_close(dbet.cpu().double(), bd.grad, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("keep", [1.0, 0.9])
+def test_layernorm_bwd_fused_bias_gradient(keep):
+    """ner_layernorm_dropout_bwd_bias: d_bias += column sums of the masked dense-branch gradient == the separate
+    ner_colsum_bf16_add pass over dz_bf16 it replaces (up to the bf16 rounding of that pass's input)."""
+    M, H = 3150, 768
+    g = torch.Generator().manual_seed(17)
+    y = torch.randn(M, H, generator=g).to(torch.bfloat16).cuda()
+    r = torch.randn(M, H, generator=g).cuda()
+    gam = (1 + 0.1 * torch.randn(H, generator=g)).cuda()
+    dout = torch.randn(M, H, generator=g).cuda()
+    dgam, dbet, dbias = (torch.zeros(H, device="cuda") for _ in range(3))
+    dbias += 1.0                                                    # accumulated into
+    dz32, dz16 = ops.layernorm_bwd(y, gam, dout, dgam, dbet, residual=r, eps=1e-12, keep_prob=keep, seed=99, d_bias=dbias)
+    dg2, db2 = torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda")
+    e32, e16 = ops.layernorm_bwd(y, gam, dout, dg2, db2, residual=r, eps=1e-12, keep_prob=keep, seed=99)
+    assert torch.equal(dz32, e32) and torch.equal(dz16, e16)
+    ref = torch.ones(H, device="cuda")
+    ops.colsum_bf16_add(dz16, ref)
+    scale = ref.abs().max().item()
+    assert (dbias - ref).abs().max().item() < 5e-3 * max(1.0, scale)   # the old pass summed bf16-rounded values
+    if keep == 1.0:                                                 # no mask: the dense-branch gradient is dz itself
+        torch.testing.assert_close(dbias - 1.0, dz32.sum(0), rtol=1e-4, atol=1e-2)
+
+
+def test_pack_group_equals_separate_packs():
+    """ner_pack_weights_group_bf16: one launch writes the [N,K] packs and the TF-layout casts of a group of kernels
+    (Q | K | V into one fused operand each) == ner_pack_weight_bf16 / ner_cast_bf16 per kernel."""
+    g = torch.Generator().manual_seed(23)
+    H, I = 768, 3072
+    q, k, v, wi, wd, odd = (torch.randn(*s, generator=g).cuda() for s in ((H, H), (H, H), (H, H), (H, I), (I, H), (100, 72)))
+    bf = lambda *s: torch.full(s, 7.0, dtype=torch.bfloat16, device="cuda")
+    nk_qkv, kn_qkv = bf(3 * H, H), bf(H, 3 * H)
+    nk_wi, kn_wi, nk_wd, kn_wd, nk_odd, kn_odd = bf(I, H), bf(H, I), bf(H, I), bf(I, H), bf(72, 100), bf(100, 72)
+    triples = [(src, nk_qkv[j * H:(j + 1) * H], kn_qkv[:, j * H:(j + 1) * H]) for j, src in enumerate((q, k, v))]
+    triples += [(wi, nk_wi, kn_wi), (wd, nk_wd, kn_wd), (odd, nk_odd, kn_odd), (wi, None, None)]
+    grp = ops.PackGroup(triples)
+    grp.run()
+    wqkv = torch.cat([q, k, v], dim=1).contiguous()
+    assert torch.equal(nk_qkv, ops.pack_weight_bf16(wqkv)) and torch.equal(kn_qkv, ops.cast_bf16(wqkv))
+    assert torch.equal(nk_wi, ops.pack_weight_bf16(wi)) and torch.equal(kn_wi, ops.cast_bf16(wi))
+    assert torch.equal(nk_wd, ops.pack_weight_bf16(wd)) and torch.equal(kn_wd, ops.cast_bf16(wd))
+    assert torch.equal(nk_odd, odd.t().contiguous().to(torch.bfloat16)) and torch.equal(kn_odd, odd.to(torch.bfloat16))
+    q.mul_(2.0)                                                      # same table, new values: re-run only
+    grp.run()
+    assert torch.equal(nk_qkv[:H], ops.pack_weight_bf16(q))
