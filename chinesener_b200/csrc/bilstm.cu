@@ -139,9 +139,12 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
   const int g = tid & 3, u = tid >> 2;
   const int ug = rank * HU + u;
   const size_t xcol = (size_t)dir * 4 * H + (size_t)g * H + ug;
-  // cell role: lane g of a unit's quad updates row r = g (R <= 4), so the R cell updates run in parallel
-  const bool cell_ok = col_ok && g < R;
-  float c_state = 0.f;
+  // cell role: lane g of a unit's quad updates rows r = g, g + 4, ... (RC = ceil(R / 4) rows per lane; R <= 4: one row, all
+  // R cell updates in parallel)
+  constexpr int RC = (R + 3) / 4;
+  float c_state[RC];
+#pragma unroll
+  for (int rr = 0; rr < RC; ++rr) c_state[rr] = 0.f;
 
   // xproj row of (row r, position pos): padded layout b*L + pos, or packed layout cu_seqlens[b] + pos
   size_t xrow0[R];
@@ -213,8 +216,10 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
         }
       }
     }
-    // quad transpose: lane r of the quad receives (z_i, z_j, z_f, z_o) of row r
-    float zi = 0.f, zj = 0.f, zf = 0.f, zo = 0.f;
+    // quad transpose: lane g of the quad receives (z_i, z_j, z_f, z_o) of its rows g, g + 4, ...
+    float zi[RC], zj[RC], zf[RC], zo[RC];
+#pragma unroll
+    for (int rr = 0; rr < RC; ++rr) zi[rr] = zj[rr] = zf[rr] = zo[rr] = 0.f;
     const int qb = (tid & 31) & ~3;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -226,63 +231,67 @@ __global__ void __launch_bounds__(H4REG > 0 ? 256 : 512, 1) bilstm_rec_kernel(co
       const float a1 = __shfl_sync(0xffffffffu, z, qb + 1);
       const float a2 = __shfl_sync(0xffffffffu, z, qb + 2);
       const float a3 = __shfl_sync(0xffffffffu, z, qb + 3);
-      if (g == r) {
-        zi = a0;
-        zj = a1;
-        zf = a2;
-        zo = a3;
+      if (g == (r & 3)) {
+        zi[r >> 2] = a0;
+        zj[r >> 2] = a1;
+        zf[r >> 2] = a2;
+        zo[r >> 2] = a3;
       }
     }
     // h is published with st.async + mbarrier transaction bytes (see the helpers above): with
     // barrier.cluster the release fence of the arrive stalled every step until this thread's global stores
     // had been acknowledged (ncu: 20 % of the kernel's samples on the barrier's ERRBAR) and the wait
     // invalidated L1.
-    float i_s = 0.f, j_a = 0.f, f_s = 0.f, o_s = 0.f, h_out = 0.f, h_state = 0.f;
-    const int r = g;
-    const int len = cell_ok ? s_len[r] : 0;
-    const int b = b0 + r;
-    const bool live = cell_ok && s < len;
-    const int pos = dir == 0 ? s : len - 1 - s;
-    if (live) {
-      i_s = sigmoidf_(zi);
-      j_a = actf<ACT>(zj);
-      f_s = sigmoidf_(zf + forget_bias);
-      o_s = sigmoidf_(zo);
-      c_state = f_s * c_state + i_s * j_a;
-      const float h_raw = o_s * actf<ACT>(c_state);
-      h_out = h_raw;
-      h_state = h_raw;
-      if (keep_prob < 1.f) {
-        // DropoutWrapper(output_keep_prob, state_keep_prob): independent masks for the emitted output
-        // and for the h part of the carried state (c is not dropped), fresh per step
-        const uint32_t e = (uint32_t)(((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug);
-        h_out = nerdev::hash3(seed_lo, seed_hi, e) < thr ? h_raw * inv_keep : 0.f;
-        h_state = nerdev::hash3(seed_lo ^ 0x5bd1e995u, seed_hi, e) < thr ? h_raw * inv_keep : 0.f;
+#pragma unroll
+    for (int rr = 0; rr < RC; ++rr) {
+      const int r = g + 4 * rr;
+      const bool cell_ok = col_ok && r < R;
+      float i_s = 0.f, j_a = 0.f, f_s = 0.f, o_s = 0.f, h_out = 0.f, h_state = 0.f;
+      const int len = cell_ok ? s_len[r] : 0;
+      const int b = b0 + r;
+      const bool live = cell_ok && s < len;
+      const int pos = dir == 0 ? s : len - 1 - s;
+      if (live) {
+        i_s = sigmoidf_(zi[rr]);
+        j_a = actf<ACT>(zj[rr]);
+        f_s = sigmoidf_(zf[rr] + forget_bias);
+        o_s = sigmoidf_(zo[rr]);
+        c_state[rr] = f_s * c_state[rr] + i_s * j_a;
+        const float h_raw = o_s * actf<ACT>(c_state[rr]);
+        h_out = h_raw;
+        h_state = h_raw;
+        if (keep_prob < 1.f) {
+          // DropoutWrapper(output_keep_prob, state_keep_prob): independent masks for the emitted output
+          // and for the h part of the carried state (c is not dropped), fresh per step
+          const uint32_t e = (uint32_t)(((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug);
+          h_out = nerdev::hash3(seed_lo, seed_hi, e) < thr ? h_raw * inv_keep : 0.f;
+          h_state = nerdev::hash3(seed_lo ^ 0x5bd1e995u, seed_hi, e) < thr ? h_raw * inv_keep : 0.f;
+        }
       }
-    }
-    if (cell_ok) {
-      // (h of a finished row is never read again — its own recurrence has stopped — so 0 is as good as
-      // the carried value dynamic_rnn keeps)
-      if (C > 1) {
-        const uint32_t la = nerdev::smem_u32(hnxt + r * H + ug), lb = nerdev::smem_u32(&hbar[(s + 1) & 1]);
-        for (int dst = 0; dst < C; ++dst) st_async_f32(mapa_u32(la, (uint32_t)dst), h_state, mapa_u32(lb, (uint32_t)dst));
-      } else {
-        hnxt[r * H + ug] = h_state;
+      if (cell_ok) {
+        // (h of a finished row is never read again — its own recurrence has stopped — so 0 is as good as
+        // the carried value dynamic_rnn keeps)
+        if (C > 1) {
+          const uint32_t la = nerdev::smem_u32(hnxt + r * H + ug), lb = nerdev::smem_u32(&hbar[(s + 1) & 1]);
+          for (int dst = 0; dst < C; ++dst) st_async_f32(mapa_u32(la, (uint32_t)dst), h_state, mapa_u32(lb, (uint32_t)dst));
+        } else {
+          hnxt[r * H + ug] = h_state;
+        }
       }
-    }
-    if (live) {
-      out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = h_out;
-      if (hstate_out != nullptr) hstate_out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = h_state;
-      if (gates_out != nullptr) {  // saved for back-propagation through time (bilstm_bwd.cu)
-        const size_t gi = ((size_t)b * L + pos) * 8 * H + (size_t)dir * 4 * H;
-        gates_out[gi + 0 * H + ug] = i_s;
-        gates_out[gi + 1 * H + ug] = j_a;
-        gates_out[gi + 2 * H + ug] = f_s;
-        gates_out[gi + 3 * H + ug] = o_s;
-        cstate_out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = c_state;
+      if (live) {
+        out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = h_out;
+        if (hstate_out != nullptr) hstate_out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = h_state;
+        if (gates_out != nullptr) {  // saved for back-propagation through time (bilstm_bwd.cu)
+          const size_t gi = ((size_t)b * L + pos) * 8 * H + (size_t)dir * 4 * H;
+          gates_out[gi + 0 * H + ug] = i_s;
+          gates_out[gi + 1 * H + ug] = j_a;
+          gates_out[gi + 2 * H + ug] = f_s;
+          gates_out[gi + 3 * H + ug] = o_s;
+          cstate_out[((size_t)b * L + pos) * 2 * H + (size_t)dir * H + ug] = c_state[rr];
+        }
+      } else if (cell_ok && b < B) {
+        out[((size_t)b * L + s) * 2 * H + (size_t)dir * H + ug] = 0.f;   // past this row's end: dynamic_rnn emits zeros
       }
-    } else if (cell_ok && b < B) {
-      out[((size_t)b * L + s) * 2 * H + (size_t)dir * H + ug] = 0.f;   // past this row's end: dynamic_rnn emits zeros
     }
     if (C == 1) __syncthreads();
   }
@@ -356,19 +365,22 @@ extern "C" int ner_bilstm_recurrence(const float* xproj, const float* wh_fw, con
   int R = 1;
   if ((long)2 * B * C > 148) R = 2;
   if ((long)2 * ((B + 1) / 2) * C > 2 * 148) R = 4;
-  if (const char* e = getenv("NER_BILSTM_ROWS")) {   // tuning hook: rows per cluster (1, 2 or 4)
+  // four stacked PREDICT batches (B = 256): 4 rows per cluster would be 256 CTAs = two waves of the one-CTA-per-SM kernel
+  if (H == 128 && (long)2 * ((B + 3) / 4) * C > 148) R = 8;
+  if (const char* e = getenv("NER_BILSTM_ROWS")) {   // tuning hook: rows per cluster (1, 2, 4 or 8)
     const int v = atoi(e);
-    if (v == 1 || v == 2 || v == 4) R = v;
+    if (v == 1 || v == 2 || v == 4 || (v == 8 && H == 128)) R = v;
   }
 #define GO(RR, HR)                                                                                          \
   return activation == 1 ? launch_rec<RR, 1, HR>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, cu_seqlens, gates_out, cstate_out, hstate_out, keep_prob, seed, st) \
                          : launch_rec<RR, 0, HR>(xproj, wh_fw, wh_bw, seq_len, out, B, L, H, C, forget_bias, cu_seqlens, gates_out, cstate_out, hstate_out, keep_prob, seed, st)
   if (H == 128 && 4 * (H / C) <= 256) {  // register-resident W_h (the bert_bilstm_crf / bilstm_crf shape)
+    if (R == 8) GO(8, 32);
     if (R == 4) GO(4, 32);
     if (R == 2) GO(2, 32);
     GO(1, 32);
   }
-  if (R == 4) GO(4, 0);
+  if (R >= 4) GO(4, 0);
   if (R == 2) GO(2, 0);
   GO(1, 0);
 #undef GO

@@ -21,7 +21,7 @@ def _weights(D, H, seed):
 
 
 @pytest.mark.parametrize("B,L,H,act", [(64, 128, 128, "relu"), (8, 64, 128, "tanh"), (5, 33, 200, "tanh"),
-                                       (150, 20, 128, "tanh"), (3, 150, 64, "relu"), (300, 12, 128, "relu")])
+                                       (150, 20, 128, "tanh"), (3, 150, 64, "relu"), (300, 12, 128, "relu"), (256, 40, 128, "relu")])
 def test_recurrence_matches_oracle_fp32_inputs(B, L, H, act):
     """Recurrence alone: xproj computed in fp64 on the host, so only the cluster kernel is under test."""
     D = 40
