@@ -56,6 +56,7 @@ SIGNATURES = {
     "ner_gelu_bf16": (_i, [_vp, _vp, _c.c_size_t, _i, _vp]),
     "ner_gelu_f32": (_i, [_vp, _vp, _c.c_size_t, _i, _vp]),
     "ner_gelu_bwd_bf16": (_i, [_vp, _vp, _vp, _c.c_size_t, _i, _vp]),
+    "ner_gelu_bwd_bias_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ner_bert_embed_bwd": (_i, [_vp] * 6 + [_i] * 5 + [_vp]),
     "ner_bert_attention_bwd": (_i, [_vp] * 5 + [_i] * 4 + [_c.c_float, _c.c_float, _c.c_float, _c.c_uint64, _vp]),
     "ner_bert_attention_bwd_packed": (_i, [_vp] * 5 + [_i] * 4 + [_c.c_float, _c.c_float, _c.c_uint64, _vp]),

@@ -30,33 +30,29 @@ __device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float4 v) {
 // dz is written as f32 (the residual-branch gradient) and as bf16 (A operand of the dgrad GEMM).
 // DROP: the forward was ner_layernorm_dropout — z is rebuilt as dropout(y) + residual from the UNdropped y and
 // the bf16 gradient (the dense-output branch) is masked the same way; dz_f32 (the residual branch) is not.
-template <bool YBF16, bool DROP>
-__global__ void __launch_bounds__(256)
+// NV = float4 per lane (ceil(H / 128)).  The column partials (dgamma, dbeta, dbias) of a warp live in the warp's OWN slab of
+// shared memory — each lane read-modify-writes only its own columns, no atomics — instead of 3 * NV float4 registers: the
+// register version needed 254 registers, i.e. one 8-warp CTA per SM, and ncu showed it latency-bound (81 % of the cycles
+// without an eligible warp at 12 % DRAM throughput).  ~120 registers -> two CTAs per SM.
+template <bool YBF16, bool DROP, int NV>
+__global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const void* __restrict__ yv, const float* __restrict__ residual, const float* __restrict__ gamma,
                      const float* __restrict__ dout, float* __restrict__ dz_f32, __nv_bfloat16* __restrict__ dz_bf16,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int M, int H, float eps,
                      float keep, uint32_t seed_lo, uint32_t seed_hi) {
   const uint32_t thr = keep_threshold(keep);
   const float inv_keep = 1.f / keep;
-  extern __shared__ float s_acc[];  // [3][H] CTA partials of dgamma / dbeta / dbias
-  for (int e = threadIdx.x; e < 3 * H; e += blockDim.x) s_acc[e] = 0.f;
+  extern __shared__ __align__(16) float s_acc[];  // [8 warps][3][H]: dgamma / dbeta / dbias partials of each warp
+  for (int e = threadIdx.x; e < 8 * 3 * H; e += blockDim.x) s_acc[e] = 0.f;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* my = s_acc + (size_t)warp * 3 * H;
   const int nv4 = (H / 4 + 31) / 32;
-  // a lane owns the same columns in every row: d_gamma / d_beta partials stay in registers across the
-  // warp's rows and reach shared memory once per warp (per-element shared atomics per row made this
-  // kernel 4x slower than its HBM time)
-  // dbias != NULL: also the column sums of the (masked) dense-branch gradient = the bias gradient of the dense layer that
-  // feeds this LayerNorm (saves the separate column-sum pass over dz_bf16)
-  float4 ag[LN_MAXV], ab[LN_MAXV], ad[LN_MAXV];
-#pragma unroll
-  for (int k = 0; k < LN_MAXV; ++k) ag[k] = ab[k] = ad[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += gridDim.x * (blockDim.x >> 5)) {
-    float4 z[LN_MAXV], g[LN_MAXV];
-    float4 mk[DROP ? LN_MAXV : 1];
+  for (int row = blockIdx.x * (blockDim.x >> 5) + warp; row < M; row += gridDim.x * (blockDim.x >> 5)) {
+    float4 z[NV], g[NV];
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < LN_MAXV; ++k) {
+    for (int k = 0; k < NV; ++k) {
       const int e = (lane + 32 * k) * 4;
       if (k < nv4 && e < H) {
         if constexpr (YBF16) z[k] = ld_bf16x4(static_cast<const __nv_bfloat16*>(yv) + (size_t)row * H + e);
@@ -64,11 +60,10 @@ layernorm_bwd_kernel(const void* __restrict__ yv, const float* __restrict__ resi
         if constexpr (DROP) {
           const size_t i = (size_t)row * H + e;
           const uint32_t hi = seed_hi ^ (uint32_t)(i >> 32), lo = (uint32_t)i;
-          mk[k].x = hash3(seed_lo, hi, lo) < thr ? inv_keep : 0.f;
-          mk[k].y = hash3(seed_lo, hi, lo + 1) < thr ? inv_keep : 0.f;
-          mk[k].z = hash3(seed_lo, hi, lo + 2) < thr ? inv_keep : 0.f;
-          mk[k].w = hash3(seed_lo, hi, lo + 3) < thr ? inv_keep : 0.f;
-          z[k].x *= mk[k].x; z[k].y *= mk[k].y; z[k].z *= mk[k].z; z[k].w *= mk[k].w;
+          z[k].x *= hash3(seed_lo, hi, lo) < thr ? inv_keep : 0.f;
+          z[k].y *= hash3(seed_lo, hi, lo + 1) < thr ? inv_keep : 0.f;
+          z[k].z *= hash3(seed_lo, hi, lo + 2) < thr ? inv_keep : 0.f;
+          z[k].w *= hash3(seed_lo, hi, lo + 3) < thr ? inv_keep : 0.f;
         }
         if (residual != nullptr) {
           const float4 r = *reinterpret_cast<const float4*>(residual + (size_t)row * H + e);
@@ -82,7 +77,7 @@ layernorm_bwd_kernel(const void* __restrict__ yv, const float* __restrict__ resi
     const float mean = s / (float)H;
     float q = 0.f;
 #pragma unroll
-    for (int k = 0; k < LN_MAXV; ++k) {
+    for (int k = 0; k < NV; ++k) {
       const int e = (lane + 32 * k) * 4;
       if (k < nv4 && e < H) {
         z[k].x -= mean; z[k].y -= mean; z[k].z -= mean; z[k].w -= mean;
@@ -93,20 +88,17 @@ layernorm_bwd_kernel(const void* __restrict__ yv, const float* __restrict__ resi
     const float rstd = rsqrtf(q / (float)H + eps);
     float m1 = 0.f, m2 = 0.f;  // sum(g*gamma), sum(g*gamma*zhat)
 #pragma unroll
-    for (int k = 0; k < LN_MAXV; ++k) {
+    for (int k = 0; k < NV; ++k) {
       const int e = (lane + 32 * k) * 4;
       if (k < nv4 && e < H) {
         const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + e));
-        // zhat
-        z[k].x *= rstd; z[k].y *= rstd; z[k].z *= rstd; z[k].w *= rstd;
-        ag[k].x = fmaf(g[k].x, z[k].x, ag[k].x);
-        ag[k].y = fmaf(g[k].y, z[k].y, ag[k].y);
-        ag[k].z = fmaf(g[k].z, z[k].z, ag[k].z);
-        ag[k].w = fmaf(g[k].w, z[k].w, ag[k].w);
-        ab[k].x += g[k].x;
-        ab[k].y += g[k].y;
-        ab[k].z += g[k].z;
-        ab[k].w += g[k].w;
+        z[k].x *= rstd; z[k].y *= rstd; z[k].z *= rstd; z[k].w *= rstd;          // zhat
+        float4 ag = *reinterpret_cast<float4*>(my + e), ab = *reinterpret_cast<float4*>(my + H + e);
+        ag.x = fmaf(g[k].x, z[k].x, ag.x); ag.y = fmaf(g[k].y, z[k].y, ag.y);
+        ag.z = fmaf(g[k].z, z[k].z, ag.z); ag.w = fmaf(g[k].w, z[k].w, ag.w);
+        ab.x += g[k].x; ab.y += g[k].y; ab.z += g[k].z; ab.w += g[k].w;
+        *reinterpret_cast<float4*>(my + e) = ag;
+        *reinterpret_cast<float4*>(my + H + e) = ab;
         g[k].x *= gm.x; g[k].y *= gm.y; g[k].z *= gm.z; g[k].w *= gm.w;
         m1 += g[k].x + g[k].y + g[k].z + g[k].w;
         m2 += g[k].x * z[k].x + g[k].y * z[k].y + g[k].z * z[k].z + g[k].w * z[k].w;
@@ -115,7 +107,7 @@ layernorm_bwd_kernel(const void* __restrict__ yv, const float* __restrict__ resi
     m1 = warp_sum(m1) / (float)H;
     m2 = warp_sum(m2) / (float)H;
 #pragma unroll
-    for (int k = 0; k < LN_MAXV; ++k) {
+    for (int k = 0; k < NV; ++k) {
       const int e = (lane + 32 * k) * 4;
       if (k < nv4 && e < H) {
         float4 d;
@@ -124,39 +116,35 @@ layernorm_bwd_kernel(const void* __restrict__ yv, const float* __restrict__ resi
         d.z = rstd * (g[k].z - m1 - z[k].z * m2);
         d.w = rstd * (g[k].w - m1 - z[k].w * m2);
         if (dz_f32 != nullptr) *reinterpret_cast<float4*>(dz_f32 + (size_t)row * H + e) = d;
-        if constexpr (DROP) {
-          d.x *= mk[k].x; d.y *= mk[k].y; d.z *= mk[k].z; d.w *= mk[k].w;
+        if constexpr (DROP) {   // the mask is regenerated (it is not kept in registers across the row)
+          const size_t i = (size_t)row * H + e;
+          const uint32_t hi = seed_hi ^ (uint32_t)(i >> 32), lo = (uint32_t)i;
+          d.x *= hash3(seed_lo, hi, lo) < thr ? inv_keep : 0.f;
+          d.y *= hash3(seed_lo, hi, lo + 1) < thr ? inv_keep : 0.f;
+          d.z *= hash3(seed_lo, hi, lo + 2) < thr ? inv_keep : 0.f;
+          d.w *= hash3(seed_lo, hi, lo + 3) < thr ? inv_keep : 0.f;
         }
         if (dz_bf16 != nullptr) st_bf16x4(dz_bf16 + (size_t)row * H + e, d);
-        ad[k].x += d.x; ad[k].y += d.y; ad[k].z += d.z; ad[k].w += d.w;
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < LN_MAXV; ++k) {
-    const int e = (lane + 32 * k) * 4;
-    if (k < nv4 && e < H) {
-      atomicAdd(&s_acc[e + 0], ag[k].x);
-      atomicAdd(&s_acc[e + 1], ag[k].y);
-      atomicAdd(&s_acc[e + 2], ag[k].z);
-      atomicAdd(&s_acc[e + 3], ag[k].w);
-      atomicAdd(&s_acc[H + e + 0], ab[k].x);
-      atomicAdd(&s_acc[H + e + 1], ab[k].y);
-      atomicAdd(&s_acc[H + e + 2], ab[k].z);
-      atomicAdd(&s_acc[H + e + 3], ab[k].w);
-      if (dbias != nullptr) {
-        atomicAdd(&s_acc[2 * H + e + 0], ad[k].x);
-        atomicAdd(&s_acc[2 * H + e + 1], ad[k].y);
-        atomicAdd(&s_acc[2 * H + e + 2], ad[k].z);
-        atomicAdd(&s_acc[2 * H + e + 3], ad[k].w);
+        if (dbias != nullptr) {
+          float4 ad = *reinterpret_cast<float4*>(my + 2 * H + e);
+          ad.x += d.x; ad.y += d.y; ad.z += d.z; ad.w += d.w;
+          *reinterpret_cast<float4*>(my + 2 * H + e) = ad;
+        }
       }
     }
   }
   __syncthreads();
   for (int e = threadIdx.x; e < H; e += blockDim.x) {
-    atomicAdd(dgamma + e, s_acc[e]);
-    atomicAdd(dbeta + e, s_acc[H + e]);
-    if (dbias != nullptr) atomicAdd(dbias + e, s_acc[2 * H + e]);
+    float a = 0.f, b = 0.f, c = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      a += s_acc[(size_t)w * 3 * H + e];
+      b += s_acc[(size_t)w * 3 * H + H + e];
+      c += s_acc[(size_t)w * 3 * H + 2 * H + e];
+    }
+    atomicAdd(dgamma + e, a);
+    atomicAdd(dbeta + e, b);
+    if (dbias != nullptr) atomicAdd(dbias + e, c);
   }
 }
 
@@ -288,6 +276,52 @@ gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __re
   }
 }
 
+// The same with the bias gradient of the dense layer in front of the GELU fused in: d_bias[c] += sum over rows of d_pre[:, c]
+// (2-D tiling of colsum_bf16_v8_kernel: a lane owns 8 consecutive columns, the CTA's 8 warps stride over rows).
+__device__ __forceinline__ float gelu_grad(float v, int erf_variant) {
+  if (erf_variant) return 0.5f * (1.f + erff(v * 0.7071067811865476f)) + v * 0.3989422804014327f * __expf(-0.5f * v * v);
+  const float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
+  const float t = tanhf(u);
+  return 0.5f * (1.f + t) + 0.5f * v * (1.f - t * t) * 0.7978845608028654f * (1.f + 3.f * 0.044715f * v * v);
+}
+__global__ void __launch_bounds__(256)
+gelu_bwd_bias_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dact,
+                     __nv_bfloat16* __restrict__ dpre, float* __restrict__ dbias, int M, int N, int erf_variant) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  __shared__ float part[8][256 + 8];
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c0 < N) {
+    for (int m = blockIdx.y * 8 + warp; m < M; m += gridDim.y * 8) {
+      const size_t o = (size_t)m * N + c0;
+      const float4 x0 = ld_bf16x4(pre + o), x1 = ld_bf16x4(pre + o + 4), g0 = ld_bf16x4(dact + o), g1 = ld_bf16x4(dact + o + 4);
+      float4 d0, d1;
+      d0.x = g0.x * gelu_grad(x0.x, erf_variant); d0.y = g0.y * gelu_grad(x0.y, erf_variant);
+      d0.z = g0.z * gelu_grad(x0.z, erf_variant); d0.w = g0.w * gelu_grad(x0.w, erf_variant);
+      d1.x = g1.x * gelu_grad(x1.x, erf_variant); d1.y = g1.y * gelu_grad(x1.y, erf_variant);
+      d1.z = g1.z * gelu_grad(x1.z, erf_variant); d1.w = g1.w * gelu_grad(x1.w, erf_variant);
+      st_bf16x4(dpre + o, d0);
+      st_bf16x4(dpre + o + 4, d1);
+      // the separate column-sum pass read the bf16-rounded d_pre: sum the rounded values here too
+      auto rb = [](float v) { return __bfloat162float(__float2bfloat16_rn(v)); };
+      acc[0] += rb(d0.x); acc[1] += rb(d0.y); acc[2] += rb(d0.z); acc[3] += rb(d0.w);
+      acc[4] += rb(d1.x); acc[5] += rb(d1.y); acc[6] += rb(d1.z); acc[7] += rb(d1.w);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < N) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += part[w][threadIdx.x];
+    atomicAdd(dbias + c, sum);
+  }
+}
+
 // gelu forward on a bf16 pre-activation (training keeps `pre` for the backward pass)
 __global__ void __launch_bounds__(256)
 gelu_fwd_kernel(const __nv_bfloat16* __restrict__ pre, __nv_bfloat16* __restrict__ act, size_t n4, int erf_variant) {
@@ -361,16 +395,24 @@ extern "C" int ner_layernorm_dropout_bwd_bias(const void* y, int y_is_bf16, cons
   if (!y || !gamma || !d_out || !d_gamma || !d_beta || (!dz_f32 && !dz_bf16)) return NER_ERR_INVALID_ARG;
   if (!(keep_prob > 0.f) || keep_prob > 1.f) return NER_ERR_INVALID_ARG;
   if (H % 4 != 0 || H > 128 * LN_MAXV) return NER_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)3 * H * 4;
+  const size_t smem = (size_t)8 * 3 * H * 4;   // per-warp column partials
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // one CTA per SM (the 160-register row state allows no more): rows per CTA sized so that the grid covers the 148 SMs
-  // — 64 rows per CTA left 2/3 of them idle at the packed M of a TRAIN step (50 us per launch for 7 us of HBM time)
-  int per_block = ((M + 147) / 148 + 7) / 8 * 8;
+  // two CTAs per SM: rows per CTA sized so that the grid covers 2 x 148 CTA slots once
+  int per_block = ((M + 2 * 148 - 1) / (2 * 148) + 7) / 8 * 8;
   per_block = per_block < 8 ? 8 : (per_block > 64 ? 64 : per_block);
   const int grid = rows_grid(M, per_block);
   const bool drop = keep_prob < 1.f;
-  auto kern = y_is_bf16 ? (drop ? layernorm_bwd_kernel<true, true> : layernorm_bwd_kernel<true, false>)
-                        : (drop ? layernorm_bwd_kernel<false, true> : layernorm_bwd_kernel<false, false>);
+  const int nv = (H / 4 + 31) / 32;
+  using KernT = void (*)(const void*, const float*, const float*, const float*, float*, __nv_bfloat16*, float*, float*, float*, int,
+                         int, float, float, uint32_t, uint32_t);
+  KernT kern = nullptr;
+#define LN_PICK(NVV)                                                                                                   \
+  kern = y_is_bf16 ? (drop ? (KernT)layernorm_bwd_kernel<true, true, NVV> : (KernT)layernorm_bwd_kernel<true, false, NVV>)  \
+                   : (drop ? (KernT)layernorm_bwd_kernel<false, true, NVV> : (KernT)layernorm_bwd_kernel<false, false, NVV>)
+  if (nv <= 2) { LN_PICK(2); } else if (nv <= 4) { LN_PICK(4); } else if (nv <= 6) { LN_PICK(6); } else { LN_PICK(8); }
+#undef LN_PICK
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   kern<<<grid, 256, smem, st>>>(y, residual, gamma, d_out, dz_f32, static_cast<__nv_bfloat16*>(dz_bf16), d_gamma, d_beta, d_bias, M,
                                 H, eps, keep_prob, (uint32_t)seed, (uint32_t)(seed >> 32));
   return ner_launch_status();
@@ -447,6 +489,23 @@ extern "C" int ner_gelu_bwd_bf16(const void* pre_bf16, const void* dact_bf16, vo
   gelu_bwd_kernel<<<flat_grid(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(pre_bf16), static_cast<const __nv_bfloat16*>(dact_bf16),
       static_cast<__nv_bfloat16*>(dpre_bf16), n / 4, erf_variant);
+  return ner_launch_status();
+}
+
+extern "C" int ner_gelu_bwd_bias_bf16(const void* pre_bf16, const void* dact_bf16, void* dpre_bf16, float* d_bias, int M, int N,
+                                      int erf_variant, ner_stream_t stream) {
+  if (M < 0 || N < 1) return NER_ERR_INVALID_ARG;
+  if (M == 0) return NER_OK;
+  if (!pre_bf16 || !dact_bf16 || !dpre_bf16 || !d_bias) return NER_ERR_INVALID_ARG;
+  if (N % 8 != 0 || ((reinterpret_cast<uintptr_t>(pre_bf16) | reinterpret_cast<uintptr_t>(dact_bf16) |
+                      reinterpret_cast<uintptr_t>(dpre_bf16)) & 15) != 0)
+    return NER_ERR_UNSUPPORTED;
+  const int cb = (N + 255) / 256;
+  int gy = (4 * 148 + cb - 1) / cb;
+  if (gy > (M + 7) / 8) gy = (M + 7) / 8;
+  gelu_bwd_bias_kernel<<<dim3(cb, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(pre_bf16), static_cast<const __nv_bfloat16*>(dact_bf16),
+      static_cast<__nv_bfloat16*>(dpre_bf16), d_bias, M, N, erf_variant);
   return ner_launch_status();
 }
 

@@ -293,8 +293,7 @@ static int train_bwd_impl(const ner_bert_config* cfg, const float* emb_ln_gamma,
                                            H, cfg->ln_eps, hidden_keep, s2, stream));   // mask: dense branch (dz16, d_bd) only
     if (!grouped) NER_TRY(wgrad(s.inter, I, nullptr, dz16, H, g.d_wd, rows, Rp, xt, dyt, st));
     NER_TRY(ner_gemm_bf16(dz16, g.wd_kn, nullptr, nullptr, dinter, rows, I, H, NER_EPI_BF16, 0, stream));
-    NER_TRY(ner_gelu_bwd_bf16(s.pre, dinter, dpre, R * I, gelu_erf, stream));
-    NER_TRY(ner_colsum_bf16_add(dpre, g.d_bi, rows, I, stream));
+    NER_TRY(ner_gelu_bwd_bias_bf16(s.pre, dinter, dpre, g.d_bi, rows, I, gelu_erf, stream));   // d_pre and the FFN1 bias gradient
     if (!grouped) NER_TRY(wgrad(s.x1_16, H, nullptr, dpre, I, g.d_wi, rows, Rp, xt, dyt, st));
     float* dx1 = (d == dA) ? dB : dA;
     NER_TRY(ner_gemm_bf16(dpre, g.wi_kn, nullptr, dz32, dx1, rows, H, I, NER_EPI_RES_F32, 0, stream));

@@ -511,6 +511,15 @@ def gelu_f32(x, erf=False, inplace=False):
     return y
 
 
+def gelu_bwd_bias_bf16(pre, dact, d_bias, erf=False):
+    """d_pre = d_act * gelu'(pre) and d_bias += column sums of d_pre, one pass (pre / dact bf16 [M, N])."""
+    require_cuda(pre, dact, d_bias)
+    M, N = pre.shape
+    out = torch.empty_like(pre)
+    check(lib().ner_gelu_bwd_bias_bf16(ptr(pre), ptr(dact), ptr(out), ptr(d_bias), M, N, 1 if erf else 0, stream()))
+    return out
+
+
 def gelu_bwd_bf16(pre, dact, erf=False):
     require_cuda(pre, dact)
     out = torch.empty_like(pre)

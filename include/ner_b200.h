@@ -477,6 +477,10 @@ int ner_gelu_bf16(const void* pre_bf16, void* act_bf16, size_t n, int erf_varian
 int ner_gelu_f32(const float* x, float* y, size_t n, int erf_variant, ner_stream_t stream);
 int ner_gelu_bwd_bf16(const void* pre_bf16, const void* dact_bf16, void* dpre_bf16, size_t n,
                       int erf_variant, ner_stream_t stream);
+/* GELU backward on [M, N] with the bias gradient of the dense layer in front of the GELU fused in:
+ * d_pre = d_act * gelu'(pre) and d_bias[N] += column sums of (the bf16-rounded) d_pre.  N % 8 == 0. */
+int ner_gelu_bwd_bias_bf16(const void* pre_bf16, const void* dact_bf16, void* dpre_bf16, float* d_bias, int M, int N,
+                           int erf_variant, ner_stream_t stream);
 /* Embedding backward: scatter-add dx [B*L,H] f32 into d_word [vocab,H], d_type [n_type,H],
  * d_pos [>=L,H] (all accumulated into). */
 int ner_bert_embed_bwd(const float* dx, const int32_t* ids, const int32_t* seg, float* d_word,

@@ -225,3 +225,18 @@ def test_pack_group_equals_separate_packs():
     q.mul_(2.0)                                                      # same table, new values: re-run only
     grp.run()
     assert torch.equal(nk_qkv[:H], ops.pack_weight_bf16(q))
+
+
+@pytest.mark.parametrize("erf", [False, True])
+def test_gelu_bwd_with_fused_bias_gradient(erf):
+    M, N = 3150, 3072
+    g = torch.Generator().manual_seed(31)
+    pre = torch.randn(M, N, generator=g).to(torch.bfloat16).cuda()
+    dact = (torch.randn(M, N, generator=g) * 0.1).to(torch.bfloat16).cuda()
+    dbias = torch.ones(N, device="cuda")
+    got = ops.gelu_bwd_bias_bf16(pre, dact, dbias, erf=erf)
+    want = ops.gelu_bwd_bf16(pre, dact, erf=erf)
+    assert torch.equal(got, want)
+    ref = torch.ones(N, device="cuda")
+    ops.colsum_bf16_add(want, ref)
+    torch.testing.assert_close(dbias, ref, rtol=1e-4, atol=1e-3)

@@ -73,6 +73,15 @@ def test_config3_bert_bilstm_crf_b64_l128_12_layers(tmp_path):
         ref_i = est.predict(batches[i])['pred_ids'].numpy()
         assert float((o['pred_ids'].numpy() == ref_i).mean()) >= 0.999
     assert (pred_fused[~valid.numpy()] == 0).all()                                  # zero beyond seq_len (tools/layer.py:147)
+    # stacked calls (bench.py's second pipeline: `group` host batches per PREDICT call): sentences are independent, so the
+    # tags are those of the separate calls (5 batches, group 4 -> one call of 4 and one of 1; group 8 -> one call of 5)
+    for streams, group in ((2, 4), (2, 8)):
+        outs_g = list(est.predict_iter(iter(batches), depth=3, streams=streams, group=group))
+        assert len(outs_g) == len(batches)
+        for i, o in enumerate(outs_g):
+            ref_i = est.predict(batches[i])['pred_ids'].numpy()
+            assert o['pred_ids'].shape == ref_i.shape
+            assert float((o['pred_ids'].numpy() == ref_i).mean()) >= 0.999, (streams, group, i)
 
     # --- emission logits of the CUDA path vs the oracle
     logits = _cuda_logits(est, dev, "bert_bilstm_crf").cpu()
