@@ -94,13 +94,13 @@ class GradExchange(object):
 
     The reference is single device; the B200 engine shards sentences over ranks and sums gradients.  Instead of one
     all-reduce after the whole backward, the flat gradient buffer (laid out in backward-completion order, FlatState) is
-    cut into contiguous buckets — the dense kernels of encoder layers [11-9] [8-6] [5-3] [2-0], then the rest (embeddings,
+    cut into contiguous buckets — the dense kernels of each encoder layer, 11 first ... 0, then the rest (embeddings,
     LayerNorm / bias ranges, the layers above BertModel) — and a layer bucket is all-reduced on a side stream as soon as the event recorded behind its last
     gradient kernel has fired (ner_bert_train_bwd_set_layer_events), while the layers below are still being differentiated.
     dtype 'bf16': a bucket travels as bf16 (half the NVLink bytes: cast, all-reduce, cast back on the side stream); the
     global-norm clip and Adam read the fp32 buffer either way."""
 
-    LAYERS_PER_BUCKET = 3
+    LAYERS_PER_BUCKET = 1      # one encoder layer (28 MB of fp32 gradients) per all-reduce: the exposed tail is the last layer + embeddings
 
     def __init__(self, fs, dtype='fp32'):
         self.fs, self.dtype = fs, dtype

@@ -63,7 +63,7 @@ def test_overlapped_bucketed_exchange_equals_single_allreduce(tmp_path):
     for p in procs:
         p.join(timeout=60)
     r0, r1 = res[0], res[1]
-    assert r0["single"]["_buckets"] is None and len(r0["overlap"]["_buckets"]) >= 3
+    assert r0["single"]["_buckets"] is None and len(r0["overlap"]["_buckets"]) >= 4
     assert [b[0][0] for b in r0["overlap"]["_buckets"]][:2] == ["layer", "layer"]
     for mode in ("single", "overlap", "overlap_bf16"):
         for k, v in r0[mode].items():
@@ -74,5 +74,7 @@ def test_overlapped_bucketed_exchange_equals_single_allreduce(tmp_path):
             continue
         # same gradient sum, same optimizer: equal up to the atomics' accumulation order inside the backward kernels
         assert torch.allclose(v, r0["overlap"][k], rtol=1e-4, atol=1e-6), k
-        # bf16 exchange: Adam normalises the update, so a 2^-9 relative gradient error moves a weight by << lr
-        assert torch.allclose(v, r0["overlap_bf16"][k], rtol=1e-3, atol=2e-5), k
+        # bf16 exchange: the gradient sum carries a 2^-9 relative error; Adam normalises the update, so a component whose
+        # gradient is near zero can move by up to ~lr per step either way (lr = 2.5e-3 in the x500 groups, 3 steps)
+        diff = (v - r0["overlap_bf16"][k]).abs()
+        assert diff.mean().item() < 2e-4 and diff.max().item() < 1.5e-2, (k, diff.mean().item(), diff.max().item())
