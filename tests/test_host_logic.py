@@ -44,3 +44,48 @@ def test_deferred_is_evaluated_once_and_only_when_fetched():
     assert float(loss) == -2.0 and calls == [1]
     assert float(loss) == -2.0 and calls == [1]
     assert float((ll + 1.0).mean()) == 3.0 and float((2.0 * ll).mean()) == 4.0
+
+
+def test_grad_exchange_buckets_cover_the_flat_buffer_in_backward_order(monkeypatch):
+    """GradExchange (host logic, no GPU): the flat gradient buffer is cut into one contiguous bucket per encoder layer —
+    layer 11 first, each waiting for its own layer's event — plus tail buckets for everything else; together they cover
+    every element exactly once."""
+    import torch
+    from chinesener_b200 import bert, variables
+    from chinesener_b200.tools import train_utils as tu
+
+    class FakeEvent(object):
+        cuda_event = 0
+
+        def record(self, *a):
+            pass
+
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "Stream", lambda: object())
+    cfg = dict(bert.BERT_BASE_CHINESE, num_hidden_layers=4, vocab_size=50, hidden_size=64, intermediate_size=128,
+               max_position_embeddings=16)
+    st = variables.VariableStore("cpu")
+    bert.create_bert_variables(cfg, st)
+    st.get_variable("logits/kernel", (64, 10), variables.zeros)
+    st.get_variable("crf_layer/transitions", (10, 10), variables.zeros)
+    keys = ["crf", "logit", "lstm"]
+
+    def group_of(name):
+        for gi, k in enumerate(keys):
+            if k in name:
+                return (gi, 0 if tu._decays(name) else 1)
+        return (len(keys), 0 if tu._decays(name) else 1)
+
+    fs = tu.FlatState(st, group_of)
+    ex = tu.GradExchange(fs)
+    kinds = [b[0] for b in ex.buckets]
+    assert kinds[:4] == [("layer", 0), ("layer", 1), ("layer", 2), ("layer", 3)]          # readiness order: layer 3 first
+    assert all(k == ("tail",) for k in kinds[4:]) and len(kinds) >= 5
+    for g, (key, s, e, ev) in enumerate(ex.buckets[:4]):
+        names = [n for n in fs.names if s <= fs.slices[n][0] < e]
+        assert names and all(f"/layer_{3 - g}/" in n and n.endswith("/kernel") for n in names)
+        assert ev is ex.layer_events[3 - g]
+    spans = sorted((s, e) for _, s, e, _ in ex.buckets)
+    assert spans[0][0] == 0 and spans[-1][1] == fs.grads.numel()
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))                            # contiguous, no overlap
+    assert all(ev is ex.tail_event for k, _, _, ev in ex.buckets if k == ("tail",))
