@@ -39,7 +39,7 @@ def _worker(rank, world, port, tmp, q):
                 est.train_step(synthetic.msra_batch(8, 64, vocab=CFG['vocab_size'], seed=10 * step + rank))
             torch.cuda.synchronize()
             ex = getattr(est.store, "_grad_exchange", None)
-            out[mode] = {k: est.store.vars[k].detach().cpu() for k in
+            out[mode] = {k: est.store.vars[k].detach().cpu().numpy() for k in      # numpy: pickled by value through the queue
                          ("bert/encoder/layer_3/output/dense/kernel", "bert/encoder/layer_0/attention/self/query/kernel",
                           "bert/embeddings/word_embeddings", "logits/kernel", "crf_layer/transitions",
                           "bert/encoder/layer_1/output/LayerNorm/gamma")}
@@ -62,6 +62,9 @@ def test_overlapped_bucketed_exchange_equals_single_allreduce(tmp_path):
     res = dict(q.get(timeout=600) for _ in procs)
     for p in procs:
         p.join(timeout=60)
+    for r in res.values():
+        for mode in r:
+            r[mode] = {k: (torch.from_numpy(v) if k != "_buckets" else v) for k, v in r[mode].items()}
     r0, r1 = res[0], res[1]
     assert r0["single"]["_buckets"] is None and len(r0["overlap"]["_buckets"]) >= 4
     assert [b[0][0] for b in r0["overlap"]["_buckets"]][:2] == ["layer", "layer"]
