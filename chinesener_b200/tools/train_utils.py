@@ -104,7 +104,8 @@ class GradExchange(object):
 
     def __init__(self, fs, dtype='fp32'):
         self.fs, self.dtype = fs, dtype
-        self.comm = torch.cuda.Stream()
+        # highest priority: the all-reduce kernels take SM slots as soon as CTAs of the (persistent, all-SM) backward GEMMs retire
+        self.comm = torch.cuda.Stream(priority=-1)
         self.tail_event = torch.cuda.Event()
         layers = sorted({int(m.group(1)) for n in fs.names for m in [_LAYER_RE.search(n)] if m})
         self.num_layers = (max(layers) + 1) if layers else 0
