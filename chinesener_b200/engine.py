@@ -143,11 +143,27 @@ class Estimator:
             if cur:
                 yield cur
 
+        # streams > 1: the host->device copies of a call run on their own stream, so the inputs of call k+1 travel while the
+        # compute streams are busy with calls k-1 / k (a compute stream that copies its own inputs idles for the ~20 small
+        # transfers of a stacked call)
+        copy_stream = torch.cuda.Stream() if side is not None else None
         k = 0
         for feats_list in grouped(batches):
             ctx = torch.cuda.stream(side[k % streams]) if side is not None else contextlib.nullcontext()
+            if copy_stream is not None:
+                with torch.cuda.stream(copy_stream):
+                    dev = self.stack_to_device(feats_list)
+                    copied = torch.cuda.Event()
+                    copied.record()
             with ctx:
-                dev = self.stack_to_device(feats_list)
+                if copy_stream is not None:
+                    st = side[k % streams]
+                    st.wait_event(copied)
+                    for t in dev.values():
+                        if torch.is_tensor(t) and t.is_cuda:
+                            t.record_stream(st)          # allocated on the copy stream, consumed here
+                else:
+                    dev = self.stack_to_device(feats_list)
                 tile0 = ops.DEFAULT_TILE
                 if side is not None or group > 1:   # partial waves are filled (other streams / 2x rows): take the fastest tile
                     ops.DEFAULT_TILE = ops.TILE_AUTO_THROUGHPUT
