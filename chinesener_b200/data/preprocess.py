@@ -24,6 +24,32 @@ MSRA_MAX_SEQ_LEN = 150
 MAPPING = {'train': 'train', 'val': 'valid', 'test': 'predict'}
 
 
+# data/msr/preprocess.py:7-22 (Chinese word segmentation as a tagging task: the auxiliary task of the multi-task plugins)
+MSR_TAG2IDX = {'[PAD]': 0, 'B': 1, 'I': 2, 'E': 3, 'S': 4, '[CLS]': 5, '[SEP]': 6}
+MSR_MAPPING = {'training': 'train', 'test_gold': 'valid', 'test': 'predict'}
+
+
+def msr_gen_tag(length):
+    """data/msr/preprocess.py:27-33"""
+    if length == 1:
+        return 'S'
+    if length == 2:
+        return 'B E'
+    return ' '.join(['B'] + ['I'] * (length - 2) + ['E'])
+
+
+def load_msr_data(data_dir, file_name):
+    """data/msr/preprocess.py:36-52 — `msr_<split>.utf8`: words separated by spaces -> characters + B/I/E/S tags."""
+    sentences, tags = [], []
+    for line in read_text(data_dir, 'msr_{}.utf8'.format(file_name)):
+        if line == '':
+            continue
+        words = [t for t in line.split(' ') if t not in ['', '"']]
+        tags.append(' '.join(msr_gen_tag(len(t)) for t in words))
+        sentences.append(' '.join(c for t in words for c in t))
+    return sentences, tags
+
+
 def read_text(data_dir, filename):
     with open(os.path.join(data_dir, filename), 'r', encoding='utf-8') as f:
         return [line.strip() for line in f]
@@ -36,10 +62,11 @@ def load_data(data_dir, file_name):
     return sentences, tags
 
 
-def dump_records(proc, src_dir, out_dir, file_name, mapping=MAPPING, word_enhance=None, embedding=None, verbose=True):
+def dump_records(proc, src_dir, out_dir, file_name, mapping=MAPPING, word_enhance=None, embedding=None, verbose=True,
+                 load_data=None):
     """One split through `proc.build_feature` -> `<out_dir>/<tokenizer>_<renamed>[_<enhance>].nerrec`; the train split
     also writes `<tokenizer>[_<enhance>]_data_params.pkl` (data/base_preprocess.py:206-227, 247-253)."""
-    sentences, tags = load_data(src_dir, file_name)
+    sentences, tags = (load_data or globals()['load_data'])(src_dir, file_name)
     feats, n_invalid = [], 0
     for sentence, tag in zip(sentences, tags):
         try:
@@ -71,16 +98,19 @@ def main():
     ap.add_argument('--bert_dir', default='./pretrain_model/ch_google/')
     ap.add_argument('--max_seq_len', type=int, default=MSRA_MAX_SEQ_LEN)
     ap.add_argument('--seed', type=int, default=1234, help='seed of the two add-on embedding rows ([PAD], [UNK])')
+    ap.add_argument('--format', default='ner', choices=['ner', 'msr'], help="'msr': word-segmented msr_<split>.utf8 files (CWS tags)")
     args = ap.parse_args()
     if args.tokenizer == TokenizerGiga:
         tok = get_giga_tokenizer(args.giga_vec)
         emb = tok.embedding(args.seed)
     else:
         tok, emb = get_bert_tokenizer(args.bert_dir), None
-    proc = get_instance(args.tokenizer, args.max_seq_len, MSRA_TAG2IDX, tok)
-    for file in MAPPING:
+    msr = args.format == 'msr'
+    proc = get_instance(args.tokenizer, args.max_seq_len, MSR_TAG2IDX if msr else MSRA_TAG2IDX, tok)
+    for file in (MSR_MAPPING if msr else MAPPING):
         print('Dumping records for {} tokenizer = {}'.format(file, args.tokenizer))
-        dump_records(proc, args.src, args.out, file, embedding=emb)
+        dump_records(proc, args.src, args.out, file, mapping=MSR_MAPPING if msr else MAPPING, embedding=emb,
+                     load_data=load_msr_data if msr else None)
 
 
 if __name__ == '__main__':

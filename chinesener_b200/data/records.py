@@ -23,6 +23,7 @@ memory and no parsing — the per-example protobuf decode of the reference's inp
 import json
 import os
 import pickle
+from collections import OrderedDict
 
 import numpy as np
 import torch
@@ -222,4 +223,84 @@ class NerDataset(object):
                 carry = order[full:]
             if len(carry):
                 yield rec.batch(carry, pin_memory, with_strings)
+        return input_fn
+
+
+class MultiDataset(object):
+    """reference dataset.py:73-141 over .nerrec files — the input pipe of the multi-task / adversarial plugins: one
+    NerDataset per directory, batches mix the datasets sample by sample and carry `task_ids` (the index of the dataset a
+    sentence came from).
+
+    `build_input_fn(file_name)`: the datasets are shuffled (window 64) and interleaved one sample at a time
+    (`choose_from_datasets` over `range(n).repeat()`; a dataset that runs out is skipped and the others continue until all
+    are exhausted), the interleaved stream is repeated `epoch_size` times and cut into batches.  `build_predict_fn(data)`:
+    one ordered pass over that dataset's `predict` split.  `params`: each dataset's params under its name, `task_list`,
+    `step_per_epoch` (the largest of the datasets', as the reference takes it), `num_train_steps`, `max_seq_len`."""
+
+    def __init__(self, root_dir, data_list, batch_size, epoch_size, model_name, seed=1234):
+        self.batch_size, self.epoch_size, self.data_list, self.seed = batch_size, epoch_size, list(data_list), seed
+        self.dataset_dict = OrderedDict((d, NerDataset(os.path.join(root_dir, d), batch_size, epoch_size, model_name, seed))
+                                        for d in self.data_list)
+        self._params = {}
+        self.init_params()
+
+    def init_params(self):
+        for data, dataset in self.dataset_dict.items():
+            self._params[data] = dataset.params
+        self._params['step_per_epoch'] = int(max(p['step_per_epoch'] for p in self._params.values()))
+        self._params['num_train_steps'] = int(self.epoch_size * self._params['step_per_epoch'])
+        self._params['task_list'] = self.data_list
+        self._params['max_seq_len'] = self._params[self.data_list[0]]['max_seq_len']
+
+    @property
+    def params(self):
+        return self._params
+
+    @staticmethod
+    def _collate(parts, pin_memory):
+        """list of (task, single-row feature dict) -> one batch dict with task_ids [B]."""
+        out = {}
+        for k in parts[0][1]:
+            vals = [f[k] for _, f in parts]
+            out[k] = torch.cat(vals, 0) if torch.is_tensor(vals[0]) else [x for v in vals for x in v]
+        out['task_ids'] = torch.tensor([t for t, _ in parts], dtype=torch.int32)
+        if pin_memory and torch.cuda.is_available():
+            out = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in out.items()}
+        return out
+
+    def build_input_fn(self, file_name, is_predict=0, pin_memory=True, with_strings=False):
+        """is_predict (used for the EVAL passes): one ordered, unshuffled pass over the interleaved stream."""
+        def input_fn():
+            recs = [RecordFile(ds.file_path(file_name)) for ds in self.dataset_dict.values()]
+            rng = np.random.default_rng(self.seed)
+            pending = []
+
+            def flush():
+                return self._collate([(t, recs[t].batch([i], False, with_strings)) for t, i in pending], pin_memory)
+
+            for _ in range(1 if is_predict else self.epoch_size):
+                orders = [np.arange(r.n) if is_predict else shuffle_window(r.n, 64, rng) for r in recs]
+                pos = [0] * len(recs)
+                while any(p < len(o) for p, o in zip(pos, orders)):
+                    for t, order in enumerate(orders):                        # choice dataset = 0, 1, ..., 0, 1, ...
+                        if pos[t] < len(order):
+                            pending.append((t, int(order[pos[t]])))
+                            pos[t] += 1
+                            if len(pending) == self.batch_size:
+                                yield flush()
+                                pending = []
+            if pending:
+                yield flush()
+        return input_fn
+
+    def build_predict_fn(self, data, pin_memory=True):
+        task = self.data_list.index(data)
+        inner = self.dataset_dict[data].build_input_fn('predict', is_predict=True, pin_memory=False)
+
+        def input_fn():
+            for feats in inner():
+                feats['task_ids'] = torch.full((feats['token_ids'].shape[0],), task, dtype=torch.int32)
+                if pin_memory and torch.cuda.is_available():
+                    feats = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in feats.items()}
+                yield feats
         return input_fn

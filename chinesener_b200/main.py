@@ -121,6 +121,10 @@ def singletask_train(args):
     TRAIN_PARAMS = dict(TRAIN_PARAMS)
     if args.epoch_size:
         TRAIN_PARAMS['epoch_size'] = args.epoch_size
+    if args.pretrain_dir:
+        TRAIN_PARAMS['pretrain_dir'] = args.pretrain_dir
+    if args.batch_size:
+        TRAIN_PARAMS['batch_size'] = args.batch_size
     input_pipe = NerDataset(data_dir, TRAIN_PARAMS['batch_size'], TRAIN_PARAMS['epoch_size'], model_name, seed=args.seed)
     TRAIN_PARAMS.update(input_pipe.params)       # label_size, max_seq_len, num_train_steps ... (main.py:25)
     print('=' * 10 + 'TRAIN PARAMS' + '=' * 10)
@@ -159,6 +163,64 @@ def singletask_train(args):
     return summary
 
 
+def multitask_train(args):
+    """reference main.py:65-118: `--data a,b` with an mtl / adv plugin.  One Estimator over
+    `./checkpoint/ner_<a_b>_<model>`, TRAIN / EVAL over the sample-by-sample mix of the datasets (MultiDataset), then one
+    PREDICT pass per dataset with that dataset's task id -> `<data_root>/<data>/<model>_<a_b>_predict.pkl`."""
+    from . import checkpoint, engine
+    from .data.records import MultiDataset
+    from .evaluation import SingleEval
+    model_name = args.rename if args.rename else args.model_name
+    data_list = args.data.split(',')
+    joined = '_'.join(data_list)
+    model_dir = os.path.join(args.checkpoint_root, 'ner_{}_{}'.format(joined, model_name))
+    data_root = args.data_dir or './data'
+    if args.clear_model:
+        clear_model(model_dir)
+
+    _, TRAIN_PARAMS = engine.load_plugin(args.model_name)
+    TRAIN_PARAMS = dict(TRAIN_PARAMS)
+    if args.epoch_size:
+        TRAIN_PARAMS['epoch_size'] = args.epoch_size
+    if args.pretrain_dir:
+        TRAIN_PARAMS['pretrain_dir'] = args.pretrain_dir
+    if args.batch_size:
+        TRAIN_PARAMS['batch_size'] = args.batch_size
+    input_pipe = MultiDataset(data_root, data_list, TRAIN_PARAMS['batch_size'], TRAIN_PARAMS['epoch_size'], model_name, seed=args.seed)
+    TRAIN_PARAMS.update(input_pipe.params)       # per-dataset params, task_list, step_per_epoch, num_train_steps, max_seq_len
+    print('=' * 10 + 'TRAIN PARAMS' + '=' * 10)
+    print(dict((i, j) for i, j in TRAIN_PARAMS.items() if i not in data_list))
+    print('=' * 10 + 'RUN PARAMS' + '=' * 10)
+    print(RUN_CONFIG)
+
+    estimator = engine.Estimator(args.model_name, TRAIN_PARAMS)
+    estimator.store.gen.manual_seed(args.seed)
+    warm = checkpoint.latest_checkpoint(model_dir)
+    if warm:
+        first = next(iter(input_pipe.build_input_fn('valid', is_predict=True)()))
+        estimator.evaluate(first)
+        print('warm start from {} (step {})'.format(warm, checkpoint.restore_checkpoint(estimator.store, warm)))
+
+    history = None
+    if not args.predict_only:
+        history = train_and_evaluate(estimator, input_pipe, model_dir, max_steps=args.max_steps)
+
+    summary = {'model': model_name, 'data': data_list, 'history': history, 'seed': args.seed, 'tasks': {}}
+    for data in data_list:
+        print('Prediction for {}'.format(data))
+        prediction = predict_to_list(estimator, input_pipe.build_predict_fn(data))
+        out_pkl = os.path.join(data_root, data, '{}_{}_predict.pkl'.format(model_name, joined))
+        with open(out_pkl, 'wb') as f:
+            pickle.dump(prediction, f)
+        tag_rep, _ = SingleEval(prediction, TRAIN_PARAMS[data]['idx2tag']).gen_report()
+        summary['tasks'][data] = {'n_predict': len(prediction), 'file': out_pkl, 'tag_weighted_f1': tag_rep['weighted avg']['f1-score']}
+        print('{} sentences -> {} (tag weighted-F1 {:.4f})'.format(len(prediction), out_pkl, tag_rep['weighted avg']['f1-score']))
+    if args.report:
+        with open(args.report, 'w') as f:
+            json.dump(summary, f, indent=1, default=float)
+    return summary
+
+
 def build_parser():
     parser = argparse.ArgumentParser()
     # the reference's flags (main.py:121-136); argparse accepts unambiguous prefixes, so `--model` works as it does there
@@ -171,10 +233,13 @@ def build_parser():
     parser.add_argument('--export_only', type=int, help='kept for compatibility (no SavedModel export: InferHelper serves in-process)',
                         required=False, default=0)
     # additions
-    parser.add_argument('--data_dir', type=str, default='', help='directory of the .nerrec files (default ./data/<data>)')
+    parser.add_argument('--data_dir', type=str, default='', help='directory of the .nerrec files (default ./data/<data>); with --data a,b: the root '
+                        'holding one directory per dataset (default ./data)')
     parser.add_argument('--checkpoint_root', type=str, default='./checkpoint')
     parser.add_argument('--predict_only', type=int, default=0)
     parser.add_argument('--epoch_size', type=int, default=0, help='override TRAIN_PARAMS["epoch_size"]')
+    parser.add_argument('--pretrain_dir', type=str, default='', help='override TRAIN_PARAMS["pretrain_dir"] (bert_config.json [+ checkpoint])')
+    parser.add_argument('--batch_size', type=int, default=0, help='override TRAIN_PARAMS["batch_size"]')
     parser.add_argument('--max_steps', type=int, default=None)
     parser.add_argument('--seed', type=int, default=1234)
     parser.add_argument('--report', type=str, default='', help='write a JSON summary (eval history + test F1) here')
@@ -186,8 +251,7 @@ def main(argv=None):
     if args.device >= 0:
         os.environ['CUDA_VISIBLE_DEVICES'] = '{}'.format(args.device)
     if len(args.data.split(',')) > 1:
-        raise SystemExit('multitask_train (main.py:65-118) is not built: the mtl / adv plugins are exercised through '
-                         'Estimator.train_step in tests; only single-dataset runs have a driver')
+        return multitask_train(args)
     return singletask_train(args)
 
 

@@ -233,3 +233,76 @@ def test_load_bert_checkpoint_assigns_by_name_and_fails_loudly(tmp_path):
     (d2 / "bert_config.json").write_text(json.dumps(cfg))
     with pytest.warns(UserWarning, match="random"):
         bert.create_bert_variables(bert.load_bert_config(str(d2)), variables.VariableStore("cpu", seed=1))
+
+
+def _msr_dir(tmp_path, rng):
+    """the sample sentences re-cut into random words, in the msr_<split>.utf8 layout (words separated by two spaces)."""
+    d = tmp_path / "msr_raw"
+    d.mkdir()
+    for split, n0, n1 in (("training", 0, 10), ("test_gold", 10, 13), ("test", 13, 18)):
+        lines = []
+        for s in SAMPLE["sentences"][n0:n1]:
+            chars, words, i = s.split(" "), [], 0
+            while i < len(chars):
+                k = int(rng.integers(1, 4))
+                words.append("".join(chars[i:i + k]))
+                i += k
+            lines.append("  ".join(words))
+        (d / "msr_{}.utf8".format(split)).write_text("\n".join(lines) + "\n\n", encoding="utf-8")
+    return str(d)
+
+
+def test_msr_word_segmentation_tags(tmp_path):
+    """data/msr/preprocess.py:27-52: a word of n characters -> S | B E | B I.. E; the sentence is its characters."""
+    assert [preprocess.msr_gen_tag(n) for n in (1, 2, 3, 5)] == ["S", "B E", "B I E", "B I I I E"]
+    (tmp_path / "msr_test.utf8").write_text("“  人们  常  说  生活是  一\n\n", encoding="utf-8")
+    s, t = preprocess.load_msr_data(str(tmp_path), "test")
+    assert s == ["“ 人 们 常 说 生 活 是 一"] and t == ["S B E S S B I E S"]
+
+
+def _prepare_two_tasks(tmp_path, tokenizer_type=TokenizerGiga, L=preprocess.MSRA_MAX_SEQ_LEN):
+    vocab = list(SAMPLE["giga_vocab_subset"]) + (["[CLS]", "[SEP]"] if tokenizer_type != TokenizerGiga else [])
+    tok = TokenizerAdapter(vocab)
+    root = tmp_path / "data"
+    src = _sample_dir(tmp_path)
+    ner = bp.get_instance(tokenizer_type, L, preprocess.MSRA_TAG2IDX, tok)
+    for split in preprocess.MAPPING:
+        preprocess.dump_records(ner, src, str(root / "msra"), split, verbose=False)
+    cws = bp.get_instance(tokenizer_type, L, preprocess.MSR_TAG2IDX, tok)
+    msr_src = _msr_dir(tmp_path, np.random.default_rng(3))
+    for split in preprocess.MSR_MAPPING:
+        preprocess.dump_records(cws, msr_src, str(root / "msr"), split, mapping=preprocess.MSR_MAPPING, verbose=False,
+                                load_data=preprocess.load_msr_data)
+    return str(root), tok
+
+
+def test_multi_dataset_interleaves_sample_by_sample(tmp_path):
+    """dataset.py:73-141: choose_from_datasets(range(2).repeat()) -> tasks alternate 0,1,0,1 until the shorter dataset runs
+    out, then the longer one alone; repeat(epoch).batch(B); params carry each dataset's own params + task_list."""
+    root, _ = _prepare_two_tasks(tmp_path)
+    md = records.MultiDataset(root, ["msra", "msr"], batch_size=4, epoch_size=2, model_name="bilstm_crf_mtl")
+    p = md.params
+    assert p["task_list"] == ["msra", "msr"] and p["max_seq_len"] == 150
+    assert p["msra"]["label_size"] == 10 and p["msr"]["label_size"] == 7 and p["msr"]["idx2tag"][4] == "S"
+    assert p["step_per_epoch"] == 16 // 4 and p["num_train_steps"] == 2 * 4          # max over the datasets (16 vs 10 samples)
+    train = list(md.build_input_fn("train")())
+    tasks = np.concatenate([b["task_ids"].numpy() for b in train])
+    assert train[0]["task_ids"].dtype == torch.int32 and tasks.shape == (2 * 26,)
+    per_epoch = [0, 1] * 10 + [0] * 6                                             # 10 msr + 16 msra sentences
+    assert tasks.tolist() == per_epoch * 2
+    sizes = [b["token_ids"].shape[0] for b in train]
+    assert sizes == [4] * 13                                                        # 52 = 13 * 4: batches run across the epoch boundary
+    # every sentence of both datasets appears once per epoch (shuffle is a permutation), labels stay inside the task's tag set
+    lab = torch.cat([b["label_ids"] for b in train])
+    assert int(lab[torch.from_numpy(tasks == 1)].max()) <= 6
+    epoch0 = torch.cat([b["token_ids"] for b in train])[:26]
+    seen = sorted(tuple(r.tolist()) for r in epoch0[torch.from_numpy(tasks[:26] == 1)])
+    rec = records.RecordFile(os.path.join(root, "msr", "giga_train.nerrec"))
+    assert seen == sorted(tuple(r.tolist()) for r in rec.batch(slice(0, rec.n), with_strings=False)["token_ids"])
+    # EVAL pass: ordered, one pass
+    ev = list(md.build_input_fn("valid", is_predict=True)())
+    assert np.concatenate([b["task_ids"].numpy() for b in ev]).tolist() == [0, 1, 0, 1, 0, 1, 0]
+    # per-dataset PREDICT pass keeps the dataset's order and its task id
+    pr = list(md.build_predict_fn("msr")())
+    assert sum(b["token_ids"].shape[0] for b in pr) == 5 and all((b["task_ids"] == 1).all() for b in pr)
+    assert "tokens" in pr[0] and pr[0]["tokens"][0][0] == SAMPLE["sentences"][13].split(" ")[0]

@@ -61,7 +61,7 @@ def test_grad_exchange_buckets_cover_the_flat_buffer_in_backward_order(monkeypat
             pass
 
     monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
-    monkeypatch.setattr(torch.cuda, "Stream", lambda: object())
+    monkeypatch.setattr(torch.cuda, "Stream", lambda **kw: object())
     cfg = dict(bert.BERT_BASE_CHINESE, num_hidden_layers=4, vocab_size=50, hidden_size=64, intermediate_size=128,
                max_position_embeddings=16)
     st = variables.VariableStore("cpu")
