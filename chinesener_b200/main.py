@@ -169,7 +169,6 @@ def multitask_train(args):
     PREDICT pass per dataset with that dataset's task id -> `<data_root>/<data>/<model>_<a_b>_predict.pkl`."""
     from . import checkpoint, engine
     from .data.records import MultiDataset
-    from .evaluation import SingleEval
     model_name = args.rename if args.rename else args.model_name
     data_list = args.data.split(',')
     joined = '_'.join(data_list)
@@ -212,9 +211,11 @@ def multitask_train(args):
         out_pkl = os.path.join(data_root, data, '{}_{}_predict.pkl'.format(model_name, joined))
         with open(out_pkl, 'wb') as f:
             pickle.dump(prediction, f)
-        tag_rep, _ = SingleEval(prediction, TRAIN_PARAMS[data]['idx2tag']).gen_report()
-        summary['tasks'][data] = {'n_predict': len(prediction), 'file': out_pkl, 'tag_weighted_f1': tag_rep['weighted avg']['f1-score']}
-        print('{} sentences -> {} (tag weighted-F1 {:.4f})'.format(len(prediction), out_pkl, tag_rep['weighted avg']['f1-score']))
+        # the entity report of evaluation.py is NER specific (a B/I/E/S segmentation tag has no entity type): tag accuracy here
+        real = [(int(a), int(b)) for i in prediction for a, b in zip(i['label_ids'], i['pred_ids']) if a > 0]
+        acc = sum(a == b for a, b in real) / max(len(real), 1)
+        summary['tasks'][data] = {'n_predict': len(prediction), 'file': out_pkl, 'tag_accuracy': acc}
+        print('{} sentences -> {} (tag accuracy {:.4f})'.format(len(prediction), out_pkl, acc))
     if args.report:
         with open(args.report, 'w') as f:
             json.dump(summary, f, indent=1, default=float)
