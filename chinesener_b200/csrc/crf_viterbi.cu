@@ -11,11 +11,16 @@
 // (s[i] + trans[i][j], max over i, then + logits[t][j]); ties -> lowest index (strict >).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "crf_common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
 using namespace crf;
+
+constexpr size_t kMaxSmem = 227 * 1024;
 
 template <int K>
 struct BpPack {
@@ -204,7 +209,7 @@ size_t viterbi_gs_smem_bytes(int L) {
   const size_t stage = (size_t)NSTAGE * NT * Gm::P * 4;
   const size_t dec = (size_t)NT * (((L + 3) & ~3) + 4);
   const size_t hi = ((size_t)L * NT * BpSplit<K>::HB + 15) & ~(size_t)15;
-  return (size_t)(2 * K * ((K + 1) / 2) + NT) * 4 + (stage > dec ? stage : dec) + hi;
+  return (size_t)(((2 * K * ((K + 1) / 2) + 3) & ~3) + NT) * 4 + (stage > dec ? stage : dec) + hi;
 }
 
 template <int K, int NT, int TT, int MINB>
@@ -219,7 +224,7 @@ crf_viterbi_gs_kernel(const float* __restrict__ logits, const int32_t* __restric
 
   extern __shared__ __align__(16) float smem[];
   float* s_tr = smem;                                           // [i][2*KP]: trans rows, pad column = 0
-  int* s_len = reinterpret_cast<int*>(s_tr + 2 * K * KP);       // [NT]
+  int* s_len = reinterpret_cast<int*>(s_tr + ((2 * K * KP + 3) & ~3));   // [NT]  (offset rounded: the ring below takes 16-byte cp.async / LDS.128)
   float* s_stage = reinterpret_cast<float*>(s_len + NT);        // [NSTAGE][NT][P]; reused as s_dec
   const int Lp = ((L + 3) & ~3) + 4;                            // byte pitch of a decoded row (Lp/4 odd-ish)
   const size_t stage_b = (size_t)NSTAGE * NT * P * 4, dec_b = (size_t)NT * Lp;
@@ -389,6 +394,255 @@ crf_viterbi_gs_kernel(const float* __restrict__ logits, const int32_t* __restric
   }
 }
 
+
+template <int K, int J = 0, typename F>
+__device__ __forceinline__ void sel_all(F& f) {
+  if constexpr (J < K) {
+    f(std::integral_constant<int, J>{});
+    sel_all<K, J + 1>(f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pipe-balanced variant (K <= 16, L*K % 4 == 0): same one-thread-per-sequence decomposition, three changes.
+//  (1) The per-(i,j) work of the argmax is split over BOTH arithmetic pipes.  The kernels above spend, per pair, one
+//      FADD2 half on the fma pipe and FSETP + FSEL + SEL on the alu pipe (one warp instruction per 2 cycles per pipe
+//      per scheduler): 277 alu vs 60 fma instructions per step at K = 10, i.e. alu-pipe bound at ~554 cycles/step.
+//      Here the max over i is a 3-input FMNMX tree (K/2 alu instructions per tag), and the arg is the FIRST i whose
+//      value equals the max: one FSETP.EQ (alu) and one predicated move of a pre-shifted immediate (fma pipe) per
+//      pair, walking i downwards so the lowest index is the one that sticks.  That is the reference's strict '>' scan
+//      for every non-NaN input (+0 / -0 compare equal in both formulations; the running score may differ in the sign
+//      of a zero, never in value).  Per step at K = 10: ~145 alu + ~145 fma instructions.
+//  (2) Emission logits arrive by TMA: one cp.async.bulk.tensor per chunk of T steps for the whole CTA (box = NT rows x
+//      (T*K + pad) floats of the [B, L*K] view, the pad keeps the row pitch an odd number of 16-byte units so the
+//      LDS.128 reads are conflict free; out-of-range columns/rows are zero filled) instead of ~18 instructions per
+//      16-byte cp.async request.
+//  (3) All backpointers stay in shared memory (4 bits per tag: 5 bytes per step at K = 10), so there is no parked
+//      traffic to L2/HBM and no 64-bit address arithmetic per step; decoded tags leave in one coalesced sweep.
+// Rows are fetched to the CTA's longest length (TMA boxes are rectangular); the DP itself stops at each row's own
+// length.  NER_CRF_VIT_VARIANT=2 selects the parked-nibble kernel above instead.
+template <int K>
+struct TmaGeom {
+  static constexpr int T = (K % 2) ? 4 : 2;                 // steps per chunk: T*K % 4 == 0
+  static constexpr int NQ = T * K / 4;                      // 16-byte units of payload per row-chunk
+  static constexpr int PW = 4 * (NQ | 1);                   // row pitch in floats (odd number of 16-byte units)
+  static constexpr int KP = (K + 1) / 2;
+  static constexpr int HB = BpSplit<K>::HB;
+};
+
+template <int K, int NT, int S>
+size_t viterbi_tma_smem_bytes(int L) {
+  using Gm = TmaGeom<K>;
+  const size_t ring = (size_t)S * NT * Gm::PW * 4;
+  const size_t dec = (size_t)NT * (((L + 3) & ~3) + 4);
+  const size_t lo = (size_t)L * NT * 4;
+  const size_t hi = ((size_t)L * NT * Gm::HB + 15) & ~(size_t)15;
+  return 128 + (ring > dec ? ring : dec) + lo + hi + (size_t)(2 * K * Gm::KP + NT) * 4 + 64;
+}
+
+// ix <- imm where v == m (walked from the highest i down, the lowest equal index is the one that remains)
+// The move is written as a predicated multiply by a register that holds 1 (a kernel argument, opaque to ptxas): a
+// predicated `mov` is turned into SEL and lands on the alu pipe with the compares; the IMAD issues on the fma pipe.
+#define NER_SEL_EQ(ix, v, m, imm, one) \
+  asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %1, %2;\n\t@p mad.lo.u32 %0, %0, %4, %3;\n\t}" : "+r"(ix) : "f"(v), "f"(m), "n"(imm), "r"(one))
+
+template <int K, int J>
+struct ArgSel {   // compile-time immediates: index i pre-shifted to tag J's nibble
+  template <int I>
+  static __device__ __forceinline__ void walk(uint32_t& ix, const float* v, float m, uint32_t one) {
+    if constexpr (I >= 0) {
+      NER_SEL_EQ(ix, v[I], m, (uint32_t)I << (4 * (J & 7)), one);
+      walk<I - 1>(ix, v, m, one);
+    }
+  }
+  static __device__ __forceinline__ uint32_t run(const float* v, float m, uint32_t one) {
+    uint32_t ix = (uint32_t)(K - 1) << (4 * (J & 7));
+    walk<K - 2>(ix, v, m, one);
+    return ix;
+  }
+};
+
+template <int K>
+__device__ __forceinline__ float max_tree(const float* v) {
+  float m = v[0];
+  int i = 1;
+#pragma unroll
+  for (; i + 1 < K; i += 2) m = max3(m, v[i], v[i + 1]);
+  if (i < K) m = fmaxf(m, v[i]);
+  return m;
+}
+
+template <int K, int NT, int S, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int32_t* __restrict__ seq_len,
+                       const float* __restrict__ trans, int32_t* __restrict__ tags_out,
+                       float* __restrict__ best_score, int B, int L, int vec_out, uint32_t one) {
+  using Gm = TmaGeom<K>;
+  constexpr int T = Gm::T, PW = Gm::PW, KP = Gm::KP, HB = Gm::HB;
+  constexpr uint32_t CHUNK_BYTES = NT * PW * 4;
+
+  extern __shared__ __align__(128) uint8_t base[];      // the ring comes first: TMA destinations are 128-byte aligned
+  const int Lp = ((L + 3) & ~3) + 4;
+  const size_t ring_b = (size_t)S * NT * PW * 4, dec_b = (size_t)NT * Lp;
+  float* s_ring = reinterpret_cast<float*>(base);                                   // [S][NT][PW]
+  uint8_t* s_dec = base;                                                            // [NT][Lp] after the forward loop
+  uint32_t* s_lo = reinterpret_cast<uint32_t*>(base + (ring_b > dec_b ? ring_b : dec_b));   // [L][NT]
+  uint8_t* s_hi = reinterpret_cast<uint8_t*>(s_lo + (size_t)L * NT);                // [L][NT] x HB bytes
+  float* s_tr = reinterpret_cast<float*>(s_hi + (((size_t)L * NT * HB + 15) & ~(size_t)15));   // [j][2*KP]: column j of trans
+  int* s_len = reinterpret_cast<int*>(s_tr + 2 * K * KP);                           // [NT]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_len + NT + ((2 * K * KP + NT) & 1));     // 8-byte aligned
+
+  const int tid = threadIdx.x;
+  const int row0 = blockIdx.x * NT;
+  const int nv = min(NT, B - row0);
+
+  if (tid == 0) {
+    tc::tma_prefetch_desc(&tm_logits);
+#pragma unroll
+    for (int s = 0; s < S; ++s) tc::mbar_init(bars + s, 1);
+    tc::fence_barrier_init();
+  }
+  for (int e = tid; e < K * 2 * KP; e += NT) {
+    const int j = e / (2 * KP), i = e - j * 2 * KP;
+    s_tr[e] = (i < K) ? trans[i * K + j] : 0.f;
+  }
+  int mylen = 1;
+  if (tid < nv) mylen = min(max(seq_len[row0 + tid], 1), L);  // len<=0 behaves like 1 (TF quirk)
+  s_len[tid] = mylen;
+  const int bmax = block_max_int<NT>(tid < nv ? mylen : 1, reinterpret_cast<int*>(s_lo));
+  const int nchunk = (bmax + T - 1) / T;
+
+  constexpr int PF = 16 / T;             // L2 prefetch distance in chunks (16 time steps ahead of the ring)
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+      if (s < nchunk) {
+        tc::mbar_arrive_expect_tx(bars + s, CHUNK_BYTES);
+        tc::tma_load_2d(s_ring + (size_t)s * NT * PW, &tm_logits, bars + s, s * T * K, row0);
+      }
+    for (int s = S; s < S + PF; ++s)
+      if (s < nchunk) tc::tma_prefetch_l2_2d(&tm_logits, s * T * K, row0);
+  }
+
+  f32x2 tr2[K * KP];       // tr2[j*KP + p] = (trans[2p][j], trans[2p+1][j])
+#pragma unroll
+  for (int e = 0; e < K * KP; ++e) tr2[e] = pk2(s_tr[2 * e], s_tr[2 * e + 1]);
+
+  f32x2 s2[KP];
+#pragma unroll
+  for (int p = 0; p < KP; ++p) s2[p] = pk2(0.f, 0.f);
+
+  const bool live = tid < nv;
+  uint32_t* lo_p = s_lo + tid;
+  uint8_t* hi_p = s_hi + (size_t)tid * HB;
+
+  for (int c = 0; c < nchunk; ++c) {
+    const int st = c % S;
+    tc::mbar_wait(bars + st, (uint32_t)(c / S) & 1u);
+    const int t0 = c * T;
+    if (live && t0 < mylen) {
+      const float4* rowp = reinterpret_cast<const float4*>(s_ring + (size_t)st * NT * PW + tid * PW);
+      float xs[T * K];
+#pragma unroll
+      for (int q = 0; q < T * K / 4; ++q) {
+        const float4 v = rowp[q];
+        xs[4 * q] = v.x; xs[4 * q + 1] = v.y; xs[4 * q + 2] = v.z; xs[4 * q + 3] = v.w;
+      }
+#pragma unroll
+      for (int g = 0; g < T; ++g) {
+        const int t = t0 + g;
+        if (t < mylen) {
+          if (t == 0) {
+#pragma unroll
+            for (int p = 0; p < KP; ++p) s2[p] = pk2(xs[2 * p], (2 * p + 1 < K) ? xs[2 * p + 1] : 0.f);
+          } else {
+            float m[2 * KP];
+            uint32_t wlo = 0u, whi = 0u;
+            auto tag_step = [&](auto jc) {
+              constexpr int J = decltype(jc)::value;
+              float v[2 * KP];
+#pragma unroll
+              for (int p = 0; p < KP; ++p) upk2(add2(s2[p], tr2[J * KP + p]), v[2 * p], v[2 * p + 1]);
+              const float mj = max_tree<K>(v);
+              m[J] = mj;
+              const uint32_t ix = ArgSel<K, J>::run(v, mj, one);
+              if (J < 8) wlo |= ix; else whi |= ix;
+            };
+            sel_all<K>(tag_step);
+            if (2 * KP > K) m[2 * KP - 1] = 0.f;
+#pragma unroll
+            for (int p = 0; p < KP; ++p)
+              s2[p] = add2(pk2(m[2 * p], m[2 * p + 1]), pk2(xs[g * K + 2 * p], (2 * p + 1 < K) ? xs[g * K + 2 * p + 1] : 0.f));
+            lo_p[(size_t)t * NT] = wlo;
+            if (HB == 1) hi_p[(size_t)t * NT] = (uint8_t)whi;
+            if (HB == 2) reinterpret_cast<uint16_t*>(hi_p)[(size_t)t * NT] = (uint16_t)whi;
+            if (HB == 4) reinterpret_cast<uint32_t*>(hi_p)[(size_t)t * NT] = whi;
+          }
+        }
+      }
+    }
+    __syncthreads();                       // every thread has copied its row of this stage into registers
+    if (tid == 0 && c + S < nchunk) {
+      tc::mbar_arrive_expect_tx(bars + st, CHUNK_BYTES);
+      tc::tma_load_2d(s_ring + (size_t)st * NT * PW, &tm_logits, bars + st, (c + S) * T * K, row0);
+      if (c + S + PF < nchunk) tc::tma_prefetch_l2_2d(&tm_logits, (c + S + PF) * T * K, row0);
+    }
+  }
+  __syncthreads();                         // the ring is dead: s_dec may overwrite it
+
+  if (live) {
+    float sv[2 * KP];
+#pragma unroll
+    for (int p = 0; p < KP; ++p) upk2(s2[p], sv[2 * p], sv[2 * p + 1]);
+    float best = sv[0];
+    int y = 0;
+#pragma unroll
+    for (int j = 1; j < K; ++j)
+      if (sv[j] > best) {
+        best = sv[j];
+        y = j;
+      }
+    if (best_score != nullptr) best_score[row0 + tid] = best;
+    uint8_t* drow = s_dec + tid * Lp;
+    for (int t = mylen - 1; t >= 1; --t) {
+      uint32_t w = lo_p[(size_t)t * NT];
+      if (HB > 0 && y >= 8) {
+        if (HB == 1) w = hi_p[(size_t)t * NT];
+        if (HB == 2) w = reinterpret_cast<const uint16_t*>(hi_p)[(size_t)t * NT];
+        if (HB == 4) w = reinterpret_cast<const uint32_t*>(hi_p)[(size_t)t * NT];
+      }
+      drow[t] = (uint8_t)y;
+      y = (int)((w >> (4 * (y & 7))) & 15u);
+    }
+    drow[0] = (uint8_t)y;
+  }
+  __syncthreads();
+
+  // Coalesced [nv, L] int32 store; zero beyond each row's length.
+  int32_t* obase = tags_out + (size_t)row0 * L;
+  if (vec_out) {
+    const int L4 = L >> 2, total4 = nv * L4;
+    int4* o4 = reinterpret_cast<int4*>(obase);
+    for (int idx = tid; idx < total4; idx += NT) {
+      const int r = idx / L4, p = (idx - r * L4) * 4;
+      const uint32_t pk = *reinterpret_cast<const uint32_t*>(s_dec + r * Lp + p);
+      const int n = s_len[r];
+      int4 o;
+      o.x = (p < n) ? (int)(pk & 255u) : 0;
+      o.y = (p + 1 < n) ? (int)((pk >> 8) & 255u) : 0;
+      o.z = (p + 2 < n) ? (int)((pk >> 16) & 255u) : 0;
+      o.w = (p + 3 < n) ? (int)(pk >> 24) : 0;
+      o4[idx] = o;
+    }
+  } else {
+    const int total = nv * L;
+    for (int idx = tid; idx < total; idx += NT) {
+      const int r = idx / L, p = idx - r * L;
+      obase[idx] = (p < s_len[r]) ? (int)s_dec[r * Lp + p] : 0;
+    }
+  }
+}
+
 template <int K, int NT, int TT, int MINB>
 int launch_viterbi_gs(const float* logits, const int32_t* seq_len, const float* trans,
                       int32_t* tags_out, float* best_score, int B, int L, cudaStream_t st) {
@@ -421,7 +675,54 @@ int launch_viterbi_nt(const float* logits, const int32_t* seq_len, const float* 
   return ner_launch_status();
 }
 
-constexpr size_t kMaxSmem = 227 * 1024;
+
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+template <int K, int NT, int S, int MINB>
+int launch_viterbi_tma(const float* logits, const int32_t* seq_len, const float* trans, int32_t* tags_out,
+                       float* best_score, int B, int L, cudaStream_t st) {
+  using Gm = TmaGeom<K>;
+  const size_t LK = (size_t)L * K;
+  if ((LK & 3) != 0 || (reinterpret_cast<uintptr_t>(logits) & 15) != 0) return NER_ERR_UNSUPPORTED;
+  const size_t smem = viterbi_tma_smem_bytes<K, NT, S>(L);
+  if (smem > kMaxSmem) return NER_ERR_UNSUPPORTED;
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return NER_ERR_UNSUPPORTED;
+  CUtensorMap map;
+  cuuint64_t dims[2] = {(cuuint64_t)LK, (cuuint64_t)B};
+  cuuint64_t strides[1] = {(cuuint64_t)LK * 4};
+  cuuint32_t box[2] = {(cuuint32_t)Gm::PW, (cuuint32_t)NT};
+  cuuint32_t estr[2] = {1, 1};
+  if (fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(logits), dims, strides, box, estr,
+         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return NER_ERR_UNSUPPORTED;
+  auto kern = crf_viterbi_tma_kernel<K, NT, S, MINB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
+  const int vec_out = ((L & 3) == 0) && ((reinterpret_cast<uintptr_t>(tags_out) & 15) == 0);
+  const int grid = (B + NT - 1) / NT;
+  kern<<<grid, NT, smem, st>>>(map, seq_len, trans, tags_out, best_score, B, L, vec_out, 0u);
+  return ner_launch_status();
+}
 
 template <int K>
 int launch_viterbi(const float* logits, const int32_t* seq_len, const float* trans,
@@ -430,7 +731,11 @@ int launch_viterbi(const float* logits, const int32_t* seq_len, const float* tra
   // spread over more SMs with 32-sequence CTAs.
   const bool big = B > 148 * 32 * 2;
   if constexpr (K <= 16) {
-    if (big && vit_variant() != 1) {   // NER_CRF_VIT_VARIANT=1: time the all-on-chip kernel instead
+    if (big && vit_variant() == 0) {   // default: the pipe-balanced TMA kernel (falls through when L*K % 4 != 0 or L is too long)
+      const int rc = launch_viterbi_tma<K, 64, 2, 4>(logits, seq_len, trans, tags_out, best_score, B, L, st);
+      if (rc != NER_ERR_UNSUPPORTED) return rc;
+    }
+    if (big && vit_variant() != 1) {   // NER_CRF_VIT_VARIANT=2: the parked-nibble kernel; =1: the all-on-chip kernel
       const int rc = launch_viterbi_gs<K, 64, 4, 6>(logits, seq_len, trans, tags_out, best_score, B, L, st);
       if (rc != NER_ERR_UNSUPPORTED) return rc;
     }

@@ -105,12 +105,14 @@ def test_loglik_alpha_workspace():
         np.testing.assert_allclose(a[b, :n], alphas[b, :n], rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
-@pytest.mark.parametrize("B,L,K", [(148 * 64 + 77, 128, 10), (9600, 37, 7), (9500, 50, 16), (9601, 21, 12), (9490, 9, 3)])
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("B,L,K", [(148 * 64 + 77, 128, 10), (9600, 37, 7), (9500, 50, 16), (9601, 21, 12), (9490, 9, 3),
+                                   (9500, 12, 5), (9533, 16, 9), (9480, 20, 8), (9479, 8, 11), (9600, 256, 10), (9500, 6, 2)])
 def test_viterbi_large_batch_kernels_bit_exact(monkeypatch, variant, B, L, K):
-    """variant 0 = the occupancy-first kernel (low backpointer nibbles parked in the tags_out slab),
-    variant 1 = the all-on-chip kernel it replaced (still the fallback for K > 16): both must reproduce the
-    oracle's tags and scores, ragged lengths and a partial tail CTA included."""
+    """variant 0 = the pipe-balanced TMA kernel (max tree + first-equal index, all backpointers in shared memory; taken
+    when L*K % 4 == 0, otherwise the call falls through to variant 2), variant 2 = the occupancy-first kernel (low
+    backpointer nibbles parked in the tags_out slab), variant 1 = the all-on-chip kernel (the fallback for K > 16): all
+    must reproduce the oracle's tags and scores, ragged lengths and a partial tail CTA included."""
     monkeypatch.setenv("NER_CRF_VIT_VARIANT", str(variant))
     x, tr, lens, _ = _case(B, L, K, seed=variant * 100 + K)
     lens[0], lens[1], lens[2] = L, 1, 0
