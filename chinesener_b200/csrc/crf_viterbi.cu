@@ -421,85 +421,151 @@ __device__ __forceinline__ void sel_all(F& f) {
 //      traffic to L2/HBM and no 64-bit address arithmetic per step; decoded tags leave in one coalesced sweep.
 // Rows are fetched to the CTA's longest length (TMA boxes are rectangular); the DP itself stops at each row's own
 // length.  NER_CRF_VIT_VARIANT=2 selects the parked-nibble kernel above instead.
-template <int K>
+template <int K, int TT>
 struct TmaGeom {
-  static constexpr int T = (K % 2) ? 4 : 2;                 // steps per chunk: T*K % 4 == 0
+  static constexpr int T = (K % 2) ? 4 : TT;                // steps per chunk: T*K % 4 == 0
   static constexpr int NQ = T * K / 4;                      // 16-byte units of payload per row-chunk
   static constexpr int PW = 4 * (NQ | 1);                   // row pitch in floats (odd number of 16-byte units)
   static constexpr int KP = (K + 1) / 2;
   static constexpr int HB = BpSplit<K>::HB;
 };
 
-template <int K, int NT, int S>
+template <int K, int NT, int S, int TT, bool PARK>
 size_t viterbi_tma_smem_bytes(int L) {
-  using Gm = TmaGeom<K>;
+  using Gm = TmaGeom<K, TT>;
   const size_t ring = (size_t)S * NT * Gm::PW * 4;
   const size_t dec = (size_t)NT * (((L + 3) & ~3) + 4);
-  const size_t lo = (size_t)L * NT * 4;
+  const size_t lo = PARK ? 0 : (size_t)L * NT * 4;
   const size_t hi = ((size_t)L * NT * Gm::HB + 15) & ~(size_t)15;
-  return 128 + (ring > dec ? ring : dec) + lo + hi + (size_t)(2 * K * Gm::KP + NT) * 4 + 64;
+  return (ring > dec ? ring : dec) + lo + hi + (size_t)(2 * K * Gm::KP + NT) * 4 + 8 + (NT / 32) * S * 8;
 }
 
-// ix <- imm where v == m (walked from the highest i down, the lowest equal index is the one that remains)
-// The move is written as a predicated multiply by a register that holds 1 (a kernel argument, opaque to ptxas): a
-// predicated `mov` is turned into SEL and lands on the alu pipe with the compares; the IMAD issues on the fma pipe.
-#define NER_SEL_EQ(ix, v, m, imm, one) \
-  asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %1, %2;\n\t@p mad.lo.u32 %0, %0, %4, %3;\n\t}" : "+r"(ix) : "f"(v), "f"(m), "n"(imm), "r"(one))
+// ix <- imm where v == m.  Walked from the highest i down, so the lowest equal index is the one that remains.
+// The move is written as a predicated multiply-add on the old value with a register that holds 0 (a kernel argument,
+// opaque to ptxas): a predicated `mov` becomes SEL and lands on the alu pipe with the compares; the IMAD issues on the
+// fma pipe.
+#define NER_SEL_EQ(ix, v, m, imm, zero) \
+  asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %1, %2;\n\t@p mad.lo.u32 %0, %0, %4, %3;\n\t}" : "+r"(ix) : "f"(v), "f"(m), "n"(imm), "r"(zero))
 
 template <int K, int J>
 struct ArgSel {   // compile-time immediates: index i pre-shifted to tag J's nibble
   template <int I>
-  static __device__ __forceinline__ void walk(uint32_t& ix, const float* v, float m, uint32_t one) {
+  static __device__ __forceinline__ void walk(uint32_t& ix, const float* v, float m, uint32_t zero) {
     if constexpr (I >= 0) {
-      NER_SEL_EQ(ix, v[I], m, (uint32_t)I << (4 * (J & 7)), one);
-      walk<I - 1>(ix, v, m, one);
+      NER_SEL_EQ(ix, v[I], m, (uint32_t)I << (4 * (J & 7)), zero);
+      walk<I - 1>(ix, v, m, zero);
     }
   }
-  static __device__ __forceinline__ uint32_t run(const float* v, float m, uint32_t one) {
+  static __device__ __forceinline__ uint32_t run(const float* v, float m, uint32_t zero) {
     uint32_t ix = (uint32_t)(K - 1) << (4 * (J & 7));
-    walk<K - 2>(ix, v, m, one);
+    walk<K - 2>(ix, v, m, zero);
     return ix;
   }
 };
 
+// Two predicate-free formulations of the same first-equal index (the compare-to-predicate instruction is the slow
+// one on this pipe mix).  Both count the leading entries that differ from the max with a Horner recurrence
+// h_i = e_i * (1 + h_{i+1}), e_i = [v_i != m], so h_0 is the lowest index whose value equals the max.
+//  SELV 1: e_i by FSET.BF (1.0f / 0.0f in a register), the recurrence in fp32 FFMAs (small integers: exact).
+//  SELV 2: e_i = sign bit of (v_i - m) (the difference of two floats is +0 exactly when they are equal, and negative
+//          otherwise because m is the max; inf - inf gives the positive canonical NaN), the recurrence in IMADs.
+__device__ __forceinline__ float fset_ne(float a, float b) {
+  float r;
+  asm("set.ne.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 template <int K>
-__device__ __forceinline__ float max_tree(const float* v) {
-  float m = v[0];
-  int i = 1;
+__device__ __forceinline__ float first_eq_f(const float* v, float m) {      // SELV 1 -> index as a float
+  if constexpr (K == 1) return 0.f;
+  float h = fset_ne(v[K - 2], m);
 #pragma unroll
-  for (; i + 1 < K; i += 2) m = max3(m, v[i], v[i + 1]);
-  if (i < K) m = fmaxf(m, v[i]);
-  return m;
+  for (int i = K - 3; i >= 0; --i) {
+    const float e = fset_ne(v[i], m);
+    h = fmaf(e, h, e);
+  }
+  return h;
+}
+template <int K>
+__device__ __forceinline__ uint32_t first_eq_u(const f32x2* v2, float m) {   // SELV 2 -> index as an integer
+  if constexpr (K == 1) return 0u;
+  constexpr int KP = (K + 1) / 2;
+  uint32_t e[2 * KP];
+  const f32x2 m2 = pk2(m, m);
+#pragma unroll
+  for (int p = 0; p < KP; ++p) {
+    float lo, hi;
+    upk2(sub2(v2[p], m2), lo, hi);
+    e[2 * p] = __float_as_uint(lo) >> 31;
+    e[2 * p + 1] = __float_as_uint(hi) >> 31;
+  }
+  uint32_t h = e[K - 2];
+#pragma unroll
+  for (int i = K - 3; i >= 0; --i) h = e[i] * h + e[i];
+  return h;
 }
 
-template <int K, int NT, int S, int MINB>
+// max of v[0..K): three-input maxima over triples, then a three-input tree over those (depth 3 at K = 10)
+template <int K>
+__device__ __forceinline__ float max_tree(const float* v) {
+  if constexpr (K == 1) {
+    return v[0];
+  } else if constexpr (K == 2) {
+    return fmaxf(v[0], v[1]);
+  } else if constexpr (K == 3) {
+    return max3(v[0], v[1], v[2]);
+  } else {
+    constexpr int G = (K + 2) / 3;
+    float g[G];
+#pragma unroll
+    for (int a = 0; a < G; ++a) {
+      const int n = (3 * a + 3 <= K) ? 3 : (K - 3 * a);
+      g[a] = (n == 3) ? max3(v[3 * a], v[3 * a + 1], v[3 * a + 2]) : (n == 2 ? fmaxf(v[3 * a], v[3 * a + 1]) : v[3 * a]);
+    }
+    return max_tree<G>(g);
+  }
+}
+
+// One WARP is one independent pipeline: its own TMA ring (box = 32 rows), its own full-barriers, its own backpointer
+// columns, backtrace and output sweep; the CTA only carves up shared memory (no CTA barrier after the prologue).
+template <int K, int NT, int S, int TT, int MINB, int SELV, bool PARK>
 __global__ void __launch_bounds__(NT, MINB)
 crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int32_t* __restrict__ seq_len,
-                       const float* __restrict__ trans, int32_t* __restrict__ tags_out,
-                       float* __restrict__ best_score, int B, int L, int vec_out, uint32_t one) {
-  using Gm = TmaGeom<K>;
-  constexpr int T = Gm::T, PW = Gm::PW, KP = Gm::KP, HB = Gm::HB;
-  constexpr uint32_t CHUNK_BYTES = NT * PW * 4;
+                       const float* __restrict__ trans, int32_t* tags_out,
+                       float* __restrict__ best_score, int B, int L, int vec_out, uint32_t zero) {
+  using Gm = TmaGeom<K, TT>;
+  constexpr int T = Gm::T, PW = Gm::PW, KP = Gm::KP, HB = Gm::HB, NW = NT / 32;
+  constexpr uint32_t CHUNK_BYTES = 32 * PW * 4;
 
-  extern __shared__ __align__(128) uint8_t base[];      // the ring comes first: TMA destinations are 128-byte aligned
+  extern __shared__ __align__(128) uint8_t base[];      // the rings come first: TMA destinations stay 16-byte aligned
   const int Lp = ((L + 3) & ~3) + 4;
   const size_t ring_b = (size_t)S * NT * PW * 4, dec_b = (size_t)NT * Lp;
-  float* s_ring = reinterpret_cast<float*>(base);                                   // [S][NT][PW]
-  uint8_t* s_dec = base;                                                            // [NT][Lp] after the forward loop
   uint32_t* s_lo = reinterpret_cast<uint32_t*>(base + (ring_b > dec_b ? ring_b : dec_b));   // [L][NT]
-  uint8_t* s_hi = reinterpret_cast<uint8_t*>(s_lo + (size_t)L * NT);                // [L][NT] x HB bytes
+  uint8_t* s_hi = reinterpret_cast<uint8_t*>(s_lo + (PARK ? 0 : (size_t)L * NT));   // [L][NT] x HB bytes
   float* s_tr = reinterpret_cast<float*>(s_hi + (((size_t)L * NT * HB + 15) & ~(size_t)15));   // [j][2*KP]: column j of trans
   int* s_len = reinterpret_cast<int*>(s_tr + 2 * K * KP);                           // [NT]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_len + NT + ((2 * K * KP + NT) & 1));     // 8-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_len + NT + ((2 * K * KP + NT) & 1));   // [NW][S], 8-byte aligned
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform: ring / barrier addresses stay in uniform registers
   const int row0 = blockIdx.x * NT;
   const int nv = min(NT, B - row0);
+  const int wrow0 = row0 + 32 * warp;                   // first row of this warp
+  const bool live = tid < nv;
+  // the ring and, later, the decoded tags of this warp share one region: the larger of the two per-warp sizes
+  const size_t wreg_b = (ring_b > dec_b ? ring_b : dec_b) / NW;
+  float* w_ring = reinterpret_cast<float*>(base + warp * wreg_b);                   // [S][32][PW]
+  uint8_t* w_dec = base + warp * wreg_b;                                            // [32][Lp] after the forward loop
+  uint64_t* w_bar = bars + warp * S;
 
-  if (tid == 0) {
-    tc::tma_prefetch_desc(&tm_logits);
+  if (lane == 0) {
+    if (tid == 0) tc::tma_prefetch_desc(&tm_logits);
 #pragma unroll
-    for (int s = 0; s < S; ++s) tc::mbar_init(bars + s, 1);
+    for (int s = 0; s < S; ++s) tc::mbar_init(w_bar + s, 1);
     tc::fence_barrier_init();
   }
   for (int e = tid; e < K * 2 * KP; e += NT) {
@@ -507,21 +573,24 @@ crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int3
     s_tr[e] = (i < K) ? trans[i * K + j] : 0.f;
   }
   int mylen = 1;
-  if (tid < nv) mylen = min(max(seq_len[row0 + tid], 1), L);  // len<=0 behaves like 1 (TF quirk)
+  if (live) mylen = min(max(seq_len[row0 + tid], 1), L);  // len<=0 behaves like 1 (TF quirk)
   s_len[tid] = mylen;
-  const int bmax = block_max_int<NT>(tid < nv ? mylen : 1, reinterpret_cast<int*>(s_lo));
-  const int nchunk = (bmax + T - 1) / T;
+  int wmax = live ? mylen : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  const int nchunk = (wmax + T - 1) / T;                // 0 for a warp past the end of the batch
+  __syncthreads();                                      // s_tr, s_len and the barrier inits are visible
 
-  constexpr int PF = 16 / T;             // L2 prefetch distance in chunks (16 time steps ahead of the ring)
-  if (tid == 0) {
+  constexpr int PF = 16 / T;                            // L2 prefetch distance in chunks (16 time steps ahead of the ring)
+  if (tc::elect_one()) {
 #pragma unroll
     for (int s = 0; s < S; ++s)
       if (s < nchunk) {
-        tc::mbar_arrive_expect_tx(bars + s, CHUNK_BYTES);
-        tc::tma_load_2d(s_ring + (size_t)s * NT * PW, &tm_logits, bars + s, s * T * K, row0);
+        tc::mbar_arrive_expect_tx(w_bar + s, CHUNK_BYTES);
+        tc::tma_load_2d(w_ring + (size_t)s * 32 * PW, &tm_logits, w_bar + s, s * T * K, wrow0);
       }
     for (int s = S; s < S + PF; ++s)
-      if (s < nchunk) tc::tma_prefetch_l2_2d(&tm_logits, s * T * K, row0);
+      if (s < nchunk) tc::tma_prefetch_l2_2d(&tm_logits, s * T * K, wrow0);
   }
 
   f32x2 tr2[K * KP];       // tr2[j*KP + p] = (trans[2p][j], trans[2p+1][j])
@@ -532,16 +601,20 @@ crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int3
 #pragma unroll
   for (int p = 0; p < KP; ++p) s2[p] = pk2(0.f, 0.f);
 
-  const bool live = tid < nv;
-  uint32_t* lo_p = s_lo + tid;
+  // PARK: the low words (tags 0..7) are parked in this warp's own [rows, L] slab of tags_out, [t][lane] layout, written and
+  // read back by the same lane (L2-resident for the warp's lifetime), which takes shared memory per CTA from 52 KB to
+  // 19 KB at L = 128: the warps per SM are then bounded by registers, not by the backpointers.
+  const int wnv = max(0, min(32, nv - 32 * warp));
+  uint32_t* lo_p = PARK ? reinterpret_cast<uint32_t*>(tags_out + (size_t)wrow0 * L) + lane : s_lo + tid;
+  const int lo_pitch = PARK ? wnv : NT;
   uint8_t* hi_p = s_hi + (size_t)tid * HB;
 
   for (int c = 0; c < nchunk; ++c) {
     const int st = c % S;
-    tc::mbar_wait(bars + st, (uint32_t)(c / S) & 1u);
+    tc::mbar_wait(w_bar + st, (uint32_t)(c / S) & 1u);
     const int t0 = c * T;
     if (live && t0 < mylen) {
-      const float4* rowp = reinterpret_cast<const float4*>(s_ring + (size_t)st * NT * PW + tid * PW);
+      const float4* rowp = reinterpret_cast<const float4*>(w_ring + (size_t)st * 32 * PW + lane * PW);
       float xs[T * K];
 #pragma unroll
       for (int q = 0; q < T * K / 4; ++q) {
@@ -558,22 +631,49 @@ crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int3
           } else {
             float m[2 * KP];
             uint32_t wlo = 0u, whi = 0u;
+            float fw[4] = {0.f, 0.f, 0.f, 0.f};       // SELV 1: four nibbles per float (exact below 2^16)
             auto tag_step = [&](auto jc) {
               constexpr int J = decltype(jc)::value;
+              f32x2 v2[KP];
               float v[2 * KP];
 #pragma unroll
-              for (int p = 0; p < KP; ++p) upk2(add2(s2[p], tr2[J * KP + p]), v[2 * p], v[2 * p + 1]);
-              const float mj = max_tree<K>(v);
+              for (int p = 0; p < KP; ++p) {
+                v2[p] = add2(s2[p], tr2[J * KP + p]);
+                upk2(v2[p], v[2 * p], v[2 * p + 1]);
+              }
+              float mj;
+              if constexpr (SELV == 3) {      // sequential three-input chain instead of the tree
+                mj = v[0];
+                int i = 1;
+#pragma unroll
+                for (; i + 1 < K; i += 2) mj = max3(mj, v[i], v[i + 1]);
+                if (i < K) mj = fmaxf(mj, v[i]);
+              } else {
+                mj = max_tree<K>(v);
+              }
               m[J] = mj;
-              const uint32_t ix = ArgSel<K, J>::run(v, mj, one);
-              if (J < 8) wlo |= ix; else whi |= ix;
+              if constexpr (SELV == 0 || SELV == 3) {
+                const uint32_t ix = ArgSel<K, J>::run(v, mj, zero);
+                if (J < 8) wlo |= ix; else whi |= ix;
+              } else if constexpr (SELV == 1) {
+                fw[J >> 2] = fmaf(first_eq_f<K>(v, mj), (float)(1 << (4 * (J & 3))), fw[J >> 2]);
+              } else {
+                const uint32_t ix = first_eq_u<K>(v2, mj);
+                if (J < 8) wlo = ix * (1u << (4 * (J & 7))) + wlo; else whi = ix * (1u << (4 * (J & 7))) + whi;
+              }
             };
             sel_all<K>(tag_step);
+            if constexpr (SELV == 1) {
+              wlo = __float2uint_rn(fw[0]);
+              if (K > 4) wlo |= __float2uint_rn(fw[1]) << 16;
+              if (K > 8) whi = __float2uint_rn(fw[2]);
+              if (K > 12) whi |= __float2uint_rn(fw[3]) << 16;
+            }
             if (2 * KP > K) m[2 * KP - 1] = 0.f;
 #pragma unroll
             for (int p = 0; p < KP; ++p)
               s2[p] = add2(pk2(m[2 * p], m[2 * p + 1]), pk2(xs[g * K + 2 * p], (2 * p + 1 < K) ? xs[g * K + 2 * p + 1] : 0.f));
-            lo_p[(size_t)t * NT] = wlo;
+            if (PARK) __stcg(lo_p + (size_t)t * lo_pitch, wlo); else lo_p[(size_t)t * NT] = wlo;
             if (HB == 1) hi_p[(size_t)t * NT] = (uint8_t)whi;
             if (HB == 2) reinterpret_cast<uint16_t*>(hi_p)[(size_t)t * NT] = (uint16_t)whi;
             if (HB == 4) reinterpret_cast<uint32_t*>(hi_p)[(size_t)t * NT] = whi;
@@ -581,14 +681,16 @@ crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int3
         }
       }
     }
-    __syncthreads();                       // every thread has copied its row of this stage into registers
-    if (tid == 0 && c + S < nchunk) {
-      tc::mbar_arrive_expect_tx(bars + st, CHUNK_BYTES);
-      tc::tma_load_2d(s_ring + (size_t)st * NT * PW, &tm_logits, bars + st, (c + S) * T * K, row0);
-      if (c + S + PF < nchunk) tc::tma_prefetch_l2_2d(&tm_logits, (c + S + PF) * T * K, row0);
+    __syncwarp();                          // every lane has consumed its row of this stage
+    if (c + S < nchunk) {                  // warp-uniform
+      if (tc::elect_one()) {
+        tc::mbar_arrive_expect_tx(w_bar + st, CHUNK_BYTES);
+        tc::tma_load_2d(w_ring + (size_t)st * 32 * PW, &tm_logits, w_bar + st, (c + S) * T * K, wrow0);
+        if (c + S + PF < nchunk) tc::tma_prefetch_l2_2d(&tm_logits, (c + S + PF) * T * K, wrow0);
+      }
     }
   }
-  __syncthreads();                         // the ring is dead: s_dec may overwrite it
+  __syncwarp();                            // this warp's ring is dead: its decoded tags may overwrite it
 
   if (live) {
     float sv[2 * KP];
@@ -603,30 +705,47 @@ crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int3
         y = j;
       }
     if (best_score != nullptr) best_score[row0 + tid] = best;
-    uint8_t* drow = s_dec + tid * Lp;
-    for (int t = mylen - 1; t >= 1; --t) {
-      uint32_t w = lo_p[(size_t)t * NT];
-      if (HB > 0 && y >= 8) {
-        if (HB == 1) w = hi_p[(size_t)t * NT];
-        if (HB == 2) w = reinterpret_cast<const uint16_t*>(hi_p)[(size_t)t * NT];
-        if (HB == 4) w = reinterpret_cast<const uint32_t*>(hi_p)[(size_t)t * NT];
+    uint8_t* drow = w_dec + lane * Lp;
+    // Backtrace: the words are at addresses independent of the path, so fetch 8 steps per round trip and resolve the
+    // chain in registers.
+    for (int t = mylen - 1; t >= 1; t -= 8) {
+      uint32_t wa[8], wb[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const bool in = t - u >= 1;
+        wa[u] = in ? (PARK ? __ldcg(lo_p + (size_t)(t - u) * lo_pitch) : lo_p[(size_t)(t - u) * NT]) : 0u;
+        wb[u] = 0u;
+        if (HB == 1) wb[u] = in ? hi_p[(size_t)(t - u) * NT] : 0u;
+        if (HB == 2) wb[u] = in ? reinterpret_cast<const uint16_t*>(hi_p)[(size_t)(t - u) * NT] : 0u;
+        if (HB == 4) wb[u] = in ? reinterpret_cast<const uint32_t*>(hi_p)[(size_t)(t - u) * NT] : 0u;
       }
-      drow[t] = (uint8_t)y;
-      y = (int)((w >> (4 * (y & 7))) & 15u);
+      uint32_t d8[2] = {0u, 0u};             // the 8 decoded tags of this batch, one byte each (tt = t-u -> byte 7-u... stored below)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int tt = t - u;
+        if (tt >= 1) {
+          drow[tt] = (uint8_t)y;
+          const uint32_t w = (HB > 0 && y >= 8) ? wb[u] : wa[u];
+          y = (int)((w >> (4 * (y & 7))) & 15u);
+        }
+      }
+      (void)d8;
     }
     drow[0] = (uint8_t)y;
   }
-  __syncthreads();
+  __syncwarp();
 
-  // Coalesced [nv, L] int32 store; zero beyond each row's length.
-  int32_t* obase = tags_out + (size_t)row0 * L;
+  // Coalesced [rows of this warp, L] int32 store; zero beyond each row's length.  (PARK: every parked word of the warp
+  // has been consumed above.)
+  int32_t* obase = tags_out + (size_t)wrow0 * L;
+  const int* wlen = s_len + 32 * warp;
   if (vec_out) {
-    const int L4 = L >> 2, total4 = nv * L4;
+    const int L4 = L >> 2, total4 = wnv * L4;
     int4* o4 = reinterpret_cast<int4*>(obase);
-    for (int idx = tid; idx < total4; idx += NT) {
+    for (int idx = lane; idx < total4; idx += 32) {
       const int r = idx / L4, p = (idx - r * L4) * 4;
-      const uint32_t pk = *reinterpret_cast<const uint32_t*>(s_dec + r * Lp + p);
-      const int n = s_len[r];
+      const uint32_t pk = *reinterpret_cast<const uint32_t*>(w_dec + r * Lp + p);
+      const int n = wlen[r];
       int4 o;
       o.x = (p < n) ? (int)(pk & 255u) : 0;
       o.y = (p + 1 < n) ? (int)((pk >> 8) & 255u) : 0;
@@ -635,10 +754,10 @@ crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int3
       o4[idx] = o;
     }
   } else {
-    const int total = nv * L;
-    for (int idx = tid; idx < total; idx += NT) {
+    const int total = wnv * L;
+    for (int idx = lane; idx < total; idx += 32) {
       const int r = idx / L, p = idx - r * L;
-      obase[idx] = (p < s_len[r]) ? (int)s_dec[r * Lp + p] : 0;
+      obase[idx] = (p < wlen[r]) ? (int)w_dec[r * Lp + p] : 0;
     }
   }
 }
@@ -655,6 +774,11 @@ int launch_viterbi_gs(const float* logits, const int32_t* seq_len, const float* 
   const int grid = (B + NT - 1) / NT;
   kern<<<grid, NT, smem, st>>>(logits, seq_len, trans, tags_out, best_score, B, L, vec16);
   return ner_launch_status();
+}
+
+int vit_tune() {
+  const char* e = getenv("NER_CRF_VIT_TUNE");
+  return e ? atoi(e) : 0;
 }
 
 int vit_variant() {
@@ -696,26 +820,26 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-template <int K, int NT, int S, int MINB>
+template <int K, int NT, int S, int TT, int MINB, int SELV, bool PARK>
 int launch_viterbi_tma(const float* logits, const int32_t* seq_len, const float* trans, int32_t* tags_out,
                        float* best_score, int B, int L, cudaStream_t st) {
-  using Gm = TmaGeom<K>;
+  using Gm = TmaGeom<K, TT>;
   const size_t LK = (size_t)L * K;
   if ((LK & 3) != 0 || (reinterpret_cast<uintptr_t>(logits) & 15) != 0) return NER_ERR_UNSUPPORTED;
-  const size_t smem = viterbi_tma_smem_bytes<K, NT, S>(L);
+  const size_t smem = viterbi_tma_smem_bytes<K, NT, S, TT, PARK>(L);
   if (smem > kMaxSmem) return NER_ERR_UNSUPPORTED;
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return NER_ERR_UNSUPPORTED;
   CUtensorMap map;
   cuuint64_t dims[2] = {(cuuint64_t)LK, (cuuint64_t)B};
   cuuint64_t strides[1] = {(cuuint64_t)LK * 4};
-  cuuint32_t box[2] = {(cuuint32_t)Gm::PW, (cuuint32_t)NT};
+  cuuint32_t box[2] = {(cuuint32_t)Gm::PW, 32u};
   cuuint32_t estr[2] = {1, 1};
   if (fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(logits), dims, strides, box, estr,
          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return NER_ERR_UNSUPPORTED;
-  auto kern = crf_viterbi_tma_kernel<K, NT, S, MINB>;
+  auto kern = crf_viterbi_tma_kernel<K, NT, S, TT, MINB, SELV, PARK>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   const int vec_out = ((L & 3) == 0) && ((reinterpret_cast<uintptr_t>(tags_out) & 15) == 0);
@@ -732,7 +856,13 @@ int launch_viterbi(const float* logits, const int32_t* seq_len, const float* tra
   const bool big = B > 148 * 32 * 2;
   if constexpr (K <= 16) {
     if (big && vit_variant() == 0) {   // default: the pipe-balanced TMA kernel (falls through when L*K % 4 != 0 or L is too long)
-      const int rc = launch_viterbi_tma<K, 64, 2, 4>(logits, seq_len, trans, tags_out, best_score, B, L, st);
+      int rc;
+      switch (K == 10 ? vit_tune() : 0) {     // NER_CRF_VIT_TUNE: tuning hook
+        case 1: rc = launch_viterbi_tma<K, 64, 2, 2, 4, 3, false>(logits, seq_len, trans, tags_out, best_score, B, L, st); break;
+        case 2: rc = launch_viterbi_tma<K, 64, 2, 2, 6, 1, true>(logits, seq_len, trans, tags_out, best_score, B, L, st); break;
+        case 3: rc = launch_viterbi_tma<K, 32, 2, 2, 8, 0, false>(logits, seq_len, trans, tags_out, best_score, B, L, st); break;
+        default: rc = launch_viterbi_tma<K, 64, 2, 2, 4, 0, false>(logits, seq_len, trans, tags_out, best_score, B, L, st);
+      }
       if (rc != NER_ERR_UNSUPPORTED) return rc;
     }
     if (big && vit_variant() != 1) {   // NER_CRF_VIT_VARIANT=2: the parked-nibble kernel; =1: the all-on-chip kernel
