@@ -404,23 +404,28 @@ __device__ __forceinline__ void sel_all(F& f) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pipe-balanced variant (K <= 16, L*K % 4 == 0): same one-thread-per-sequence decomposition, three changes.
+// Pipe-balanced variant (K <= 16, L*K % 4 == 0): same one-thread-per-sequence decomposition, four changes.
 //  (1) The per-(i,j) work of the argmax is split over BOTH arithmetic pipes.  The kernels above spend, per pair, one
-//      FADD2 half on the fma pipe and FSETP + FSEL + SEL on the alu pipe (one warp instruction per 2 cycles per pipe
-//      per scheduler): 277 alu vs 60 fma instructions per step at K = 10, i.e. alu-pipe bound at ~554 cycles/step.
-//      Here the max over i is a 3-input FMNMX tree (K/2 alu instructions per tag), and the arg is the FIRST i whose
-//      value equals the max: one FSETP.EQ (alu) and one predicated move of a pre-shifted immediate (fma pipe) per
-//      pair, walking i downwards so the lowest index is the one that sticks.  That is the reference's strict '>' scan
-//      for every non-NaN input (+0 / -0 compare equal in both formulations; the running score may differ in the sign
-//      of a zero, never in value).  Per step at K = 10: ~145 alu + ~145 fma instructions.
-//  (2) Emission logits arrive by TMA: one cp.async.bulk.tensor per chunk of T steps for the whole CTA (box = NT rows x
-//      (T*K + pad) floats of the [B, L*K] view, the pad keeps the row pitch an odd number of 16-byte units so the
+//      FADD2 half on the fma pipe and FSETP + FSEL + SEL on the alu pipe: 277 alu vs 60 fma instructions per step at
+//      K = 10.  Here the max over i is a tree of 3-input FMNMX (K/2 alu instructions per tag), and the arg is the
+//      FIRST i whose value equals the max: one FSETP.EQ (alu) and one predicated IMAD of a pre-shifted immediate (fma
+//      pipe) per pair, walking i downwards so the lowest index is the one that sticks.  That is the reference's strict
+//      '>' scan for every non-NaN input (+0 / -0 compare equal in both formulations; the running score may differ in
+//      the sign of a zero, never in value).  Per step at K = 10: ~150 alu + ~150 fma instructions (was 277 + 60).
+//      scripts/ubench/vit_core.cu times this core without memory: 390 cycles per warp-step at 2 warps per scheduler
+//      (465 for the strict '>' scan); FSET + FFMA, sign(v - max) + SHF and predicated-FFMA variants measure the same or
+//      worse, in the model and in this kernel.
+//  (2) Emission logits arrive by TMA: one cp.async.bulk.tensor per chunk of T steps per WARP (box = 32 rows x
+//      (T*K + pad) floats of the [B, L*K] view; the pad keeps the row pitch an odd number of 16-byte units so the
 //      LDS.128 reads are conflict free; out-of-range columns/rows are zero filled) instead of ~18 instructions per
-//      16-byte cp.async request.
+//      16-byte cp.async request, plus an L2 prefetch (cp.async.bulk.prefetch.tensor) 16 steps ahead of the ring.
 //  (3) All backpointers stay in shared memory (4 bits per tag: 5 bytes per step at K = 10), so there is no parked
 //      traffic to L2/HBM and no 64-bit address arithmetic per step; decoded tags leave in one coalesced sweep.
-// Rows are fetched to the CTA's longest length (TMA boxes are rectangular); the DP itself stops at each row's own
-// length.  NER_CRF_VIT_VARIANT=2 selects the parked-nibble kernel above instead.
+//  (4) Every warp is its own pipeline (ring, full-barriers, backtrace, output sweep): no CTA barrier after the prologue,
+//      and a warp fetches only to ITS longest row.  The backtrace prefetches the words of 8 steps (their addresses do
+//      not depend on the path) and resolves the chain in registers.
+// NER_CRF_VIT_VARIANT=2 selects the parked-nibble kernel above instead (it is also the fallback when L*K % 4 != 0 or the
+// backpointers of L steps do not fit in shared memory).
 template <int K, int TT>
 struct TmaGeom {
   static constexpr int T = (K % 2) ? 4 : TT;                // steps per chunk: T*K % 4 == 0
@@ -430,12 +435,12 @@ struct TmaGeom {
   static constexpr int HB = BpSplit<K>::HB;
 };
 
-template <int K, int NT, int S, int TT, bool PARK>
+template <int K, int NT, int S, int TT>
 size_t viterbi_tma_smem_bytes(int L) {
   using Gm = TmaGeom<K, TT>;
   const size_t ring = (size_t)S * NT * Gm::PW * 4;
   const size_t dec = (size_t)NT * (((L + 3) & ~3) + 4);
-  const size_t lo = PARK ? 0 : (size_t)L * NT * 4;
+  const size_t lo = (size_t)L * NT * 4;
   const size_t hi = ((size_t)L * NT * Gm::HB + 15) & ~(size_t)15;
   return (ring > dec ? ring : dec) + lo + hi + (size_t)(2 * K * Gm::KP + NT) * 4 + 8 + (NT / 32) * S * 8;
 }
@@ -463,52 +468,6 @@ struct ArgSel {   // compile-time immediates: index i pre-shifted to tag J's nib
   }
 };
 
-// Two predicate-free formulations of the same first-equal index (the compare-to-predicate instruction is the slow
-// one on this pipe mix).  Both count the leading entries that differ from the max with a Horner recurrence
-// h_i = e_i * (1 + h_{i+1}), e_i = [v_i != m], so h_0 is the lowest index whose value equals the max.
-//  SELV 1: e_i by FSET.BF (1.0f / 0.0f in a register), the recurrence in fp32 FFMAs (small integers: exact).
-//  SELV 2: e_i = sign bit of (v_i - m) (the difference of two floats is +0 exactly when they are equal, and negative
-//          otherwise because m is the max; inf - inf gives the positive canonical NaN), the recurrence in IMADs.
-__device__ __forceinline__ float fset_ne(float a, float b) {
-  float r;
-  asm("set.ne.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
-  f32x2 r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-template <int K>
-__device__ __forceinline__ float first_eq_f(const float* v, float m) {      // SELV 1 -> index as a float
-  if constexpr (K == 1) return 0.f;
-  float h = fset_ne(v[K - 2], m);
-#pragma unroll
-  for (int i = K - 3; i >= 0; --i) {
-    const float e = fset_ne(v[i], m);
-    h = fmaf(e, h, e);
-  }
-  return h;
-}
-template <int K>
-__device__ __forceinline__ uint32_t first_eq_u(const f32x2* v2, float m) {   // SELV 2 -> index as an integer
-  if constexpr (K == 1) return 0u;
-  constexpr int KP = (K + 1) / 2;
-  uint32_t e[2 * KP];
-  const f32x2 m2 = pk2(m, m);
-#pragma unroll
-  for (int p = 0; p < KP; ++p) {
-    float lo, hi;
-    upk2(sub2(v2[p], m2), lo, hi);
-    e[2 * p] = __float_as_uint(lo) >> 31;
-    e[2 * p + 1] = __float_as_uint(hi) >> 31;
-  }
-  uint32_t h = e[K - 2];
-#pragma unroll
-  for (int i = K - 3; i >= 0; --i) h = e[i] * h + e[i];
-  return h;
-}
-
 // max of v[0..K): three-input maxima over triples, then a three-input tree over those (depth 3 at K = 10)
 template <int K>
 __device__ __forceinline__ float max_tree(const float* v) {
@@ -532,10 +491,10 @@ __device__ __forceinline__ float max_tree(const float* v) {
 
 // One WARP is one independent pipeline: its own TMA ring (box = 32 rows), its own full-barriers, its own backpointer
 // columns, backtrace and output sweep; the CTA only carves up shared memory (no CTA barrier after the prologue).
-template <int K, int NT, int S, int TT, int MINB, int SELV, bool PARK>
+template <int K, int NT, int S, int TT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int32_t* __restrict__ seq_len,
-                       const float* __restrict__ trans, int32_t* tags_out,
+                       const float* __restrict__ trans, int32_t* __restrict__ tags_out,
                        float* __restrict__ best_score, int B, int L, int vec_out, uint32_t zero) {
   using Gm = TmaGeom<K, TT>;
   constexpr int T = Gm::T, PW = Gm::PW, KP = Gm::KP, HB = Gm::HB, NW = NT / 32;
@@ -545,7 +504,7 @@ crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int3
   const int Lp = ((L + 3) & ~3) + 4;
   const size_t ring_b = (size_t)S * NT * PW * 4, dec_b = (size_t)NT * Lp;
   uint32_t* s_lo = reinterpret_cast<uint32_t*>(base + (ring_b > dec_b ? ring_b : dec_b));   // [L][NT]
-  uint8_t* s_hi = reinterpret_cast<uint8_t*>(s_lo + (PARK ? 0 : (size_t)L * NT));   // [L][NT] x HB bytes
+  uint8_t* s_hi = reinterpret_cast<uint8_t*>(s_lo + (size_t)L * NT);                // [L][NT] x HB bytes
   float* s_tr = reinterpret_cast<float*>(s_hi + (((size_t)L * NT * HB + 15) & ~(size_t)15));   // [j][2*KP]: column j of trans
   int* s_len = reinterpret_cast<int*>(s_tr + 2 * K * KP);                           // [NT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_len + NT + ((2 * K * KP + NT) & 1));   // [NW][S], 8-byte aligned
@@ -601,12 +560,8 @@ crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int3
 #pragma unroll
   for (int p = 0; p < KP; ++p) s2[p] = pk2(0.f, 0.f);
 
-  // PARK: the low words (tags 0..7) are parked in this warp's own [rows, L] slab of tags_out, [t][lane] layout, written and
-  // read back by the same lane (L2-resident for the warp's lifetime), which takes shared memory per CTA from 52 KB to
-  // 19 KB at L = 128: the warps per SM are then bounded by registers, not by the backpointers.
   const int wnv = max(0, min(32, nv - 32 * warp));
-  uint32_t* lo_p = PARK ? reinterpret_cast<uint32_t*>(tags_out + (size_t)wrow0 * L) + lane : s_lo + tid;
-  const int lo_pitch = PARK ? wnv : NT;
+  uint32_t* lo_p = s_lo + tid;
   uint8_t* hi_p = s_hi + (size_t)tid * HB;
 
   for (int c = 0; c < nchunk; ++c) {
@@ -631,49 +586,22 @@ crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int3
           } else {
             float m[2 * KP];
             uint32_t wlo = 0u, whi = 0u;
-            float fw[4] = {0.f, 0.f, 0.f, 0.f};       // SELV 1: four nibbles per float (exact below 2^16)
             auto tag_step = [&](auto jc) {
               constexpr int J = decltype(jc)::value;
-              f32x2 v2[KP];
               float v[2 * KP];
 #pragma unroll
-              for (int p = 0; p < KP; ++p) {
-                v2[p] = add2(s2[p], tr2[J * KP + p]);
-                upk2(v2[p], v[2 * p], v[2 * p + 1]);
-              }
-              float mj;
-              if constexpr (SELV == 3) {      // sequential three-input chain instead of the tree
-                mj = v[0];
-                int i = 1;
-#pragma unroll
-                for (; i + 1 < K; i += 2) mj = max3(mj, v[i], v[i + 1]);
-                if (i < K) mj = fmaxf(mj, v[i]);
-              } else {
-                mj = max_tree<K>(v);
-              }
+              for (int p = 0; p < KP; ++p) upk2(add2(s2[p], tr2[J * KP + p]), v[2 * p], v[2 * p + 1]);
+              const float mj = max_tree<K>(v);
               m[J] = mj;
-              if constexpr (SELV == 0 || SELV == 3) {
-                const uint32_t ix = ArgSel<K, J>::run(v, mj, zero);
-                if (J < 8) wlo |= ix; else whi |= ix;
-              } else if constexpr (SELV == 1) {
-                fw[J >> 2] = fmaf(first_eq_f<K>(v, mj), (float)(1 << (4 * (J & 3))), fw[J >> 2]);
-              } else {
-                const uint32_t ix = first_eq_u<K>(v2, mj);
-                if (J < 8) wlo = ix * (1u << (4 * (J & 7))) + wlo; else whi = ix * (1u << (4 * (J & 7))) + whi;
-              }
+              const uint32_t ix = ArgSel<K, J>::run(v, mj, zero);
+              if (J < 8) wlo |= ix; else whi |= ix;
             };
             sel_all<K>(tag_step);
-            if constexpr (SELV == 1) {
-              wlo = __float2uint_rn(fw[0]);
-              if (K > 4) wlo |= __float2uint_rn(fw[1]) << 16;
-              if (K > 8) whi = __float2uint_rn(fw[2]);
-              if (K > 12) whi |= __float2uint_rn(fw[3]) << 16;
-            }
             if (2 * KP > K) m[2 * KP - 1] = 0.f;
 #pragma unroll
             for (int p = 0; p < KP; ++p)
               s2[p] = add2(pk2(m[2 * p], m[2 * p + 1]), pk2(xs[g * K + 2 * p], (2 * p + 1 < K) ? xs[g * K + 2 * p + 1] : 0.f));
-            if (PARK) __stcg(lo_p + (size_t)t * lo_pitch, wlo); else lo_p[(size_t)t * NT] = wlo;
+            lo_p[(size_t)t * NT] = wlo;
             if (HB == 1) hi_p[(size_t)t * NT] = (uint8_t)whi;
             if (HB == 2) reinterpret_cast<uint16_t*>(hi_p)[(size_t)t * NT] = (uint16_t)whi;
             if (HB == 4) reinterpret_cast<uint32_t*>(hi_p)[(size_t)t * NT] = whi;
@@ -713,7 +641,7 @@ crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int3
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const bool in = t - u >= 1;
-        wa[u] = in ? (PARK ? __ldcg(lo_p + (size_t)(t - u) * lo_pitch) : lo_p[(size_t)(t - u) * NT]) : 0u;
+        wa[u] = in ? lo_p[(size_t)(t - u) * NT] : 0u;
         wb[u] = 0u;
         if (HB == 1) wb[u] = in ? hi_p[(size_t)(t - u) * NT] : 0u;
         if (HB == 2) wb[u] = in ? reinterpret_cast<const uint16_t*>(hi_p)[(size_t)(t - u) * NT] : 0u;
@@ -735,8 +663,7 @@ crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int3
   }
   __syncwarp();
 
-  // Coalesced [rows of this warp, L] int32 store; zero beyond each row's length.  (PARK: every parked word of the warp
-  // has been consumed above.)
+  // Coalesced [rows of this warp, L] int32 store; zero beyond each row's length.
   int32_t* obase = tags_out + (size_t)wrow0 * L;
   const int* wlen = s_len + 32 * warp;
   if (vec_out) {
@@ -774,11 +701,6 @@ int launch_viterbi_gs(const float* logits, const int32_t* seq_len, const float* 
   const int grid = (B + NT - 1) / NT;
   kern<<<grid, NT, smem, st>>>(logits, seq_len, trans, tags_out, best_score, B, L, vec16);
   return ner_launch_status();
-}
-
-int vit_tune() {
-  const char* e = getenv("NER_CRF_VIT_TUNE");
-  return e ? atoi(e) : 0;
 }
 
 int vit_variant() {
@@ -820,13 +742,13 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-template <int K, int NT, int S, int TT, int MINB, int SELV, bool PARK>
+template <int K, int NT, int S, int TT, int MINB>
 int launch_viterbi_tma(const float* logits, const int32_t* seq_len, const float* trans, int32_t* tags_out,
                        float* best_score, int B, int L, cudaStream_t st) {
   using Gm = TmaGeom<K, TT>;
   const size_t LK = (size_t)L * K;
   if ((LK & 3) != 0 || (reinterpret_cast<uintptr_t>(logits) & 15) != 0) return NER_ERR_UNSUPPORTED;
-  const size_t smem = viterbi_tma_smem_bytes<K, NT, S, TT, PARK>(L);
+  const size_t smem = viterbi_tma_smem_bytes<K, NT, S, TT>(L);
   if (smem > kMaxSmem) return NER_ERR_UNSUPPORTED;
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return NER_ERR_UNSUPPORTED;
@@ -839,7 +761,7 @@ int launch_viterbi_tma(const float* logits, const int32_t* seq_len, const float*
          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return NER_ERR_UNSUPPORTED;
-  auto kern = crf_viterbi_tma_kernel<K, NT, S, TT, MINB, SELV, PARK>;
+  auto kern = crf_viterbi_tma_kernel<K, NT, S, TT, MINB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return NER_ERR_CUDA_BASE - (int)e;
   const int vec_out = ((L & 3) == 0) && ((reinterpret_cast<uintptr_t>(tags_out) & 15) == 0);
@@ -856,13 +778,7 @@ int launch_viterbi(const float* logits, const int32_t* seq_len, const float* tra
   const bool big = B > 148 * 32 * 2;
   if constexpr (K <= 16) {
     if (big && vit_variant() == 0) {   // default: the pipe-balanced TMA kernel (falls through when L*K % 4 != 0 or L is too long)
-      int rc;
-      switch (K == 10 ? vit_tune() : 0) {     // NER_CRF_VIT_TUNE: tuning hook
-        case 1: rc = launch_viterbi_tma<K, 64, 2, 2, 4, 3, false>(logits, seq_len, trans, tags_out, best_score, B, L, st); break;
-        case 2: rc = launch_viterbi_tma<K, 64, 2, 2, 6, 1, true>(logits, seq_len, trans, tags_out, best_score, B, L, st); break;
-        case 3: rc = launch_viterbi_tma<K, 32, 2, 2, 8, 0, false>(logits, seq_len, trans, tags_out, best_score, B, L, st); break;
-        default: rc = launch_viterbi_tma<K, 64, 2, 2, 4, 0, false>(logits, seq_len, trans, tags_out, best_score, B, L, st);
-      }
+      const int rc = launch_viterbi_tma<K, 64, 2, 2, 4>(logits, seq_len, trans, tags_out, best_score, B, L, st);
       if (rc != NER_ERR_UNSUPPORTED) return rc;
     }
     if (big && vit_variant() != 1) {   // NER_CRF_VIT_VARIANT=2: the parked-nibble kernel; =1: the all-on-chip kernel
