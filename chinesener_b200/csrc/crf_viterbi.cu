@@ -415,15 +415,18 @@ __device__ __forceinline__ void sel_all(F& f) {
 //      scripts/ubench/vit_core.cu times this core without memory: 390 cycles per warp-step at 2 warps per scheduler
 //      (465 for the strict '>' scan); FSET + FFMA, sign(v - max) + SHF and predicated-FFMA variants measure the same or
 //      worse, in the model and in this kernel.
-//  (2) Emission logits arrive by TMA: one cp.async.bulk.tensor per chunk of T steps per WARP (box = 32 rows x
+//  (2) Emission logits arrive by TMA: one cp.async.bulk.tensor per chunk of T steps per warp (box = 32 rows x
 //      (T*K + pad) floats of the [B, L*K] view; the pad keeps the row pitch an odd number of 16-byte units so the
 //      LDS.128 reads are conflict free; out-of-range columns/rows are zero filled) instead of ~18 instructions per
-//      16-byte cp.async request, plus an L2 prefetch (cp.async.bulk.prefetch.tensor) 16 steps ahead of the ring.
+//      16-byte cp.async request.  Two-stage ring; a stage is refilled as soon as its rows sit in registers, i.e. before
+//      the arithmetic of the chunk (an L2 prefetch further ahead measured slower and is not issued).
 //  (3) All backpointers stay in shared memory (4 bits per tag: 5 bytes per step at K = 10), so there is no parked
 //      traffic to L2/HBM and no 64-bit address arithmetic per step; decoded tags leave in one coalesced sweep.
-//  (4) Every warp is its own pipeline (ring, full-barriers, backtrace, output sweep): no CTA barrier after the prologue,
-//      and a warp fetches only to ITS longest row.  The backtrace prefetches the words of 8 steps (their addresses do
-//      not depend on the path) and resolves the chain in registers.
+//  (4) One warp = one CTA = one pipeline (ring, full-barriers, backtrace, output sweep): no CTA barrier in the loop, a
+//      warp fetches only to ITS longest row, 8 CTAs per SM.  Chunks that end before the warp's shortest row take a path
+//      without per-row length checks; chunk 0 (t = 0 has no predecessor) is peeled.  The backtrace prefetches the words
+//      of 8 steps (their addresses do not depend on the path) and resolves the chain in registers.  The transition
+//      matrix goes from global memory straight into registers (every thread reads the same K*K words).
 // NER_CRF_VIT_VARIANT=2 selects the parked-nibble kernel above instead (it is also the fallback when L*K % 4 != 0 or the
 // backpointers of L steps do not fit in shared memory).
 template <int K, int TT>
@@ -442,7 +445,7 @@ size_t viterbi_tma_smem_bytes(int L) {
   const size_t dec = (size_t)NT * (((L + 3) & ~3) + 4);
   const size_t lo = (size_t)L * NT * 4;
   const size_t hi = ((size_t)L * NT * Gm::HB + 15) & ~(size_t)15;
-  return (ring > dec ? ring : dec) + lo + hi + (size_t)(2 * K * Gm::KP + NT) * 4 + 8 + (NT / 32) * S * 8;
+  return (ring > dec ? ring : dec) + lo + hi + (size_t)NT * 4 + 8 + (NT / 32) * S * 8;
 }
 
 // ix <- imm where v == m.  Walked from the highest i down, so the lowest equal index is the one that remains.
@@ -505,9 +508,8 @@ crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int3
   const size_t ring_b = (size_t)S * NT * PW * 4, dec_b = (size_t)NT * Lp;
   uint32_t* s_lo = reinterpret_cast<uint32_t*>(base + (ring_b > dec_b ? ring_b : dec_b));   // [L][NT]
   uint8_t* s_hi = reinterpret_cast<uint8_t*>(s_lo + (size_t)L * NT);                // [L][NT] x HB bytes
-  float* s_tr = reinterpret_cast<float*>(s_hi + (((size_t)L * NT * HB + 15) & ~(size_t)15));   // [j][2*KP]: column j of trans
-  int* s_len = reinterpret_cast<int*>(s_tr + 2 * K * KP);                           // [NT]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_len + NT + ((2 * K * KP + NT) & 1));   // [NW][S], 8-byte aligned
+  int* s_len = reinterpret_cast<int*>(s_hi + (((size_t)L * NT * HB + 15) & ~(size_t)15));     // [NT]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_len + NT);                         // [NW][S], 8-byte aligned
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform: ring / barrier addresses stay in uniform registers
@@ -527,10 +529,6 @@ crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int3
     for (int s = 0; s < S; ++s) tc::mbar_init(w_bar + s, 1);
     tc::fence_barrier_init();
   }
-  for (int e = tid; e < K * 2 * KP; e += NT) {
-    const int j = e / (2 * KP), i = e - j * 2 * KP;
-    s_tr[e] = (i < K) ? trans[i * K + j] : 0.f;
-  }
   int mylen = 1;
   if (live) mylen = min(max(seq_len[row0 + tid], 1), L);  // len<=0 behaves like 1 (TF quirk)
   s_len[tid] = mylen;
@@ -540,7 +538,6 @@ crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int3
   const int nchunk = (wmax + T - 1) / T;                // 0 for a warp past the end of the batch
   __syncthreads();                                      // s_tr, s_len and the barrier inits are visible
 
-  constexpr int PF = 16 / T;                            // L2 prefetch distance in chunks (16 time steps ahead of the ring)
   if (tc::elect_one()) {
 #pragma unroll
     for (int s = 0; s < S; ++s)
@@ -548,13 +545,14 @@ crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int3
         tc::mbar_arrive_expect_tx(w_bar + s, CHUNK_BYTES);
         tc::tma_load_2d(w_ring + (size_t)s * 32 * PW, &tm_logits, w_bar + s, s * T * K, wrow0);
       }
-    for (int s = S; s < S + PF; ++s)
-      if (s < nchunk) tc::tma_prefetch_l2_2d(&tm_logits, s * T * K, wrow0);
   }
 
-  f32x2 tr2[K * KP];       // tr2[j*KP + p] = (trans[2p][j], trans[2p+1][j])
+  f32x2 tr2[K * KP];       // tr2[j*KP + p] = (trans[2p][j], trans[2p+1][j]); every thread reads the same K*K words (L1 broadcast)
 #pragma unroll
-  for (int e = 0; e < K * KP; ++e) tr2[e] = pk2(s_tr[2 * e], s_tr[2 * e + 1]);
+  for (int j = 0; j < K; ++j)
+#pragma unroll
+    for (int p = 0; p < KP; ++p)
+      tr2[j * KP + p] = pk2(__ldg(trans + (2 * p) * K + j), (2 * p + 1 < K) ? __ldg(trans + (2 * p + 1) * K + j) : 0.f);
 
   f32x2 s2[KP];
 #pragma unroll
@@ -564,12 +562,67 @@ crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int3
   uint32_t* lo_p = s_lo + tid;
   uint8_t* hi_p = s_hi + (size_t)tid * HB;
 
-  for (int c = 0; c < nchunk; ++c) {
+  int wmin = live ? mylen : L;             // shortest live row of the warp: chunks that end before it need no per-row checks
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wmin = min(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+
+  // one DP step for this lane: s2 <- max-plus(s2, trans) + x_t, backpointers of step t to shared memory
+  auto dp_step = [&](const float* xs, const int g, const int t) {
+    float m[2 * KP];
+    uint32_t wlo = 0u, whi = 0u;
+    auto tag_step = [&](auto jc) {
+      constexpr int J = decltype(jc)::value;
+      float v[2 * KP];
+#pragma unroll
+      for (int p = 0; p < KP; ++p) upk2(add2(s2[p], tr2[J * KP + p]), v[2 * p], v[2 * p + 1]);
+      const float mj = max_tree<K>(v);
+      m[J] = mj;
+      const uint32_t ix = ArgSel<K, J>::run(v, mj, zero);
+      if (J < 8) wlo |= ix; else whi |= ix;
+    };
+    sel_all<K>(tag_step);
+    if (2 * KP > K) m[2 * KP - 1] = 0.f;
+#pragma unroll
+    for (int p = 0; p < KP; ++p)
+      s2[p] = add2(pk2(m[2 * p], m[2 * p + 1]), pk2(xs[g * K + 2 * p], (2 * p + 1 < K) ? xs[g * K + 2 * p + 1] : 0.f));
+    lo_p[(size_t)t * NT] = wlo;
+    if (HB == 1) hi_p[(size_t)t * NT] = (uint8_t)whi;
+    if (HB == 2) reinterpret_cast<uint16_t*>(hi_p)[(size_t)t * NT] = (uint16_t)whi;
+    if (HB == 4) reinterpret_cast<uint32_t*>(hi_p)[(size_t)t * NT] = whi;
+  };
+
+  // refill of the stage this warp has just copied into registers (warp-uniform condition, one elected lane).  The
+  // __syncwarp before it orders every lane's LDS of the stage before the TMA write, the same release the usual
+  // consumer-arrive / producer-wait pair gives.
+  auto refill = [&](const int c, const int st) {
+    __syncwarp();
+    if (c + S < nchunk) {
+      if (tc::elect_one()) {
+        tc::mbar_arrive_expect_tx(w_bar + st, CHUNK_BYTES);
+        tc::tma_load_2d(w_ring + (size_t)st * 32 * PW, &tm_logits, w_bar + st, (c + S) * T * K, wrow0);
+      }
+    }
+  };
+
+  auto do_chunk = [&](const int c, auto first_tag) {
+    constexpr bool FIRST = decltype(first_tag)::value;       // chunk 0 holds t = 0 (s_0 = x_0, no backpointer)
     const int st = c % S;
     tc::mbar_wait(w_bar + st, (uint32_t)(c / S) & 1u);
     const int t0 = c * T;
+    const float4* rowp = reinterpret_cast<const float4*>(w_ring + (size_t)st * 32 * PW + lane * PW);
+    if (!FIRST && t0 + T <= wmin) {        // warp-uniform fast path: every live row has all T steps, no per-row checks
+      float xs[T * K];
+#pragma unroll
+      for (int q = 0; q < T * K / 4; ++q) {
+        const float4 v = rowp[q];
+        xs[4 * q] = v.x; xs[4 * q + 1] = v.y; xs[4 * q + 2] = v.z; xs[4 * q + 3] = v.w;
+      }
+      refill(c, st);                       // early: the next-but-one chunk is in flight during this chunk's arithmetic
+#pragma unroll
+      for (int g = 0; g < T; ++g) dp_step(xs, g, t0 + g);
+      return;
+    }
     if (live && t0 < mylen) {
-      const float4* rowp = reinterpret_cast<const float4*>(w_ring + (size_t)st * 32 * PW + lane * PW);
       float xs[T * K];
 #pragma unroll
       for (int q = 0; q < T * K / 4; ++q) {
@@ -580,44 +633,20 @@ crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int3
       for (int g = 0; g < T; ++g) {
         const int t = t0 + g;
         if (t < mylen) {
-          if (t == 0) {
+          if (FIRST && t == 0) {
 #pragma unroll
             for (int p = 0; p < KP; ++p) s2[p] = pk2(xs[2 * p], (2 * p + 1 < K) ? xs[2 * p + 1] : 0.f);
           } else {
-            float m[2 * KP];
-            uint32_t wlo = 0u, whi = 0u;
-            auto tag_step = [&](auto jc) {
-              constexpr int J = decltype(jc)::value;
-              float v[2 * KP];
-#pragma unroll
-              for (int p = 0; p < KP; ++p) upk2(add2(s2[p], tr2[J * KP + p]), v[2 * p], v[2 * p + 1]);
-              const float mj = max_tree<K>(v);
-              m[J] = mj;
-              const uint32_t ix = ArgSel<K, J>::run(v, mj, zero);
-              if (J < 8) wlo |= ix; else whi |= ix;
-            };
-            sel_all<K>(tag_step);
-            if (2 * KP > K) m[2 * KP - 1] = 0.f;
-#pragma unroll
-            for (int p = 0; p < KP; ++p)
-              s2[p] = add2(pk2(m[2 * p], m[2 * p + 1]), pk2(xs[g * K + 2 * p], (2 * p + 1 < K) ? xs[g * K + 2 * p + 1] : 0.f));
-            lo_p[(size_t)t * NT] = wlo;
-            if (HB == 1) hi_p[(size_t)t * NT] = (uint8_t)whi;
-            if (HB == 2) reinterpret_cast<uint16_t*>(hi_p)[(size_t)t * NT] = (uint16_t)whi;
-            if (HB == 4) reinterpret_cast<uint32_t*>(hi_p)[(size_t)t * NT] = whi;
+            dp_step(xs, g, t);
           }
         }
       }
     }
-    __syncwarp();                          // every lane has consumed its row of this stage
-    if (c + S < nchunk) {                  // warp-uniform
-      if (tc::elect_one()) {
-        tc::mbar_arrive_expect_tx(w_bar + st, CHUNK_BYTES);
-        tc::tma_load_2d(w_ring + (size_t)st * 32 * PW, &tm_logits, w_bar + st, (c + S) * T * K, wrow0);
-        if (c + S + PF < nchunk) tc::tma_prefetch_l2_2d(&tm_logits, (c + S + PF) * T * K, wrow0);
-      }
-    }
-  }
+    refill(c, st);
+  };
+  if (nchunk > 0) do_chunk(0, std::true_type{});
+#pragma unroll 1
+  for (int c = 1; c < nchunk; ++c) do_chunk(c, std::false_type{});
   __syncwarp();                            // this warp's ring is dead: its decoded tags may overwrite it
 
   if (live) {
@@ -669,8 +698,10 @@ crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int3
   if (vec_out) {
     const int L4 = L >> 2, total4 = wnv * L4;
     int4* o4 = reinterpret_cast<int4*>(obase);
+    int r = 0, q = lane;                   // (row, int4 column) of the flat index, kept incrementally: no division
+    while (q >= L4) { q -= L4; ++r; }
     for (int idx = lane; idx < total4; idx += 32) {
-      const int r = idx / L4, p = (idx - r * L4) * 4;
+      const int p = 4 * q;
       const uint32_t pk = *reinterpret_cast<const uint32_t*>(w_dec + r * Lp + p);
       const int n = wlen[r];
       int4 o;
@@ -679,6 +710,8 @@ crf_viterbi_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const int3
       o.z = (p + 2 < n) ? (int)((pk >> 16) & 255u) : 0;
       o.w = (p + 3 < n) ? (int)(pk >> 24) : 0;
       o4[idx] = o;
+      q += 32;
+      while (q >= L4) { q -= L4; ++r; }
     }
   } else {
     const int total = wnv * L;
@@ -778,7 +811,7 @@ int launch_viterbi(const float* logits, const int32_t* seq_len, const float* tra
   const bool big = B > 148 * 32 * 2;
   if constexpr (K <= 16) {
     if (big && vit_variant() == 0) {   // default: the pipe-balanced TMA kernel (falls through when L*K % 4 != 0 or L is too long)
-      const int rc = launch_viterbi_tma<K, 64, 2, 2, 4>(logits, seq_len, trans, tags_out, best_score, B, L, st);
+      const int rc = launch_viterbi_tma<K, 32, 2, 2, 8>(logits, seq_len, trans, tags_out, best_score, B, L, st);
       if (rc != NER_ERR_UNSUPPORTED) return rc;
     }
     if (big && vit_variant() != 1) {   // NER_CRF_VIT_VARIANT=2: the parked-nibble kernel; =1: the all-on-chip kernel
