@@ -316,6 +316,25 @@ def _time_launches(fn, warm=3, iters=10, flush=None):
     return float(np.mean(ts)), float(min(ts))
 
 
+def crf_sample_check(x, tr, lens, tags, ll, pred, n=2048, seed=4321):
+    """Checker of the roofline-sized CRF launches (outside every timed region): `n` rows sampled from the B rows the
+    kernels processed, re-run through the numpy oracle.  Viterbi tags must be bit-equal (integer output); the
+    log-likelihood must agree with the fp64 oracle within 1e-4 relative + 1e-4 absolute (the tolerance of
+    tests/test_crf_gpu.py).  Takes tensors on any device."""
+    from oracle import crf as ocrf
+    B = x.shape[0]
+    idx = torch.from_numpy(np.sort(np.random.RandomState(seed).choice(B, size=min(n, B), replace=False))).to(x.device)
+    xs, ls = x.index_select(0, idx).cpu().numpy(), lens.index_select(0, idx).cpu().numpy()
+    t = tr.cpu().numpy()
+    ref_pred, _ = ocrf.crf_decode(xs, t, ls, dtype=np.float32)
+    ref_ll = ocrf.crf_log_likelihood(xs, tags.index_select(0, idx).cpu().numpy(), ls, t)
+    got_pred, got_ll = pred.index_select(0, idx).cpu().numpy(), ll.index_select(0, idx).cpu().numpy()
+    return {"rows_checked": int(idx.numel()), "viterbi_bit_exact": bool(np.array_equal(got_pred, ref_pred)),
+            "loglik_max_rel_err_vs_fp64": float(np.max(np.abs(got_ll - ref_ll) / (np.abs(ref_ll) + 1.0))),
+            "loglik_within_tolerance": bool(np.allclose(got_ll, ref_ll, rtol=1e-4, atol=1e-4)),
+            "what": "rows sampled (fixed seed) from the roofline launch's own inputs and outputs vs oracle/crf.py"}
+
+
 def crf_rooflines(hbm_peak, peak_src, B=262144, L=128, K=LABELS):
     """SURVEY 8(d) "CRF kernel roofline run": B = 262 144 sequences, L = 128, K = 10, full lengths (1.34 GB of emission
     logits >> 126 MB L2, so every launch is L2-cold by construction).  Algorithmic bytes per sentence:
@@ -335,6 +354,13 @@ def crf_rooflines(hbm_peak, peak_src, B=262144, L=128, K=LABELS):
         out[key] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
                     "ms_per_launch": ms, "best_ms": best, "algorithmic_bytes_per_launch": byts, "launches_timed": 10,
                     "workload": f"B={B} L={L} K={K} full lengths, fp32 logits (working set 1.5 GB >> L2)", "peak_source": peak_src}
+    try:        # untimed: the outputs of one more launch of each kernel against the oracle on a row sample
+        chk = crf_sample_check(x, tr, lens, tags, ops.crf_loglik_fwd(x, tags, lens, tr)[0], ops.crf_viterbi(x, lens, tr))
+        out["roofline_crf_viterbi"]["parity_checked"] = chk["viterbi_bit_exact"]
+        out["roofline_crf_fwd"]["parity_checked"] = chk["loglik_within_tolerance"]
+        out["crf_roofline_parity"] = chk
+    except Exception as exc:      # the checker must never cost the line its timings
+        out["crf_roofline_parity"] = {"error": repr(exc)[:200]}
     del x, tags
     torch.cuda.empty_cache()
     return out
