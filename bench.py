@@ -317,22 +317,37 @@ def _time_launches(fn, warm=3, iters=10, flush=None):
 
 
 def crf_sample_check(x, tr, lens, tags, ll, pred, n=2048, seed=4321):
-    """Checker of the roofline-sized CRF launches (outside every timed region): `n` rows sampled from the B rows the
-    kernels processed, re-run through the numpy oracle.  Viterbi tags must be bit-equal (integer output); the
-    log-likelihood must agree with the fp64 oracle within 1e-4 relative + 1e-4 absolute (the tolerance of
-    tests/test_crf_gpu.py).  Takes tensors on any device."""
-    from oracle import crf as ocrf
+    """Checker of the roofline-sized CRF launches (outside every timed region).  With the C restatement of the oracle
+    (oracle/crf_c.c, built by __graft_entry__.build()) EVERY row the kernels processed is re-run on the host cores;
+    without it, `n` rows sampled with a fixed seed go through the numpy restatement.  Viterbi tags must be bit-equal
+    (integer output); the log-likelihood must agree with the fp64 oracle within 1e-4 relative + 1e-4 absolute (the
+    tolerance of tests/test_crf_gpu.py).  Takes tensors on any device."""
+    from oracle import crf as ocrf, native as onative
     B = x.shape[0]
-    idx = torch.from_numpy(np.sort(np.random.RandomState(seed).choice(B, size=min(n, B), replace=False))).to(x.device)
-    xs, ls = x.index_select(0, idx).cpu().numpy(), lens.index_select(0, idx).cpu().numpy()
     t = tr.cpu().numpy()
-    ref_pred, _ = ocrf.crf_decode(xs, t, ls, dtype=np.float32)
-    ref_ll = ocrf.crf_log_likelihood(xs, tags.index_select(0, idx).cpu().numpy(), ls, t)
-    got_pred, got_ll = pred.index_select(0, idx).cpu().numpy(), ll.index_select(0, idx).cpu().numpy()
-    return {"rows_checked": int(idx.numel()), "viterbi_bit_exact": bool(np.array_equal(got_pred, ref_pred)),
-            "loglik_max_rel_err_vs_fp64": float(np.max(np.abs(got_ll - ref_ll) / (np.abs(ref_ll) + 1.0))),
-            "loglik_within_tolerance": bool(np.allclose(got_ll, ref_ll, rtol=1e-4, atol=1e-4)),
-            "what": "rows sampled (fixed seed) from the roofline launch's own inputs and outputs vs oracle/crf.py"}
+    if onative.available():
+        xs, ls, ys = x.cpu().numpy(), lens.cpu().numpy(), tags.cpu().numpy()
+        t0 = time.perf_counter()
+        ref_pred, _ = onative.crf_decode(xs, t, ls)
+        t1 = time.perf_counter()
+        ref_ll = onative.crf_log_likelihood(xs, ys, ls, t)
+        t2 = time.perf_counter()
+        got_pred, got_ll = pred.cpu().numpy(), ll.cpu().numpy()
+        how = {"checker": "oracle/crf_c.c (plain C, OpenMP) on every row", "cpu_decode_s": t1 - t0, "cpu_loglik_s": t2 - t1,
+               "cpu_threads": os.cpu_count()}
+    else:
+        idx = torch.from_numpy(np.sort(np.random.RandomState(seed).choice(B, size=min(n, B), replace=False))).to(x.device)
+        xs, ls = x.index_select(0, idx).cpu().numpy(), lens.index_select(0, idx).cpu().numpy()
+        ref_pred, _ = ocrf.crf_decode(xs, t, ls, dtype=np.float32)
+        ref_ll = ocrf.crf_log_likelihood(xs, tags.index_select(0, idx).cpu().numpy(), ls, t)
+        got_pred, got_ll = pred.index_select(0, idx).cpu().numpy(), ll.index_select(0, idx).cpu().numpy()
+        how = {"checker": "oracle/crf.py (numpy) on rows sampled with a fixed seed"}
+    return dict(how, rows_checked=int(ref_pred.shape[0]), rows_launched=int(B),
+                viterbi_bit_exact=bool(np.array_equal(got_pred, ref_pred)),
+                viterbi_rows_differing=int((got_pred != ref_pred).any(axis=1).sum()),
+                loglik_max_rel_err_vs_fp64=float(np.max(np.abs(got_ll - ref_ll) / (np.abs(ref_ll) + 1.0))),
+                loglik_within_tolerance=bool(np.allclose(got_ll, ref_ll, rtol=1e-4, atol=1e-4)),
+                what="inputs and outputs of one untimed launch of each roofline-sized kernel vs the oracle")
 
 
 def crf_rooflines(hbm_peak, peak_src, B=262144, L=128, K=LABELS):

@@ -13,4 +13,7 @@ pin is checked in tests/test_golden.py (prediction pickles: crf_decode zero-fill
 tener shift docstring; decode_prediction example; warm-up request feature layout).  Numeric
 values of logits / log-likelihoods are NOT pinned by any reference fixture ("parity unpinned"
 for those) and are cross-checked against brute-force enumeration instead.
+
+crf_c.c / native.py: the same CRF decode and log-likelihood in plain C (gcc, OpenMP), pinned to crf.py bit for bit
+(tests/test_oracle_native.py); bench.py uses it to re-run every row of the roofline-sized CRF launches.
 """
