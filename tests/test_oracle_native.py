@@ -76,3 +76,30 @@ def test_bad_arguments_are_rejected():
         native.crf_log_likelihood(x, y, lens, tr)
     with pytest.raises(RuntimeError):
         native.crf_decode(np.zeros((2, 3, 65), np.float32), np.zeros((65, 65), np.float32), np.array([3, 3], np.int32))
+
+
+def test_bench_roofline_checker_flags_a_wrong_tag_and_a_wrong_loglik(monkeypatch):
+    """bench.crf_sample_check is the untimed checker of the roofline-sized CRF launches: fed the oracle's own outputs it must
+    pass on every row, one flipped tag / one shifted log-likelihood must fail it; without the C library it falls back to a
+    row sample through the numpy restatement."""
+    import sys
+    import os
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    B, T, K = 3000, 16, 10
+    x, tr, lens, y = _case(B, T, K, seed=5)
+    tags, _ = crf.crf_decode(x, tr, lens, dtype=np.float32)
+    ll = crf.crf_log_likelihood(x, y, lens, tr).astype(np.float32)
+    tx, ttr, tl, ty = torch.from_numpy(x), torch.from_numpy(tr), torch.from_numpy(lens), torch.from_numpy(y)
+    tp, tll = torch.from_numpy(tags.astype(np.int32)), torch.from_numpy(ll)
+    ok = bench.crf_sample_check(tx, ttr, tl, ty, tll, tp)
+    assert ok["rows_checked"] == B and ok["viterbi_bit_exact"] and ok["loglik_within_tolerance"]
+    bad_p, bad_l = tp.clone(), tll.clone()
+    bad_p[0, 0] = (bad_p[0, 0] + 1) % K
+    bad_l[1] += 0.5
+    bad = bench.crf_sample_check(tx, ttr, tl, ty, bad_l, bad_p)
+    assert not bad["viterbi_bit_exact"] and bad["viterbi_rows_differing"] == 1 and not bad["loglik_within_tolerance"]
+    monkeypatch.setattr(native, "available", lambda: False)
+    sampled = bench.crf_sample_check(tx, ttr, tl, ty, tll, tp, n=512)
+    assert sampled["rows_checked"] == 512 and sampled["viterbi_bit_exact"] and sampled["loglik_within_tolerance"]
