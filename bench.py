@@ -296,12 +296,17 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def _time_launches(fn, warm=3, iters=10, flush=None):
+def _time_launches(fn, warm=3, iters=10, flush=None, park=False):
     """Average CUDA-event duration (ms) of `fn`'s launches on the current stream: >= 3 warm-ups, a synchronize on both
-    sides, optional untimed L2 flush before every timed launch.  -> (mean_ms, min_ms)."""
+    sides, optional untimed L2 flush before every timed launch.  park=True (single-kernel rooflines): the GPU waits behind
+    a spin kernel while the launches are enqueued.  -> (mean_ms, min_ms)."""
     for _ in range(max(warm, 3)):
         fn()
     torch.cuda.synchronize()
+    # the launches come from Python (allocation + ctypes + launch, tens of us each): park the GPU behind a spin kernel so
+    # that they are all enqueued before the first one runs and every event pair brackets execution, not launch latency
+    if park:
+        torch.cuda._sleep(6_000_000)
     evs = []
     for _ in range(iters):
         if flush is not None:
@@ -364,7 +369,7 @@ def crf_rooflines(hbm_peak, peak_src, B=262144, L=128, K=LABELS):
     for key, fn, byts in (
             ("roofline_crf_fwd", lambda: ops.crf_loglik_fwd(x, tags, lens, tr), B * L * (4 * K + 4) + 8 * B + 4 * K * K),
             ("roofline_crf_viterbi", lambda: ops.crf_viterbi(x, lens, tr), B * L * 4 * K + 4 * B + 4 * K * K + B * L * 4 + 4 * B)):
-        ms, best = _time_launches(fn, warm=3, iters=10)
+        ms, best = _time_launches(fn, warm=3, iters=10, park=True)
         gbs = byts / (ms * 1e-3) / 1e9
         out[key] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
                     "ms_per_launch": ms, "best_ms": best, "algorithmic_bytes_per_launch": byts, "launches_timed": 10,
@@ -397,7 +402,7 @@ def softlexicon_roofline(hbm_peak, peak_src, flush, V=704370, E=50, L=128):
             out = torch.empty((B * L, 4 * E), dtype=torch.float32, device="cuda")
             nnz = int((w != 0).sum())
             byts = B * L * (40 * 8 + 4 * E * 4) + nnz * E * 4
-            ms, best = _time_launches(lambda: ops.softlexicon_pool(table, ids, w, 4, 10, out=out), warm=3, iters=10, flush=flush)
+            ms, best = _time_launches(lambda: ops.softlexicon_pool(table, ids, w, 4, 10, out=out), warm=3, iters=10, flush=flush, park=True)
             gbs = byts / (ms * 1e-3) / 1e9
             res[f"{'realistic' if realistic else 'dense'}_B{B}"] = {
                 "achieved": gbs, "frac": gbs / hbm_peak, "ms_per_launch": ms, "best_ms": best, "algorithmic_bytes_per_launch": byts,
