@@ -374,7 +374,7 @@ def crf_rooflines(hbm_peak, peak_src, B=262144, L=128, K=LABELS):
         out[key] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
                     "ms_per_launch": ms, "best_ms": best, "algorithmic_bytes_per_launch": byts, "launches_timed": 10,
                     "workload": f"B={B} L={L} K={K} full lengths, fp32 logits (working set 1.5 GB >> L2)", "peak_source": peak_src}
-    try:        # untimed: the outputs of one more launch of each kernel against the oracle on a row sample
+    try:        # untimed: the outputs of one more launch of each kernel against the oracle (every row with the C oracle)
         chk = crf_sample_check(x, tr, lens, tags, ops.crf_loglik_fwd(x, tags, lens, tr)[0], ops.crf_viterbi(x, lens, tr))
         out["roofline_crf_viterbi"]["parity_checked"] = chk["viterbi_bit_exact"]
         out["roofline_crf_fwd"]["parity_checked"] = chk["loglik_within_tolerance"]
